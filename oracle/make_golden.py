@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference (via oracle/ref_loader.py)
+in this container.  The reference cannot travel to the GPU box, the fixtures can.  Run from the repo root:
+
+    python -m oracle.make_golden
+
+Every fixture stores the reference state_dict (reference key names), the seeded inputs and the reference's outputs.
+Sampled sequences use the noise-driven sampler shim of ref_loader.NoiseSampler (the reference's torch.multinomial
+cannot take external noise); argmax sequences additionally come from the real GenerateLoopV2.run.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sd_arrays(sd):
+    return {"sd/" + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def gen_network(name, net, prompts, n_steps, meta):
+    B = prompts.shape[0]
+    noise = torch.rand(B, n_steps, generator=torch.Generator().manual_seed(4321))
+    tvec = torch.linspace(.85, .999, B)
+    out = dict(sd_arrays(net.state_dict()), prompts=prompts.numpy(), noise=noise.numpy(), tvec=tvec.numpy(),
+               **{"meta/" + k: np.asarray(v) for k, v in meta.items()})
+    seq, lg = ref_loader.run_generate_loop(net, prompts, n_steps, None, noise)
+    out["seq_argmax"], out["logits_argmax"] = seq.numpy(), lg.numpy()
+    real = ref_loader.run_real_generate_loop(net, prompts, n_steps)
+    assert torch.equal(real, seq), "restated driver != GenerateLoopV2.run"
+    out["seq_argmax_real_loop"] = real.numpy()
+    seq, lg = ref_loader.run_generate_loop(net, prompts, n_steps, 1.0, noise)
+    out["seq_t1"], out["logits_t1"] = seq.numpy(), lg.numpy()
+    seq, lg = ref_loader.run_generate_loop(net, prompts, n_steps, tvec, noise)
+    out["seq_tvec"], out["logits_tvec"] = seq.numpy(), lg.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(1234)
+
+    # ---- mu-law (functionals.py:313-373)
+    x = torch.rand(1 << 16, generator=g) * 2 - 1
+    x[:12] = torch.tensor([0., -0., 1., -1., 1e-30, -1e-30, .5, -.5, 1e-3, -1e-3, 0.999999, -0.999999])
+    d = dict(x=x.numpy())
+    for q, C in [(256, 1.), (256, .5), (64, 2.), (1024, 1.)]:
+        d[f"idx_q{q}_c{C}"] = ref.MuLawCompress(q, C).torch_func(x).numpy()
+        d[f"expand_q{q}_c{C}"] = ref.MuLawExpand(q, C).torch_func(torch.arange(q)).numpy()
+    xi = torch.randint(-300, 300, (64,), generator=g)  # non-float input is cast to fp32 first (:332-333)
+    d["x_int"], d["idx_int_q256_c1.0"] = xi.numpy(), ref.MuLawCompress(256, 1.).torch_func(xi).numpy()
+    np.savez_compressed(os.path.join(OUT, "mulaw.npz"), **d)
+    print("mulaw", len(d))
+
+    # ---- STFT magnitudes (functionals.py:450-528, 576-606)
+    d = {}
+    for tag, L, n_fft, hop in [("a", 6000, 512, 128), ("b", 9000, 2048, 512), ("c", 2100, 256, 64)]:
+        xs = torch.rand(2, L, generator=g) * 2 - 1
+        d[f"x_{tag}"] = xs.numpy()
+        d[f"cfg_{tag}"] = np.asarray([n_fft, hop])
+        for center in (True, False):
+            d[f"mag_{tag}_center{int(center)}"] = ref.MagSpec(n_fft, hop, center=center).torch_func(xs).numpy()
+    # frame-count KATs over many lengths (reference tests/test_fft_alignment.py:28-110 style)
+    kat = []
+    for L in list(range(2048, 2048 + 1100, 37)) + [22050, 220500, 32000]:
+        for center in (True, False):
+            n = ref.MagSpec(2048, 512, center=center).torch_func(torch.zeros(L)).shape[0]
+            kat.append((L, int(center), n))
+    d["frame_kat"] = np.asarray(kat)
+    np.savez_compressed(os.path.join(OUT, "magspec.npz"), **d)
+    print("magspec", {k: v.shape for k, v in d.items()})
+
+    # ---- mel filterbank cross-check (torchaudio; librosa itself is absent => "parity unpinned")
+    import torchaudio.functional as AF
+    fb = AF.melscale_fbanks(1025, 0., 11025., 128, 22050, norm="slaney", mel_scale="slaney").T.numpy()
+    nz = np.nonzero(fb)
+    np.savez_compressed(os.path.join(OUT, "mel_fb_torchaudio.npz"), rows=nz[0].astype(np.int16),
+                        cols=nz[1].astype(np.int16), vals=fb[nz], shape=np.asarray(fb.shape))
+
+    # ---- structural KATs of WaveNet (reference tests/test_wavenet.py:251-275)
+    kat = []
+    for blocks, ks in [((3,), (2,)), ((4,), (2,)), ((2, 2), (2,)), ((8, 8, 7, 7), (2,)), ((8, 8, 8, 8), (2,)),
+                       ((3,), (2, 2, 2)), ((2, 2), (2, 2)), ((2, 3), (2, 3, 2, 2, 2)), ((), (2, 2, 2))]:
+        cfg = ref.WaveNet.Config(io_spec=ref.IOSpec.mulaw_io(ref.IOSpec.MuLawIOConfig(input_module_type="embedding")),
+                                 blocks=blocks, kernel_sizes=ks, dims_dilated=(8,))
+        net = ref.WaveNet.from_config(cfg)
+        kat.append(dict(blocks=list(blocks), kernel_sizes=list(ks), rf=int(net.rf),
+                        dilations=[int(l.dilation) for l in net.layers],
+                        kernels=[int(l.kernel_size) for l in net.layers]))
+    import json
+    with open(os.path.join(OUT, "wavenet_structure_kat.json"), "w") as f:
+        json.dump(kat, f, indent=1)
+
+    # ---- networks
+    net = ref_loader.make_wavenet(blocks=(4,), dims=32, seed=0, mlp_dim=32)
+    gen_network("wavenet_default_small", net, torch.randint(0, 256, (3, 40), generator=g), 48,
+                dict(blocks=(4,), dims=32, mlp_dim=32))
+    net = ref_loader.make_wavenet(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, seed=1, mlp_dim=32)
+    gen_network("wavenet_res_skip_small", net, torch.randint(0, 256, (4, 24), generator=g), 40,
+                dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32))
+    net = ref_loader.make_wavenet(blocks=(4, 4), dims=64, residuals_dim=64, skips_dim=48, seed=2, mlp_dim=64)
+    gen_network("wavenet_res_skip_mid", net, torch.randint(0, 256, (5, 64), generator=g), 64,
+                dict(blocks=(4, 4), dims=64, residuals_dim=64, skips_dim=48, mlp_dim=64))
+    net = ref_loader.make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=32, seed=0, mlp_dim=32)
+    gen_network("samplernn_821_small", net, torch.randint(0, 256, (3, 64), generator=g), 48,
+                dict(frame_sizes=(8, 2, 1), hidden_dim=32, mlp_dim=32))
+    gen_network("samplernn_821_small_ragged", net, torch.randint(0, 256, (2, 67), generator=g), 40,
+                dict(frame_sizes=(8, 2, 1), hidden_dim=32, mlp_dim=32))
+    net = ref_loader.make_samplernn(frame_sizes=(16, 4, 2), hidden_dim=64, seed=3, mlp_dim=32)
+    gen_network("samplernn_1642_small", net, torch.randint(0, 256, (4, 64), generator=g), 48,
+                dict(frame_sizes=(16, 4, 2), hidden_dim=64, mlp_dim=32))
+    net = ref_loader.make_samplernn(frame_sizes=(4, 1), hidden_dim=32, seed=4, mlp_dim=32)
+    gen_network("samplernn_41_small", net, torch.randint(0, 256, (2, 32), generator=g), 32,
+                dict(frame_sizes=(4, 1), hidden_dim=32, mlp_dim=32))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

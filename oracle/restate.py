@@ -1,0 +1,520 @@
+"""TEST INFRASTRUCTURE ONLY (oracle) — CPU restatement, in numpy fp32, of the reference's hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  The product package (mimikit_b200/) never does; it fails loudly without its CUDA library.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).  Pinning status:
+  * mu-law            : C restatement (oracle/c/oracle_feat.c) — bit-exact vs the live reference, pinned by
+                        tests/golden/mulaw_*.npz and the exhaustive log1pf sweep (oracle/validate_mulaw.py).
+  * WaveNet / SampleRNN: pinned by tests/golden/{wavenet,samplernn}_*.npz generated from the live reference
+                        (oracle/make_golden.py); structural KATs (rf, output lengths) follow
+                        tests/test_wavenet.py:251-275 of the reference.
+  * STFT magnitudes   : pinned by tests/golden/magspec_*.npz (live reference, torch.stft) and the frame-count
+                        KATs of the reference's tests/test_fft_alignment.py:28-110.
+  * mel               : PARITY UNPINNED at the librosa boundary — librosa (pyproject.toml:38 `librosa>=0.9.1`,
+                        no upper pin, not vendored, not installed here) holds the arithmetic; restated from its
+                        published Slaney-filterbank algorithm and cross-checked against
+                        torchaudio.functional.melscale_fbanks(norm="slaney", mel_scale="slaney").
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+f32 = np.float32
+
+
+def clib():
+    """The C part of the oracle (oracle/c/oracle_feat.c), built by `make -C oracle` / __graft_entry__.build()."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_log1pf.restype = ctypes.c_float
+        _LIB.orc_log1pf.argtypes = [ctypes.c_float]
+        _LIB.orc_expf.restype = ctypes.c_float
+        _LIB.orc_expf.argtypes = [ctypes.c_float]
+    return _LIB
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+# ---------------------------------------------------------------------------------------------
+# features
+# ---------------------------------------------------------------------------------------------
+
+def mulaw_compress(x, q_levels=256, compression=1.0):
+    """mimikit/features/functionals.py:330-338 (MuLawCompress.torch_func, fp32 CPU)."""
+    x = np.ascontiguousarray(x, dtype=f32)
+    out = np.empty(x.shape, dtype=np.int64)
+    clib().orc_mulaw_compress(_ptr(x), _ptr(out), ctypes.c_int64(x.size), ctypes.c_int(int(q_levels)),
+                              ctypes.c_float(float(compression)))
+    return out
+
+
+def mulaw_expand(idx, q_levels=256, compression=1.0):
+    """mimikit/features/functionals.py:361-369 (MuLawExpand.torch_func); exp is the u10 Sleef algorithm, which is
+    within 1 ulp of (not bit-identical to) torch's AVX-512 exp — float output, tolerance 1e-6 abs."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.empty(idx.shape, dtype=f32)
+    clib().orc_mulaw_expand(_ptr(idx), _ptr(out), ctypes.c_int64(idx.size), ctypes.c_int(int(q_levels)),
+                            ctypes.c_float(float(compression)))
+    return out
+
+
+def expf_portable(x):
+    x = np.ascontiguousarray(x, dtype=f32)
+    out = np.empty_like(x)
+    clib().orc_expf_arr(_ptr(x), _ptr(out), ctypes.c_int64(x.size))
+    return out
+
+
+def stft_target_length(L, n_fft, hop, center):
+    """STFT._fix_length (functionals.py:468-486) through item_spec.convert (item_spec.py:58-98)."""
+    extra = 0 if center else (n_fft - hop)
+    n = (L - extra) // hop + int(center)  # Sample -> Frame (as_length) + int(center)
+    n -= int(center)                      # Frame -> Sample: x -= int(has_padding)
+    return int(n * hop) + extra
+
+
+def stft_n_frames(L, n_fft, hop, center):
+    t = stft_target_length(L, n_fft, hop, center)
+    return t // hop + 1 if center else (t - n_fft) // hop + 1
+
+
+def stft_fix_length(x, n_fft, hop, center, alignment="end"):
+    if alignment is None:
+        return x
+    t = stft_target_length(x.shape[-1], n_fft, hop, center)
+    if alignment == "end":
+        return x[..., -t:] if t != 0 else x  # python's x[-0:] keeps everything (reference quirk)
+    if alignment == "start":
+        return x[..., :t]
+    return x
+
+
+def hann_periodic(n_fft):
+    """torch.hann_window(n_fft) (periodic) — functionals.py:513 always uses it on the torch path."""
+    n = np.arange(n_fft, dtype=np.float64)
+    return 0.5 * (1.0 - np.cos(2.0 * np.pi * n / n_fft))
+
+
+def magspec(x, n_fft=2048, hop=512, center=True, alignment="end"):
+    """MagSpec.torch_func -> STFT(coordinate='mag').torch_func (functionals.py:507-524, 576-606):
+    length fix, zero ("constant") centre padding, periodic hann, rFFT, |.|, layout (..., frames, n_fft/2+1).
+    Evaluated in fp64 and rounded to fp32 (the reference evaluates in fp32; tolerance 1e-4, see tests)."""
+    x = np.asarray(x, dtype=np.float64)
+    x = stft_fix_length(x, n_fft, hop, center, alignment)
+    if center:
+        pad = [(0, 0)] * (x.ndim - 1) + [(n_fft // 2, n_fft // 2)]
+        x = np.pad(x, pad)
+    n_frames = (x.shape[-1] - n_fft) // hop + 1
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    frames = x[..., idx] * hann_periodic(n_fft)
+    return np.abs(np.fft.rfft(frames, axis=-1)).astype(f32)
+
+
+def _hz_to_mel(f, htk=False):
+    f = np.asarray(f, dtype=np.float64)
+    if htk:
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-30) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz(m, htk=False):
+    m = np.asarray(m, dtype=np.float64)
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(n_fft=2048, n_mels=128, fmin=0.0, fmax=None, htk=False, sr=22050):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk, norm='slaney') as reached from
+    MelSpec.np_func (functionals.py:665-668) -> librosa.feature.melspectrogram(S=...).  The reference never passes
+    `sr`, so librosa's default 22050 applies whatever the audio's rate is.  Returns (n_mels, n_fft/2+1) fp32."""
+    if fmax is None:
+        fmax = sr / 2.0
+    n_bins = 1 + n_fft // 2
+    fftfreqs = np.linspace(0.0, sr / 2.0, n_bins)
+    mel_pts = _mel_to_hz(np.linspace(_hz_to_mel(fmin, htk), _hz_to_mel(fmax, htk), n_mels + 2), htk)
+    fdiff = np.diff(mel_pts)
+    ramps = mel_pts[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, n_bins), dtype=np.float64)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0.0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_pts[2:n_mels + 2] - mel_pts[:n_mels])
+    w *= enorm[:, None]
+    return w.astype(f32)
+
+
+def melspec(mag, n_mels=128, fmin=0.0, fmax=None, htk=False, n_fft=None):
+    """MelSpec.np_func (functionals.py:665-668): mel_basis @ S with S = mag.T, transposed back.
+    `mag` is (..., frames, n_bins) fp32; accumulation in fp64, rounded to fp32."""
+    mag = np.asarray(mag)
+    n_fft = 2 * (mag.shape[-1] - 1) if n_fft is None else n_fft
+    fb = mel_filterbank(n_fft, n_mels, fmin, fmax, htk)
+    return (mag.astype(np.float64) @ fb.T.astype(np.float64)).astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------
+# sampling contract (ours; SURVEY.md App. A.3, blocked-scan order — see DESIGN.md §sampling)
+# ---------------------------------------------------------------------------------------------
+
+def sample_inverse_cdf(logits, temperature, u):
+    """Replaces torch.multinomial in CategoricalSampler.forward (mimikit/modules/targets.py:40-52), which cannot
+    be driven by external noise.
+
+      l_k = logits_k / T_b (fp32);  m = max_k l_k;  e_k = expf_u10(l_k - m)
+      the Q classes are dealt to 32 lanes in runs of n = ceil(Q/32) consecutive classes; each lane forms its
+      sequential fp32 inclusive prefix; lane totals are scanned with the 5-stage Kogge-Stone pattern
+      (offsets 1,2,4,8,16); c_k = exclusive_lane_prefix + in-lane prefix; total = inclusive prefix of lane 31
+      q = min(Q-1, #{k : c_k <= u * total})
+
+    logits (B,Q) fp32, temperature (1,) or (B,) fp32, u (B,) fp32 in [0,1).  Returns (B,) int64."""
+    logits = np.asarray(logits, dtype=f32)
+    B, Q = logits.shape
+    T = np.broadcast_to(np.asarray(temperature, dtype=f32).reshape(-1), (B,)) if np.size(temperature) != B \
+        else np.asarray(temperature, dtype=f32).reshape(B)
+    u = np.asarray(u, dtype=f32).reshape(B)
+    l = (logits / T[:, None]).astype(f32)
+    m = l.max(axis=1, keepdims=True)
+    e = expf_portable((l - m).astype(f32))
+    n = (Q + 31) // 32
+    pad = np.zeros((B, 32 * n), dtype=f32)
+    pad[:, :Q] = e
+    lanes = pad.reshape(B, 32, n)
+    pref = np.empty_like(lanes)
+    acc = np.zeros((B, 32), dtype=f32)
+    for i in range(n):
+        acc = (acc + lanes[:, :, i]).astype(f32)
+        pref[:, :, i] = acc
+    v = acc.copy()
+    for off in (1, 2, 4, 8, 16):
+        nv = v.copy()
+        nv[:, off:] = (v[:, off:] + v[:, :-off]).astype(f32)
+        v = nv
+    excl = np.zeros_like(v)
+    excl[:, 1:] = v[:, :-1]
+    c = (excl[:, :, None] + pref).astype(f32).reshape(B, 32 * n)[:, :Q]
+    thr = (u * v[:, 31]).astype(f32)
+    cnt = (c <= thr[:, None]).sum(axis=1)
+    return np.minimum(Q - 1, cnt).astype(np.int64)
+
+
+def argmax_first(logits):
+    """targets.py:43 — torch argmax: lowest index among equal maxima (numpy has the same rule)."""
+    return np.argmax(logits, axis=-1).astype(np.int64)
+
+
+def normalize_temperature(temperature, B):
+    """targets.py:27-34 (as_tensor): None | float | 1-sequence | (B,) -> None or fp32 (1,)/(B,)."""
+    if temperature is None:
+        return None
+    t = np.asarray(temperature, dtype=f32).reshape(-1)
+    if t.size not in (1, B):
+        raise ValueError(f"temperature must have 1 or {B} entries, got {t.size}")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# shared pieces of the networks
+# ---------------------------------------------------------------------------------------------
+
+def _sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(f32)))).astype(f32)
+
+
+def _mish(x):
+    x = x.astype(f32)
+    sp = np.where(x > 20.0, x, np.log1p(np.exp(np.minimum(x, 20.0)))).astype(f32)  # F.softplus threshold 20
+    return (x * np.tanh(sp)).astype(f32)
+
+
+def mlp_head(x, W1, b1, W2, b2, min_temp, Q):
+    """networks/mlp.py:44-63 with n_hidden_layers=0: Linear, Mish, Linear(+1), learned-temperature divide."""
+    z = _mish(x @ W1.T + b1) @ W2.T + b2
+    temp = np.maximum(_sigmoid(z[..., Q:Q + 1]), f32(min_temp))
+    return (z[..., :Q] / temp).astype(f32)
+
+
+def _np(sd, key):
+    v = sd[key]
+    return np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=f32)
+
+
+def fold_weight_norm(sd):
+    """nn.utils.weight_norm (sample_rnn_v2.py:67-81): w = g * v / ||v|| with the norm over all dims but 0."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith("_g") or k.endswith("_v"):
+            continue
+        out[k] = v
+    for k in sd:
+        if k.endswith("_v"):
+            base = k[:-2]
+            v, g = _np(sd, k).astype(np.float64), _np(sd, base + "_g").astype(np.float64)
+            norm = np.sqrt((v.reshape(v.shape[0], -1) ** 2).sum(1)).reshape((-1,) + (1,) * (v.ndim - 1))
+            out[base] = (g * v / norm).astype(f32)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# WaveNet
+# ---------------------------------------------------------------------------------------------
+
+def wavenet_kernels_and_dilations(kernel_sizes, blocks):
+    """WaveNet.get_kernels_and_dilation (networks/wavenet_v2.py:295-327)."""
+    kernel_sizes, blocks = tuple(kernel_sizes), tuple(blocks)
+    if not blocks:
+        dil, acc = [], 1
+        for k in (1,) + kernel_sizes:
+            acc *= k
+            dil.append(acc)
+        return list(kernel_sizes), dil  # NB: the reference yields one more dilation than kernels; zip() trims it
+    if len(set(blocks)) == 1 and blocks[0] == len(kernel_sizes):
+        dil = []
+        for _ in blocks:
+            acc = 1
+            dil.append(acc)
+            for k in kernel_sizes[:-1]:
+                acc *= k
+                dil.append(acc)
+        return list(kernel_sizes) * len(blocks), dil
+    if len(kernel_sizes) == sum(blocks):
+        dil, start = [], 0
+        for b in blocks:
+            acc = 1
+            dil.append(acc)
+            for k in kernel_sizes[start:start + b - 1]:
+                acc *= k
+                dil.append(acc)
+            start += b
+        return list(kernel_sizes), dil
+    if len(kernel_sizes) == 1:
+        k = kernel_sizes[0]
+        return [k] * sum(blocks), [k ** i for b in blocks for i in range(b)]
+    raise ValueError(f"number of layers and number of kernel sizes not compatible."
+                     f" Got kernel_sizes={kernel_sizes} ; blocks={blocks}")
+
+
+def wavenet_rf(kernel_sizes, blocks):
+    """WaveNet.rf (wavenet_v2.py:337-339): sum of (k-1)*d over layers + 1."""
+    ks, ds = wavenet_kernels_and_dilations(kernel_sizes, blocks)
+    return sum((k - 1) * d for k, d in zip(ks, ds)) + 1
+
+
+class WaveNetOracle:
+    """Cached-step restatement of WaveNet.generate_step == forward on the last rf samples
+    (networks/wavenet_v2.py:447-452, 276-293; WNLayer.forward 131-176), for the mu-law embedding-input, gated,
+    pad_side=0, kernel_size=2 configuration."""
+
+    def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256):
+        sd = state_dict
+        ks, ds = wavenet_kernels_and_dilations(kernel_sizes, blocks)
+        self.dilations = [int(d) for _, d in zip(ks, ds)]
+        assert all(k == 2 for k in ks), "oracle restates kernel_size=2 only"
+        self.L = len(self.dilations)
+        self.Q = q_levels
+        self.E = _np(sd, "input_modules.0.0.weight")
+        self.C = self.E.shape[1]
+        self.Wd0, self.Wd1, self.bd, self.Ws, self.bs, self.Wr, self.br = [], [], [], [], [], [], []
+        self.has_skips = "layers.0.conv_skip.weight" in sd
+        for l in range(self.L):
+            w = _np(sd, f"layers.{l}.conv_dil.0.0.weight")  # (2C, C, 2): tap 0 = older sample (cross-correlation)
+            self.Wd0.append(np.ascontiguousarray(w[:, :, 0]))
+            self.Wd1.append(np.ascontiguousarray(w[:, :, 1]))
+            self.bd.append(_np(sd, f"layers.{l}.conv_dil.0.0.bias"))
+            if self.has_skips:
+                self.Ws.append(_np(sd, f"layers.{l}.conv_skip.weight")[:, :, 0])
+                self.bs.append(_np(sd, f"layers.{l}.conv_skip.bias"))
+            if f"layers.{l}.conv_res.weight" in sd:
+                self.Wr.append(_np(sd, f"layers.{l}.conv_res.weight")[:, :, 0])
+                self.br.append(_np(sd, f"layers.{l}.conv_res.bias"))
+            else:
+                self.Wr.append(None)
+                self.br.append(None)
+        p = "output_modules.0.estimator.0."
+        self.W1, self.b1 = _np(sd, p + "fc.0.weight"), _np(sd, p + "fc.0.bias")
+        self.W2, self.b2 = _np(sd, p + "fc.2.weight"), _np(sd, p + "fc.2.bias")
+        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
+        self.rf = sum(self.dilations) + 1
+
+    def _layer(self, l, x0, x1, skips):
+        C = self.C
+        a = x0 @ self.Wd0[l].T + x1 @ self.Wd1[l].T + self.bd[l]          # wavenet_v2.py:101,150
+        y = (np.tanh(a[..., :C]) * _sigmoid(a[..., C:])).astype(f32)     # :102,151
+        if self.has_skips:
+            s = y @ self.Ws[l].T + self.bs[l]                            # :165-171
+            skips = s if skips is None else (s + skips).astype(f32)
+        h = (x1 + (y @ self.Wr[l].T + self.br[l])).astype(f32) if self.Wr[l] is not None else y  # :172-175
+        return h, skips
+
+    def logits_teacher_forced(self, x):
+        """x (B,T>=rf) int64 -> (B, T-rf+1, Q): entry i uses x[:, i:i+rf] and predicts sample i+rf
+        (== train-mode forward of the reference)."""
+        h = self.E[np.asarray(x)]
+        skips = None
+        for l, d in enumerate(self.dilations):
+            sk = None if skips is None else skips[:, d:]
+            h, skips = self._layer(l, h[:, :-d], h[:, d:], sk)
+        out = skips if self.has_skips else h
+        return mlp_head(out, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+
+    def generate(self, prompts, n_steps, temperature=None, noise=None, forced=None):
+        """GenerateLoopV2.run semantics (loops/generate.py:184-229) with cached per-layer histories.
+        `forced` (B, P+n_steps) teacher-forces the fed-back samples (decisions are still returned).
+        Returns (sequence (B,P+n) int64, logits (B,n,Q) fp32)."""
+        prompts = np.asarray(prompts, dtype=np.int64)
+        B, P = prompts.shape
+        if P < self.rf:
+            raise ValueError(f"prompt length {P} < receptive field {self.rf}")
+        T = normalize_temperature(temperature, B)
+        W = self.rf
+        seq = np.concatenate([prompts, np.zeros((B, n_steps), dtype=np.int64)], 1)
+        # hist[l][:, j] = h_l(P - W + j): inputs of layer l; prefill densely over the last rf prompt samples
+        hist = [np.zeros((B, W + n_steps, self.C), dtype=f32) for _ in range(self.L)]
+        h = self.E[prompts[:, P - W:]]
+        off = 0
+        for l, d in enumerate(self.dilations):
+            hist[l][:, off:W] = h
+            h, _ = self._layer(l, h[:, :-d], h[:, d:], None)
+            off += d
+        logits_out = np.zeros((B, n_steps, self.Q), dtype=f32)
+        for i in range(n_steps):
+            t = P + i
+            j = W + i - 1                      # column of time t-1
+            src = seq if forced is None else np.asarray(forced)
+            x1 = self.E[src[:, t - 1]]
+            skips = None
+            for l, d in enumerate(self.dilations):
+                hist[l][:, j] = x1
+                x1, skips = self._layer(l, hist[l][:, j - d], x1, skips)
+            out = skips if self.has_skips else x1
+            lg = mlp_head(out, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+            logits_out[:, i] = lg
+            seq[:, t] = argmax_first(lg) if T is None else sample_inverse_cdf(lg, T, noise[:, i])
+        return seq, logits_out
+
+
+# ---------------------------------------------------------------------------------------------
+# SampleRNN
+# ---------------------------------------------------------------------------------------------
+
+class SampleRNNOracle:
+    """Restatement of SampleRNN.before_generate / generate_step
+    (networks/sample_rnn_v2.py:226-260) with SampleRNNTier.forward (83-99), FramedLinearIO / FramedConv1dIO
+    (modules/io.py:106-133,185-198), LinearResampler (modules/resamplers.py:13-23) and GRU cells (PyTorch gate
+    order r,z,n).  n_rnn=1, h0 zeros, inputs_mode='sum', single mu-law input."""
+
+    def __init__(self, state_dict, frame_sizes, q_levels=256):
+        sd = fold_weight_norm(state_dict) if any(k.endswith("_g") for k in state_dict) else state_dict
+        self.fs = tuple(int(f) for f in frame_sizes)
+        self.n_tiers = len(self.fs)
+        self.Q = q_levels
+        self.tiers = []
+        for i in range(self.n_tiers - 1):
+            p = f"tiers.{i}."
+            self.tiers.append(dict(
+                Win=_np(sd, p + "input_module.heads.0.2.weight"), bin=_np(sd, p + "input_module.heads.0.2.bias"),
+                Wih=_np(sd, p + "rnn.weight_ih_l0"), Whh=_np(sd, p + "rnn.weight_hh_l0"),
+                bih=_np(sd, p + "rnn.bias_ih_l0"), bhh=_np(sd, p + "rnn.bias_hh_l0"),
+                Wup=_np(sd, p + "up_sampler.fc.weight"), bup=_np(sd, p + "up_sampler.fc.bias")))
+        p = f"tiers.{self.n_tiers - 1}.input_module.heads.0.2.2.cv."
+        self.Wc = _np(sd, p + "weight")[:, 0, :]  # (H, fs_last)
+        self.bc = _np(sd, p + "bias")
+        self.H = self.Wc.shape[0]
+        p = "output_modules.0.estimator.0."
+        self.W1, self.b1 = _np(sd, p + "fc.0.weight"), _np(sd, p + "fc.0.bias")
+        self.W2, self.b2 = _np(sd, p + "fc.2.weight"), _np(sd, p + "fc.2.bias")
+        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
+        self.rf = self.fs[0]
+        # sample_rnn_v2.py:155-158
+        self.up = [self.fs[i] // (self.fs[i + 1] if i < self.n_tiers - 2 else 1) for i in range(self.n_tiers - 1)]
+
+    def lin(self, q):
+        """Linearizer (modules/io.py:111-112)."""
+        return ((q.astype(f32) / f32(self.Q)) - f32(0.5)) * f32(2.0)
+
+    def _gru(self, tier, x, h):
+        H = self.H
+        gi = x @ tier["Wih"].T + tier["bih"]
+        gh = h @ tier["Whh"].T + tier["bhh"]
+        r = _sigmoid(gi[:, :H] + gh[:, :H])
+        z = _sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:]).astype(f32)
+        return ((1.0 - z) * n + z * h).astype(f32)
+
+    def _frame_tiers(self, window, t, hid, O):
+        """the `for i in range(len(tiers) - 1)` part of generate_step (sample_rnn_v2.py:245-253);
+        window = the rf samples preceding (logical) time t."""
+        fs = self.fs
+        for i, tier in enumerate(self.tiers):
+            if t % fs[i] == 0:
+                x = self.lin(window[:, -fs[i]:]) @ tier["Win"].T + tier["bin"]
+                if i > 0:
+                    x = x + O[i - 1][:, (t // fs[i]) % (fs[i - 1] // fs[i])]
+                hid[i] = self._gru(tier, x.astype(f32), hid[i])
+                O[i] = (hid[i] @ tier["Wup"].T + tier["bup"]).reshape(-1, self.up[i], self.H)
+
+    def generate(self, prompts, n_steps, temperature=None, noise=None, forced=None):
+        prompts = np.asarray(prompts, dtype=np.int64)
+        B, P = prompts.shape
+        fs, rf = self.fs, self.rf
+        if P < rf:
+            raise ValueError(f"prompt length {P} < frame size {rf}")
+        T = normalize_temperature(temperature, B)
+        hid = [np.zeros((B, self.H), dtype=f32) for _ in self.tiers]
+        O = [None] * len(self.tiers)
+        offset = P % rf                      # sample_rnn_v2.py:229-231
+        plen = P - offset
+        for t in range(rf, plen):            # warm-up, :232-234
+            self._frame_tiers(prompts[:, t + offset - rf:t + offset], t, hid, O)
+        seq = np.concatenate([prompts, np.zeros((B, n_steps), dtype=np.int64)], 1)
+        logits_out = np.zeros((B, n_steps, self.Q), dtype=f32)
+        for i in range(n_steps):
+            t = P + i                        # loops/generate.py:207-211: absolute t, window seq[:, t-rf:t]
+            src = seq if forced is None else np.asarray(forced)
+            window = src[:, t - rf:t]
+            self._frame_tiers(window, t, hid, O)
+            x = self.lin(window[:, -fs[-1]:]) @ self.Wc.T + self.bc          # Conv1d(1,H,k=fs_last), one frame
+            x = (x + O[-1][:, (t % fs[-2]) - fs[-2]]).astype(f32)            # :256-257
+            lg = mlp_head(x, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+            logits_out[:, i] = lg
+            seq[:, t] = argmax_first(lg) if T is None else sample_inverse_cdf(lg, T, noise[:, i])
+        return seq, logits_out
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------------------------
+
+def synthetic_waveform(B, n, sr=16000, seed=1234):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    phi = 2 * np.pi * np.arange(B)[:, None] / max(B, 1)
+    x = 0.6 * np.sin(2 * np.pi * 220 * t[None] + phi) + 0.3 * np.sin(2 * np.pi * 659 * t[None]) \
+        + 0.05 * rng.standard_normal((B, n))
+    x = x / np.abs(x).max(axis=1, keepdims=True)
+    return x.astype(f32)
+
+
+def synthetic_prompts(B, P, sr=16000, seed=1234, q_levels=256):
+    return mulaw_compress(synthetic_waveform(B, P, sr, seed), q_levels, 1.0)

@@ -1,0 +1,130 @@
+"""CPU tests: the oracle (oracle/restate.py + oracle/c) against the golden vectors generated from the live
+reference (oracle/make_golden.py) and against the reference's own structural KATs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_state_dict, load_golden
+from oracle import restate
+
+
+def test_mulaw_compress_bit_exact_vs_reference():
+    d = load_golden("mulaw")
+    for q, C in [(256, 1.), (256, .5), (64, 2.), (1024, 1.)]:
+        got = restate.mulaw_compress(d["x"], q, C)
+        assert got.dtype == np.int64
+        assert np.array_equal(got, d[f"idx_q{q}_c{C}"]), (q, C)
+        exp = restate.mulaw_expand(np.arange(q), q, C)
+        np.testing.assert_allclose(exp, d[f"expand_q{q}_c{C}"], rtol=0, atol=1e-6)
+    got = restate.mulaw_compress(d["x_int"].astype(np.float32), 256, 1.)
+    assert np.array_equal(got, d["idx_int_q256_c1.0"])
+
+
+def test_mulaw_roundtrip_is_idempotent():
+    # compress(expand(i)) == i for every class: size-independent property used at full size on the GPU
+    for q, C in [(256, 1.), (256, .5), (512, 1.)]:
+        idx = np.arange(q)
+        assert np.array_equal(restate.mulaw_compress(restate.mulaw_expand(idx, q, C), q, C), idx)
+
+
+def test_magspec_vs_reference_within_1e4():
+    d = load_golden("magspec")
+    for tag in "abc":
+        n_fft, hop = (int(v) for v in d[f"cfg_{tag}"])
+        for center in (True, False):
+            ref = d[f"mag_{tag}_center{int(center)}"]
+            got = restate.magspec(d[f"x_{tag}"], n_fft, hop, center)
+            assert got.shape == ref.shape
+            # tolerance: 1e-4 relative to the clip's peak magnitude (north star: "STFT/mel within 1e-4")
+            assert np.abs(got - ref).max() <= 1e-4 * max(1.0, ref.max())
+
+
+def test_stft_frame_count_kats():
+    d = load_golden("magspec")
+    for L, center, n in d["frame_kat"]:
+        assert restate.stft_n_frames(int(L), 2048, 512, bool(center)) == int(n), (L, center)
+    # reference tests/test_fft_alignment.py: centered -> L//hop + 1 frames
+    assert restate.stft_n_frames(220500, 2048, 512, True) == 431
+    assert restate.stft_n_frames(220500, 2048, 512, False) == 427
+
+
+def test_mel_filterbank_vs_torchaudio_slaney():
+    d = np.load(os.path.join(GOLDEN, "mel_fb_torchaudio.npz"))
+    fb = np.zeros(tuple(d["shape"]), dtype=np.float32)
+    fb[d["rows"].astype(int), d["cols"].astype(int)] = d["vals"]
+    mine = restate.mel_filterbank(2048, 128, 0., None, False)
+    assert mine.shape == (128, 1025)
+    assert np.abs(mine - fb).max() < 1e-6
+
+
+def test_wavenet_structure_kats():
+    with open(os.path.join(GOLDEN, "wavenet_structure_kat.json")) as f:
+        kats = json.load(f)
+    for k in kats:
+        ks, ds = restate.wavenet_kernels_and_dilations(k["kernel_sizes"], k["blocks"])
+        pairs = list(zip(ks, ds))
+        assert [d for _, d in pairs] == k["dilations"], k
+        assert [kk for kk, _ in pairs] == k["kernels"], k
+        assert sum((kk - 1) * d for kk, d in pairs) + 1 == k["rf"]
+    # reference tests/test_wavenet.py:251-275: rf == 8 for these layouts
+    for blocks, ks in [((3,), (2,)), ((3,), (2, 2, 2)), ((), (2, 2, 2))]:
+        assert restate.wavenet_rf(ks, blocks) == 8
+    assert restate.wavenet_rf((2,), (8, 8, 7, 7)) == 765
+    assert restate.wavenet_rf((2,), (8, 8, 8, 8)) == 1021
+
+
+@pytest.mark.parametrize("name", ["wavenet_default_small", "wavenet_res_skip_small", "wavenet_res_skip_mid"])
+def test_wavenet_oracle_vs_reference(name):
+    d = load_golden(name)
+    orc = restate.WaveNetOracle(golden_state_dict(d), tuple(int(b) for b in d["meta/blocks"]))
+    n = d["noise"].shape[1]
+    for tag, T in [("argmax", None), ("t1", 1.0), ("tvec", d["tvec"])]:
+        seq, lg = orc.generate(d["prompts"], n, T, d["noise"])
+        assert np.array_equal(seq, d["seq_" + tag]), tag
+        np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
+    assert np.array_equal(d["seq_argmax"], d["seq_argmax_real_loop"])
+    # window recompute (the reference's algorithm) == cached step: teacher-forced logits on the reference's own sequence
+    tf = orc.logits_teacher_forced(d["seq_argmax"])
+    P = d["prompts"].shape[1]
+    np.testing.assert_allclose(tf[:, P - orc.rf:P - orc.rf + n], d["logits_argmax"], rtol=1e-3, atol=1e-5)
+    # prompt shorter than the receptive field is an error (reference: RuntimeError, tests/test_wavenet.py:271-275)
+    with pytest.raises(ValueError):
+        orc.generate(d["prompts"][:, :orc.rf - 1], 2)
+
+
+@pytest.mark.parametrize("name", ["samplernn_821_small", "samplernn_821_small_ragged", "samplernn_1642_small",
+                                  "samplernn_41_small"])
+def test_samplernn_oracle_vs_reference(name):
+    d = load_golden(name)
+    orc = restate.SampleRNNOracle(golden_state_dict(d), tuple(int(b) for b in d["meta/frame_sizes"]))
+    n = d["noise"].shape[1]
+    for tag, T in [("argmax", None), ("t1", 1.0), ("tvec", d["tvec"])]:
+        seq, lg = orc.generate(d["prompts"], n, T, d["noise"])
+        assert np.array_equal(seq, d["seq_" + tag]), tag
+        np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
+
+
+def test_sampling_contract_properties():
+    rng = np.random.default_rng(0)
+    lg = rng.standard_normal((64, 256)).astype(np.float32) * 3
+    # u -> 0 picks the first class with mass, u -> 1 the last; monotone in u
+    lo = restate.sample_inverse_cdf(lg, [1.0], np.zeros(64, np.float32))
+    hi = restate.sample_inverse_cdf(lg, [1.0], np.full(64, np.float32(1) - np.float32(2 ** -24)))
+    assert (lo == 0).all() and (hi >= 250).all()
+    us = np.sort(rng.random((64, 50)).astype(np.float32), axis=1)
+    prev = np.zeros(64, dtype=np.int64)
+    for j in range(50):
+        cur = restate.sample_inverse_cdf(lg, [0.9], us[:, j])
+        assert (cur >= prev).all()
+        prev = cur
+    # low temperature converges to argmax
+    cold = restate.sample_inverse_cdf(lg, [1e-3], np.full(64, .5, np.float32))
+    assert np.array_equal(cold, restate.argmax_first(lg))
+    # empirical frequencies follow softmax
+    l1 = np.tile(lg[:1], (20000, 1))
+    s = restate.sample_inverse_cdf(l1, [1.0], rng.random(20000).astype(np.float32))
+    p = np.exp(lg[0] - lg[0].max()); p /= p.sum()
+    freq = np.bincount(s, minlength=256) / 20000
+    assert np.abs(freq - p).max() < 0.02
