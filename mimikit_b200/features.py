@@ -1,0 +1,287 @@
+"""Feature functionals on the hot path — same names, fields and call contract as the reference's
+`mimikit/features/functionals.py` (`Functional.__call__` dispatching on the input type, `.inv`, `.unit`,
+`.elem_type`, functionals.py:81-111), computed by the sm_100a kernels behind the C ABI.
+
+Inputs may be CUDA tensors (zero-copy), CPU tensors or numpy arrays (host buffers: copied to the device, computed
+there and copied back — the output lives where the input lived).  There is no CPU implementation.
+"""
+import ctypes
+import dataclasses as dtc
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+
+__all__ = ["Continuous", "Discrete", "Sample", "Frame", "Functional", "MuLawCompress", "MuLawExpand", "STFT",
+           "MagSpec", "MelSpec", "mel_filterbank", "stft_n_frames"]
+
+N_FFT = 2048
+HOP_LENGTH = 512
+SR = 22050
+Q_LEVELS = 256
+
+
+@dtc.dataclass
+class Continuous:  # functionals.py:64-68
+    min_value: Union[float, int]
+    max_value: Union[float, int]
+    size: int
+
+
+@dtc.dataclass
+class Discrete:  # functionals.py:71-73
+    size: int
+
+
+@dtc.dataclass(frozen=True)
+class Sample:  # item_spec.py:24-29
+    sr: Optional[int]
+
+
+@dtc.dataclass(frozen=True)
+class Frame:  # item_spec.py:32-38
+    frame_size: int
+    hop_length: int
+    padding: Optional[bool] = None
+
+
+def _to_device(x, dtype=None):
+    """-> (cuda tensor, restore) where restore maps a cuda result back to the caller's container."""
+    _capi.require_cuda()
+    if isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        return t.cuda(non_blocking=False), (lambda r: r.cpu().numpy())
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"expected np.ndarray or torch.Tensor, got {type(x)}")
+    if x.is_cuda:
+        return x, (lambda r: r)
+    return x.cuda(), (lambda r: r.cpu())
+
+
+class Functional:
+    """functionals.py:76-111."""
+
+    @property
+    def unit(self):
+        return None
+
+    @property
+    def elem_type(self):
+        return None
+
+    def torch_func(self, inputs: torch.Tensor):
+        raise NotImplementedError
+
+    def np_func(self, inputs: np.ndarray):
+        return self.torch_func(inputs)
+
+    def __call__(self, inputs):
+        if not isinstance(inputs, (np.ndarray, torch.Tensor)):
+            raise KeyError(type(inputs))  # the reference's dict dispatch raises KeyError
+        return self.torch_func(inputs)
+
+
+@dtc.dataclass
+class MuLawCompress(Functional):
+    """functionals.py:313-342.  Bit-exact with the reference's torch_func on CPU (fp32)."""
+    q_levels: int = Q_LEVELS
+    compression: float = 1.
+
+    @property
+    def elem_type(self):
+        return Discrete(self.q_levels)
+
+    def torch_func(self, inputs, out_dtype=torch.int64):
+        x, restore = _to_device(inputs)
+        if not x.is_floating_point():
+            x = x.to(torch.float)            # functionals.py:332-333
+        if x.dtype != torch.float32:
+            raise TypeError("MuLawCompress: the B200 path computes in fp32 (the reference's dtype for audio)")
+        x = x.contiguous()
+        lib = _capi.lib()
+        if out_dtype == torch.int64:
+            out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+            fn = lib.mmk_mulaw_compress
+        elif out_dtype == torch.uint8:
+            out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+            fn = lib.mmk_mulaw_compress_u8
+        else:
+            raise TypeError("out_dtype must be torch.int64 (drop-in) or torch.uint8")
+        with torch.cuda.device(x.device):
+            _capi.check(fn(x.data_ptr(), out.data_ptr(), x.numel(), int(self.q_levels), float(self.compression),
+                           _capi.stream_ptr()))
+        return restore(out)
+
+    @property
+    def inv(self):
+        return MuLawExpand(self.q_levels, self.compression)
+
+
+@dtc.dataclass
+class MuLawExpand(Functional):
+    """functionals.py:345-373."""
+    q_levels: int = Q_LEVELS
+    compression: float = 1.
+
+    @property
+    def elem_type(self):
+        return Continuous(-1., 1., 1)
+
+    def torch_func(self, inputs):
+        q, restore = _to_device(inputs)
+        if q.dtype != torch.int64:
+            q = q.to(torch.int64)
+        q = q.contiguous()
+        out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            _capi.check(_capi.lib().mmk_mulaw_expand(q.data_ptr(), out.data_ptr(), q.numel(), int(self.q_levels),
+                                                     float(self.compression), _capi.stream_ptr()))
+        return restore(out)
+
+    @property
+    def inv(self):
+        return MuLawCompress(self.q_levels, self.compression)
+
+
+_ALIGN = {None: 0, "end": 1, "start": 2}
+
+
+def stft_n_frames(length, n_fft=N_FFT, hop_length=HOP_LENGTH, center=True, alignment="end"):
+    """(n_frames, kept_length) after STFT._fix_length (functionals.py:468-486; item_spec.convert :58-98)."""
+    nf, kept = ctypes.c_int64(), ctypes.c_int64()
+    _capi.check(_capi.lib().mmk_stft_n_frames(int(length), int(n_fft), int(hop_length), int(bool(center)),
+                                              _ALIGN[alignment], ctypes.byref(nf), ctypes.byref(kept)))
+    return nf.value, kept.value
+
+
+def mel_filterbank(n_fft=N_FFT, n_mels=128, fmin=0., fmax=None, htk=False):
+    """The librosa Slaney-normalised mel basis the reference reaches from functionals.py:665-668 (sr is always
+    librosa's default 22050 there).  Host-side; returns (n_mels, n_fft/2+1) fp32 CPU tensor."""
+    out = torch.empty(n_mels, n_fft // 2 + 1, dtype=torch.float32)
+    _capi.check(_capi.lib().mmk_mel_filterbank(int(n_fft), int(n_mels), float(fmin),
+                                               float(-1.0 if fmax is None else fmax), int(bool(htk)),
+                                               out.data_ptr()))
+    return out
+
+
+def _stft_mag_mel(x, n_fft, hop, center, alignment, want_mag, fb):
+    """x: cuda fp32 (..., L) -> (mag or None, mel or None)."""
+    lead = x.shape[:-1]
+    L = x.shape[-1]
+    x2 = x.reshape(-1, L).contiguous()
+    n_clips = x2.shape[0]
+    n_frames, _ = stft_n_frames(L, n_fft, hop, center, alignment)
+    nb = n_fft // 2 + 1
+    mag = torch.empty((n_clips, n_frames, nb), dtype=torch.float32, device=x.device) if want_mag else None
+    mel = torch.empty((n_clips, n_frames, fb.shape[0]), dtype=torch.float32, device=x.device) if fb is not None else None
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().mmk_stft_mag_mel(
+            x2.data_ptr(), n_clips, L, x2.stride(0), int(n_fft), int(hop), int(bool(center)), _ALIGN[alignment],
+            mag.data_ptr() if mag is not None else None, fb.data_ptr() if fb is not None else None,
+            fb.shape[0] if fb is not None else 0, mel.data_ptr() if mel is not None else None, _capi.stream_ptr()))
+    if mag is not None:
+        mag = mag.reshape(*lead, n_frames, nb)
+    if mel is not None:
+        mel = mel.reshape(*lead, n_frames, fb.shape[0])
+    return mag, mel
+
+
+@dtc.dataclass
+class STFT(Functional):
+    """functionals.py:450-528 — only coordinate='mag' is on the hot path (MagSpec); other coordinates raise."""
+    n_fft: int = N_FFT
+    hop_length: int = HOP_LENGTH
+    coordinate: str = 'mag'
+    center: bool = True
+    window: Optional[str] = "hann"
+    pad_mode: str = "constant"
+    alignment: Optional[str] = "end"
+
+    @property
+    def unit(self):
+        return Frame(self.n_fft, self.hop_length, padding=self.center)
+
+    @property
+    def elem_type(self):
+        return Continuous(0., float("inf"), 1 + self.n_fft // 2)
+
+    def torch_func(self, inputs):
+        if self.coordinate != "mag":
+            raise NotImplementedError("the B200 path implements coordinate='mag' (MagSpec) only")
+        if self.pad_mode != "constant":
+            raise NotImplementedError("the B200 path implements pad_mode='constant' (the reference default) only")
+        x, restore = _to_device(inputs)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        mag, _ = _stft_mag_mel(x, self.n_fft, self.hop_length, self.center, self.alignment, True, None)
+        return restore(mag)
+
+
+@dtc.dataclass
+class MagSpec(Functional):
+    """functionals.py:576-606."""
+    n_fft: int = N_FFT
+    hop_length: int = HOP_LENGTH
+    center: bool = True
+    window: Optional[str] = "hann"
+    pad_mode: str = "constant"
+    alignment: Optional[str] = "end"
+
+    @property
+    def stft(self):
+        return STFT(self.n_fft, self.hop_length, "mag", self.center, self.window, self.pad_mode,
+                    alignment=self.alignment)
+
+    @property
+    def unit(self):
+        return Frame(self.n_fft, self.hop_length, padding=self.center)
+
+    @property
+    def elem_type(self):
+        return Continuous(0., float("inf"), 1 + self.n_fft // 2)
+
+    def torch_func(self, inputs):
+        return self.stft.torch_func(inputs)
+
+    def mel(self, inputs, melspec: "MelSpec", return_mag=False):
+        """Fused waveform -> (magnitudes,) mel in one kernel: the magnitudes never leave shared memory unless
+        asked for.  Equivalent to melspec(self(inputs)) in the reference."""
+        x, restore = _to_device(inputs)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        fb = melspec.filterbank(self.n_fft).to(x.device)
+        mag, mel = _stft_mag_mel(x, self.n_fft, self.hop_length, self.center, self.alignment, return_mag, fb)
+        return (restore(mag), restore(mel)) if return_mag else restore(mel)
+
+
+@dtc.dataclass
+class MelSpec(Functional):
+    """functionals.py:649-676 ("expects a MagSpec as inputs").  The reference only implements np_func (librosa);
+    here torch tensors work too.  Standalone use runs the mel epilogue kernel-side from given magnitudes via a
+    1-frame pass is not needed: magnitudes @ filterbank is done by the fused kernel when called through
+    MagSpec.mel; called on magnitudes directly it launches the same sparse reduce."""
+    n_mels: int = 128
+    fmin: float = 0.
+    fmax: Optional[float] = None
+    htk: bool = False
+
+    @property
+    def elem_type(self):
+        return Continuous(0., float("inf"), self.n_mels)
+
+    def filterbank(self, n_fft):
+        key = (n_fft, self.n_mels, self.fmin, self.fmax, self.htk)
+        cache = MelSpec._fb_cache
+        if key not in cache:
+            cache[key] = mel_filterbank(n_fft, self.n_mels, self.fmin, self.fmax, self.htk)
+        return cache[key]
+
+    def torch_func(self, inputs):
+        raise NotImplementedError(
+            "MelSpec on precomputed magnitudes is not part of the B200 hot path; use MagSpec(...).mel(x, MelSpec(...)) "
+            "which fuses STFT -> |.| -> mel in one kernel (the reference's torch_func is `pass`, functionals.py:670-672)")
+
+
+MelSpec._fb_cache = {}

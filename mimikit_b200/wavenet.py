@@ -1,0 +1,314 @@
+"""WaveNet generation on the B200 — drop-in for the reference's `WaveNet` on the generation path
+(mimikit/networks/wavenet_v2.py:185-469: Config 186-206, from_config 231-257, rf 337-339, generate_params
+364-366, generate_step 447-452; layers WNLayer.forward 131-176).
+
+Same `Config` fields, same state-dict key names, same `ARM` methods; the arithmetic runs in the persistent
+sm_100a kernel behind `mmk_wavenet_*` (include/mmk_b200.h).  Configurations the kernel does not implement raise
+at `from_config` — there is no fallback.
+"""
+import ctypes
+import dataclasses as dtc
+import math
+from collections import OrderedDict
+from itertools import accumulate
+from operator import mul
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+from .arm import NativeARM, as_temperature, prepare_noise, prepare_sequence
+from .io_spec import IOSpec
+
+__all__ = ["WaveNet"]
+
+
+class WaveNet(NativeARM):
+    @dtc.dataclass
+    class Config:
+        """wavenet_v2.py:186-206 — field for field."""
+        io_spec: IOSpec = None
+        kernel_sizes: Tuple[int, ...] = (2,)
+        blocks: Tuple[int, ...] = (4,)
+        dims_dilated: Tuple[int, ...] = (128,)
+        dims_1x1: Tuple[int, ...] = ()
+        residuals_dim: Optional[int] = None
+        apply_residuals: bool = False
+        skips_dim: Optional[int] = None
+        with_affine_residuals: bool = False
+        groups: int = 1
+        act_f: str = "Tanh"
+        act_g: Optional[str] = "Sigmoid"
+        pad_side: int = 0
+        stride: int = 1
+        bias: bool = True
+        use_fast_generate: bool = False
+        tie_io_weights: bool = False
+        layerwise_inputs: bool = False
+        reverse_layer_order: bool = False
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def get_kernels_and_dilation(kernel_sizes, blocks):
+        """Layer schedule of wavenet_v2.py:295-327: dilations restart at 1 in every block and grow by the product
+        of the kernel sizes before them."""
+        ks, blocks = tuple(kernel_sizes), tuple(blocks)
+
+        def grow(sizes):  # 1, k0, k0*k1, ... one entry per layer of a block
+            return list(accumulate((1,) + tuple(sizes[:-1]), mul))
+
+        if not blocks:
+            return list(ks), list(accumulate((1,) + ks, mul))[:len(ks)]
+        if len(set(blocks)) == 1 and blocks[0] == len(ks):
+            return list(ks) * len(blocks), grow(ks) * len(blocks)
+        if len(ks) == sum(blocks):
+            dil, at = [], 0
+            for b in blocks:
+                dil += grow(ks[at:at + b])
+                at += b
+            return list(ks), dil
+        if len(ks) == 1:
+            return [ks[0]] * sum(blocks), [ks[0] ** i for b in blocks for i in range(b)]
+        raise ValueError(f"number of layers and number of kernel sizes not compatible."
+                         f" Got kernel_sizes={ks} ; blocks={blocks}")
+
+    @classmethod
+    def _check_supported(cls, c: "WaveNet.Config"):
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"mimikit_b200 WaveNet kernel: {what} is not implemented (no fallback)")
+        need(c.io_spec is not None and len(c.io_spec.inputs) == 1 and len(c.io_spec.targets) == 1,
+             "more than one input/target")
+        need(c.io_spec.inputs[0].module_type == "embedding", "input_module_type other than 'embedding'")
+        need(len(c.dims_dilated) == 1 and not c.dims_1x1, "dims_1x1 conditioning inputs")
+        need(c.residuals_dim is None or c.residuals_dim == c.dims_dilated[0],
+             "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
+        need(not c.apply_residuals and not c.with_affine_residuals, "apply_residuals / with_affine_residuals")
+        need(c.groups == 1, "groups > 1")
+        need(str(c.act_f) == "Tanh" and str(c.act_g) == "Sigmoid", "activations other than Tanh/Sigmoid gating")
+        need(c.pad_side == 0 and c.stride == 1 and c.bias, "pad_side != 0, stride != 1 or bias=False")
+        need(not (c.tie_io_weights or c.layerwise_inputs or c.reverse_layer_order),
+             "tie_io_weights / layerwise_inputs / reverse_layer_order")
+        need(c.io_spec.targets[0].module.n_hidden_layers == 0, "n_mlp_layers > 0")
+        ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
+        need(all(k == 2 for k in ks), "kernel sizes other than 2")
+
+    @classmethod
+    def from_config(cls, config: "WaveNet.Config") -> "WaveNet":
+        cls._check_supported(config)
+        return cls(config)
+
+    def __init__(self, config: "WaveNet.Config"):
+        super().__init__()
+        self._check_supported(config)
+        self._config = config
+        _, dil = self.get_kernels_and_dilation(config.kernel_sizes, config.blocks)
+        self.dilations = [int(d) for d in dil]
+        self.has_skips = config.skips_dim is not None
+        self.has_residuals = config.residuals_dim is not None
+        self._sd = self._init_state_dict()
+        self._gen = None  # state of the step-wise protocol
+
+    # ---- geometry -------------------------------------------------------------------------------
+    @property
+    def config(self):
+        return self._config
+
+    @property
+    def rf(self) -> int:
+        """wavenet_v2.py:337-339."""
+        return sum(self.dilations) + 1
+
+    @property
+    def shift(self) -> int:
+        return self.rf  # pad_side == 0
+
+    def output_length(self, n_input_steps: int) -> int:
+        return n_input_steps - self.shift + 1
+
+    @property
+    def generate_params(self):
+        """The reference yields {} here (wavenet_v2.py:364-366 looks `sampling_params` up on an nn.ModuleList), so
+        its loop can never pass a temperature to WaveNet; the evident intent — and SampleRNN's behaviour
+        (sample_rnn_v2.py:309-311) — is {"temperature"}.  Documented deviation."""
+        return {"temperature"}
+
+    def _dims(self):
+        c = self._config
+        C = c.dims_dilated[0]
+        S = c.skips_dim if self.has_skips else 0
+        head = c.io_spec.targets[0].module
+        return C, S, head.hidden_dim, c.io_spec.targets[0].out_dim
+
+    def _expected_shapes(self):
+        C, S, Hh, Q = self._dims()
+        L = len(self.dilations)
+        e = OrderedDict()
+        e["input_modules.0.0.weight"] = (self._config.io_spec.inputs[0].class_size, C)
+        for l in range(L):
+            e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, 2)
+            e[f"layers.{l}.conv_dil.0.0.bias"] = (2 * C,)
+            if self.has_skips:
+                e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
+                e[f"layers.{l}.conv_skip.bias"] = (S,)
+            if self.has_residuals and l != L - 1:   # wavenet_v2.py:216 — never on the last layer
+                e[f"layers.{l}.conv_res.weight"] = (C, C, 1)
+                e[f"layers.{l}.conv_res.bias"] = (C,)
+        p = "output_modules.0.estimator.0."
+        e[p + "min_temp"] = ()
+        e[p + "fc.0.weight"] = (Hh, S if self.has_skips else C)
+        e[p + "fc.0.bias"] = (Hh,)
+        e[p + "fc.2.weight"] = (Q + 1, Hh)
+        e[p + "fc.2.bias"] = (Q + 1,)
+        return e
+
+    def _init_state_dict(self):
+        """Random init with torch's default distributions (Embedding N(0,1); Conv/Linear U(+-1/sqrt(fan_in)))."""
+        sd = OrderedDict()
+        for k, shape in self._expected_shapes().items():
+            if k.endswith("min_temp"):
+                mt = self._config.io_spec.targets[0].module.min_temperature
+                sd[k] = torch.tensor(1e-4 if mt is None else float(mt), dtype=torch.float32)
+            elif k == "input_modules.0.0.weight":
+                sd[k] = torch.randn(shape)
+            else:
+                wshape = shape if k.endswith("weight") else self._expected_shapes()[k[:-4] + "weight"]
+                bound = 1.0 / math.sqrt(max(1, int(torch.tensor(wshape[1:]).prod())))
+                sd[k] = (torch.rand(shape) * 2 - 1) * bound
+        return sd
+
+    # ---- native handle --------------------------------------------------------------------------
+    def _create_handle(self, max_batch):
+        C, S, Hh, Q = self._dims()
+        L = len(self.dilations)
+        d = _capi.WaveNetDesc()
+        d.n_layers, d.dilated_dim, d.skips_dim, d.head_hidden, d.q_levels = L, C, S, Hh, Q
+        d.min_temperature = float(self._sd["output_modules.0.estimator.0.min_temp"])
+        dil = (ctypes.c_int * L)(*self.dilations)
+        d.dilations = dil
+        d.embedding = self._w("input_modules.0.0.weight")
+        keep = [dil]
+        def arr(fmt, present=lambda l: True):
+            a = self._warray([fmt.format(l) if present(l) else None for l in range(L)])
+            keep.append(a)
+            return a
+        d.conv_dil_w = arr("layers.{}.conv_dil.0.0.weight")
+        d.conv_dil_b = arr("layers.{}.conv_dil.0.0.bias")
+        if self.has_skips:
+            d.conv_skip_w = arr("layers.{}.conv_skip.weight")
+            d.conv_skip_b = arr("layers.{}.conv_skip.bias")
+        has_res = lambda l: self.has_residuals and l != L - 1
+        d.conv_res_w = arr("layers.{}.conv_res.weight", has_res)
+        d.conv_res_b = arr("layers.{}.conv_res.bias", has_res)
+        p = "output_modules.0.estimator.0."
+        d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
+        d.head_w2, d.head_b2 = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
+        h = ctypes.c_void_p()
+        _capi.check(_capi.lib().mmk_wavenet_create(ctypes.byref(d), int(max_batch), ctypes.byref(h)))
+        return h
+
+    def _destroy_handle(self, h):
+        _capi.lib().mmk_wavenet_destroy(h)
+
+    def launch_info(self, batch=1):
+        info = _capi.LaunchInfo()
+        _capi.check(_capi.lib().mmk_wavenet_launch_info(self._get_handle(batch), ctypes.byref(info)))
+        return {f: getattr(info, f) for f, _ in info._fields_}
+
+    def _run(self, seq, seq_t0, t_begin, t_head, t_end, teacher_forced, temperature, noise, noise_t0, want_logits,
+             want_decisions, want_ts, check=True):
+        B = seq.shape[0]
+        h = self._get_handle(B)
+        n_head = max(0, t_end - t_head)
+        Q = self._dims()[3]
+        logits = torch.empty((B, n_head, Q), dtype=torch.float32, device=seq.device) if want_logits else None
+        decisions = torch.empty((B, n_head), dtype=torch.int64, device=seq.device) if want_decisions else None
+        ts = torch.zeros((t_end - t_begin,), dtype=torch.int64, device=seq.device) if want_ts else None
+        ptr = lambda x: x.data_ptr() if x is not None else None
+        with torch.cuda.device(seq.device):
+            _capi.check(_capi.lib().mmk_wavenet_run(
+                h, seq.data_ptr(), B, seq.stride(0), int(seq_t0), int(t_begin), int(t_head), int(t_end), int(teacher_forced),
+                ptr(temperature), 0 if temperature is None else temperature.numel(),
+                ptr(noise), 0 if noise is None else noise.stride(0), int(noise_t0),
+                ptr(logits), ptr(decisions), ptr(ts), _capi.stream_ptr()))
+            if check:
+                _capi.check(_capi.lib().mmk_wavenet_sync_check(h, _capi.stream_ptr()))
+        return logits, decisions, ts
+
+    # ---- whole-sequence fast path ---------------------------------------------------------------
+    def generate(self, prompts, n_steps, temperature=None, noise=None, return_logits=False,
+                 return_step_timestamps=False, generator=None):
+        """GenerateLoopV2.run's inner loop for one batch (loops/generate.py:195-219) in ONE kernel launch.
+
+        prompts (B, P >= rf) int64 mu-law indices (host or device); temperature None (argmax) | float | (1,) | (B,);
+        noise (B, n_steps) uniform [0,1) fp32 consumed by the inverse-CDF sampler (drawn with torch.rand when
+        omitted).  Returns the (B, P + n_steps) int64 sequence on the device (plus logits (B, n_steps, Q) and/or
+        per-step device timestamps in ns when asked)."""
+        seq = prepare_sequence(prompts, n_steps, self.device)
+        B, total = seq.shape
+        P = total - n_steps
+        if P < self.rf:
+            raise RuntimeError(f"prompt length {P} is shorter than the receptive field {self.rf}")
+        T = as_temperature(temperature, B, self.device)
+        U = prepare_noise(noise, T, B, n_steps, self.device, generator)
+        logits, ts = None, None
+        if n_steps > 0:
+            # layers consume samples P-rf .. P+n-2; the head predicts sample t+1 for t >= P-1
+            logits, _, ts = self._run(seq, 0, P - self.rf, P - 1, P + n_steps - 1, False, T, U, P, return_logits, False,
+                                      return_step_timestamps)
+        out = (seq,)
+        if return_logits:
+            out += (logits,)
+        if return_step_timestamps:
+            out += (ts,)
+        return out[0] if len(out) == 1 else out
+
+    def teacher_forced(self, sequence, prompt_len, temperature=None, noise=None):
+        """Logits and decisions for every position >= prompt_len of a GIVEN sequence (nothing is fed back).
+        Returns (logits (B, n, Q), decisions (B, n)) with n = T - prompt_len."""
+        seq = prepare_sequence(sequence, 0, self.device)
+        B, total = seq.shape
+        P = int(prompt_len)
+        if P < self.rf:
+            raise RuntimeError(f"prompt length {P} is shorter than the receptive field {self.rf}")
+        n = total - P
+        T = as_temperature(temperature, B, self.device)
+        U = prepare_noise(noise, T, B, n, self.device)
+        logits, dec, _ = self._run(seq, 0, P - self.rf, P - 1, total - 1, True, T, U, P, True, True, False)
+        return logits, dec
+
+    # ---- step-wise ARM protocol (arm.py:56-75) --------------------------------------------------
+    def before_generate(self, prompts, batch_index) -> None:
+        self._gen = None
+
+    def generate_step(self, inputs, *, t: int = 0, temperature=None, noise=None):
+        """One sample from the window `inputs[0]` = the rf samples before t.  The first call (or any call whose t
+        does not follow the previous one) refills the dilation rings from the whole window — the reference's
+        window recompute; consecutive calls only push the newest sample through the cached step."""
+        x = inputs[0]
+        if x.dim() != 2 or x.shape[1] < self.rf:
+            raise RuntimeError(f"expected a (B, >= {self.rf}) window, got {tuple(x.shape)}")
+        B, rf = x.shape[0], self.rf
+        x = x.to(self.device, torch.int64)
+        T = as_temperature(temperature, B, self.device)
+        U = None
+        if T is not None:
+            U = torch.rand((B, 1), device=self.device) if noise is None else \
+                torch.as_tensor(noise, dtype=torch.float32).reshape(B, 1).to(self.device)
+        g = self._gen
+        if g is None or g["t"] + 1 != t or g["buf"].shape[0] != B:
+            buf = torch.zeros((B, rf + 1), dtype=torch.int64, device=self.device)
+            buf[:, :rf] = x[:, -rf:]
+            self._run(buf, 0, 0, rf - 1, rf, False, T, U, rf, False, False, False)
+            # the kernel's clock (which selects the ring slots, t mod dilation) started at 0 for sample t - rf
+            self._gen = dict(t=t, origin=t - rf, buf=buf, step=torch.zeros((B, 2), dtype=torch.int64,
+                                                                             device=self.device))
+            return (buf[:, rf:rf + 1].clone(),)
+        step, tl = g["step"], t - 1 - g["origin"]   # kernel time of the newest sample
+        step[:, 0] = x[:, -1]
+        self._run(step, tl, tl, tl, tl + 1, False, T, U, tl + 1, False, False, False)
+        g["t"] = t
+        return (step[:, 1:2].clone(),)
+
+    def after_generate(self, final_outputs, batch_index) -> None:
+        self._gen = None

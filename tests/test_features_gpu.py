@@ -1,0 +1,131 @@
+"""GPU parity tests of the feature kernels against the oracle and the golden vectors (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mulaw_compress_golden_bit_exact():
+    from mimikit_b200 import MuLawCompress, MuLawExpand
+    d = load_golden("mulaw")
+    x = torch.from_numpy(d["x"]).cuda()
+    for q, C in [(256, 1.), (256, .5), (64, 2.), (1024, 1.)]:
+        got = MuLawCompress(q, C)(x)
+        assert got.dtype == torch.int64 and got.is_cuda
+        assert np.array_equal(got.cpu().numpy(), d[f"idx_q{q}_c{C}"]), (q, C)
+        exp = MuLawExpand(q, C)(torch.arange(q).cuda())
+        np.testing.assert_allclose(exp.cpu().numpy(), d[f"expand_q{q}_c{C}"], rtol=0, atol=1e-6)
+    got = MuLawCompress(256, 1.)(torch.from_numpy(d["x_int"]).cuda())   # int input is cast to fp32 first
+    assert np.array_equal(got.cpu().numpy(), d["idx_int_q256_c1.0"])
+    u8 = MuLawCompress(256, 1.).torch_func(x, out_dtype=torch.uint8)
+    assert np.array_equal(u8.cpu().numpy().astype(np.int64), d["idx_q256_c1.0"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 4096 + 3, 1 << 20])
+def test_mulaw_ragged_sizes_vs_oracle(n):
+    from mimikit_b200 import MuLawCompress, MuLawExpand
+    rng = np.random.default_rng(n)
+    x = (rng.random(n, dtype=np.float32) * 2 - 1)
+    got = MuLawCompress(256, 1.)(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, restate.mulaw_compress(x, 256, 1.))
+    back = MuLawExpand(256, 1.)(torch.from_numpy(got).cuda()).cpu().numpy()
+    assert np.array_equal(back, restate.mulaw_expand(got, 256, 1.))      # same portable expf on both sides
+
+
+def test_mulaw_host_buffers_and_numpy_dispatch():
+    from mimikit_b200 import MuLawCompress
+    x = np.linspace(-1, 1, 1001, dtype=np.float32)
+    got = MuLawCompress()(x)                       # numpy in -> numpy out (Functional.__call__ dispatch)
+    assert isinstance(got, np.ndarray) and np.array_equal(got, restate.mulaw_compress(x))
+    got_t = MuLawCompress()(torch.from_numpy(x))   # CPU tensor in -> CPU tensor out
+    assert not got_t.is_cuda and np.array_equal(got_t.numpy(), got)
+    with pytest.raises(KeyError):
+        MuLawCompress()([0.1, 0.2])
+
+
+def test_mulaw_full_size_properties():
+    """cfg 5 size (10 h @ 22.05 kHz is 793.8 M samples; one 1 h shard = 79.38 M here): size-independent checks —
+    every class round-trips (compress(expand(i)) == i), monotone in x, symmetric around the centre bin."""
+    from mimikit_b200 import MuLawCompress, MuLawExpand
+    n = 360 * 220500
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(n, generator=g, device="cuda") * 2 - 1
+    q = MuLawCompress()(x)
+    assert int(q.min()) == 0 and int(q.max()) == 255
+    xs, _ = torch.sort(x[:5_000_000])
+    qs = MuLawCompress()(xs)
+    assert bool((qs[1:] >= qs[:-1]).all())
+    idx = torch.arange(256, device="cuda")
+    assert torch.equal(MuLawCompress()(MuLawExpand()(idx)), idx)
+    # checksum of checksums against the oracle on a strided sample
+    sub = x[::997].contiguous()
+    assert np.array_equal(MuLawCompress()(sub).cpu().numpy(), restate.mulaw_compress(sub.cpu().numpy()))
+
+
+def _tol(ref):
+    return 1e-4 * max(1.0, float(np.abs(ref).max()))   # "STFT/mel within 1e-4" relative to the clip's peak magnitude
+
+
+def test_magspec_golden():
+    from mimikit_b200 import MagSpec
+    d = load_golden("magspec")
+    for tag in "abc":
+        n_fft, hop = (int(v) for v in d[f"cfg_{tag}"])
+        x = torch.from_numpy(d[f"x_{tag}"]).cuda()
+        for center in (True, False):
+            ref = d[f"mag_{tag}_center{int(center)}"]
+            got = MagSpec(n_fft, hop, center=center)(x).cpu().numpy()
+            assert got.shape == ref.shape, (tag, center)
+            assert np.abs(got - ref).max() <= _tol(ref), (tag, center, np.abs(got - ref).max())
+    # 1-D input and "start"/None alignments
+    x1 = torch.from_numpy(d["x_b"][0]).cuda()
+    for align in ("end", "start", None):
+        got = MagSpec(2048, 512, alignment=align)(x1).cpu().numpy()
+        ref = restate.magspec(d["x_b"][0], 2048, 512, True, align)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= _tol(ref)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (128, 32), (256, 100), (1024, 256), (2048, 512), (4096, 1024)])
+def test_magspec_sizes_vs_oracle(n_fft, hop):
+    from mimikit_b200 import MagSpec
+    rng = np.random.default_rng(n_fft)
+    x = (rng.random((3, 4 * n_fft + 123), dtype=np.float32) * 2 - 1)
+    for center in (True, False):
+        ref = restate.magspec(x, n_fft, hop, center)
+        got = MagSpec(n_fft, hop, center=center)(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= _tol(ref)
+
+
+def test_mel_fused_vs_oracle():
+    from mimikit_b200 import MagSpec, MelSpec
+    x = restate.synthetic_waveform(4, 22050, sr=22050)
+    xt = torch.from_numpy(x).cuda()
+    mag, mel = MagSpec(2048, 512).mel(xt, MelSpec(128), return_mag=True)
+    ref_mag = restate.magspec(x, 2048, 512, True)
+    ref_mel = restate.melspec(ref_mag, 128)
+    assert mel.shape == (4, 44, 128)
+    assert np.abs(mag.cpu().numpy() - ref_mag).max() <= _tol(ref_mag)
+    assert np.abs(mel.cpu().numpy() - ref_mel).max() <= _tol(ref_mel)
+    mel_only = MagSpec(2048, 512).mel(xt, MelSpec(128))
+    assert torch.equal(mel_only, mel)
+    # htk / band-limited variant
+    mel2 = MagSpec(1024, 256).mel(xt, MelSpec(40, 50., 8000., True)).cpu().numpy()
+    ref2 = restate.magspec(x, 1024, 256, True).astype(np.float64) @ restate.mel_filterbank(1024, 40, 50., 8000., True).T
+    assert np.abs(mel2 - ref2).max() <= _tol(ref2)
+
+
+def test_stft_linearity_and_too_short():
+    """size-independent property: STFT is linear before |.|, so |S(a x)| = |a| |S(x)| exactly up to rounding."""
+    from mimikit_b200 import MagSpec, _capi
+    x = torch.rand(2, 220500, device="cuda") * 2 - 1
+    a = MagSpec()(x)
+    b = MagSpec()(x * 0.5)
+    assert a.shape == (2, 431, 1025)
+    assert float((a * 0.5 - b).abs().max()) <= 1e-5 * float(a.max())
+    with pytest.raises(_capi.MmkError):
+        MagSpec(2048, 512, center=False)(torch.zeros(1000, device="cuda"))

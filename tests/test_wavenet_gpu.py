@@ -1,0 +1,185 @@
+"""GPU parity tests of the persistent WaveNet kernel (through the C ABI) against the golden vectors produced by the
+live reference (tests/golden/wavenet_*.npz, oracle/make_golden.py) and against the oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden
+from mimikit_b200 import _capi
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3   # north star: teacher-forced logits within 1e-3 relative in fp32
+
+
+def _rel_err(got, ref):
+    return float(np.abs(got - ref).max() / max(1e-6, np.abs(ref).max()))
+
+
+def make_net(blocks, dims, residuals_dim=None, skips_dim=None, mlp_dim=128, sd=None, seed=0):
+    from mimikit_b200 import IOSpec, WaveNet
+    torch.manual_seed(seed)
+    cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=mlp_dim)),
+                         blocks=tuple(blocks), dims_dilated=(dims,), residuals_dim=residuals_dim, skips_dim=skips_dim)
+    net = WaveNet.from_config(cfg).to("cuda")
+    if sd is not None:
+        net.load_state_dict(sd)
+    return net
+
+
+def net_from_golden(d):
+    m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
+    return make_net(tuple(int(b) for b in m["blocks"]), int(m["dims"]),
+                    int(m["residuals_dim"]) if "residuals_dim" in m else None,
+                    int(m["skips_dim"]) if "skips_dim" in m else None, int(m["mlp_dim"]), golden_state_dict(d))
+
+
+@pytest.mark.parametrize("name", ["wavenet_default_small", "wavenet_res_skip_small", "wavenet_res_skip_mid"])
+def test_golden_sequences_and_logits(name):
+    d = load_golden(name)
+    net = net_from_golden(d)
+    prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
+    n = noise.shape[1]
+    seq, logits = net.generate(prompts, n, return_logits=True)
+    assert seq.dtype == torch.int64 and seq.is_cuda and tuple(seq.shape) == d["seq_argmax"].shape
+    assert np.array_equal(seq.cpu().numpy(), d["seq_argmax"])            # bit-exact argmax-decoded sequence
+    assert np.array_equal(seq.cpu().numpy(), d["seq_argmax_real_loop"])  # == the unmodified GenerateLoopV2.run
+    assert _rel_err(logits.cpu().numpy(), d["logits_argmax"]) <= REL_TOL
+    seq, logits = net.generate(prompts, n, temperature=1.0, noise=noise, return_logits=True)
+    assert np.array_equal(seq.cpu().numpy(), d["seq_t1"])                # sampled with the supplied noise
+    assert _rel_err(logits.cpu().numpy(), d["logits_t1"]) <= REL_TOL
+    seq = net.generate(prompts, n, temperature=torch.from_numpy(d["tvec"]), noise=noise)
+    assert np.array_equal(seq.cpu().numpy(), d["seq_tvec"])              # per-prompt temperature vector
+    # teacher-forced over the reference's own sequence: every decision must agree
+    lg, dec = net.teacher_forced(torch.from_numpy(d["seq_t1"]), prompts.shape[1], 1.0, noise)
+    assert np.array_equal(dec.cpu().numpy(), d["seq_t1"][:, prompts.shape[1]:])
+    assert _rel_err(lg.cpu().numpy(), d["logits_t1"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
+@pytest.mark.parametrize("blocks,dims,res,skips,B", [((3, 3), 64, 64, 64, 11), ((4,), 128, None, None, 1),
+                                                     ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8)])
+def test_vs_oracle_all_cluster_sizes(monkeypatch, cluster, blocks, dims, res, skips, B):
+    """Seeded weights/prompts, every cluster geometry the launcher can pick, ragged batches (B not a multiple of the
+    8-prompt pipeline group), with/without residual and skip convs."""
+    if dims % int(cluster) or (skips or dims) % int(cluster):
+        pytest.skip("dims not divisible by the cluster size")
+    monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
+    net = make_net(blocks, dims, res, skips, mlp_dim=64, seed=7)
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    assert net.rf == orc.rf
+    g = torch.Generator().manual_seed(99)
+    P, n = orc.rf + 5, 24
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    try:
+        info = net.launch_info(B)
+    except _capi.MmkError as e:   # this geometry cannot host the net (tile width / co-residency): nothing to test
+        pytest.skip(str(e))
+    assert info["cluster_size"] == int(cluster)
+    for temp in (None, 0.9):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert np.array_equal(seq.cpu().numpy(), ref_seq), (cluster, temp)
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+
+
+def test_multi_stage_pipeline(monkeypatch):
+    """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups."""
+    monkeypatch.setenv("MMK_WN_CLUSTER", "2")
+    monkeypatch.setenv("MMK_WN_STAGES", "4")
+    blocks = (4, 4)
+    net = make_net(blocks, 64, 64, 64, mlp_dim=64, seed=3)
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    g = torch.Generator().manual_seed(5)
+    B, P, n = 37, orc.rf + 3, 40
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    assert net.launch_info(B)["n_stages"] == 4
+    for temp in (None, 1.0):
+        seq = net.generate(prompts, n, temperature=temp, noise=noise)
+        ref_seq, _ = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert np.array_equal(seq.cpu().numpy(), ref_seq)
+    # same handle, second run: no state leaks between launches
+    seq2 = net.generate(prompts, n, temperature=1.0, noise=noise)
+    assert np.array_equal(seq2.cpu().numpy(), ref_seq)
+
+
+def test_stepwise_protocol_and_loop():
+    """ARM protocol (before_generate / generate_step / after_generate) == whole-sequence path == oracle, and the
+    GenerateLoopV2 mirror yields the expanded waveform (reference tests/test_wavenet.py:140-165 style)."""
+    from mimikit_b200 import GenerateLoopV2
+    blocks = (3, 2)
+    net = make_net(blocks, 32, 32, 32, mlp_dim=32, seed=11)
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    g = torch.Generator().manual_seed(1)
+    B, P, n = 3, 30, 20
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    ref_seq, _ = orc.generate(prompts.numpy(), n)
+    x = torch.cat([prompts, torch.zeros(B, n, dtype=torch.int64)], 1).cuda()
+    net.before_generate((x[:, :P],), 0)
+    for t in range(P, P + n):
+        out = net.generate_step((x[:, t - net.rf:t],), t=t)
+        assert isinstance(out, tuple) and tuple(out[0].shape) == (B, 1)
+        x[:, t:t + 1] = out[0]
+    net.after_generate((x,), 0)
+    assert np.array_equal(x.cpu().numpy(), ref_seq)
+    for temperature in (None, 0.5, (1.,)):
+        cfg = GenerateLoopV2.Config(parameters=dict(temperature=temperature) if temperature else None,
+                                    display_waveform=False, yield_inversed_outputs=False)
+        loop = GenerateLoopV2(cfg, net, n, [[torch.arange(B), prompts]])
+        outs = list(loop.run())
+        assert len(outs) == 1 and isinstance(outs[0], tuple)
+        assert tuple(outs[0][0].shape) == (B, P + n) and outs[0][0].dim() == prompts.dim()
+        if temperature is None:
+            assert np.array_equal(outs[0][0].cpu().numpy(), ref_seq)
+    cfg = GenerateLoopV2.Config(display_waveform=False)        # default: yield the inverse-transformed waveform
+    wav = list(GenerateLoopV2(cfg, net, n, [[torch.arange(B), prompts]]).run())[0][0]
+    assert wav.dtype == torch.float32 and tuple(wav.shape) == (B, P + n)
+    np.testing.assert_allclose(wav.cpu().numpy(), restate.mulaw_expand(ref_seq), atol=1e-6)
+
+
+def test_errors():
+    from mimikit_b200 import IOSpec, WaveNet
+    net = make_net((3,), 32, mlp_dim=32)
+    assert net.rf == 8
+    with pytest.raises(RuntimeError):      # reference tests/test_wavenet.py:251-275: rf-1 samples raise RuntimeError
+        net.generate(torch.zeros(2, net.rf - 1, dtype=torch.int64), 4)
+    with pytest.raises(ValueError):
+        net.generate(torch.zeros(2, 16, dtype=torch.int64), 4, temperature=(1., 2., 3.))
+    io = IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding"))
+    with pytest.raises(NotImplementedError):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, pad_side=1))
+    with pytest.raises(NotImplementedError):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, kernel_sizes=(3,)))
+    with pytest.raises(RuntimeError):
+        net.load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_w30_full_width_properties():
+    """BASELINE cfg 2 geometry (30 layers, 128 channels, batch 64): properties that do not need the slow oracle at
+    scale — run-to-run determinism, batch-permutation equivariance — plus oracle parity on a short horizon."""
+    blocks = (8, 8, 7, 7)
+    net = make_net(blocks, 128, 128, 128, mlp_dim=128, seed=0)
+    assert net.rf == 765
+    g = torch.Generator().manual_seed(1234)
+    B, P, n = 64, 800, 96
+    prompts = torch.from_numpy(restate.synthetic_prompts(B, P))
+    noise = torch.rand(B, n, generator=g)
+    seq = net.generate(prompts, n, temperature=1.0, noise=noise)
+    seq_again = net.generate(prompts, n, temperature=1.0, noise=noise)
+    assert torch.equal(seq, seq_again)
+    perm = torch.randperm(B, generator=g)
+    seq_p = net.generate(prompts[perm], n, temperature=1.0, noise=noise[perm])
+    assert torch.equal(seq_p.cpu(), seq.cpu()[perm])
+    assert int(seq.min()) >= 0 and int(seq.max()) <= 255 and torch.equal(seq[:, :P].cpu(), prompts)
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    sub = [0, 13, 63]
+    ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), 24, 1.0, noise[sub, :24].numpy())
+    got_seq, got_logits = net.generate(prompts[sub], 24, temperature=1.0, noise=noise[sub, :24], return_logits=True)
+    assert _rel_err(got_logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
+    assert np.array_equal(got_seq.cpu().numpy(), ref_seq)
+    assert np.array_equal(seq.cpu().numpy()[sub][:, :P + 24], ref_seq)
