@@ -172,6 +172,8 @@ typedef struct {
 int mmk_samplernn_create(const mmk_samplernn_desc* desc, int max_batch, mmk_samplernn_t* out);
 int mmk_samplernn_destroy(mmk_samplernn_t h);
 int mmk_samplernn_launch_info(mmk_samplernn_t h, mmk_launch_info* out);
+/* As mmk_wavenet_sync_check: waits for the stream and fails if a grid barrier of the last launch timed out. */
+int mmk_samplernn_sync_check(mmk_samplernn_t h, void* stream);
 
 /* One persistent-kernel launch covering two consecutive ranges of generate_step calls (sample_rnn_v2.py:236-260):
  *   warm-up  : logical t in [warm_begin, warm_end) — frame tiers only, reading the window that ends at data index

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "mmk_samplernn_create": (c_int, [POINTER(SampleRNNDesc), c_int, POINTER(c_void_p)]),
     "mmk_samplernn_destroy": (c_int, [c_void_p]),
     "mmk_samplernn_launch_info": (c_int, [c_void_p, POINTER(LaunchInfo)]),
+    "mmk_samplernn_sync_check": (c_int, [c_void_p, c_void_p]),
     "mmk_samplernn_run": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                   c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),

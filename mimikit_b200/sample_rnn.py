@@ -185,6 +185,7 @@ class SampleRNN(NativeARM):
                 ptr(temperature), 0 if temperature is None else temperature.numel(),
                 ptr(noise), 0 if noise is None else noise.stride(0), int(noise_t0),
                 ptr(logits), ptr(decisions), ptr(ts), _capi.stream_ptr()))
+            _capi.check(_capi.lib().mmk_samplernn_sync_check(h, _capi.stream_ptr()))
         return logits, decisions, ts
 
     def _warm_range(self, P):
