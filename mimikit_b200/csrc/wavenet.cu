@@ -21,6 +21,8 @@
 //     inverse-CDF sampling from externally supplied uniform noise are fused; nothing but the sampled index (and,
 //     on request, the logits) leaves the chip.
 #include "common.cuh"
+#include "sampler.cuh"
+#include "wavenet_impl.h"
 #include "../../include/mmk_b200.h"
 
 #include <cooperative_groups.h>
@@ -147,11 +149,6 @@ __device__ __forceinline__ void wait_s64(const long long* flag, long long target
     __syncthreads();
 }
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float mish_acc(float x) {
-    float sp = x > 20.0f ? x : log1pf(expf(x));  // F.softplus, threshold 20
-    return x * tanhf(sp);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Slice contraction.  out[col][p] = sum_k W[k][col] * x[k][p] for the CTA's ncolp (multiple of 4) columns and GB
@@ -545,6 +542,7 @@ static int pad4(int v) { return (v + 3) / 4 * 4; }
 using namespace mmk;
 
 struct mmk_wavenet_s {
+    wn2_handle* v2 = nullptr;   // set when the latency-engineered kernel (wavenet2.cu) hosts this network
     WnParams p{};
     int device = 0;
     int max_batch = 0;
@@ -649,6 +647,22 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
     auto* h = new mmk_wavenet_s();
     WnParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
+    {
+        const char* force = getenv("MMK_WN_KERNEL");   // "1" = general kernel, "2" = chain kernel only
+        if (!(force && atoi(force) == 1)) {
+            int unsupported = 0;
+            if (wn2_create(d, max_batch, &h->v2, &unsupported) == 0) {
+                int rf2 = 1;
+                for (int l = 0; l < d->n_layers; ++l) rf2 += d->dilations[l];
+                h->rf = rf2; h->max_batch = max_batch;
+                *out = h;
+                return 0;
+            }
+            h->v2 = nullptr;
+            if (!unsupported) { delete h; return 1; }
+            if (force && atoi(force) == 2) { delete h; MMK_FAIL("configuration not supported by the chain kernel (MMK_WN_KERNEL=2)"); }
+        }
+    }
     p.L = d->n_layers; p.C = d->dilated_dim; p.S = d->skips_dim; p.Hh = d->head_hidden; p.Q = d->q_levels;
     p.Kh = p.S > 0 ? p.S : p.C;
     p.min_temp = d->min_temperature;
@@ -802,6 +816,7 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
 
 extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
     if (!h) return 0;
+    if (h->v2) wn2_destroy(h->v2);
     cudaFree(h->d_wpack); cudaFree(h->d_hpack); cudaFree(h->d_E); cudaFree(h->d_rings);
     cudaFree(h->d_mail_h); cudaFree(h->d_mail_s); cudaFree(h->d_flags);
     delete h;
@@ -810,6 +825,7 @@ extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
 
 extern "C" int mmk_wavenet_sync_check(mmk_wavenet_t h, void* stream) {
     MMK_CHECK(h, "null handle");
+    if (h->v2) return wn2_sync_check(h->v2, stream);
     unsigned aborted = 0;
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -821,6 +837,7 @@ extern "C" int mmk_wavenet_rf(mmk_wavenet_t h) { return h ? h->rf : -1; }
 
 extern "C" int mmk_wavenet_launch_info(mmk_wavenet_t h, mmk_launch_info* out) {
     MMK_CHECK(h && out, "null argument");
+    if (h->v2) return wn2_launch_info(h->v2, out);
     out->cluster_size = h->p.CS; out->n_stages = h->p.NST; out->group_size = WN_GB; out->threads = WN_NT;
     out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.CS * h->p.NST;
     return 0;
@@ -845,6 +862,9 @@ extern "C" int mmk_wavenet_run(mmk_wavenet_t h, int64_t* d_seq, int B, int64_t s
     MMK_CHECK(d_temperature == nullptr || (n_temperature == 1 || n_temperature == B), "temperature must have 1 or B entries");
     MMK_CHECK(d_temperature == nullptr || d_noise != nullptr, "sampling (temperature given) needs a noise tensor");
     if (t_begin == t_end) return 0;
+    if (h->v2)
+        return wn2_run(h->v2, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
+                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     cudaStream_t st = (cudaStream_t)stream;
     WnParams p = h->p;
     p.seq = reinterpret_cast<long long*>(d_seq) - seq_t0;   // column j of d_seq holds time seq_t0 + j

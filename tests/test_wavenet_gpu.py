@@ -59,14 +59,18 @@ def test_golden_sequences_and_logits(name):
     assert _rel_err(lg.cpu().numpy(), d["logits_t1"]) <= REL_TOL
 
 
+@pytest.mark.parametrize("kernel", ["1", "2"])
 @pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
 @pytest.mark.parametrize("blocks,dims,res,skips,B", [((3, 3), 64, 64, 64, 11), ((4,), 128, None, None, 1),
-                                                     ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8)])
-def test_vs_oracle_all_cluster_sizes(monkeypatch, cluster, blocks, dims, res, skips, B):
-    """Seeded weights/prompts, every cluster geometry the launcher can pick, ragged batches (B not a multiple of the
-    8-prompt pipeline group), with/without residual and skip convs."""
+                                                     ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8),
+                                                     ((3, 2), 128, 128, 128, 40)])
+def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims, res, skips, B):
+    """Seeded weights/prompts, both kernels (1 = general, 2 = latency-engineered chain kernel), every cluster
+    geometry the launcher can pick, ragged batches (B not a multiple of the 8-prompt pipeline group), with/without
+    residual and skip convs."""
     if dims % int(cluster) or (skips or dims) % int(cluster):
         pytest.skip("dims not divisible by the cluster size")
+    monkeypatch.setenv("MMK_WN_KERNEL", kernel)
     monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
     net = make_net(blocks, dims, res, skips, mlp_dim=64, seed=7)
     orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
@@ -87,12 +91,19 @@ def test_vs_oracle_all_cluster_sizes(monkeypatch, cluster, blocks, dims, res, sk
         assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
 
 
-def test_multi_stage_pipeline(monkeypatch):
-    """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups."""
-    monkeypatch.setenv("MMK_WN_CLUSTER", "2")
+@pytest.mark.parametrize("kernel,cluster,hazard,res,skips", [("1", "2", None, 64, 64), ("2", "2", "0", 64, 64),
+                                                             ("2", "4", "1", 64, 64), ("2", "2", "0", None, 64),
+                                                             ("2", "4", None, None, None), ("2", "2", "0", 64, None)])
+def test_multi_stage_pipeline(monkeypatch, kernel, cluster, hazard, res, skips):
+    """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups; the chain
+    kernel in both ring modes (prefetched TMA ring reads / barrier-ordered) and every residual/skip combination."""
+    monkeypatch.setenv("MMK_WN_KERNEL", kernel)
+    monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
     monkeypatch.setenv("MMK_WN_STAGES", "4")
+    if hazard is not None:
+        monkeypatch.setenv("MMK_WN_RING_HAZARD", hazard)
     blocks = (4, 4)
-    net = make_net(blocks, 64, 64, 64, mlp_dim=64, seed=3)
+    net = make_net(blocks, 64, res, skips, mlp_dim=64, seed=3)
     orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
     g = torch.Generator().manual_seed(5)
     B, P, n = 37, orc.rf + 3, 40
