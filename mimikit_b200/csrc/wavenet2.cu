@@ -21,6 +21,7 @@
 #include "wavenet_impl.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <vector>
 
 namespace mmk2 {
@@ -33,6 +34,7 @@ constexpr int NW = NT / 32;
 constexpr int GB = 8;     // prompts per pipeline group
 constexpr int MAX_LAYERS = 96;
 constexpr int MAX_STAGES = 32;
+constexpr int TRACE_EV = 40;   // events per (stage, group) in the debug timeline
 
 struct Layer {
     int dilation, has_res;
@@ -61,6 +63,7 @@ struct Params {
     const float* temperature; const float* noise;
     long long noise_stride, noise_t0;
     float* logits_out; long long* decisions; unsigned long long* step_ts;
+    long long* trace; long long trace_t;   // debug timeline (MMK_WN_TRACE_T): clock64 stamps of one step, rank 0 of each stage
 };
 
 // barrier slots in shared memory (8 bytes each)
@@ -277,6 +280,11 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
     int xb = 0, yb = 0, rb = 0, zb = 0;
     const bool has_skip = S > 0;
     bool dead = false;   // a wait of this thread gave up: leave at the next CTA-wide check
+    long long* trace_row = nullptr;
+    int trace_n = 0;
+    auto stamp = [&]() {
+        if (trace_row && trace_n < TRACE_EV) trace_row[trace_n++] = clock64();
+    };
 
     // all-gather of a staged quad: chunk i (16 B = 4 prompts of one channel) -> byte offset dst_off[i] in every peer
     auto send_quad = [&](int nchunk, int lanes_per_peer_shift, unsigned dst_off, unsigned bar_id) {
@@ -299,6 +307,11 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
         const unsigned delivery = (unsigned)(t - P.t_begin);
         const bool head_on = t >= P.t_head;
         for (int g = 0; g < P.n_groups; ++g) {
+            trace_row = (P.trace && t == P.trace_t && rank == 0 && tid == 0)
+                            ? P.trace + ((size_t)stage * P.G + g) * TRACE_EV : nullptr;
+            trace_n = 0;
+            if (trace_row) trace_row[trace_n++] = (long long)globaltimer();
+            stamp();
             // ---------------- stage input -> x1[xb] ----------------
             if (tid == 0) issue_ring_load(l_lo, t, g, rb);
             if (first_stage) {
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                 if (tid == 0) red_release_add(P.ack + stage * P.G + g, 1u);
             }
             __syncthreads();
+            stamp();
             bool h_local = true;   // x1[xb] was filled by this CTA itself: no mbarrier to wait on
 
             // ---------------- owned layers ----------------
@@ -353,7 +367,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                         gatebuf[q * 32 + lane] = v + W[P.o_gb + q * 4 + (lane >> 3)];
                     }
                 }
+                stamp();
                 __syncthreads();   // #1: both halves of the pre-activation are in gatebuf; x1c and x0c are fully consumed
+                stamp();
                 if (!h_local) ph_h ^= 1u << xb;
                 ph_r ^= 1u << rb;
                 if (!h_local && tid == 0) mbar_expect_tx(bar(BAR_H0 + xb), xbytes);   // re-arm for its next use
@@ -383,19 +399,24 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                 // ---- phase B: residual / skip 1x1 convs on the gathered y
                 const int nB = (has_res ? P.RQ : 0) + (has_skip ? P.SQ : 0);
                 const bool to_mail = last_owned && !last_layer;
+                stamp();
                 if (to_mail && wait_u32(P.ack + (stage + 1) * P.G + g, delivery >= 1 ? (delivery - 1) * CS : 0u, abort_flag, dead))
                     goto done;
                 float* mh_out = nullptr;
                 if (to_mail) mh_out = P.mail_h + (((size_t)(stage + 1) * P.G + g) * 2 + (delivery & 1)) * blk;
                 if (use_y) {
+                    stamp();
                     dead |= !mbar_wait(bar(BAR_Y0 + yb), (ph_y >> yb) & 1u, abort_flag);
+                    stamp();
                     // ring write of this layer's input (own channel slice): every peer has finished reading the slot
-                    if (warp == NW - 1 && lane < nf * GB / 4) {
+                    if (warp == NW - 1) {
                         // nf*GB/4 chunks of 16 B: chunk i -> half = i / nf, channel = rank*nf + i % nf
-                        const int hf = lane / nf, ch = rank * nf + lane % nf;
-                        const float4 v = *reinterpret_cast<const float4*>(x1c + (hf * C + ch) * 4);
-                        float* dst = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk + (hf * C + ch) * 4;
-                        __stcg(reinterpret_cast<float4*>(dst), v);
+                        for (int i = lane; i < nf * GB / 4; i += 32) {
+                            const int hf = i / nf, ch = rank * nf + i % nf;
+                            const float4 v = *reinterpret_cast<const float4*>(x1c + (hf * C + ch) * 4);
+                            float* dst = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk + (hf * C + ch) * 4;
+                            __stcg(reinterpret_cast<float4*>(dst), v);
+                        }
                     }
                     for (int task = warp; task < nB; task += NW) {
                         const bool is_res = has_res && task < P.RQ;
@@ -432,22 +453,29 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                     }
                     if (!has_res && to_mail) {
                         // h_{l+1} = y: own channel slice of the gathered y goes to the mailbox
-                        if (warp == NW - 2 && lane < nf * GB / 4) {
-                            const int hf = lane / nf, ch = rank * nf + lane % nf;
-                            __stcg(reinterpret_cast<float4*>(mh_out + (hf * C + ch) * 4),
-                                   *reinterpret_cast<const float4*>(yc + (hf * C + ch) * 4));
+                        if (warp == NW - 2) {
+                            for (int i = lane; i < nf * GB / 4; i += 32) {
+                                const int hf = i / nf, ch = rank * nf + i % nf;
+                                __stcg(reinterpret_cast<float4*>(mh_out + (hf * C + ch) * 4),
+                                       *reinterpret_cast<const float4*>(yc + (hf * C + ch) * 4));
+                            }
                         }
                     }
                     ph_y ^= 1u << yb;
                 }
                 if (!use_y) {
                     // no residual and no skip convs (e.g. the reference's default config): h_{l+1} = y went straight
-                    // to the peers' next input buffer; ring write + barrier below (hazard mode is forced for such nets)
-                    if (warp == NW - 1 && lane < nf * GB / 4) {
-                        const int hf = lane / nf, ch = rank * nf + lane % nf;
-                        const float4 v = *reinterpret_cast<const float4*>(x1c + (hf * C + ch) * 4);
-                        float* dst = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk + (hf * C + ch) * 4;
-                        __stcg(reinterpret_cast<float4*>(dst), v);
+                    // to the peers' next input buffer.  Nothing here proves that every peer's TMA read of the ring slot
+                    // has landed (there is no y gather to wait on), so a cluster barrier separates the reads from the
+                    // write; hazard mode (forced for such nets) adds the barrier that orders the write before later reads
+                    cluster_sync_all();
+                    if (warp == NW - 1) {
+                        for (int i = lane; i < nf * GB / 4; i += 32) {
+                            const int hf = i / nf, ch = rank * nf + i % nf;
+                            const float4 v = *reinterpret_cast<const float4*>(x1c + (hf * C + ch) * 4);
+                            float* dst = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk + (hf * C + ch) * 4;
+                            __stcg(reinterpret_cast<float4*>(dst), v);
+                        }
                     }
                     if (to_mail) {
                         // own y slice: still in this warp's gate registers only -> re-read from gatebuf is not possible;
@@ -488,6 +516,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                 }
                 if (!last_owned) { xb ^= 1; h_local = false; }
                 rb ^= 1;
+                stamp();
             }  // layers
             xb ^= 1;   // the next group's stage input goes to the other buffer
 
@@ -496,6 +525,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                 const float* H1 = head_s + P.o_h1; const float* b1 = head_s + P.o_h1b;
                 const float* H2 = head_s + P.o_h2; const float* b2 = head_s + P.o_h2b;
                 dead |= !mbar_wait(bar(BAR_HI), ph_hi & 1u, abort_flag);
+                stamp();
                 for (int q = warp; q < P.HQ; q += NW) {        // hidden = mish(W1 x + b1), all-gathered
                     const int c = lane >> 3, p = lane & 7;
                     float v = quad_dot(reinterpret_cast<const float4*>(H1) + (size_t)q * P.KJh * 32, hin, P.Kh, P.KJh);
@@ -507,7 +537,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                     send_quad(8, 3, sbase + (unsigned)P.s_hid * 4u + coff, BAR_HD);
                     __syncwarp();
                 }
+                stamp();
                 dead |= !mbar_wait(bar(BAR_HD), ph_hd & 1u, abort_flag);
+                stamp();
                 for (int q = warp; q < P.ZQ; q += NW) {        // z = W2 hidden + b2 -> rank 0, logit-major [o][8]
                     const int c = lane >> 3, p = lane & 7;
                     float v = quad_dot(reinterpret_cast<const float4*>(H2) + (size_t)q * P.KJ2 * 32, hid, P.Hh, P.KJ2);
@@ -530,7 +562,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                     mbar_expect_tx(bar(BAR_HD), (unsigned)P.Hh * GB * 4u);
                 }
                 if (rank == 0) {
+                    stamp();
                     dead |= !mbar_wait(bar(BAR_Z0 + zb), (ph_z >> zb) & 1u, abort_flag);
+                    stamp();
                     const float* zsrc = zbuf + zb * (P.Q + 1) * GB;
                     for (int i = tid; i < (P.Q + 1) * GB; i += NT) zrows[(i & 7) * P.zrow + (i >> 3)] = zsrc[i];
                     __syncthreads();
@@ -554,6 +588,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_chain_kernel(const __grid_const
                         }
                     }
                     __syncthreads();
+                    stamp();
                     if (tid == 0 && !P.teacher_forced) { __threadfence(); st_release_s64(P.avail + g, t + 2); }
                 }
                 ph_z ^= 1u << zb;
@@ -581,6 +616,8 @@ struct wn2_handle {
     size_t smem_bytes = 0;
     std::vector<void*> allocs;
     size_t flags_bytes = 0;
+    long long* d_trace = nullptr;   // debug timeline, only with MMK_WN_TRACE_T set
+    long long trace_t = -1;
 };
 
 // fills geometry + weight block offsets + smem carve-up; returns dynamic smem bytes
@@ -671,7 +708,6 @@ int wn2_create(const mmk_wavenet_desc* d, int max_batch, wn2_handle** out, int* 
         if (p.C % CS || p.S % CS || p.Hh % CS) continue;
         const int nf = p.C / CS, ns = p.S / CS, nh = p.Hh / CS;
         if (nf % 4 || ns % 4 || nh % 4) continue;            // whole quads per CTA
-        if (nf * GB / 4 > 32) continue;                      // the ring write is one warp's worth of 16-byte chunks
         int nst_min = 0;
         for (int nst = 1; nst <= std::min(p.L, MAX_STAGES); ++nst) {
             Params q = p;
@@ -792,6 +828,10 @@ int wn2_create(const mmk_wavenet_desc* d, int max_batch, wn2_handle** out, int* 
     p.ready = (unsigned*)(p.avail + p.G);
     p.ack = p.ready + (size_t)(NST + 1) * p.G;
     p.abort_flag = p.ack + (size_t)(NST + 1) * p.G;
+    if (const char* e = getenv("MMK_WN_TRACE_T")) {
+        h->trace_t = atoll(e);
+        h->d_trace = (long long*)dev_alloc((size_t)NST * p.G * TRACE_EV * sizeof(long long), nullptr);
+    }
     MMK_CUDA(cudaDeviceSynchronize());
     *out = h;
     return 0;
@@ -808,6 +848,22 @@ int wn2_sync_check(wn2_handle* h, void* stream) {
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MMK_CHECK(aborted == 0, "WaveNet kernel watchdog fired: an inter-stage wait timed out (results invalid)");
+    if (h->d_trace) {   // debug: dump the timeline of step MMK_WN_TRACE_T as text (stage group stamps...)
+        const size_t n = (size_t)h->p.NST * h->p.G * TRACE_EV;
+        std::vector<long long> tr(n);
+        MMK_CUDA(cudaMemcpy(tr.data(), h->d_trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        const char* path = getenv("MMK_WN_TRACE_FILE");
+        if (FILE* f = fopen(path ? path : "wn_trace.txt", "w")) {
+            for (int s = 0; s < h->p.NST; ++s)
+                for (int g = 0; g < h->p.G; ++g) {
+                    fprintf(f, "%d %d", s, g);
+                    for (int e = 0; e < TRACE_EV; ++e) fprintf(f, " %lld", tr[((size_t)s * h->p.G + g) * TRACE_EV + e]);
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
+        MMK_CUDA(cudaMemset(h->d_trace, 0, n * sizeof(long long)));
+    }
     return 0;
 }
 
@@ -829,6 +885,7 @@ int wn2_run(wn2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     p.temperature = d_temperature; p.n_temperature = n_temperature;
     p.noise = d_noise; p.noise_stride = noise_stride; p.noise_t0 = noise_t0;
     p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
+    p.trace = h->d_trace; p.trace_t = h->d_trace ? t_begin + h->trace_t : -1;
     const int n_u32 = 2 * (p.NST + 1) * p.G + 1;
     const long long avail0 = teacher_forced ? (t_end + 1) : (t_head + 1);
     wn2_init_flags_kernel<<<(std::max(p.G, n_u32) + 255) / 256, 256, 0, st>>>(p.avail, p.G, avail0, p.ready, n_u32);
