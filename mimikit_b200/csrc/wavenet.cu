@@ -543,6 +543,7 @@ using namespace mmk;
 
 struct mmk_wavenet_s {
     wn2_handle* v2 = nullptr;   // set when the latency-engineered kernel (wavenet2.cu) hosts this network
+    wn3_handle* v3 = nullptr;   // set when the warp-autonomous kernel (wavenet3.cu) hosts this network
     WnParams p{};
     int device = 0;
     int max_batch = 0;
@@ -648,7 +649,20 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
     WnParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
     {
-        const char* force = getenv("MMK_WN_KERNEL");   // "1" = general kernel, "2" = chain kernel only
+        const char* force = getenv("MMK_WN_KERNEL");   // "1" = general kernel, "2" = chain kernel, "3" = warp kernel only
+        if (!force || atoi(force) == 3) {
+            int unsupported = 0;
+            if (wn3_create(d, max_batch, &h->v3, &unsupported) == 0) {
+                int rf3 = 1;
+                for (int l = 0; l < d->n_layers; ++l) rf3 += d->dilations[l];
+                h->rf = rf3; h->max_batch = max_batch;
+                *out = h;
+                return 0;
+            }
+            h->v3 = nullptr;
+            if (!unsupported) { delete h; return 1; }
+            if (force) { delete h; MMK_FAIL("configuration not supported by the warp kernel (MMK_WN_KERNEL=3)"); }
+        }
         if (!(force && atoi(force) == 1)) {
             int unsupported = 0;
             if (wn2_create(d, max_batch, &h->v2, &unsupported) == 0) {
@@ -816,6 +830,7 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
 
 extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
     if (!h) return 0;
+    if (h->v3) wn3_destroy(h->v3);
     if (h->v2) wn2_destroy(h->v2);
     cudaFree(h->d_wpack); cudaFree(h->d_hpack); cudaFree(h->d_E); cudaFree(h->d_rings);
     cudaFree(h->d_mail_h); cudaFree(h->d_mail_s); cudaFree(h->d_flags);
@@ -825,6 +840,7 @@ extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
 
 extern "C" int mmk_wavenet_sync_check(mmk_wavenet_t h, void* stream) {
     MMK_CHECK(h, "null handle");
+    if (h->v3) return wn3_sync_check(h->v3, stream);
     if (h->v2) return wn2_sync_check(h->v2, stream);
     unsigned aborted = 0;
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -837,6 +853,7 @@ extern "C" int mmk_wavenet_rf(mmk_wavenet_t h) { return h ? h->rf : -1; }
 
 extern "C" int mmk_wavenet_launch_info(mmk_wavenet_t h, mmk_launch_info* out) {
     MMK_CHECK(h && out, "null argument");
+    if (h->v3) return wn3_launch_info(h->v3, out);
     if (h->v2) return wn2_launch_info(h->v2, out);
     out->cluster_size = h->p.CS; out->n_stages = h->p.NST; out->group_size = WN_GB; out->threads = WN_NT;
     out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.CS * h->p.NST;
@@ -862,6 +879,9 @@ extern "C" int mmk_wavenet_run(mmk_wavenet_t h, int64_t* d_seq, int B, int64_t s
     MMK_CHECK(d_temperature == nullptr || (n_temperature == 1 || n_temperature == B), "temperature must have 1 or B entries");
     MMK_CHECK(d_temperature == nullptr || d_noise != nullptr, "sampling (temperature given) needs a noise tensor");
     if (t_begin == t_end) return 0;
+    if (h->v3)
+        return wn3_run(h->v3, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
+                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     if (h->v2)
         return wn2_run(h->v2, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
                        n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);

@@ -14,3 +14,14 @@ int wn2_run(wn2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
             int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
             int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
             unsigned long long* d_step_ts, void* stream);
+
+// The warp-autonomous kernel (wavenet3.cu): same contract as the wn2_* functions; tried first.
+struct wn3_handle;
+int wn3_create(const mmk_wavenet_desc* d, int max_batch, wn3_handle** out, int* unsupported);
+int wn3_destroy(wn3_handle* h);
+int wn3_launch_info(wn3_handle* h, mmk_launch_info* out);
+int wn3_sync_check(wn3_handle* h, void* stream);
+int wn3_run(wn3_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
+            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream);

@@ -59,13 +59,13 @@ def test_golden_sequences_and_logits(name):
     assert _rel_err(lg.cpu().numpy(), d["logits_t1"]) <= REL_TOL
 
 
-@pytest.mark.parametrize("kernel", ["1", "2"])
+@pytest.mark.parametrize("kernel", ["1", "2", "3"])
 @pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
 @pytest.mark.parametrize("blocks,dims,res,skips,B", [((3, 3), 64, 64, 64, 11), ((4,), 128, None, None, 1),
                                                      ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8),
                                                      ((3, 2), 128, 128, 128, 40)])
 def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims, res, skips, B):
-    """Seeded weights/prompts, both kernels (1 = general, 2 = latency-engineered chain kernel), every cluster
+    """Seeded weights/prompts, all kernels (1 = general, 2 = chain kernel, 3 = warp-autonomous kernel), every cluster
     geometry the launcher can pick, ragged batches (B not a multiple of the 8-prompt pipeline group), with/without
     residual and skip convs."""
     if dims % int(cluster) or (skips or dims) % int(cluster):
@@ -93,7 +93,10 @@ def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims,
 
 @pytest.mark.parametrize("kernel,cluster,hazard,res,skips", [("1", "2", None, 64, 64), ("2", "2", "0", 64, 64),
                                                              ("2", "4", "1", 64, 64), ("2", "2", "0", None, 64),
-                                                             ("2", "4", None, None, None), ("2", "2", "0", 64, None)])
+                                                             ("2", "4", None, None, None), ("2", "2", "0", 64, None),
+                                                             ("3", "2", None, 64, 64), ("3", "4", None, None, 64),
+                                                             ("3", "16", None, 64, None), ("3", "8", None, None, None),
+                                                             ("3", "1", None, 64, 64)])
 def test_multi_stage_pipeline(monkeypatch, kernel, cluster, hazard, res, skips):
     """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups; the chain
     kernel in both ring modes (prefetched TMA ring reads / barrier-ordered) and every residual/skip combination."""
