@@ -14,24 +14,16 @@
 // Roofline: HBM.  Algorithmic bytes per frame: hop*4 in (each sample is read from DRAM once; the 4x frame
 // overlap is served by L2) + n_mels*4 out (+ (n_fft/2+1)*4 when the magnitudes are materialised).
 #include "common.cuh"
+#include "stft_warp.cuh"
 #include "../../include/mmk_b200.h"
 
 #include <math.h>
+#include <algorithm>
 #include <vector>
 
 namespace mmk {
 
 constexpr int STFT_THREADS = 256;
-
-struct StftParams {
-    const float* x;
-    float* mag_out;
-    const float* mel_fb;
-    const int* mel_range;  // (n_mels, 2): [lo, hi) non-zero bin range of each filter
-    float* mel_out;
-    long long clip_stride, start, kept_len, n_frames, total_frames;
-    int n_fft, hop, pad, n_mels, log2_half;
-};
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -207,6 +199,17 @@ extern "C" int mmk_stft_mag_mel(const float* d_x, int n_clips, int64_t clip_len,
         mel_range_kernel<<<(n_mels + 7) / 8, 256, 0, st>>>(d_mel_fb, n_mels, n_fft / 2 + 1, d_range);
         MMK_CUDA(cudaGetLastError());
         p.mel_range = d_range;
+    }
+    if (n_fft == 2048) {   // warp-per-frame register FFT (stft_warp.cuh)
+        MMK_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        long long grid = std::min<long long>(sms, (p.total_frames + FW_WARPS - 1) / FW_WARPS);
+        stft2048_warp_kernel<<<(int)grid, FW_THREADS, FW_SMEM_BYTES, st>>>(p);
+        MMK_CUDA(cudaGetLastError());
+        if (d_range) MMK_CUDA(cudaFreeAsync(d_range, st));
+        return 0;
     }
     const int H = n_fft / 2;
     size_t smem = sizeof(float2) * 4 * H + sizeof(float) * (n_fft + H + 8);

@@ -94,9 +94,9 @@ def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims,
 @pytest.mark.parametrize("kernel,cluster,hazard,res,skips", [("1", "2", None, 64, 64), ("2", "2", "0", 64, 64),
                                                              ("2", "4", "1", 64, 64), ("2", "2", "0", None, 64),
                                                              ("2", "4", None, None, None), ("2", "2", "0", 64, None),
-                                                             ("3", "2", None, 64, 64), ("3", "4", None, None, 64),
+                                                             ("3", "4", None, 64, 64), ("3", "4", None, None, 64),
                                                              ("3", "16", None, 64, None), ("3", "8", None, None, None),
-                                                             ("3", "1", None, 64, 64)])
+                                                             ("3", "8", None, 64, 64)])
 def test_multi_stage_pipeline(monkeypatch, kernel, cluster, hazard, res, skips):
     """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups; the chain
     kernel in both ring modes (prefetched TMA ring reads / barrier-ordered) and every residual/skip combination."""
