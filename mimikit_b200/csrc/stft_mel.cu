@@ -206,6 +206,7 @@ extern "C" int mmk_stft_mag_mel(const float* d_x, int n_clips, int64_t clip_len,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         long long grid = std::min<long long>(sms, (p.total_frames + FW_WARPS - 1) / FW_WARPS);
+        p.mel_cap = d_mel_out ? FW_MEL_CAP : 0;
         stft2048_warp_kernel<<<(int)grid, FW_THREADS, FW_SMEM_BYTES, st>>>(p);
         MMK_CUDA(cudaGetLastError());
         if (d_range) MMK_CUDA(cudaFreeAsync(d_range, st));

@@ -31,6 +31,7 @@ struct StftParams {
     float* mel_out;
     long long clip_stride, start, kept_len, n_frames, total_frames;
     int n_fft, hop, pad, n_mels, log2_half;
+    int mel_cap;           // warp kernel: rows of the lane-interleaved filter table that fit in shared memory (0 = none)
 };
 
 __device__ __forceinline__ float2 w32(int j) {   // exp(-2 pi i j / 32)
@@ -97,6 +98,31 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* tile = reinterpret_cast<float2*>(win + N) + (size_t)warp * FW_TILE;
     float* magb = reinterpret_cast<float*>(tile);      // magnitudes overwrite the tile once Z has been consumed
+    // lane-interleaved filter table: lane L owns filters L, L+32, ...; its non-zero weights, filter after filter, sit in
+    // column L of wsm[row][32] (conflict-free reads).  Built once per CTA from the dense filterbank.
+    float* wsm = reinterpret_cast<float*>(reinterpret_cast<float2*>(win + N) + (size_t)FW_WARPS * FW_TILE);
+    const int n_grp = (p.n_mels + 31) / 32;
+    bool mel_packed = false;
+    if (p.mel_out && p.mel_cap > 0 && tid < 32) {
+        int rows = 0;
+        for (int g = 0; g < n_grp; ++g) {
+            const int m = tid + 32 * g;
+            if (m < p.n_mels) rows += p.mel_range[2 * m + 1] - p.mel_range[2 * m];
+        }
+        int mx = rows;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (mx <= p.mel_cap) {
+            int row = 0;
+            for (int g = 0; g < n_grp; ++g) {
+                const int m = tid + 32 * g;
+                if (m >= p.n_mels) break;
+                const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
+                for (int k = lo; k < hi; ++k) wsm[(row++) * 32 + tid] = __ldg(p.mel_fb + (long long)m * (H + 1) + k);
+            }
+        }
+        if (tid == 0) *reinterpret_cast<int*>(wsm + (size_t)p.mel_cap * 32) = mx <= p.mel_cap ? 1 : 0;
+    }
 
     for (int i = tid; i < H; i += FW_THREADS) {
         const int k1 = i >> 5, n2 = i & 31;
@@ -111,6 +137,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
     }
     for (int n = tid; n < N; n += FW_THREADS) win[n] = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)N);
     __syncthreads();
+    if (p.mel_out && p.mel_cap > 0) mel_packed = *reinterpret_cast<const int*>(wsm + (size_t)p.mel_cap * 32) != 0;
 
     const int nb = H + 1;
     // warps of a CTA take adjacent frames (their 75 % input overlap is served by L1)
@@ -195,17 +222,30 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
         }
         if (p.mel_out) {
             float* orow = p.mel_out + f * (long long)p.n_mels;
-            for (int m = lane; m < p.n_mels; m += 32) {
-                const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
-                const float* fb = p.mel_fb + (long long)m * nb;
-                float acc = 0.0f;
-                for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(fb + k), magb[k], acc);
-                __stcs(orow + m, acc);
+            if (mel_packed) {
+                const float* wl = wsm + lane;
+                for (int m = lane; m < p.n_mels; m += 32) {
+                    const int2 rg = __ldg(reinterpret_cast<const int2*>(p.mel_range) + m);
+                    float acc = 0.0f;
+#pragma unroll 4
+                    for (int k = rg.x; k < rg.y; ++k, wl += 32) acc = fmaf(*wl, magb[k], acc);
+                    __stcs(orow + m, acc);
+                }
+            } else {
+                for (int m = lane; m < p.n_mels; m += 32) {
+                    const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
+                    const float* fb = p.mel_fb + (long long)m * nb;
+                    float acc = 0.0f;
+                    for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(fb + k), magb[k], acc);
+                    __stcs(orow + m, acc);
+                }
             }
         }
     }
 }
 
-constexpr size_t FW_SMEM_BYTES = sizeof(float2) * (1024 + 512) + sizeof(float) * 2048 + sizeof(float2) * FW_TILE * FW_WARPS;
+constexpr size_t FW_SMEM_BASE = sizeof(float2) * (1024 + 512) + sizeof(float) * 2048 + sizeof(float2) * FW_TILE * FW_WARPS;
+constexpr int FW_MEL_CAP = 384;   // rows of the packed filter table (x 128 B) + one flag word
+constexpr size_t FW_SMEM_BYTES = FW_SMEM_BASE + (size_t)FW_MEL_CAP * 128 + 16;
 
 }  // namespace mmk
