@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "sampler.cuh"
 #include "tile_gemm.cuh"
+#include "samplernn_impl.h"
 #include "../../include/mmk_b200.h"
 
 #include <algorithm>
@@ -327,6 +328,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 using namespace mmk;
 
 struct mmk_samplernn_s {
+    sr2_handle* v2 = nullptr;     // the cluster kernel (samplernn2.cu) when the configuration fits it
     SrParams p{};
     int device = 0, max_batch = 0, rf = 0;
     size_t smem_bytes = 0;
@@ -337,6 +339,7 @@ struct mmk_samplernn_s {
 
 static int sr_free(mmk_samplernn_s* h) {
     if (!h) return 0;
+    if (h->v2) sr2_destroy(h->v2);
     for (void* a : h->allocs) cudaFree(a);
     delete h;
     return 0;
@@ -361,6 +364,20 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
     auto* h = new mmk_samplernn_s();
     SrParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
+    {   // MMK_SR_KERNEL: "1" = general kernel only, "2" = cluster kernel only, unset = cluster kernel when it fits
+        const char* force = getenv("MMK_SR_KERNEL");
+        if (!force || atoi(force) != 1) {
+            int unsupported = 0;
+            if (sr2_create(d, max_batch, &h->v2, &unsupported) == 0) {
+                h->max_batch = max_batch; h->rf = d->frame_sizes[0];
+                *out = h;
+                return 0;
+            }
+            h->v2 = nullptr;
+            if (!unsupported) { sr_free(h); return 1; }
+            if (force && atoi(force) == 2) { sr_free(h); MMK_FAIL("configuration not supported by the cluster kernel (MMK_SR_KERNEL=2)"); }
+        }
+    }
     int sms = 0, max_optin = 0, coop = 0;
     MMK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     MMK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -485,6 +502,7 @@ extern "C" int mmk_samplernn_destroy(mmk_samplernn_t h) { return sr_free(h); }
 
 extern "C" int mmk_samplernn_launch_info(mmk_samplernn_t h, mmk_launch_info* out) {
     MMK_CHECK(h && out, "null argument");
+    if (h->v2) return sr2_launch_info(h->v2, out);
     out->cluster_size = 1; out->n_stages = h->p.NC; out->group_size = SR_PB; out->threads = SR_NT;
     out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.NC;
     return 0;
@@ -507,6 +525,10 @@ extern "C" int mmk_samplernn_run(mmk_samplernn_t h, int64_t* d_seq, int B, int64
                   "warm-up range reads outside the sequence buffer");
     if (gen_end > gen_begin)
         MMK_CHECK(gen_begin - rf >= seq_t0 && gen_end - seq_t0 <= seq_stride, "generate range falls outside the sequence buffer");
+    if (h->v2)
+        return sr2_run(h->v2, d_seq, B, seq_stride, seq_t0, warm_begin, warm_end, warm_offset, gen_begin, gen_end,
+                       reset_hidden, teacher_forced, d_temperature, n_temperature, d_noise, noise_stride, noise_t0,
+                       d_logits_out, d_decisions, d_step_ts, stream);
     cudaStream_t st = (cudaStream_t)stream;
     SrParams p = h->p;
     if (reset_hidden) {
@@ -542,6 +564,7 @@ extern "C" int mmk_samplernn_run(mmk_samplernn_t h, int64_t* d_seq, int B, int64
 
 extern "C" int mmk_samplernn_sync_check(mmk_samplernn_t h, void* stream) {
     MMK_CHECK(h, "null handle");
+    if (h->v2) return sr2_sync_check(h->v2, stream);
     unsigned aborted = 0;
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

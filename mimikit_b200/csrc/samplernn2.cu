@@ -1,0 +1,973 @@
+// Cluster SampleRNN generation kernel (sm_100a) — the fast path behind mmk_samplernn_*.  Same function as
+// samplernn.cu (the general kernel; see that file for the reference lines: sample_rnn_v2.py:83-119, 226-260;
+// modules/io.py:106-133, 185-198; modules/resamplers.py:13-23; networks/mlp.py:44-63; modules/targets.py:40-52).
+//
+// What changed against the general kernel, and why (B = 128 prompts, (8,2,1)/512: 126 us per sample there):
+//   * the sample-level tier + MLP head + sampler never touch a grid barrier.  A thread-block cluster of CS CTAs owns a
+//     group of 8 prompts end to end: W1 and W2 are split along K over the cluster (a CTA needs only its H/CS rows of
+//     the conditioning vector), partial sums meet through distributed shared memory (st.async + mbarrier
+//     complete_tx): partial hidden -> reduce-scatter by row, Mish, partial logits -> reduce-scatter by prompt, one
+//     warp per prompt applies the learned temperature and samples, the index is broadcast to the cluster.  Three
+//     DSMEM exchanges per sample instead of three grid barriers and three full-batch activation reloads per CTA.
+//   * frame tiers stay weight-stationary over all CTAs (GRU rows split by hidden index, up-sampler rows evenly; the
+//     19 MB of fp32 weights only fit spread over >= 100 SMs), but the activations now stream through a 3-stage
+//     cp.async pipeline (16 rows x <=128 prompts per chunk, one __syncthreads per chunk) into 4x4 register tiles; the
+//     frame-linear input term is added by the thread that issued the copy, so it costs no extra barrier.
+//   * grid barriers only around tier firings: 3 per firing step instead of 3 per sample + 2 per firing.
+#include "common.cuh"
+#include "sampler.cuh"
+#include "samplernn_impl.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+namespace mmk_sr2 {
+
+using mmk::decide_warp;
+using mmk::mish_acc;
+using mmk::sigmoid_acc;
+
+constexpr int NT = 256;          // threads per CTA
+constexpr int KC = 16;           // activation rows per streamed chunk
+constexpr int NSTAGE = 3;        // cp.async stages
+constexpr int PBW = 128;         // prompts per streamed block
+constexpr int WMAX = 32;         // widest streamed weight slice (columns per CTA)
+constexpr int MAX_TIERS = 6;
+constexpr int XSTAGE = KC * PBW, WSTAGE = KC * WMAX;
+constexpr int REGION = NSTAGE * (XSTAGE + WSTAGE);   // floats: stage buffers / partial sums / head buffers
+constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;
+
+struct Tier {
+    int fs, up, kdiv, NU, up_rows;
+    int off_wih, off_whh, off_wup;   // float offsets in the CTA's packed global block: W[H][N] followed by bias[N]
+    int so_wih, so_whh, so_wup;      // float offsets in shared memory, or -1: streamed from L2 with the activations
+    const float* in_w; const float* in_b;
+    float* hbuf; float* obuf;
+};
+
+struct Params {
+    int n_ft, H, Hh, Q, NC, CS, GP, JP, NG, fs_last, fs_lt;
+    int n_res, res_goff[3 * MAX_TIERS + 3], res_soff[3 * MAX_TIERS + 3], res_len[3 * MAX_TIERS + 3];   // resident pieces
+    int KS, RS, ZR;                  // head: x rows per CTA (H/CS), hidden rows per CTA (Hh/CS), padded logit rows
+    int off_w1, off_b1, off_w2, cta_block;     // global block offsets
+    int so_w1, so_b1, so_w2;
+    int s_region, s_gi, s_bar, smem_floats;
+    int h_x, h_inh, h_hid, h_un, h_zs;      // head buffers inside the region (float offsets)
+    const float* wpack; const float* conv_w; const float* conv_b; const float* b2;
+    unsigned long long* bar; unsigned* abort_flag;
+    float min_temp;
+    Tier tiers[MAX_TIERS];
+    // this run
+    int B, Bp, teacher_forced, n_temperature;
+    int hsel[MAX_TIERS];
+    long long* seq;
+    long long seq_stride, warm_begin, warm_end, warm_off, gen_begin, gen_end;
+    const float* temperature; const float* noise;
+    long long noise_stride, noise_t0;
+    float* logits_out; long long* decisions; unsigned long long* step_ts;
+    unsigned long long* dbg;         // MMK_SR_DEBUG: time (ns) spent by CTA 0 per section
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, float4 v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(unsigned raddr, unsigned v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_id_x() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// mbarrier wait with the watchdog out of line
+__device__ __noinline__ bool mbar_wait_slow(unsigned bar, unsigned parity, unsigned* abort_flag) {
+    const unsigned long long t0 = globaltimer();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 63u) == 0u) {
+            if (ld_relaxed_u32(abort_flag) != 0u) return false;
+            if (globaltimer() - t0 > WAIT_LIMIT_NS) { atomicExch(abort_flag, 1u); return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, unsigned* abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, abort_flag);
+}
+
+// All CTAs of the grid meet here (co-resident by construction).  Returns false when the launch was aborted.
+__device__ __forceinline__ bool grid_barrier(const Params& P, unsigned long long& epoch) {
+    __shared__ int ok_s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += (unsigned long long)P.NC;
+        __threadfence();
+        red_release_add_u64(P.bar, 1ull);
+        int ok = 1;
+        if (ld_acquire_u64(P.bar) < epoch) {
+            const unsigned long long t0 = globaltimer();
+            unsigned spins = 0;
+            while (ld_acquire_u64(P.bar) < epoch) {
+                if ((++spins & 63u) == 0u) {
+                    if (ld_relaxed_u32(P.abort_flag) != 0u) { ok = 0; break; }
+                    if (globaltimer() - t0 > WAIT_LIMIT_NS) { atomicExch(P.abort_flag, 1u); ok = 0; break; }
+                }
+            }
+        }
+        ok_s = ok;
+    }
+    __syncthreads();
+    return ok_s != 0;
+}
+
+// Linearizer (modules/io.py:111-112): ((q / Q) - .5) * 2 in fp32
+__device__ __forceinline__ float linearize(long long q, float Qf) {
+    return __fmul_rn(__fsub_rn(__fdiv_rn((float)q, Qf), 0.5f), 2.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Streamed contraction: acc[4 cols][4 prompts] += W[k][4 cq ..] * x[k][4 pq ..], x rows streamed from global
+// ([K][ld] floats, prompts pb0 .. pb0 + pbw) through the cp.async stages.  The K rows of a chunk are dealt to
+// `nslice` thread slices; the caller reduces the slices in slice order (fixed summation order).
+// ------------------------------------------------------------------------------------------------------------
+struct Map {
+    int tiles, nslice, tile, slice, cq, pq, npq;
+    bool active;
+};
+__device__ __forceinline__ Map make_map(int ncol4, int pbw) {
+    Map m;
+    m.npq = pbw >> 2;
+    m.tiles = ncol4 * m.npq;
+    int ns = NT / m.tiles, p2 = 1;
+    while (p2 * 2 <= ns && p2 * 2 <= KC) p2 *= 2;
+    m.nslice = p2;
+    m.active = (int)threadIdx.x < m.tiles * p2;
+    m.tile = threadIdx.x % m.tiles;
+    m.slice = threadIdx.x / m.tiles;
+    m.cq = m.tile / m.npq;
+    m.pq = m.tile - m.cq * m.npq;
+    return m;
+}
+
+// The frame-linear input term x = Linear(frame) + bias (+ conditioning already in the landed chunk), FramedLinearIO
+// (modules/io.py:106-133).  It is added to a chunk by the thread that copied the element; the Linear rows of the
+// next chunk are fetched into registers one iteration ahead so that their latency hides behind the contraction.
+constexpr int MAXFS = 16;     // frame sizes the register prefetch covers
+constexpr int EL = 2;         // float4 elements a thread owns per chunk (KC * PBW / 4 / NT)
+struct FrameTerm {
+    const float* in_w; const float* in_b; const float* lin_s;   // (H, fs) global, (H) global, [fs][pbw] shared
+    int fs;
+    bool has_cond;
+};
+
+template <int R>
+__device__ __forceinline__ void tile_rows(float (&acc)[16], const float* __restrict__ wp, int ldw,
+                                          const float* __restrict__ xp, int pbw) {
+#pragma unroll (R >= 4 ? 4 : R)
+    for (int j = 0; j < R; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(wp + j * ldw);
+        const float4 x = *reinterpret_cast<const float4*>(xp + j * pbw);
+        const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) acc[ci * 4 + pi] = fmaf(wv[ci], xv[pi], acc[ci * 4 + pi]);
+    }
+}
+
+// W: resident weights in shared memory, or nullptr when Wg (the same [K][ldw] matrix in global memory) is streamed.
+// Slice s of the map takes the KC / nslice consecutive rows s * (KC / nslice) .. of every chunk.
+template <bool FRAME>
+__device__ __forceinline__ void gemm_stream(float (&acc)[16], const Map& m, const float* __restrict__ W,
+                                            const float* __restrict__ Wg, int ldw,
+                                            const float* __restrict__ src, int ld, int pb0, int pbw, int K,
+                                            float* stage, const FrameTerm ft, int rot) {
+    // rot: this CTA walks the K chunks starting at chunk `rot` (every CTA reads the same activations: starting them at
+    // different rows keeps 128 SMs from asking the same L2 lines in the same cycle; the order is fixed per CTA)
+    const int tid = threadIdx.x;
+    const int n4row = pbw >> 2, n4 = KC * n4row, nchunk = K / KC, n4w = (KC * ldw) >> 2;
+    float* wstage = stage + NSTAGE * XSTAGE;
+    // the (row, prompt quad) of the <= EL float4 elements this thread copies / fixes in every chunk
+    int er[EL], ec[EL];
+    bool ev[EL];
+#pragma unroll
+    for (int e = 0; e < EL; ++e) {
+        const int i = tid + e * NT;
+        ev[e] = i < n4;
+        er[e] = i / n4row;
+        ec[e] = i - er[e] * n4row;
+    }
+    auto chunk_of = [&](int c) { const int cc = c + rot; return cc >= nchunk ? cc - nchunk : cc; };
+    auto issue = [&](int c) {
+        if (c < nchunk) {
+            const int cc = chunk_of(c);
+            if (src != nullptr) {
+                float* buf = stage + (c % NSTAGE) * XSTAGE;
+#pragma unroll
+                for (int e = 0; e < EL; ++e)
+                    if (ev[e]) cp_async16(buf + er[e] * pbw + 4 * ec[e], src + (size_t)(cc * KC + er[e]) * ld + pb0 + 4 * ec[e]);
+            }
+            if (W == nullptr) {
+                float* wb = wstage + (c % NSTAGE) * WSTAGE;
+                for (int i = tid; i < n4w; i += NT) cp_async16(wb + 4 * i, Wg + (size_t)cc * KC * ldw + 4 * i);
+            }
+        }
+        cp_async_commit();
+    };
+    float cw[EL][MAXFS], cb[EL];
+    auto fetch = [&](int c) {
+        if (FRAME && c < nchunk) {
+#pragma unroll
+            for (int e = 0; e < EL; ++e) {
+                const int k = chunk_of(c) * KC + er[e];
+                if (ev[e]) {
+#pragma unroll
+                    for (int f = 0; f < MAXFS; ++f)
+                        if (f < ft.fs) cw[e][f] = __ldg(ft.in_w + (size_t)k * ft.fs + f);
+                    cb[e] = __ldg(ft.in_b + k);
+                }
+            }
+        }
+    };
+    issue(0);
+    issue(1);
+    fetch(0);
+    const int R = KC / m.nslice;
+    for (int c = 0; c < nchunk; ++c) {
+        cp_async_wait1();                                   // this thread's copies of chunk c have landed
+        float* buf = stage + (c % NSTAGE) * XSTAGE;
+        if (FRAME) {
+#pragma unroll
+            for (int e = 0; e < EL; ++e) {
+                if (ev[e]) {
+                    float4* x4 = reinterpret_cast<float4*>(buf + er[e] * pbw + 4 * ec[e]);
+                    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int f = 0; f < MAXFS; ++f) {
+                        if (f < ft.fs) {
+                            const float4 l = *reinterpret_cast<const float4*>(ft.lin_s + f * pbw + 4 * ec[e]);
+                            a[0] = fmaf(l.x, cw[e][f], a[0]); a[1] = fmaf(l.y, cw[e][f], a[1]);
+                            a[2] = fmaf(l.z, cw[e][f], a[2]); a[3] = fmaf(l.w, cw[e][f], a[3]);
+                        }
+                    }
+                    float4 r = make_float4(a[0] + cb[e], a[1] + cb[e], a[2] + cb[e], a[3] + cb[e]);
+                    if (ft.has_cond) { const float4 cv = *x4; r.x += cv.x; r.y += cv.y; r.z += cv.z; r.w += cv.w; }
+                    *x4 = r;
+                }
+            }
+        }
+        __syncthreads();                                    // chunk c complete; everyone is done with chunk c - 1
+        issue(c + 2);
+        fetch(c + 1);
+        if (m.active) {
+            const float* wp = (W != nullptr ? W + (size_t)(chunk_of(c) * KC) * ldw : wstage + (c % NSTAGE) * WSTAGE)
+                              + (size_t)(m.slice * R) * ldw + m.cq * 4;
+            const float* xp = buf + (m.slice * R) * pbw + m.pq * 4;
+            switch (R) {
+                case 16: tile_rows<16>(acc, wp, ldw, xp, pbw); break;
+                case 8: tile_rows<8>(acc, wp, ldw, xp, pbw); break;
+                case 4: tile_rows<4>(acc, wp, ldw, xp, pbw); break;
+                case 2: tile_rows<2>(acc, wp, ldw, xp, pbw); break;
+                default: tile_rows<1>(acc, wp, ldw, xp, pbw); break;
+            }
+        }
+    }
+    __syncthreads();                                        // stage buffers are free again
+}
+
+__device__ __forceinline__ void store_partials(const float (&acc)[16], const Map& m, float* part) {
+    if (m.active) {
+        float4* d = reinterpret_cast<float4*>(part + ((size_t)m.slice * m.tiles + m.tile) * 16);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) d[ci] = make_float4(acc[ci * 4], acc[ci * 4 + 1], acc[ci * 4 + 2], acc[ci * 4 + 3]);
+    }
+}
+// sum over the slices, in slice order, of output (col, p) of the prompt block
+__device__ __forceinline__ float reduce_partials(const float* part, const Map& m, int col, int p) {
+    const float* q = part + ((size_t)((col >> 2) * m.npq + (p >> 2))) * 16 + (col & 3) * 4 + (p & 3);
+    float s = 0.0f;
+    for (int sl = 0; sl < m.nslice; ++sl) s += q[(size_t)sl * m.tiles * 16];
+    return s;
+}
+
+enum { BAR_HID = 0, BAR_Z, BAR_Q, BAR_COUNT };
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, NC = P.NC, H = P.H, Bp = P.Bp, CS = P.CS;
+    const int rank = (int)cluster_ctarank();
+    const int cluster = c / CS, n_clusters = NC / CS;
+    const float* w_s = smem;
+    float* region = smem + P.s_region;
+    float* gi_s = smem + P.s_gi;          // [NG][pbw] input-side gate pre-activations; before that: lin_s[fs][pbw]
+    const unsigned sbase = smem_u32(smem);
+    const unsigned off_bar0 = (unsigned)P.s_bar * 4u;
+    auto bar = [&](int i) { return sbase + off_bar0 + 8u * (unsigned)i; };
+    unsigned* abort_flag = P.abort_flag;
+
+    const float* gblock = P.wpack + (size_t)c * P.cta_block;   // this CTA's packed weights in global memory
+    for (int r = 0; r < P.n_res; ++r) {   // resident pieces (what does not fit is streamed from L2 when used)
+        const float4* src = reinterpret_cast<const float4*>(gblock + P.res_goff[r]);
+        float4* dst = reinterpret_cast<float4*>(smem + P.res_soff[r]);
+        for (int i = tid; i < P.res_len[r] / 4; i += NT) dst[i] = __ldg(src + i);
+    }
+    const int GP = P.GP, npq_h = GP >> 2;
+    const unsigned hid_bytes = (unsigned)(CS * P.RS * GP) * 4u;
+    const unsigned z_bytes = (unsigned)((GP / CS) * CS * P.ZR) * 4u;
+    const unsigned q_bytes = (unsigned)GP * 4u;
+    if (tid == 0) {
+        for (int i = 0; i < BAR_COUNT; ++i) mbar_init(bar(i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar(BAR_HID), hid_bytes);
+        mbar_expect_tx(bar(BAR_Z), z_bytes);
+        mbar_expect_tx(bar(BAR_Q), q_bytes);
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    const int j_lo = c * P.JP;
+    const int rot = (int)(((unsigned)c * 11u) % (unsigned)(H / KC));
+    int hsel[MAX_TIERS];
+#pragma unroll
+    for (int i = 0; i < MAX_TIERS; ++i) hsel[i] = P.hsel[i];
+    unsigned long long epoch = 0;
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = globaltimer();
+    auto lap = [&](int slot) { if (P.dbg && c == 0 && tid == 0) { const unsigned long long n = globaltimer(); tacc[slot] += n - tlast; tlast = n; } };
+    unsigned head_phase = 0;              // completed head exchanges (parity of the three mbarriers)
+    bool dead = false;
+    bool heads_pending = false;           // head steps ran since the last grid barrier
+    const float Qf = (float)P.Q;
+    const int n_groups = (P.B + GP - 1) / GP;
+    const int Bl = (P.B + 3) & ~3;        // live prompts, padded to the float4 granule
+
+    for (int phase = 0; phase < 2 && !dead; ++phase) {
+        const bool gen = phase == 1;
+        const long long t_lo = gen ? P.gen_begin : P.warm_begin, t_hi = gen ? P.gen_end : P.warm_end;
+        const long long off = gen ? 0 : P.warm_off;
+        for (long long t = t_lo; t < t_hi && !dead; ++t) {
+            const long long tw = t + off;   // the window ends at data index tw (exclusive)
+            // ---------------- frame tiers (weight-stationary over the whole grid) ----------------
+            bool fired = false;
+            for (int i = 0; i < P.n_ft && !dead; ++i) {
+                const Tier& T = P.tiers[i];
+                if (t % T.fs != 0) continue;
+                lap(0);
+                if (!fired && heads_pending) {              // the samples of the last head steps must be visible
+                    if (!grid_barrier(P, epoch)) { dead = true; break; }
+                    heads_pending = false;
+                }
+                lap(1);
+                fired = true;
+                const float* cond = nullptr;
+                if (i > 0) cond = P.tiers[i - 1].obuf + (size_t)((t / T.fs) % T.kdiv) * H * Bp;
+                const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
+                float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
+                const float* Wih = w_s + T.so_wih; const float* bih = Wih + (size_t)H * P.NG;
+                const float* Whh_g = gblock + T.off_whh;
+                const float* Whh = T.so_whh >= 0 ? w_s + T.so_whh : nullptr;
+                const float* bhh = T.so_whh >= 0 ? Whh + (size_t)H * P.NG : Whh_g + (size_t)H * P.NG;
+                const int fs = T.fs;
+                // ---- GRU cell on this CTA's hidden indices ----
+                const int cap_g = min(PBW, (NT / (P.NG >> 2)) << 2);
+                for (int pb0 = 0; pb0 < Bl; pb0 += cap_g) {
+                    const int pbw = min(cap_g, Bl - pb0);
+                    float* lin_s = gi_s;
+                    for (int idx = tid; idx < fs * pbw; idx += NT) {
+                        const int f = idx / pbw, p = idx - f * pbw, b = pb0 + p;
+                        long long q = 0;
+                        if (b < P.B) q = __ldcg(P.seq + (size_t)b * P.seq_stride + (tw - fs + f));
+                        lin_s[idx] = linearize(q, Qf);
+                    }
+                    __syncthreads();
+                    const Map m = make_map(P.NG >> 2, pbw);
+                    float acc[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+                    {
+                        FrameTerm ft{T.in_w, T.in_b, lin_s, fs, cond != nullptr};
+                        gemm_stream<true>(acc, m, Wih, nullptr, P.NG, cond, Bp, pb0, pbw, H, region, ft, rot);
+                    }
+                    lap(2);
+                    store_partials(acc, m, region);
+                    __syncthreads();
+                    for (int o = tid; o < P.NG * pbw; o += NT) {
+                        const int col = o / pbw, p = o - col * pbw;
+                        gi_s[o] = reduce_partials(region, m, col, p) + bih[col];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+                    gemm_stream<false>(acc, m, Whh, Whh_g, P.NG, hcur, Bp, pb0, pbw, H, region, FrameTerm{}, rot);
+                    store_partials(acc, m, region);
+                    __syncthreads();
+                    for (int o = tid; o < P.JP * pbw; o += NT) {
+                        const int jj = o / pbw, p = o - jj * pbw;
+                        const int cr = jj, cz = P.JP + jj, cn = 2 * P.JP + jj;
+                        const float hr = reduce_partials(region, m, cr, p) + bhh[cr];
+                        const float hz = reduce_partials(region, m, cz, p) + bhh[cz];
+                        const float hn = reduce_partials(region, m, cn, p) + bhh[cn];
+                        const float r = sigmoid_acc(gi_s[cr * pbw + p] + hr);
+                        const float zg = sigmoid_acc(gi_s[cz * pbw + p] + hz);
+                        const float n = tanhf(gi_s[cn * pbw + p] + r * hn);
+                        const float hold = __ldcg(hcur + (size_t)(j_lo + jj) * Bp + pb0 + p);
+                        const float hnew = (1.0f - zg) * n + zg * hold;
+                        if (pb0 + p < P.B) __stcg(hnext + (size_t)(j_lo + jj) * Bp + pb0 + p, hnew);
+                    }
+                    __syncthreads();
+                }
+                hsel[i] ^= 1;
+                lap(3);
+                if (!grid_barrier(P, epoch)) { dead = true; break; }
+                lap(4);
+                // ---- LinearResampler rows of this CTA (modules/resamplers.py:13-23) ----
+                {
+                    const int nu = T.up_rows / NC, u_lo = c * nu;
+                    const float* Wup_g = gblock + T.off_wup;
+                    const float* Wup = T.so_wup >= 0 ? w_s + T.so_wup : nullptr;
+                    const float* bup = T.so_wup >= 0 ? Wup + (size_t)H * T.NU : Wup_g + (size_t)H * T.NU;
+                    const int cap_u = min(PBW, (NT / (T.NU >> 2)) << 2);
+                    for (int pb0 = 0; pb0 < Bl; pb0 += cap_u) {
+                        const int pbw = min(cap_u, Bl - pb0);
+                        const Map m = make_map(T.NU >> 2, pbw);
+                        float acc[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+                        gemm_stream<false>(acc, m, Wup, Wup_g, T.NU, hnext, Bp, pb0, pbw, H, region, FrameTerm{}, rot);
+                        store_partials(acc, m, region);
+                        __syncthreads();
+                        for (int o = tid; o < nu * pbw; o += NT) {
+                            const int col = o / pbw, p = o - col * pbw;
+                            if (pb0 + p < P.B)
+                                __stcg(T.obuf + (size_t)(u_lo + col) * Bp + pb0 + p, reduce_partials(region, m, col, p) + bup[col]);
+                        }
+                        __syncthreads();
+                    }
+                }
+                lap(5);
+                if (!grid_barrier(P, epoch)) { dead = true; break; }
+                lap(6);
+            }
+            if (!gen || dead) continue;
+
+            // ---------------- sample-level tier + head + sampler: cluster-local, 8 prompts per group ----------------
+            const Tier& TL = P.tiers[P.n_ft - 1];
+            const float* condL = TL.obuf + (size_t)(t % TL.fs) * H * Bp;     // outputs[-1][:, (t % fs[-2]) - fs[-2]]
+            const float* W1s = w_s + P.so_w1;       // [KS][Hh]  rows rank*KS .. of x
+            const float* b1s = w_s + P.so_b1;       // [RS]      biases of this CTA's hidden rows
+            const float* W2s = w_s + P.so_w2;       // [RS][ZR]  hidden rows rank*RS ..
+            float* xh = region + P.h_x;             // [KS][GP]
+            float* inbox_h = region + P.h_inh;      // [CS][RS][GP]
+            float* hid_s = region + P.h_hid;        // [RS][GP]
+            float* part_h = region + P.h_un;        // [nq][tiles][16]   (dead before the logits arrive)
+            float* inbox_z = region + P.h_un;       // [GP/CS][CS][ZR]
+            float* zs = region + P.h_zs;            // [GP/CS][ZR + 4]
+            unsigned* qbuf = reinterpret_cast<unsigned*>(smem + P.s_bar) + 2 * BAR_COUNT;   // [groups per cluster][GP]
+            const int KS = P.KS, RS = P.RS, ZR = P.ZR, Hh = P.Hh, fsl = P.fs_last;
+            const long long hstep = t - P.gen_begin, n_gen = P.gen_end - P.gen_begin;
+            int gl = 0;
+            for (int g = cluster; g < n_groups && !dead; g += n_clusters, ++gl) {
+                const int b0 = g * GP;
+                const unsigned par = head_phase & 1u;
+                // -- 1. this CTA's rows of x = Conv1d(lin(q[t-fs:t])) + conditioning (modules/io.py:185-198)
+                for (int idx = tid; idx < KS * GP; idx += NT) {
+                    const int kl = idx / GP, p = idx - kl * GP, k = rank * KS + kl, b = b0 + p;
+                    float a = 0.0f;
+                    for (int f = 0; f < fsl; ++f) {
+                        long long q = 0;
+                        if (b < P.B) {
+                            if (f == fsl - 1 && !P.teacher_forced && t > P.gen_begin) q = (long long)qbuf[gl * GP + p];
+                            else q = __ldcg(P.seq + (size_t)b * P.seq_stride + (tw - fsl + f));
+                        }
+                        a = fmaf(linearize(q, Qf), __ldg(P.conv_w + (size_t)k * fsl + f), a);
+                    }
+                    a += __ldg(P.conv_b + k);
+                    a += (b < P.B) ? __ldcg(condL + (size_t)k * Bp + b) : 0.0f;
+                    xh[idx] = a;
+                }
+                __syncthreads();
+                // -- 2. partial hidden over this CTA's K slice, reduce-scattered by hidden row
+                {
+                    const int tiles = (Hh >> 2) * npq_h;
+                    int nq = NT / tiles, p2 = 1;
+                    while (p2 * 2 <= nq && p2 * 2 <= KS) p2 *= 2;
+                    nq = p2;
+                    for (int tb = 0; tb < tiles * nq; tb += NT) {   // one pass unless Hh > 128
+                        const int id = tb + tid;
+                        if (id < tiles * nq) {
+                            const int tile = id % tiles, s = id / tiles, rq = tile / npq_h, pq = tile - rq * npq_h;
+                            float acc[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+                            for (int kl = s; kl < KS; kl += nq) {
+                                const float4 w = *reinterpret_cast<const float4*>(W1s + (size_t)kl * Hh + 4 * rq);
+                                const float4 x = *reinterpret_cast<const float4*>(xh + kl * GP + 4 * pq);
+                                const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                                    for (int pi = 0; pi < 4; ++pi) acc[ci * 4 + pi] = fmaf(wv[ci], xv[pi], acc[ci * 4 + pi]);
+                            }
+                            float4* d = reinterpret_cast<float4*>(part_h + ((size_t)s * tiles + tile) * 16);
+#pragma unroll
+                            for (int ci = 0; ci < 4; ++ci) d[ci] = make_float4(acc[ci * 4], acc[ci * 4 + 1], acc[ci * 4 + 2], acc[ci * 4 + 3]);
+                        }
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < Hh * npq_h; i += NT) {
+                        const int row = i / npq_h, half = i - row * npq_h, tile = (row >> 2) * npq_h + half;
+                        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        for (int s = 0; s < nq; ++s) {
+                            const float4 a = *reinterpret_cast<const float4*>(part_h + ((size_t)s * tiles + tile) * 16 + (row & 3) * 4);
+                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                        }
+                        const unsigned dst = (unsigned)(row / RS);
+                        const unsigned win = mapa(sbase, dst) - sbase;
+                        const unsigned off = (unsigned)(P.s_region + P.h_inh + ((rank * RS + row % RS) * GP + half * 4)) * 4u;
+                        st_async_v4(win + sbase + off, v, win + bar(BAR_HID));
+                    }
+                }
+                dead |= !mbar_wait(bar(BAR_HID), par, abort_flag);
+                if (tid == 0) mbar_expect_tx(bar(BAR_HID), hid_bytes);
+                // -- 3. hidden rows of this CTA: sum the partials in rank order, bias, Mish (mlp.py:44-53)
+                for (int i = tid; i < RS * GP; i += NT) {
+                    float s = 0.0f;
+                    for (int src = 0; src < CS; ++src) s += inbox_h[src * RS * GP + i];
+                    hid_s[i] = mish_acc(s + b1s[i / GP]);
+                }
+                __syncthreads();
+                // -- 4. partial logits over this CTA's hidden rows, reduce-scattered by prompt
+                {
+                    const int tiles = (ZR >> 2) * npq_h;
+                    for (int tile = tid; tile < tiles; tile += NT) {
+                        const int rq = tile / npq_h, pq = tile - rq * npq_h;
+                        float acc[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+                        for (int k = 0; k < RS; ++k) {
+                            const float4 w = *reinterpret_cast<const float4*>(W2s + (size_t)k * ZR + 4 * rq);
+                            const float4 x = *reinterpret_cast<const float4*>(hid_s + k * GP + 4 * pq);
+                            const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                                for (int pi = 0; pi < 4; ++pi) acc[ci * 4 + pi] = fmaf(wv[ci], xv[pi], acc[ci * 4 + pi]);
+                        }
+#pragma unroll
+                        for (int pi = 0; pi < 4; ++pi) {
+                            const int p = 4 * pq + pi;
+                            const unsigned dst = (unsigned)(p % CS), slot = (unsigned)(p / CS);
+                            const unsigned win = mapa(sbase, dst) - sbase;
+                            const unsigned off = (unsigned)(P.s_region + P.h_un + ((slot * CS + rank) * ZR + 4 * rq)) * 4u;
+                            st_async_v4(win + sbase + off, make_float4(acc[pi], acc[4 + pi], acc[8 + pi], acc[12 + pi]),
+                                        win + bar(BAR_Z));
+                        }
+                    }
+                }
+                dead |= !mbar_wait(bar(BAR_Z), par, abort_flag);
+                if (tid == 0) mbar_expect_tx(bar(BAR_Z), z_bytes);
+                // -- 5. one warp per prompt: sum the partial logits in rank order, learned temperature, decision
+                if (warp < GP / CS) {
+                    const int p = warp * CS + rank, b = b0 + p;
+                    float* zr = zs + warp * (ZR + 4);
+                    for (int o = lane; o <= P.Q; o += 32) {
+                        float s = 0.0f;
+                        for (int src = 0; src < CS; ++src) s += inbox_z[(size_t)(warp * CS + src) * ZR + o];
+                        zr[o] = s + __ldg(P.b2 + o);
+                    }
+                    __syncwarp();
+                    int choice = 0;
+                    if (b < P.B) {
+                        const bool sample = P.temperature != nullptr;
+                        float Tt = 1.0f, u = 0.0f;
+                        if (sample) {
+                            Tt = P.temperature[P.n_temperature == 1 ? 0 : b];
+                            u = P.noise[(size_t)b * P.noise_stride + (t - P.noise_t0)];
+                        }
+                        float* lout = P.logits_out ? P.logits_out + ((size_t)b * n_gen + hstep) * P.Q : nullptr;
+                        choice = decide_warp(zr, P.Q, P.min_temp, lout, sample, Tt, u);
+                        if (lane == 0) {
+                            if (P.decisions) P.decisions[(size_t)b * n_gen + hstep] = choice;
+                            if (!P.teacher_forced) __stcg(P.seq + (size_t)b * P.seq_stride + t, (long long)choice);
+                        }
+                    }
+                    // broadcast the index to every CTA of the cluster (their next x needs it)
+                    if (lane < CS) {
+                        const unsigned win = mapa(sbase, (unsigned)lane) - sbase;
+                        const unsigned off = off_bar0 + (unsigned)(2 * BAR_COUNT + gl * GP + p) * 4u;
+                        st_async_u32(win + sbase + off, (unsigned)choice, win + bar(BAR_Q));
+                    }
+                }
+                dead |= !mbar_wait(bar(BAR_Q), par, abort_flag);
+                if (tid == 0) mbar_expect_tx(bar(BAR_Q), q_bytes);
+                ++head_phase;
+                if (__syncthreads_or(dead ? 1 : 0)) dead = true;
+            }
+            heads_pending = true;
+            lap(7);
+            if (c == 0 && tid == 0 && P.step_ts) P.step_ts[hstep] = globaltimer();
+        }
+    }
+    if (P.dbg && c == 0 && tid == 0)
+        for (int i = 0; i < 8; ++i) P.dbg[i] += tacc[i];
+    // no CTA may exit while peers can still store into its shared memory
+    __syncthreads();
+    cluster_sync_all();
+}
+
+static int pad4(int v) { return (v + 3) / 4 * 4; }
+
+}  // namespace mmk_sr2
+
+using namespace mmk_sr2;
+
+struct sr2_handle {
+    Params p{};
+    int device = 0, max_batch = 0, rf = 0;
+    size_t smem_bytes = 0;
+    std::vector<void*> allocs;
+    size_t hbuf_floats[MAX_TIERS] = {0};
+};
+
+int sr2_destroy(sr2_handle* h) {
+    if (!h) return 0;
+    for (void* a : h->allocs) cudaFree(a);
+    delete h;
+    return 0;
+}
+
+static int sr2_max_clusters(int CS, size_t smem, int sms) {
+    const void* k = (const void*)samplernn_cluster_kernel;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (CS == 1) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return per_sm * sms;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CS * 4);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int* unsupported) {
+    *unsupported = 1;
+    const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels;
+    if (H % KC != 0 || Hh % 4 != 0 || n_ft > MAX_TIERS) return 1;
+    int dev = 0, sms = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const char* force_cs = getenv("MMK_SR_CLUSTER");
+    const char* force_nc = getenv("MMK_SR_CTAS");
+
+    auto* h = new sr2_handle();
+    h->device = dev;
+    Params best{};
+    size_t best_smem = 0;
+    bool found = false;
+    const int groups_per_cluster_max = 16;
+    for (int CS : {8, 4, 2, 1}) {
+        if (force_cs && atoi(force_cs) != CS) continue;
+        if (H % CS || Hh % CS) continue;
+        // NC: the largest multiple of CS that divides H (GRU rows split evenly by hidden index) and fits the device
+        int NC = 0;
+        for (int n = std::min(sms, H) / CS * CS; n >= CS; n -= CS)
+            if (H % n == 0 && (!force_nc || n <= atoi(force_nc))) { NC = n; break; }
+        if (!NC) continue;
+        Params p{};
+        const int GP = CS == 8 ? 8 : 4;
+        p.n_ft = n_ft; p.H = H; p.Hh = Hh; p.Q = Q; p.NC = NC; p.CS = CS; p.GP = GP;
+        p.JP = H / NC; p.NG = pad4(3 * p.JP);
+        p.fs_last = d->frame_sizes[n_ft]; p.fs_lt = d->frame_sizes[n_ft - 1];
+        p.KS = H / CS; p.RS = Hh / CS; p.ZR = pad4(Q + 1);
+        p.min_temp = d->min_temperature;
+        // ---- the CTA's packed block in global memory holds everything
+        int o = 0, fs_max = 1;
+        auto take = [&](int floats) { int r = o; o += pad4(floats); return r; };
+        bool ok = true;
+        for (int i = 0; i < n_ft; ++i) {
+            Tier& T = p.tiers[i];
+            T.fs = d->frame_sizes[i];
+            T.up = T.fs / (i < n_ft - 1 ? d->frame_sizes[i + 1] : 1);     // sample_rnn_v2.py:155-158
+            T.kdiv = i > 0 ? d->frame_sizes[i - 1] / T.fs : 1;
+            T.up_rows = T.up * H;
+            if (T.up_rows % NC) ok = false;
+            T.NU = pad4(T.up_rows / NC);
+            T.off_wih = take(H * p.NG + p.NG);
+            T.off_whh = take(H * p.NG + p.NG);
+            T.off_wup = take(H * T.NU + T.NU);
+            T.so_wih = T.so_whh = T.so_wup = -1;
+            fs_max = std::max(fs_max, T.fs);
+            if ((T.NU >> 2) > NT || (p.NG >> 2) > NT || T.fs > MAXFS) ok = false;
+        }
+        if (!ok) continue;
+        p.off_w1 = take(p.KS * Hh);
+        p.off_b1 = take(p.RS);
+        p.off_w2 = take(p.RS * p.ZR);
+        p.cta_block = o;
+        // ---- shared memory: buffers first, then the resident weights by priority until the budget is spent
+        o = 0;
+        p.s_region = take(REGION);
+        p.s_gi = take(std::max(p.NG, fs_max) * PBW);
+        p.s_bar = take(2 * BAR_COUNT + groups_per_cluster_max * GP);
+        p.n_res = 0;
+        const int budget = max_optin / (int)sizeof(float) - 256;     // floats; 1 KB of slack for static shared memory
+        auto resident = [&](int goff, int len, int* soff) {
+            len = pad4(len);
+            if (o + len > budget) return false;
+            *soff = o;
+            p.res_goff[p.n_res] = goff; p.res_soff[p.n_res] = o; p.res_len[p.n_res] = len; ++p.n_res;
+            o += len;
+            return true;
+        };
+        // must be resident: the head slices (used every sample) and the input-side GRU matrices (critical path)
+        ok = resident(p.off_w1, p.KS * Hh, &p.so_w1) && resident(p.off_b1, p.RS, &p.so_b1) &&
+             resident(p.off_w2, p.RS * p.ZR, &p.so_w2);
+        for (int i = n_ft - 1; i >= 0 && ok; --i) ok = resident(p.tiers[i].off_wih, H * p.NG + p.NG, &p.tiers[i].so_wih);
+        if (!ok) continue;
+        // optional, most frequently firing tier first; the rest streams from L2 next to the activations
+        for (int i = n_ft - 1; i >= 0; --i) {
+            Tier& T = p.tiers[i];
+            if (!resident(T.off_whh, H * p.NG + p.NG, &T.so_whh) && p.NG > WMAX) ok = false;
+            if (!resident(T.off_wup, H * T.NU + T.NU, &T.so_wup) && T.NU > WMAX) ok = false;
+        }
+        if (!ok) continue;
+        p.smem_floats = o;
+        // head buffers inside the region
+        int ho = 0;
+        auto htake = [&](int floats) { int r = ho; ho += pad4(floats); return r; };
+        p.h_x = htake(p.KS * GP);
+        p.h_inh = htake(Hh * GP);
+        p.h_hid = htake(p.RS * GP);
+        p.h_un = ho;
+        const int tiles_h = (Hh / 4) * (GP / 4);
+        int nq = std::max(1, NT / tiles_h), p2 = 1;
+        while (p2 * 2 <= nq && p2 * 2 <= p.KS) p2 *= 2;
+        const int part_floats = tiles_h * p2 * 16;
+        const int inz_floats = GP * p.ZR;                      // (GP/CS) slots x CS sources
+        p.h_zs = p.h_un + pad4(inz_floats);
+        const int un_floats = std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
+        if (ho + un_floats > REGION) continue;
+        const size_t smem = (size_t)o * sizeof(float);
+        const int max_clusters = sr2_max_clusters(CS, smem, sms);
+        if (getenv("MMK_SR_DEBUG")) {
+            fprintf(stderr, "[sr2] CS=%d NC=%d GP=%d smem=%zu max_clusters=%d resident:", CS, NC, GP, smem, max_clusters);
+            for (int i = 0; i < n_ft; ++i) fprintf(stderr, " t%d(hh=%d up=%d)", i, p.tiers[i].so_whh >= 0, p.tiers[i].so_wup >= 0);
+            fprintf(stderr, "\n");
+        }
+        if (max_clusters * CS < NC) continue;   // the grid could not be co-resident with this cluster size
+        best = p; best_smem = smem; found = true;
+        break;
+    }
+    if (!found) { sr2_destroy(h); return 1; }
+    *unsupported = 0;
+    Params& p = h->p;
+    p = best;
+    h->smem_bytes = best_smem;
+    h->max_batch = max_batch; h->rf = d->frame_sizes[0];
+    p.Bp = (max_batch + 3) / 4 * 4;
+    const int NC = p.NC, CS = p.CS, GP = p.GP;
+    MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    {
+        const int n_groups = (max_batch + GP - 1) / GP, n_clusters = NC / CS;
+        if ((n_groups + n_clusters - 1) / n_clusters > groups_per_cluster_max) { sr2_destroy(h); *unsupported = 1; return 1; }
+    }
+
+    // ---- pack per-CTA weight blocks
+    std::vector<float> wpack((size_t)NC * p.cta_block, 0.0f);
+    for (int c = 0; c < NC; ++c) {
+        float* blk = wpack.data() + (size_t)c * p.cta_block;
+        const int j_lo = c * p.JP, rank = c % CS;
+        for (int i = 0; i < n_ft; ++i) {
+            const Tier& T = p.tiers[i];
+            for (int m = 0; m < 2; ++m) {
+                const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
+                const float* b = m == 0 ? d->b_ih[i] : d->b_hh[i];
+                float* Ws = blk + (m == 0 ? T.off_wih : T.off_whh);
+                float* bs = Ws + (size_t)H * p.NG;
+                for (int g = 0; g < 3; ++g)
+                    for (int jj = 0; jj < p.JP; ++jj) {
+                        const int col = g * p.JP + jj, row = g * H + j_lo + jj;
+                        for (int k = 0; k < H; ++k) Ws[(size_t)k * p.NG + col] = W[(size_t)row * H + k];
+                        bs[col] = b[row];
+                    }
+            }
+            const int nu = T.up_rows / NC, u_lo = c * nu;
+            float* Wu = blk + T.off_wup; float* bu = Wu + (size_t)H * T.NU;
+            for (int col = 0; col < nu; ++col) {
+                for (int k = 0; k < H; ++k) Wu[(size_t)k * T.NU + col] = d->up_w[i][(size_t)(u_lo + col) * H + k];
+                bu[col] = d->up_b[i][u_lo + col];
+            }
+        }
+        // head: K slices.  W1s[kl][row] = W1[row][rank*KS + kl];  W2s[kl][o] = W2[o][rank*RS + kl]
+        float* W1s = blk + p.off_w1; float* b1s = blk + p.off_b1; float* W2s = blk + p.off_w2;
+        for (int kl = 0; kl < p.KS; ++kl)
+            for (int row = 0; row < Hh; ++row) W1s[(size_t)kl * Hh + row] = d->head_w1[(size_t)row * H + rank * p.KS + kl];
+        for (int r = 0; r < p.RS; ++r) b1s[r] = d->head_b1[rank * p.RS + r];
+        for (int kl = 0; kl < p.RS; ++kl)
+            for (int o2 = 0; o2 <= Q; ++o2) W2s[(size_t)kl * p.ZR + o2] = d->head_w2[(size_t)o2 * Hh + rank * p.RS + kl];
+    }
+    auto dev_alloc = [&](size_t bytes, const void* src) -> void* {
+        void* ptr = nullptr;
+        if (cudaMalloc(&ptr, bytes) != cudaSuccess) return nullptr;
+        h->allocs.push_back(ptr);
+        if (src) cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); else cudaMemset(ptr, 0, bytes);
+        return ptr;
+    };
+    bool ok = true;
+    auto up = [&](const float* src, size_t n) { void* q = dev_alloc(n * sizeof(float), src); ok = ok && q; return (float*)q; };
+    p.wpack = up(wpack.data(), wpack.size());
+    for (int i = 0; i < n_ft; ++i) {
+        Tier& T = p.tiers[i];
+        T.in_w = up(d->in_w[i], (size_t)H * T.fs);
+        T.in_b = up(d->in_b[i], H);
+        h->hbuf_floats[i] = (size_t)2 * H * p.Bp;
+        T.hbuf = up(nullptr, h->hbuf_floats[i]);
+        T.obuf = up(nullptr, (size_t)T.up_rows * p.Bp);
+    }
+    p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
+    p.conv_b = up(d->conv_b, H);
+    p.b2 = up(d->head_b2, (size_t)Q + 1);
+    p.bar = (unsigned long long*)dev_alloc(64, nullptr);
+    ok = ok && p.bar;
+    if (!ok) { sr2_destroy(h); MMK_FAIL("cudaMalloc failed while creating the SampleRNN handle"); }
+    p.abort_flag = (unsigned*)(p.bar + 1);
+    if (getenv("MMK_SR_DEBUG")) p.dbg = (unsigned long long*)dev_alloc(64, nullptr);
+    MMK_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+int sr2_launch_info(sr2_handle* h, mmk_launch_info* out) {
+    out->cluster_size = h->p.CS; out->n_stages = h->p.NC / h->p.CS; out->group_size = h->p.GP; out->threads = NT;
+    out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.NC;
+    return 0;
+}
+
+int sr2_sync_check(sr2_handle* h, void* stream) {
+    unsigned aborted = 0;
+    MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    MMK_CHECK(aborted == 0, "SampleRNN kernel watchdog fired: a barrier wait timed out (results invalid)");
+    if (h->p.dbg) {
+        unsigned long long t[8];
+        MMK_CUDA(cudaMemcpy(t, h->p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
+        MMK_CUDA(cudaMemset(h->p.dbg, 0, sizeof(t)));
+        fprintf(stderr, "[sr2] CTA0 ms: other %.2f pre-barrier %.2f gemm_ih %.2f gemm_hh+gate %.2f barrier %.2f up %.2f barrier %.2f head %.2f\n",
+                t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6, t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6);
+    }
+    return 0;
+}
+
+int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t warm_begin,
+            int64_t warm_end, int64_t warm_offset, int64_t gen_begin, int64_t gen_end, int reset_hidden,
+            int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reset_hidden) {
+        for (int i = 0; i < h->p.n_ft; ++i) {
+            MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].hbuf, 0, h->hbuf_floats[i] * sizeof(float), st));
+            h->p.hsel[i] = 0;
+        }
+    }
+    if (warm_end == warm_begin && gen_end == gen_begin) return 0;
+    Params p = h->p;
+    MMK_CUDA(cudaMemsetAsync(p.bar, 0, 64, st));
+    p.seq = reinterpret_cast<long long*>(d_seq) - seq_t0;
+    p.seq_stride = seq_stride;
+    p.warm_begin = warm_begin; p.warm_end = warm_end; p.warm_off = warm_offset;
+    p.gen_begin = gen_begin; p.gen_end = gen_end;
+    p.B = B; p.teacher_forced = teacher_forced ? 1 : 0;
+    p.temperature = d_temperature; p.n_temperature = n_temperature;
+    p.noise = d_noise; p.noise_stride = noise_stride; p.noise_t0 = noise_t0;
+    p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.NC);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    void* args[] = {&p};
+    MMK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)samplernn_cluster_kernel, args));
+    // the hidden ping-pong advances once per tier firing: keep the handle's view in step with the device
+    for (int i = 0; i < p.n_ft; ++i) {
+        const long long fs = p.tiers[i].fs;
+        auto firings = [&](long long lo, long long hi) { return hi > lo ? (hi + fs - 1) / fs - (lo + fs - 1) / fs : 0; };
+        const long long n = firings(warm_begin, warm_end) + firings(gen_begin, gen_end);
+        h->p.hsel[i] ^= (int)(n & 1);
+    }
+    return 0;
+}

@@ -58,6 +58,7 @@ def test_golden_sequences_and_logits(name):
 def test_vs_oracle_partitions(monkeypatch, ctas, fs, H, B, P):
     """Seeded weights and prompts; different row partitions (number of CTAs), ragged batches (B not a multiple of
     the 16-prompt chunk), prompt lengths that are not a multiple of the top frame size (warm-up offset quirk)."""
+    monkeypatch.setenv("MMK_SR_KERNEL", "1")    # the general (grid-barrier) kernel
     if ctas is not None:
         monkeypatch.setenv("MMK_SR_CTAS", ctas)
     net = make_net(fs, H, mlp_dim=32, seed=5)
@@ -76,6 +77,41 @@ def test_vs_oracle_partitions(monkeypatch, ctas, fs, H, B, P):
         assert _rel_err(logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
         assert np.array_equal(seq.cpu().numpy(), ref_seq), (ctas, temp)
         assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("ctas", [None, "8"])
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 64, 19, 43), ((4, 4), 32, 3, 16), ((16, 4, 2), 48, 33, 64),
+                                      ((8, 4, 2, 1), 32, 6, 27), ((8, 2, 1), 64, 70, 40), ((4, 2), 128, 9, 10)])
+def test_cluster_kernel_vs_oracle(monkeypatch, cluster, ctas, fs, H, B, P):
+    """The cluster kernel (samplernn2.cu: cluster-local head over distributed shared memory, streamed tier
+    contractions) at every cluster size, small grids (several prompt groups per cluster), ragged batches and the
+    warm-up offset quirk; free-running argmax / sampled sequences bit-exact, logits within tolerance, and the
+    teacher-forced decisions on the oracle's own sequence."""
+    monkeypatch.setenv("MMK_SR_KERNEL", "2")
+    monkeypatch.setenv("MMK_SR_CLUSTER", cluster)
+    if ctas is not None:
+        monkeypatch.setenv("MMK_SR_CTAS", ctas)
+    net = make_net(fs, H, mlp_dim=32, seed=5)
+    try:
+        info = net.launch_info(B)
+    except _capi.MmkError as e:   # this geometry cannot host the net
+        pytest.skip(str(e))
+    assert info["cluster_size"] == int(cluster)
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    g = torch.Generator().manual_seed(17)
+    n = 37
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    for temp in (None, 0.95):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert _rel_err(logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
+        assert np.array_equal(seq.cpu().numpy(), ref_seq), (cluster, temp)
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+    lg, dec = net.teacher_forced(torch.from_numpy(ref_seq), P, 0.95, noise)
+    assert np.array_equal(dec.cpu().numpy(), ref_seq[:, P:])
+    assert _rel_err(lg.cpu().numpy(), ref_logits) <= REL_TOL
 
 
 def test_stepwise_protocol_and_loop():
