@@ -29,20 +29,24 @@ using mmk::decide_warp;
 using mmk::mish_acc;
 using mmk::sigmoid_acc;
 
-constexpr int NT = 256;          // threads per CTA
-constexpr int KC = 16;           // activation rows per streamed chunk
-constexpr int NSTAGE = 3;        // cp.async stages
+constexpr int NT = 512;          // threads per CTA
+constexpr int HT = 256;          // threads that take tiles in the head contractions
+constexpr int KC = 16;           // activation rows per streamed chunk at full width (x 2, 4, 8 for narrower batches)
+constexpr int NSTAGE_DEFAULT = 2; // full-width cp.async stages (MMK_SR_NSTAGE; more stages when the chunks are small)
+constexpr int KCFULL_DEFAULT = 64; // rows per full-width chunk (MMK_SR_KC)
 constexpr int PBW = 128;         // prompts per streamed block
 constexpr int WMAX = 32;         // widest streamed weight slice (columns per CTA)
 constexpr int MAX_TIERS = 6;
-constexpr int XSTAGE = KC * PBW, WSTAGE = KC * WMAX;
-constexpr int REGION = NSTAGE * (XSTAGE + WSTAGE);   // floats: stage buffers / partial sums / head buffers
+// floats per stage (activations, streamed weights) = kcfull * PBW, kcfull * WMAX with kcfull = MMK_SR_KC (default KC)
+constexpr int MAXST = 8;
 constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;
 
 struct Tier {
     int fs, up, kdiv, NU, up_rows;
     int off_wih, off_whh, off_wup;   // float offsets in the CTA's packed global block: W[H][N] followed by bias[N]
+    int off_inw;                     // frame Linear: in_w (H, fs) followed by in_b (H)
     int so_wih, so_whh, so_wup;      // float offsets in shared memory, or -1: streamed from L2 with the activations
+    int so_inw;
     const float* in_w; const float* in_b;
     float* hbuf; float* obuf;
 };
@@ -54,6 +58,7 @@ struct Params {
     int off_w1, off_b1, off_w2, cta_block;     // global block offsets
     int so_w1, so_b1, so_w2;
     int s_region, s_gi, s_bar, smem_floats;
+    int xstage, wstage, xregion, wregion, region;    // per stage; floats: activation stages, streamed-weight stages, both (= partial sums / head buffers)
     int h_x, h_inh, h_hid, h_un, h_zs;      // head buffers inside the region (float offsets)
     const float* wpack; const float* conv_w; const float* conv_b; const float* b2;
     unsigned long long* bar; unsigned* abort_flag;
@@ -68,6 +73,7 @@ struct Params {
     long long noise_stride, noise_t0;
     float* logits_out; long long* decisions; unsigned long long* step_ts;
     unsigned long long* dbg;         // MMK_SR_DEBUG: time (ns) spent by CTA 0 per section
+    int exp;                         // MMK_SR_EXP: timing experiments (results invalid)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -191,15 +197,20 @@ __device__ __forceinline__ float linearize(long long q, float Qf) {
 // `nslice` thread slices; the caller reduces the slices in slice order (fixed summation order).
 // ------------------------------------------------------------------------------------------------------------
 struct Map {
-    int tiles, nslice, tile, slice, cq, pq, npq;
+    int tiles, nslice, tile, slice, cq, pq, npq, kc;
     bool active;
 };
-__device__ __forceinline__ Map make_map(int ncol4, int pbw) {
+// kc: rows per streamed chunk — 16 at full width, more for narrow batches so that a chunk stays ~8 KB and the
+// per-chunk barrier is amortised (kc * pbw <= XSTAGE, kc divides K)
+__device__ __forceinline__ Map make_map(int ncol4, int pbw, int part_cap, int K, bool wstream, int XSTAGE, int WSTAGE) {
     Map m;
     m.npq = pbw >> 2;
     m.tiles = ncol4 * m.npq;
+    int kc = KC;
+    while (kc * 2 * pbw <= XSTAGE && (!wstream || kc * 2 * ncol4 * 4 <= WSTAGE) && kc < 128 && K % (kc * 2) == 0) kc *= 2;
+    m.kc = kc;
     int ns = NT / m.tiles, p2 = 1;
-    while (p2 * 2 <= ns && p2 * 2 <= KC) p2 *= 2;
+    while (p2 * 2 <= ns && p2 * 2 <= 16 && p2 * 2 <= kc && (p2 * 2 - 1) * m.tiles * 16 <= part_cap) p2 *= 2;
     m.nslice = p2;
     m.active = (int)threadIdx.x < m.tiles * p2;
     m.tile = threadIdx.x % m.tiles;
@@ -211,11 +222,9 @@ __device__ __forceinline__ Map make_map(int ncol4, int pbw) {
 
 // The frame-linear input term x = Linear(frame) + bias (+ conditioning already in the landed chunk), FramedLinearIO
 // (modules/io.py:106-133).  It is added to a chunk by the thread that copied the element; the Linear rows of the
-// next chunk are fetched into registers one iteration ahead so that their latency hides behind the contraction.
-constexpr int MAXFS = 16;     // frame sizes the register prefetch covers
-constexpr int EL = 2;         // float4 elements a thread owns per chunk (KC * PBW / 4 / NT)
+// Linear table (in_w | in_b) stays resident in shared memory.
 struct FrameTerm {
-    const float* in_w; const float* in_b; const float* lin_s;   // (H, fs) global, (H) global, [fs][pbw] shared
+    const float* inw_s; const float* inb_s; const float* lin_s;   // [H][fs], [H], [fs][pbw] — all in shared memory
     int fs;
     bool has_cond;
 };
@@ -235,119 +244,122 @@ __device__ __forceinline__ void tile_rows(float (&acc)[16], const float* __restr
     }
 }
 
+__device__ __forceinline__ void cp_async_wait_n(int n) {   // at most n groups still in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    }
+}
+
 // W: resident weights in shared memory, or nullptr when Wg (the same [K][ldw] matrix in global memory) is streamed.
-// Slice s of the map takes the KC / nslice consecutive rows s * (KC / nslice) .. of every chunk.
+// Slice s of the map takes the kc / nslice consecutive rows s * (kc / nslice) .. of every chunk.
 template <bool FRAME>
 __device__ __forceinline__ void gemm_stream(float (&acc)[16], const Map& m, const float* __restrict__ W,
                                             const float* __restrict__ Wg, int ldw,
                                             const float* __restrict__ src, int ld, int pb0, int pbw, int K,
-                                            float* stage, const FrameTerm ft, int rot) {
+                                            float* stage, int XREGION, int WREGION, const FrameTerm ft, int rot,
+                                            int exp = 0) {
     // rot: this CTA walks the K chunks starting at chunk `rot` (every CTA reads the same activations: starting them at
     // different rows keeps 128 SMs from asking the same L2 lines in the same cycle; the order is fixed per CTA)
     const int tid = threadIdx.x;
-    const int n4row = pbw >> 2, n4 = KC * n4row, nchunk = K / KC, n4w = (KC * ldw) >> 2;
-    float* wstage = stage + NSTAGE * XSTAGE;
-    // the (row, prompt quad) of the <= EL float4 elements this thread copies / fixes in every chunk
-    int er[EL], ec[EL];
-    bool ev[EL];
-#pragma unroll
-    for (int e = 0; e < EL; ++e) {
-        const int i = tid + e * NT;
-        ev[e] = i < n4;
-        er[e] = i / n4row;
-        ec[e] = i - er[e] * n4row;
-    }
+    const int kc = m.kc, n4row = pbw >> 2, n4 = kc * n4row, nchunk = K / kc, n4w = (kc * ldw) >> 2;
+    const int xstride = kc * pbw, wstride = kc * ldw;
+    // stages: as many as fit (chunks are small for narrow batches), so that the L2 latency hides behind >= 3 chunks
+    int nst = min(MAXST, XREGION / xstride);
+    if (W == nullptr) nst = min(nst, WREGION / wstride);
+    float* wstage = stage + XREGION;
+    if (rot >= nchunk) rot %= nchunk;
+    // thread `tid` copies / fixes the float4 elements tid, tid + NT, ... of a chunk (row e / n4row, prompt quad e % n4row)
     auto chunk_of = [&](int c) { const int cc = c + rot; return cc >= nchunk ? cc - nchunk : cc; };
+    int st_i = 0;                                              // stage of the chunk being issued
     auto issue = [&](int c) {
-        if (c < nchunk) {
+        if (c < nchunk && !(exp & 1)) {
             const int cc = chunk_of(c);
-            if (src != nullptr) {
-                float* buf = stage + (c % NSTAGE) * XSTAGE;
-#pragma unroll
-                for (int e = 0; e < EL; ++e)
-                    if (ev[e]) cp_async16(buf + er[e] * pbw + 4 * ec[e], src + (size_t)(cc * KC + er[e]) * ld + pb0 + 4 * ec[e]);
-            }
+            if (src != nullptr)
+                for (int e = tid; e < n4; e += NT) {
+                    const int r = e / n4row, q = e - r * n4row;
+                    cp_async16(stage + st_i * xstride + r * pbw + 4 * q, src + ((size_t)cc * kc + r) * ld + pb0 + 4 * q);
+                }
             if (W == nullptr) {
-                float* wb = wstage + (c % NSTAGE) * WSTAGE;
-                for (int i = tid; i < n4w; i += NT) cp_async16(wb + 4 * i, Wg + (size_t)cc * KC * ldw + 4 * i);
+                float* wb = wstage + st_i * wstride;
+                for (int i = tid; i < n4w; i += NT) cp_async16(wb + 4 * i, Wg + (size_t)cc * wstride + 4 * i);
             }
         }
         cp_async_commit();
+        st_i = st_i + 1 == nst ? 0 : st_i + 1;
     };
-    float cw[EL][MAXFS], cb[EL];
-    auto fetch = [&](int c) {
-        if (FRAME && c < nchunk) {
-#pragma unroll
-            for (int e = 0; e < EL; ++e) {
-                const int k = chunk_of(c) * KC + er[e];
-                if (ev[e]) {
-#pragma unroll
-                    for (int f = 0; f < MAXFS; ++f)
-                        if (f < ft.fs) cw[e][f] = __ldg(ft.in_w + (size_t)k * ft.fs + f);
-                    cb[e] = __ldg(ft.in_b + k);
-                }
-            }
-        }
-    };
-    issue(0);
-    issue(1);
-    fetch(0);
-    const int R = KC / m.nslice;
+    for (int c = 0; c < nst - 1; ++c) issue(c);
+    const int R = kc / m.nslice;
+    int st_c = 0;                                              // stage of the chunk being consumed
     for (int c = 0; c < nchunk; ++c) {
-        cp_async_wait1();                                   // this thread's copies of chunk c have landed
-        float* buf = stage + (c % NSTAGE) * XSTAGE;
-        if (FRAME) {
-#pragma unroll
-            for (int e = 0; e < EL; ++e) {
-                if (ev[e]) {
-                    float4* x4 = reinterpret_cast<float4*>(buf + er[e] * pbw + 4 * ec[e]);
-                    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-                    for (int f = 0; f < MAXFS; ++f) {
-                        if (f < ft.fs) {
-                            const float4 l = *reinterpret_cast<const float4*>(ft.lin_s + f * pbw + 4 * ec[e]);
-                            a[0] = fmaf(l.x, cw[e][f], a[0]); a[1] = fmaf(l.y, cw[e][f], a[1]);
-                            a[2] = fmaf(l.z, cw[e][f], a[2]); a[3] = fmaf(l.w, cw[e][f], a[3]);
-                        }
-                    }
-                    float4 r = make_float4(a[0] + cb[e], a[1] + cb[e], a[2] + cb[e], a[3] + cb[e]);
-                    if (ft.has_cond) { const float4 cv = *x4; r.x += cv.x; r.y += cv.y; r.z += cv.z; r.w += cv.w; }
-                    *x4 = r;
-                }
+        cp_async_wait_n(nst - 2);                           // this thread's copies of chunk c have landed
+        float* buf = stage + st_c * xstride;
+        if (FRAME) for (int e = tid; e < n4; e += NT) {
+            const int r = e / n4row, ec = e - r * n4row;
+            float4* x4 = reinterpret_cast<float4*>(buf + r * pbw + 4 * ec);
+            const int k = chunk_of(c) * kc + r;
+            const float* wr = ft.inw_s + (size_t)k * ft.fs;
+            float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int f = 0; f < ft.fs; ++f) {
+                const float wv = wr[f];
+                const float4 l = *reinterpret_cast<const float4*>(ft.lin_s + f * pbw + 4 * ec);
+                a[0] = fmaf(l.x, wv, a[0]); a[1] = fmaf(l.y, wv, a[1]);
+                a[2] = fmaf(l.z, wv, a[2]); a[3] = fmaf(l.w, wv, a[3]);
             }
+            const float bv = ft.inb_s[k];
+            float4 xv = make_float4(a[0] + bv, a[1] + bv, a[2] + bv, a[3] + bv);
+            if (ft.has_cond) { const float4 cv = *x4; xv.x += cv.x; xv.y += cv.y; xv.z += cv.z; xv.w += cv.w; }
+            *x4 = xv;
         }
-        __syncthreads();                                    // chunk c complete; everyone is done with chunk c - 1
-        issue(c + 2);
-        fetch(c + 1);
-        if (m.active) {
-            const float* wp = (W != nullptr ? W + (size_t)(chunk_of(c) * KC) * ldw : wstage + (c % NSTAGE) * WSTAGE)
+        if (!(exp & 4)) __syncthreads();                    // chunk c complete; everyone is done with chunk c - 1
+        issue(c + nst - 1);                                 // into the stage chunk c - 1 occupied
+        if (m.active && !(exp & 2)) {
+            const float* wp = (W != nullptr ? W + (size_t)(chunk_of(c) * kc) * ldw : wstage + st_c * wstride)
                               + (size_t)(m.slice * R) * ldw + m.cq * 4;
             const float* xp = buf + (m.slice * R) * pbw + m.pq * 4;
-            switch (R) {
-                case 16: tile_rows<16>(acc, wp, ldw, xp, pbw); break;
-                case 8: tile_rows<8>(acc, wp, ldw, xp, pbw); break;
-                case 4: tile_rows<4>(acc, wp, ldw, xp, pbw); break;
-                case 2: tile_rows<2>(acc, wp, ldw, xp, pbw); break;
-                default: tile_rows<1>(acc, wp, ldw, xp, pbw); break;
+            for (int r0 = 0; r0 < R; r0 += 16) {
+                switch (R) {
+                    case 1: tile_rows<1>(acc, wp, ldw, xp, pbw); break;
+                    case 2: tile_rows<2>(acc, wp, ldw, xp, pbw); break;
+                    case 4: tile_rows<4>(acc, wp, ldw, xp, pbw); break;
+                    case 8: tile_rows<8>(acc, wp, ldw, xp, pbw); break;
+                    default: tile_rows<16>(acc, wp + (size_t)r0 * ldw, ldw, xp + r0 * pbw, pbw); break;
+                }
             }
         }
+        st_c = st_c + 1 == nst ? 0 : st_c + 1;
     }
     __syncthreads();                                        // stage buffers are free again
 }
 
+// Slices >= 1 park their tile sums; after a __syncthreads the slice-0 thread of every tile adds them to its own
+// registers in slice order (fixed summation order).
 __device__ __forceinline__ void store_partials(const float (&acc)[16], const Map& m, float* part) {
-    if (m.active) {
-        float4* d = reinterpret_cast<float4*>(part + ((size_t)m.slice * m.tiles + m.tile) * 16);
+    if (m.active && m.slice > 0) {
+        float4* d = reinterpret_cast<float4*>(part + ((size_t)(m.slice - 1) * m.tiles + m.tile) * 16);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) d[ci] = make_float4(acc[ci * 4], acc[ci * 4 + 1], acc[ci * 4 + 2], acc[ci * 4 + 3]);
     }
 }
-// sum over the slices, in slice order, of output (col, p) of the prompt block
-__device__ __forceinline__ float reduce_partials(const float* part, const Map& m, int col, int p) {
-    const float* q = part + ((size_t)((col >> 2) * m.npq + (p >> 2))) * 16 + (col & 3) * 4 + (p & 3);
-    float s = 0.0f;
-    for (int sl = 0; sl < m.nslice; ++sl) s += q[(size_t)sl * m.tiles * 16];
-    return s;
+__device__ __forceinline__ void reduce_partials(float (&acc)[16], const Map& m, const float* part) {
+    for (int sl = 1; sl < m.nslice; sl += 2) {              // two slices per round: independent loads, ordered adds
+        const float4* q0 = reinterpret_cast<const float4*>(part + ((size_t)(sl - 1) * m.tiles + m.tile) * 16);
+        const float4* q1 = reinterpret_cast<const float4*>(part + ((size_t)sl * m.tiles + m.tile) * 16);
+        const bool two = sl + 1 < m.nslice;
+        float4 v0[4], v1[4];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) { v0[ci] = q0[ci]; v1[ci] = two ? q1[ci] : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            acc[ci * 4] += v0[ci].x; acc[ci * 4 + 1] += v0[ci].y; acc[ci * 4 + 2] += v0[ci].z; acc[ci * 4 + 3] += v0[ci].w;
+            if (two) { acc[ci * 4] += v1[ci].x; acc[ci * 4 + 1] += v1[ci].y; acc[ci * 4 + 2] += v1[ci].z; acc[ci * 4 + 3] += v1[ci].w; }
+        }
+    }
 }
 
 enum { BAR_HID = 0, BAR_Z, BAR_Q, BAR_COUNT };
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
     cluster_sync_all();
 
     const int j_lo = c * P.JP;
-    const int rot = (int)(((unsigned)c * 11u) % (unsigned)(H / KC));
+    const int rot = (int)(((unsigned)c * 11u) % (unsigned)(H / KC));   // reduced modulo the chunk count where used
     int hsel[MAX_TIERS];
 #pragma unroll
     for (int i = 0; i < MAX_TIERS; ++i) hsel[i] = P.hsel[i];
@@ -424,13 +436,17 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 if (i > 0) cond = P.tiers[i - 1].obuf + (size_t)((t / T.fs) % T.kdiv) * H * Bp;
                 const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
                 float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
-                const float* Wih = w_s + T.so_wih; const float* bih = Wih + (size_t)H * P.NG;
+                const float* Wih_g = gblock + T.off_wih;
+                const float* Wih = T.so_wih >= 0 ? w_s + T.so_wih : nullptr;
+                const float* bih = T.so_wih >= 0 ? Wih + (size_t)H * P.NG : Wih_g + (size_t)H * P.NG;
                 const float* Whh_g = gblock + T.off_whh;
                 const float* Whh = T.so_whh >= 0 ? w_s + T.so_whh : nullptr;
                 const float* bhh = T.so_whh >= 0 ? Whh + (size_t)H * P.NG : Whh_g + (size_t)H * P.NG;
+                const float* inw_s = w_s + T.so_inw;
                 const int fs = T.fs;
                 // ---- GRU cell on this CTA's hidden indices ----
                 const int cap_g = min(PBW, (NT / (P.NG >> 2)) << 2);
+                float* gh_s = region + P.region - P.NG * PBW;          // [NG][pbw] hidden-side gate pre-activations
                 for (int pb0 = 0; pb0 < Bl; pb0 += cap_g) {
                     const int pbw = min(cap_g, Bl - pb0);
                     float* lin_s = gi_s;
@@ -441,36 +457,50 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                         lin_s[idx] = linearize(q, Qf);
                     }
                     __syncthreads();
-                    const Map m = make_map(P.NG >> 2, pbw);
+                    const Map m = make_map(P.NG >> 2, pbw, P.region - P.NG * PBW, H, Whh == nullptr || Wih == nullptr, P.xstage, P.wstage);
                     float acc[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
                     {
-                        FrameTerm ft{T.in_w, T.in_b, lin_s, fs, cond != nullptr};
-                        gemm_stream<true>(acc, m, Wih, nullptr, P.NG, cond, Bp, pb0, pbw, H, region, ft, rot);
+                        FrameTerm ft{inw_s, inw_s + (size_t)H * fs, lin_s, fs, cond != nullptr};
+                        gemm_stream<true>(acc, m, Wih, Wih_g, P.NG, cond, Bp, pb0, pbw, H, region, P.xregion, P.wregion, ft, rot, P.exp);
                     }
                     lap(2);
                     store_partials(acc, m, region);
                     __syncthreads();
-                    for (int o = tid; o < P.NG * pbw; o += NT) {
-                        const int col = o / pbw, p = o - col * pbw;
-                        gi_s[o] = reduce_partials(region, m, col, p) + bih[col];
+                    if (m.active && m.slice == 0) {                   // gi = W_ih x + b_ih  -> gi_s[col][p]
+                        reduce_partials(acc, m, region);
+#pragma unroll
+                        for (int ci = 0; ci < 4; ++ci) {
+                            const int col = m.cq * 4 + ci;
+                            const float bv = bih[col];
+                            *reinterpret_cast<float4*>(gi_s + col * pbw + 4 * m.pq) =
+                                make_float4(acc[ci * 4] + bv, acc[ci * 4 + 1] + bv, acc[ci * 4 + 2] + bv, acc[ci * 4 + 3] + bv);
+                        }
                     }
                     __syncthreads();
 #pragma unroll
                     for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
-                    gemm_stream<false>(acc, m, Whh, Whh_g, P.NG, hcur, Bp, pb0, pbw, H, region, FrameTerm{}, rot);
+                    gemm_stream<false>(acc, m, Whh, Whh_g, P.NG, hcur, Bp, pb0, pbw, H, region, P.xregion, P.wregion, FrameTerm{}, rot, P.exp);
                     store_partials(acc, m, region);
                     __syncthreads();
-                    for (int o = tid; o < P.JP * pbw; o += NT) {
+                    if (m.active && m.slice == 0) {                   // gh = W_hh h + b_hh  -> gh_s[col][p]
+                        reduce_partials(acc, m, region);
+#pragma unroll
+                        for (int ci = 0; ci < 4; ++ci) {
+                            const int col = m.cq * 4 + ci;
+                            const float bv = bhh[col];
+                            *reinterpret_cast<float4*>(gh_s + col * pbw + 4 * m.pq) =
+                                make_float4(acc[ci * 4] + bv, acc[ci * 4 + 1] + bv, acc[ci * 4 + 2] + bv, acc[ci * 4 + 3] + bv);
+                        }
+                    }
+                    __syncthreads();
+                    for (int o = tid; o < P.JP * pbw; o += NT) {      // PyTorch GRU cell, gates r, z, n
                         const int jj = o / pbw, p = o - jj * pbw;
                         const int cr = jj, cz = P.JP + jj, cn = 2 * P.JP + jj;
-                        const float hr = reduce_partials(region, m, cr, p) + bhh[cr];
-                        const float hz = reduce_partials(region, m, cz, p) + bhh[cz];
-                        const float hn = reduce_partials(region, m, cn, p) + bhh[cn];
-                        const float r = sigmoid_acc(gi_s[cr * pbw + p] + hr);
-                        const float zg = sigmoid_acc(gi_s[cz * pbw + p] + hz);
-                        const float n = tanhf(gi_s[cn * pbw + p] + r * hn);
+                        const float r = sigmoid_acc(gi_s[cr * pbw + p] + gh_s[cr * pbw + p]);
+                        const float zg = sigmoid_acc(gi_s[cz * pbw + p] + gh_s[cz * pbw + p]);
+                        const float n = tanhf(gi_s[cn * pbw + p] + r * gh_s[cn * pbw + p]);
                         const float hold = __ldcg(hcur + (size_t)(j_lo + jj) * Bp + pb0 + p);
                         const float hnew = (1.0f - zg) * n + zg * hold;
                         if (pb0 + p < P.B) __stcg(hnext + (size_t)(j_lo + jj) * Bp + pb0 + p, hnew);
@@ -490,17 +520,24 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                     const int cap_u = min(PBW, (NT / (T.NU >> 2)) << 2);
                     for (int pb0 = 0; pb0 < Bl; pb0 += cap_u) {
                         const int pbw = min(cap_u, Bl - pb0);
-                        const Map m = make_map(T.NU >> 2, pbw);
+                        const Map m = make_map(T.NU >> 2, pbw, P.region, H, Wup == nullptr, P.xstage, P.wstage);
                         float acc[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
-                        gemm_stream<false>(acc, m, Wup, Wup_g, T.NU, hnext, Bp, pb0, pbw, H, region, FrameTerm{}, rot);
+                        gemm_stream<false>(acc, m, Wup, Wup_g, T.NU, hnext, Bp, pb0, pbw, H, region, P.xregion, P.wregion, FrameTerm{}, rot, P.exp);
                         store_partials(acc, m, region);
                         __syncthreads();
-                        for (int o = tid; o < nu * pbw; o += NT) {
-                            const int col = o / pbw, p = o - col * pbw;
-                            if (pb0 + p < P.B)
-                                __stcg(T.obuf + (size_t)(u_lo + col) * Bp + pb0 + p, reduce_partials(region, m, col, p) + bup[col]);
+                        if (m.active && m.slice == 0) {
+                            reduce_partials(acc, m, region);
+#pragma unroll
+                            for (int ci = 0; ci < 4; ++ci) {
+                                const int col = m.cq * 4 + ci;
+                                if (col < nu) {                       // padded prompts (>= B) receive values nobody reads
+                                    const float bv = bup[col];
+                                    __stcg(reinterpret_cast<float4*>(T.obuf + (size_t)(u_lo + col) * Bp + pb0 + 4 * m.pq),
+                                           make_float4(acc[ci * 4] + bv, acc[ci * 4 + 1] + bv, acc[ci * 4 + 2] + bv, acc[ci * 4 + 3] + bv));
+                                }
+                            }
                         }
                         __syncthreads();
                     }
@@ -550,10 +587,10 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 // -- 2. partial hidden over this CTA's K slice, reduce-scattered by hidden row
                 {
                     const int tiles = (Hh >> 2) * npq_h;
-                    int nq = NT / tiles, p2 = 1;
+                    int nq = HT / tiles, p2 = 1;
                     while (p2 * 2 <= nq && p2 * 2 <= KS) p2 *= 2;
                     nq = p2;
-                    for (int tb = 0; tb < tiles * nq; tb += NT) {   // one pass unless Hh > 128
+                    for (int tb = 0; tb < tiles * nq; tb += NT) {   // one pass unless the head is very wide
                         const int id = tb + tid;
                         if (id < tiles * nq) {
                             const int tile = id % tiles, s = id / tiles, rq = tile / npq_h, pq = tile - rq * npq_h;
@@ -765,9 +802,10 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
             T.off_wih = take(H * p.NG + p.NG);
             T.off_whh = take(H * p.NG + p.NG);
             T.off_wup = take(H * T.NU + T.NU);
-            T.so_wih = T.so_whh = T.so_wup = -1;
+            T.off_inw = take(H * T.fs + H);
+            T.so_wih = T.so_whh = T.so_wup = T.so_inw = -1;
             fs_max = std::max(fs_max, T.fs);
-            if ((T.NU >> 2) > NT || (p.NG >> 2) > NT || T.fs > MAXFS) ok = false;
+            if ((T.NU >> 2) > NT || (p.NG >> 2) > NT) ok = false;
         }
         if (!ok) continue;
         p.off_w1 = take(p.KS * Hh);
@@ -776,6 +814,15 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         p.cta_block = o;
         // ---- shared memory: buffers first, then the resident weights by priority until the budget is spent
         o = 0;
+        int nstage = NSTAGE_DEFAULT;
+        if (const char* e = getenv("MMK_SR_NSTAGE")) nstage = std::max(2, std::min(MAXST, atoi(e)));
+        int kcfull = KCFULL_DEFAULT;
+        if (const char* e = getenv("MMK_SR_KC")) kcfull = std::max(KC, std::min(128, atoi(e) / KC * KC));
+        int wmax = p.NG;
+        for (int i = 0; i < n_ft; ++i) wmax = std::max(wmax, p.tiers[i].NU);
+        p.xstage = kcfull * PBW; p.wstage = kcfull * std::min(WMAX, wmax);
+        p.xregion = nstage * p.xstage; p.wregion = nstage * p.wstage; p.region = p.xregion + p.wregion;
+        const int REGION = p.region;
         p.s_region = take(REGION);
         p.s_gi = take(std::max(p.NG, fs_max) * PBW);
         p.s_bar = take(2 * BAR_COUNT + groups_per_cluster_max * GP);
@@ -789,14 +836,17 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
             o += len;
             return true;
         };
-        // must be resident: the head slices (used every sample) and the input-side GRU matrices (critical path)
+        // must be resident: the head slices (used every sample) and the frame Linear tables
         ok = resident(p.off_w1, p.KS * Hh, &p.so_w1) && resident(p.off_b1, p.RS, &p.so_b1) &&
              resident(p.off_w2, p.RS * p.ZR, &p.so_w2);
-        for (int i = n_ft - 1; i >= 0 && ok; --i) ok = resident(p.tiers[i].off_wih, H * p.NG + p.NG, &p.tiers[i].so_wih);
+        for (int i = n_ft - 1; i >= 0 && ok; --i)
+            ok = resident(p.tiers[i].off_inw, H * p.tiers[i].fs + H, &p.tiers[i].so_inw);
         if (!ok) continue;
-        // optional, most frequently firing tier first; the rest streams from L2 next to the activations
+        // optional, most frequently firing tier first (input-side GRU matrix, hidden-side, up-sampler); the rest
+        // streams from L2 next to the activations
         for (int i = n_ft - 1; i >= 0; --i) {
             Tier& T = p.tiers[i];
+            if (!resident(T.off_wih, H * p.NG + p.NG, &T.so_wih) && p.NG > WMAX) ok = false;
             if (!resident(T.off_whh, H * p.NG + p.NG, &T.so_whh) && p.NG > WMAX) ok = false;
             if (!resident(T.off_wup, H * T.NU + T.NU, &T.so_wup) && T.NU > WMAX) ok = false;
         }
@@ -810,18 +860,18 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         p.h_hid = htake(p.RS * GP);
         p.h_un = ho;
         const int tiles_h = (Hh / 4) * (GP / 4);
-        int nq = std::max(1, NT / tiles_h), p2 = 1;
+        int nq = std::max(1, HT / tiles_h), p2 = 1;
         while (p2 * 2 <= nq && p2 * 2 <= p.KS) p2 *= 2;
         const int part_floats = tiles_h * p2 * 16;
         const int inz_floats = GP * p.ZR;                      // (GP/CS) slots x CS sources
         p.h_zs = p.h_un + pad4(inz_floats);
         const int un_floats = std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
-        if (ho + un_floats > REGION) continue;
+        if (ho + un_floats > REGION || p.NG * PBW * 2 > REGION) continue;
         const size_t smem = (size_t)o * sizeof(float);
         const int max_clusters = sr2_max_clusters(CS, smem, sms);
         if (getenv("MMK_SR_DEBUG")) {
             fprintf(stderr, "[sr2] CS=%d NC=%d GP=%d smem=%zu max_clusters=%d resident:", CS, NC, GP, smem, max_clusters);
-            for (int i = 0; i < n_ft; ++i) fprintf(stderr, " t%d(hh=%d up=%d)", i, p.tiers[i].so_whh >= 0, p.tiers[i].so_wup >= 0);
+            for (int i = 0; i < n_ft; ++i) fprintf(stderr, " t%d(ih=%d hh=%d up=%d)", i, p.tiers[i].so_wih >= 0, p.tiers[i].so_whh >= 0, p.tiers[i].so_wup >= 0);
             fprintf(stderr, "\n");
         }
         if (max_clusters * CS < NC) continue;   // the grid could not be co-resident with this cluster size
@@ -861,6 +911,8 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
                         bs[col] = b[row];
                     }
             }
+            std::copy(d->in_w[i], d->in_w[i] + (size_t)H * T.fs, blk + T.off_inw);
+            std::copy(d->in_b[i], d->in_b[i] + H, blk + T.off_inw + (size_t)H * T.fs);
             const int nu = T.up_rows / NC, u_lo = c * nu;
             float* Wu = blk + T.off_wup; float* bu = Wu + (size_t)H * T.NU;
             for (int col = 0; col < nu; ++col) {
@@ -902,6 +954,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     if (!ok) { sr2_destroy(h); MMK_FAIL("cudaMalloc failed while creating the SampleRNN handle"); }
     p.abort_flag = (unsigned*)(p.bar + 1);
     if (getenv("MMK_SR_DEBUG")) p.dbg = (unsigned long long*)dev_alloc(64, nullptr);
+    if (const char* e = getenv("MMK_SR_EXP")) p.exp = atoi(e);
     MMK_CUDA(cudaDeviceSynchronize());
     *out = h;
     return 0;
