@@ -44,6 +44,14 @@ int mmk_mulaw_compress(const float* d_x, int64_t* d_q, size_t n, int q_levels, f
 /* Same arithmetic, uint8 output (q_levels <= 256): the compact form used inside the generation path. */
 int mmk_mulaw_compress_u8(const float* d_x, uint8_t* d_q, size_t n, int q_levels, float compression, void* stream);
 
+/* The default compress/expand kernels use a threshold table that is built with the exact arithmetic and then PROVEN
+ * equal to it on every float in [-1, 1] on the device, once per (device, q_levels, compression) — on the first call
+ * that needs it (one ~20 ms launch + a stream synchronisation; not possible inside a stream capture, where the exact
+ * kernel runs instead).  mmk_mulaw_prepare does that step explicitly.  *table_in_use = 1 if the proven table kernels
+ * will serve this parameter pair, 0 if the exact-arithmetic kernels will (proof failed: *mismatches > 0; q_levels >
+ * 2048; or MMK_MULAW_EXACT=1 in the environment).  Both pointers are nullable HOST pointers. */
+int mmk_mulaw_prepare(int q_levels, float compression, int* table_in_use, uint64_t* mismatches, void* stream);
+
 /* MuLawExpand.torch_func — mimikit/features/functionals.py:361-369 (the `feature.inv` that
  * GenerateLoopV2.process_outputs applies, mimikit/loops/generate.py:245).  d_q int64 (n) -> d_x fp32 (n). */
 int mmk_mulaw_expand(const int64_t* d_q, float* d_x, size_t n, int q_levels, float compression, void* stream);

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "mmk_get_device_info": (c_int, [POINTER(DeviceInfo)]),
     "mmk_mulaw_compress": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_mulaw_compress_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
+    "mmk_mulaw_prepare": (c_int, [c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "mmk_mulaw_expand": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_stft_mag_mel": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_int, c_void_p, c_void_p]),
