@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mag_mel_kernel(StftParams p
     float2* twN = twH + H;                               // exp(-2 pi i k / N), k < H
     float* win = reinterpret_cast<float*>(twN + H);      // N
     float* mag = win + N;                                // nb (+pad)
+    int* s_rng = reinterpret_cast<int*>(mag + H + 8);    // [n_mels][2] non-zero bin range of each filter
     const int tid = threadIdx.x;
+    if (p.mel_out) mel_ranges_to_smem(p.mel_fb, p.n_mels, nb, s_rng);
 
     for (int k = tid; k < H; k += STFT_THREADS) {
         float s, c;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mag_mel_kernel(StftParams p
             const int warp = tid >> 5, lane = tid & 31;
             float* orow = p.mel_out + f * (long long)p.n_mels;
             for (int m = warp; m < p.n_mels; m += STFT_THREADS / 32) {
-                const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
+                const int lo = s_rng[2 * m], hi = s_rng[2 * m + 1];
                 const float* fb = p.mel_fb + (long long)m * nb;
                 float acc = 0.0f;
                 for (int k = lo + lane; k < hi; k += 32) acc = fmaf(__ldg(fb + k), mag[k], acc);
@@ -126,20 +128,6 @@ __global__ void __launch_bounds__(STFT_THREADS) stft_mag_mel_kernel(StftParams p
         }
         __syncthreads();
     }
-}
-
-// [lo, hi) of the non-zero support of each dense filter row (one warp per filter).
-__global__ void mel_range_kernel(const float* __restrict__ fb, int n_mels, int nb, int* __restrict__ range) {
-    const int m = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (m >= n_mels) return;
-    int lo = nb, hi = 0;
-    for (int k = lane; k < nb; k += 32)
-        if (fb[(long long)m * nb + k] != 0.0f) { lo = min(lo, k); hi = max(hi, k + 1); }
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if (lane == 0) { range[2 * m] = (lo < hi) ? lo : 0; range[2 * m + 1] = (lo < hi) ? hi : 0; }
 }
 
 static long long target_length(long long L, int n_fft, int hop, int center) {
@@ -193,27 +181,21 @@ extern "C" int mmk_stft_mag_mel(const float* d_x, int n_clips, int64_t clip_len,
     p.n_fft = n_fft; p.hop = hop; p.pad = center ? n_fft / 2 : 0; p.n_mels = d_mel_out ? n_mels : 0;
     int lg = 0; while ((1 << lg) < n_fft / 2) ++lg;
     p.log2_half = lg;
-    int* d_range = nullptr;
-    if (d_mel_out) {
-        MMK_CUDA(cudaMallocAsync(&d_range, sizeof(int) * 2 * n_mels, st));
-        mel_range_kernel<<<(n_mels + 7) / 8, 256, 0, st>>>(d_mel_fb, n_mels, n_fft / 2 + 1, d_range);
-        MMK_CUDA(cudaGetLastError());
-        p.mel_range = d_range;
-    }
-    if (n_fft == 2048) {   // warp-per-frame register FFT (stft_warp.cuh)
-        MMK_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
+    MMK_CHECK(n_mels <= 8192, "n_mels must be <= 8192");
+    if (n_fft == 2048 && n_mels <= FW_MAX_MELS) {   // warp-per-frame register FFT (stft_warp.cuh)
+        const size_t fw_smem = FW_SMEM_BYTES + (d_mel_out ? sizeof(int) * 2 * (size_t)n_mels : 0);
+        MMK_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw_smem));
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         long long grid = std::min<long long>(sms, (p.total_frames + FW_WARPS - 1) / FW_WARPS);
         p.mel_cap = d_mel_out ? FW_MEL_CAP : 0;
-        stft2048_warp_kernel<<<(int)grid, FW_THREADS, FW_SMEM_BYTES, st>>>(p);
+        stft2048_warp_kernel<<<(int)grid, FW_THREADS, fw_smem, st>>>(p);
         MMK_CUDA(cudaGetLastError());
-        if (d_range) MMK_CUDA(cudaFreeAsync(d_range, st));
         return 0;
     }
     const int H = n_fft / 2;
-    size_t smem = sizeof(float2) * 4 * H + sizeof(float) * (n_fft + H + 8);
+    size_t smem = sizeof(float2) * 4 * H + sizeof(float) * (n_fft + H + 8) + (d_mel_out ? sizeof(int) * 2 * (size_t)n_mels : 0);
     MMK_CUDA(cudaFuncSetAttribute(stft_mag_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -224,7 +206,6 @@ extern "C" int mmk_stft_mag_mel(const float* d_x, int n_clips, int64_t clip_len,
     if (grid > p.total_frames) grid = p.total_frames;
     stft_mag_mel_kernel<<<(int)grid, STFT_THREADS, smem, st>>>(p);
     MMK_CUDA(cudaGetLastError());
-    if (d_range) MMK_CUDA(cudaFreeAsync(d_range, st));
     return 0;
 }
 

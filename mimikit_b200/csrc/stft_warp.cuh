@@ -21,18 +21,35 @@ namespace mmk {
 
 constexpr int FW_WARPS = 16;
 constexpr int FW_THREADS = FW_WARPS * 32;
+constexpr int FW_MEL_CAP = 384;    // rows of the packed filter table (x 128 B) + one flag word
 constexpr int FW_TILE = 32 * 33;   // float2 per warp tile (row stride 33: conflict-free column reads)
 
 struct StftParams {
     const float* x;
     float* mag_out;
     const float* mel_fb;
-    const int* mel_range;  // (n_mels, 2): [lo, hi) non-zero bin range of each filter
     float* mel_out;
     long long clip_stride, start, kept_len, n_frames, total_frames;
     int n_fft, hop, pad, n_mels, log2_half;
     int mel_cap;           // warp kernel: rows of the lane-interleaved filter table that fit in shared memory (0 = none)
 };
+
+// [lo, hi) of the non-zero support of each dense filter row, computed by the whole CTA into shared memory at kernel
+// start (one warp per filter; 525 KB of L2 reads per CTA for 128 x 1025 — no side allocation, no extra launch).
+__device__ __forceinline__ void mel_ranges_to_smem(const float* __restrict__ fb, int n_mels, int nb, int* s_rng) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int m = warp; m < n_mels; m += n_warps) {
+        int lo = nb, hi = 0;
+        for (int k = lane; k < nb; k += 32)
+            if (__ldg(fb + (long long)m * nb + k) != 0.0f) { lo = min(lo, k); hi = max(hi, k + 1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { s_rng[2 * m] = (lo < hi) ? lo : 0; s_rng[2 * m + 1] = (lo < hi) ? hi : 0; }
+    }
+}
 
 __device__ __forceinline__ float2 w32(int j) {   // exp(-2 pi i j / 32)
     switch (j) {
@@ -101,13 +118,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
     // lane-interleaved filter table: lane L owns filters L, L+32, ...; its non-zero weights, filter after filter, sit in
     // column L of wsm[row][32] (conflict-free reads).  Built once per CTA from the dense filterbank.
     float* wsm = reinterpret_cast<float*>(reinterpret_cast<float2*>(win + N) + (size_t)FW_WARPS * FW_TILE);
+    int* s_rng = reinterpret_cast<int*>(wsm + (size_t)FW_MEL_CAP * 32 + 4);   // [n_mels][2], after the flag word
     const int n_grp = (p.n_mels + 31) / 32;
     bool mel_packed = false;
+    if (p.mel_out) {
+        mel_ranges_to_smem(p.mel_fb, p.n_mels, H + 1, s_rng);
+        __syncthreads();
+    }
     if (p.mel_out && p.mel_cap > 0 && tid < 32) {
         int rows = 0;
         for (int g = 0; g < n_grp; ++g) {
             const int m = tid + 32 * g;
-            if (m < p.n_mels) rows += p.mel_range[2 * m + 1] - p.mel_range[2 * m];
+            if (m < p.n_mels) rows += s_rng[2 * m + 1] - s_rng[2 * m];
         }
         int mx = rows;
 #pragma unroll
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
             for (int g = 0; g < n_grp; ++g) {
                 const int m = tid + 32 * g;
                 if (m >= p.n_mels) break;
-                const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
+                const int lo = s_rng[2 * m], hi = s_rng[2 * m + 1];
                 for (int k = lo; k < hi; ++k) wsm[(row++) * 32 + tid] = __ldg(p.mel_fb + (long long)m * (H + 1) + k);
             }
         }
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
             if (mel_packed) {
                 const float* wl = wsm + lane;
                 for (int m = lane; m < p.n_mels; m += 32) {
-                    const int2 rg = __ldg(reinterpret_cast<const int2*>(p.mel_range) + m);
+                    const int2 rg = *(reinterpret_cast<const int2*>(s_rng) + m);
                     float acc = 0.0f;
 #pragma unroll 4
                     for (int k = rg.x; k < rg.y; ++k, wl += 32) acc = fmaf(*wl, magb[k], acc);
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
                 }
             } else {
                 for (int m = lane; m < p.n_mels; m += 32) {
-                    const int lo = p.mel_range[2 * m], hi = p.mel_range[2 * m + 1];
+                    const int lo = s_rng[2 * m], hi = s_rng[2 * m + 1];
                     const float* fb = p.mel_fb + (long long)m * nb;
                     float acc = 0.0f;
                     for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(fb + k), magb[k], acc);
@@ -245,7 +267,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) stft2048_warp_kernel(const Stft
 }
 
 constexpr size_t FW_SMEM_BASE = sizeof(float2) * (1024 + 512) + sizeof(float) * 2048 + sizeof(float2) * FW_TILE * FW_WARPS;
-constexpr int FW_MEL_CAP = 384;   // rows of the packed filter table (x 128 B) + one flag word
-constexpr size_t FW_SMEM_BYTES = FW_SMEM_BASE + (size_t)FW_MEL_CAP * 128 + 16;
+constexpr size_t FW_SMEM_BYTES = FW_SMEM_BASE + (size_t)FW_MEL_CAP * 128 + 16;   // + 8 bytes per mel filter (ranges)
+constexpr int FW_MAX_MELS = 2048;
 
 }  // namespace mmk

@@ -251,7 +251,7 @@ class MagSpec(Functional):
         x, restore = _to_device(inputs)
         if x.dtype != torch.float32:
             x = x.to(torch.float32)
-        fb = melspec.filterbank(self.n_fft).to(x.device)
+        fb = melspec.filterbank(self.n_fft, x.device)
         mag, mel = _stft_mag_mel(x, self.n_fft, self.hop_length, self.center, self.alignment, return_mag, fb)
         return (restore(mag), restore(mel)) if return_mag else restore(mel)
 
@@ -271,12 +271,18 @@ class MelSpec(Functional):
     def elem_type(self):
         return Continuous(0., float("inf"), self.n_mels)
 
-    def filterbank(self, n_fft):
+    def filterbank(self, n_fft, device=None):
+        """Host filterbank (device=None) or its cached copy on `device` (no per-call H2D copy on the hot path)."""
         key = (n_fft, self.n_mels, self.fmin, self.fmax, self.htk)
         cache = MelSpec._fb_cache
         if key not in cache:
             cache[key] = mel_filterbank(n_fft, self.n_mels, self.fmin, self.fmax, self.htk)
-        return cache[key]
+        if device is None:
+            return cache[key]
+        dkey = key + (str(torch.device(device)),)
+        if dkey not in cache:
+            cache[dkey] = cache[key].to(device)
+        return cache[dkey]
 
     def torch_func(self, inputs):
         raise NotImplementedError(

@@ -1,0 +1,33 @@
+"""GPU-box probe: device time of the feature kernels alone at several sizes (events around each call)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mimikit_b200 import MagSpec, MelSpec, MuLawCompress, MuLawExpand
+
+def timeit(fn, reps=5):
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); r = fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1)); del r
+    return ts
+
+L = 220500
+ms_, mel, mu, ex = MagSpec(2048, 512), MelSpec(128), MuLawCompress(), MuLawExpand()
+for clips in (36, 360, 1800, 3600):
+    x = torch.rand((clips, L), device="cuda") * 2 - 1
+    t = timeit(lambda: ms_.mel(x, mel))
+    print(f"stft+mel clips={clips}: ms {['%.3f' % v for v in t]}  -> {4*clips*L/min(t)/1e6:.1f} GB/s in", flush=True)
+    for mode in ("0", "1"):
+        os.environ["MMK_MULAW_EXACT"] = mode
+        t = timeit(lambda: mu(x))
+        print(f"  mulaw compress exact={mode}: ms {['%.3f' % v for v in t]} -> {12*clips*L/min(t)/1e6:.1f} GB/s")
+        t = timeit(lambda: mu.torch_func(x, out_dtype=torch.uint8))
+        print(f"  mulaw compress u8 exact={mode}: ms {['%.3f' % v for v in t]} -> {5*clips*L/min(t)/1e6:.1f} GB/s")
+        q = mu(x)
+        t = timeit(lambda: ex(q))
+        print(f"  mulaw expand exact={mode}: ms {['%.3f' % v for v in t]} -> {12*clips*L/min(t)/1e6:.1f} GB/s")
+        del q
+    os.environ.pop("MMK_MULAW_EXACT")
+    del x

@@ -66,6 +66,46 @@ def test_mulaw_full_size_properties():
     assert np.array_equal(MuLawCompress()(sub).cpu().numpy(), restate.mulaw_compress(sub.cpu().numpy()))
 
 
+def test_mulaw_table_is_proven_and_equals_exact_arithmetic_everywhere(monkeypatch):
+    """The default mu-law kernels use a threshold table that the library proves on the device against the exact
+    (Sleef-u10, reference op order) arithmetic for every float in [-1, 1].  Here: (1) the proof passed for the
+    parameter pairs of the golden file, (2) independently, table kernel == exact kernel on ALL 2^32 fp32 bit patterns
+    (out-of-range values, infinities and NaNs included) for the default pair, (3) the exact kernels still match the
+    golden vectors when forced."""
+    import ctypes
+    from mimikit_b200 import MuLawCompress, MuLawExpand, _capi
+    lib = _capi.lib()
+    for q, C in [(256, 1.), (256, .5), (64, 2.), (1024, 1.), (2, 1.), (2048, 1.)]:
+        used, bad = ctypes.c_int(-1), ctypes.c_uint64(99)
+        _capi.check(lib.mmk_mulaw_prepare(q, C, ctypes.byref(used), ctypes.byref(bad), _capi.stream_ptr()))
+        assert used.value == 1 and bad.value == 0, (q, C, used.value, bad.value)
+    used = ctypes.c_int(-1)
+    _capi.check(lib.mmk_mulaw_prepare(4096, 1., ctypes.byref(used), None, _capi.stream_ptr()))
+    assert used.value == 0          # beyond the shared-memory table: exact kernels, still correct
+    chunk = 1 << 28
+    mu = MuLawCompress(256, 1.)
+    for c in range(16):
+        bits = torch.arange(c * chunk, (c + 1) * chunk, device="cuda", dtype=torch.int64).to(torch.int32)
+        x = bits.view(torch.float32)
+        del bits
+        monkeypatch.delenv("MMK_MULAW_EXACT", raising=False)
+        fast = mu(x)
+        monkeypatch.setenv("MMK_MULAW_EXACT", "1")
+        exact = mu(x)
+        assert torch.equal(fast, exact), f"table != exact in bit-pattern chunk {c}"
+        del fast, exact, x
+    idx = torch.arange(-7, 300, device="cuda")
+    exact = MuLawExpand(256, 1.)(idx)
+    monkeypatch.delenv("MMK_MULAW_EXACT")
+    fast = MuLawExpand(256, 1.)(idx)
+    assert torch.equal(fast.view(torch.int32), exact.view(torch.int32))
+    monkeypatch.setenv("MMK_MULAW_EXACT", "1")
+    d = load_golden("mulaw")
+    x = torch.from_numpy(d["x"]).cuda()
+    for q, C in [(256, 1.), (256, .5), (64, 2.), (1024, 1.)]:
+        assert np.array_equal(MuLawCompress(q, C)(x).cpu().numpy(), d[f"idx_q{q}_c{C}"]), (q, C)
+
+
 def _tol(ref):
     return 1e-4 * max(1.0, float(np.abs(ref).max()))   # "STFT/mel within 1e-4" relative to the clip's peak magnitude
 
