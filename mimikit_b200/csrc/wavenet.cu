@@ -544,6 +544,7 @@ using namespace mmk;
 struct mmk_wavenet_s {
     wn2_handle* v2 = nullptr;   // set when the latency-engineered kernel (wavenet2.cu) hosts this network
     wn3_handle* v3 = nullptr;   // set when the warp-autonomous kernel (wavenet3.cu) hosts this network
+    wn4_handle* v4 = nullptr;   // set when the bf16 tensor-core kernel (wavenet_tc.cu) hosts this network (compute_mode 1)
     WnParams p{};
     int device = 0;
     int max_batch = 0;
@@ -631,8 +632,15 @@ static size_t wn_plan(WnParams& p, int CS, int max_layers_per_stage, bool has_he
     return (size_t)o * sizeof(float);
 }
 
+extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, int compute_mode, mmk_wavenet_t* out);
+
 extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_wavenet_t* out) {
+    return mmk_wavenet_create_ex(d, max_batch, MMK_COMPUTE_FP32, out);
+}
+
+extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, int compute_mode, mmk_wavenet_t* out) {
     MMK_CHECK(d && out, "mmk_wavenet_create: null argument");
+    MMK_CHECK(compute_mode == MMK_COMPUTE_FP32 || compute_mode == MMK_COMPUTE_BF16_TC, "unknown compute_mode");
     MMK_CHECK(d->n_layers >= 1 && d->n_layers <= WN_MAX_LAYERS, "n_layers out of range [1, 96]");
     MMK_CHECK(d->dilated_dim >= 4 && d->dilated_dim % 4 == 0, "dilated_dim must be a positive multiple of 4");
     MMK_CHECK(d->skips_dim >= 0 && d->skips_dim % 4 == 0, "skips_dim must be 0 or a multiple of 4");
@@ -648,6 +656,18 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
     auto* h = new mmk_wavenet_s();
     WnParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
+    if (compute_mode == MMK_COMPUTE_BF16_TC) {
+        // explicit request: no silent fall-back to another precision
+        int unsupported = 0;
+        for (int l = 0; l < d->n_layers; ++l)
+            if (!d->conv_dil_w[l] || !d->conv_dil_b[l]) { delete h; MMK_FAIL("missing conv_dil weights"); }
+        if (wn4_create(d, max_batch, &h->v4, &unsupported) != 0) { delete h; return 1; }
+        int rf4 = 1;
+        for (int l = 0; l < d->n_layers; ++l) rf4 += d->dilations[l];
+        h->rf = rf4; h->max_batch = max_batch;
+        *out = h;
+        return 0;
+    }
     {
         const char* force = getenv("MMK_WN_KERNEL");   // "1" = general kernel, "2" = chain kernel, "3" = warp kernel only
         if (!force || atoi(force) == 3) {
@@ -830,6 +850,7 @@ extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_
 
 extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
     if (!h) return 0;
+    if (h->v4) wn4_destroy(h->v4);
     if (h->v3) wn3_destroy(h->v3);
     if (h->v2) wn2_destroy(h->v2);
     cudaFree(h->d_wpack); cudaFree(h->d_hpack); cudaFree(h->d_E); cudaFree(h->d_rings);
@@ -840,6 +861,7 @@ extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
 
 extern "C" int mmk_wavenet_sync_check(mmk_wavenet_t h, void* stream) {
     MMK_CHECK(h, "null handle");
+    if (h->v4) return wn4_sync_check(h->v4, stream);
     if (h->v3) return wn3_sync_check(h->v3, stream);
     if (h->v2) return wn2_sync_check(h->v2, stream);
     unsigned aborted = 0;
@@ -853,6 +875,7 @@ extern "C" int mmk_wavenet_rf(mmk_wavenet_t h) { return h ? h->rf : -1; }
 
 extern "C" int mmk_wavenet_launch_info(mmk_wavenet_t h, mmk_launch_info* out) {
     MMK_CHECK(h && out, "null argument");
+    if (h->v4) return wn4_launch_info(h->v4, out);
     if (h->v3) return wn3_launch_info(h->v3, out);
     if (h->v2) return wn2_launch_info(h->v2, out);
     out->cluster_size = h->p.CS; out->n_stages = h->p.NST; out->group_size = WN_GB; out->threads = WN_NT;
@@ -879,6 +902,9 @@ extern "C" int mmk_wavenet_run(mmk_wavenet_t h, int64_t* d_seq, int B, int64_t s
     MMK_CHECK(d_temperature == nullptr || (n_temperature == 1 || n_temperature == B), "temperature must have 1 or B entries");
     MMK_CHECK(d_temperature == nullptr || d_noise != nullptr, "sampling (temperature given) needs a noise tensor");
     if (t_begin == t_end) return 0;
+    if (h->v4)
+        return wn4_run(h->v4, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
+                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     if (h->v3)
         return wn3_run(h->v3, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
                        n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);

@@ -25,3 +25,14 @@ int wn3_run(wn3_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
             int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
             int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
             unsigned long long* d_step_ts, void* stream);
+
+// The bf16 tensor-core kernel (wavenet_tc.cu, tcgen05 + TMEM): same contract; used when compute_mode = MMK_COMPUTE_BF16_TC.
+struct wn4_handle;
+int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* unsupported);
+int wn4_destroy(wn4_handle* h);
+int wn4_launch_info(wn4_handle* h, mmk_launch_info* out);
+int wn4_sync_check(wn4_handle* h, void* stream);
+int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
+            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream);

@@ -1,0 +1,836 @@
+// Tensor-core WaveNet generation kernel (sm_100a: tcgen05.mma + TMEM + cp.async.bulk) — the bf16 mode of
+// mmk_wavenet_* (compute_mode = 1).  Same function as wavenet3.cu / wavenet.cu (reference: wavenet_v2.py:131-176,
+// 276-293, 447-452; modules/io.py:148-154; networks/mlp.py:44-63; modules/targets.py:40-52), operands rounded to bf16,
+// fp32 accumulation.  Parity bar: teacher-forced logits within 5e-2 relative (BASELINE.json north_star, bf16).
+//
+// Design: the PROMPT BATCH is the MMA M dimension.  One CTA owns a group of up to 128 prompts for the whole launch
+// (prefill + every generated sample) and never talks to another CTA: no collective, no grid or cluster barrier.
+//   * every 1x1 / 2-tap contraction of a layer is a tcgen05.mma with M = 128 (prompts), fp32 accumulators in TMEM:
+//       D1[128 x 2C]  = [h_l(t) | h_l(t-d)] . W1^T      (gate pre-activations; N-chunks of 32 channels: f and g side by side)
+//       H [128 x C]  += y . Wres^T                      (the residual stream stays in TMEM across the 30 layers)
+//       SK[128 x S]  += y . Wskip^T                     (so does the running skip sum)
+//     TMEM columns: D1 [0,256) | H [256,384) | SK [384,512); the head reuses them (hidden -> D1, logits -> H|SK).
+//   * weights (bf16, pre-packed on the host in the UMMA canonical K-major no-swizzle layout) are streamed from L2 through
+//     a 7-slot x 16 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx by a producer warp; slots are
+//     released by tcgen05.commit.  Nothing is resident: 5.8 MB per step per group, all L2 hits.
+//   * the older conv tap h_l(t-d) comes from a per-layer ring in global memory (L2), written by the epilogue in the same
+//     canonical layout and fetched d steps later with one bulk copy by a second producer warp.
+//   * 8 epilogue warps (2 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (one MUFU
+//     tanh.approx.f16x2 per gate), bf16 pack straight into the next MMA's A tile, per 32-channel chunk so that the
+//     res/skip MMAs of a chunk start while the gate MMAs of the next chunk run.
+//   * head: skip sum -> bf16 -> MMA (W1) -> Mish -> MMA (W2, + learned-temperature row) -> logits staged in shared
+//     memory -> the same decide_warp sampler as the fp32 kernels (argmax or inverse-CDF on external noise).
+// Work per step per group: 30 x (16 + 8) MMAs of 128 x 256 x 16: ~3 070 tensor cycles per layer (the floor of this
+// design); algorithmic FLOPs 2 x 2 982 016 per sample per prompt.
+#include "common.cuh"
+#include "sampler.cuh"
+#include "wavenet_impl.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace mmk_tc {
+
+constexpr int NT = 384;            // 8 epilogue warps, MMA warp, weight producer, tap producer, one spare
+constexpr int NEPI = 256;
+constexpr int W_MMA = 8, W_WP = 9, W_XP = 10;
+constexpr int MROWS = 128;         // prompts per group = MMA M
+constexpr int NSLOT = 7;
+constexpr int SLOT_BYTES = 16384;
+constexpr int MAXL = 96;
+constexpr int TM_D1 = 0, TM_H = 256, TM_SK = 384, TM_TEMP = 128, TM_LOGIT = 256;
+
+// shared-memory map (bytes)
+constexpr int SM_XN = 0;                         // A tile: h_l(t) bf16 [128 x C]; head: hidden
+constexpr int SM_Y = 32768;                      // A tile: gated output y; head: skip sum
+constexpr int SM_ZX = 65536;                     // + 2 KB: with XN|Y the logits staging area (64 rows x 260 floats)
+constexpr int SM_XO = 67584;                     // A tile: h_l(t-d) from the ring
+constexpr int SM_W = 100352;                     // weight ring
+constexpr int SM_BAR = SM_W + NSLOT * SLOT_BYTES;
+constexpr int SM_STAGES = SM_BAR + 1024;      // uint2 {src / 16, bytes} per stage of a step
+constexpr int SM_FIXED = SM_STAGES;
+constexpr int ZROW = 260;
+
+enum {
+    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_D1FULL, B_YFULL = B_D1FULL + 4,
+    B_D2FULL = B_YFULL + 4, B_HAFULL, B_H1DFULL, B_H2AFULL, B_H2DFULL, B_HEADDONE, B_EPISYNC, B_COUNT
+};
+
+struct StageRec { unsigned src16, bytes; };   // src16: offset into wpack in 16-byte units
+
+struct Params {
+    int L, C, S, Hh, Q, n_ch, n_h1, n_h2, n_stages;
+    float min_temp;
+    int dil[MAXL];
+    unsigned char has_res[MAXL];
+    long long ring_off[MAXL];      // byte offset of layer l's ring inside a group's block
+    long long ring_group_bytes;
+    const unsigned char* wpack;
+    const StageRec* stages;        // [L * 3 n_ch + n_h1 + n_h2]
+    const float* E;                // (Q, C)
+    const float* b1;               // [L][2C] gate biases (filter rows then gate rows)
+    const float* cbr;              // [L + 1][C] cumulative residual-conv biases (sum over layers < l)
+    const float* cbs;              // [S] sum of the skip-conv biases
+    const float* hb1; const float* hb2;
+    unsigned char* rings;
+    unsigned* abort_flag;
+    // this run
+    long long* seq;
+    long long seq_stride, t_begin, t_head, t_end;
+    int B, teacher_forced, n_temperature;
+    const float* temperature; const float* noise;
+    long long noise_stride, noise_t0;
+    float* logits_out; long long* decisions; unsigned long long* step_ts;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long WAIT_LIMIT_NS = 2000000000ull;   // watchdog: 2 s on one wait means a lost signal
+__device__ __noinline__ bool mbar_wait_slow(unsigned bar, unsigned parity, unsigned* abort_flag) {
+    const unsigned long long t0 = globaltimer();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned*>(abort_flag) != 0u) return false;
+            if (globaltimer() - t0 > WAIT_LIMIT_NS) { atomicExch(abort_flag, 1u); return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, unsigned* abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, abort_flag);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulate, M = 128, K = 16
+__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                          unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+                   "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                   "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO (K direction) = 128 B; SBO (next 8 rows) = row_bytes * 8.  (cute::UMMA::SmemDescriptor, version 1.)
+__host__ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr & 0x3ffffu) >> 4);
+    d |= (unsigned long long)(128u >> 4) << 16;
+    d |= (unsigned long long)(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
+__host__ __device__ __forceinline__ unsigned umma_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(MROWS >> 4) << 24);
+}
+// byte offset of (row m, 8-element chunk kc) in a canonical tile with K elements per row
+__host__ __device__ __forceinline__ unsigned tile_off(int m, int kc, int K) {
+    return (unsigned)((m >> 3) * (K * 16) + kc * 128 + (m & 7) * 16);
+}
+__device__ __forceinline__ unsigned pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<unsigned*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+// tanh(f) * sigmoid(g) with ONE MUFU op: tanh.approx.f16x2 on (f, g / 2); sigmoid(g) = 0.5 tanh(g / 2) + 0.5
+__device__ __forceinline__ float gate_fast(float f, float g) {
+    const __half2 in = __floats2half2_rn(f, 0.5f * g);
+    unsigned o;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(o) : "r"(*reinterpret_cast<const unsigned*>(&in)));
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&o));
+    return t.x * fmaf(0.5f, t.y, 0.5f);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mish_fast(float x) {   // x * tanh(softplus(x)), softplus threshold 20 (F.softplus)
+    const float sp = x > 20.0f ? x : __logf(1.0f + __expf(x));
+    return x * tanh_fast(sp);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The kernel: one CTA per group of 128 prompts.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int grp = blockIdx.x;
+    const unsigned sb = smem_u32(smem);
+    auto bar = [&](int i) { return sb + (unsigned)SM_BAR + 8u * (unsigned)i; };
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(smem + SM_BAR + 8 * B_COUNT);
+    int* s_idx = reinterpret_cast<int*>(smem + SM_BAR + 8 * B_COUNT + 16);
+    unsigned* abort_flag = P.abort_flag;
+    const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q, n_ch = P.n_ch;
+    const int KC = C / 16;                                // k-steps of a C-deep contraction
+    const unsigned tile_bytes = (unsigned)(MROWS * C * 2);
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+        mbar_init(bar(B_XOFULL), 1); mbar_init(bar(B_XOFREE), 1);
+        mbar_init(bar(B_XNFULL), NEPI);
+        for (int j = 0; j < 4; ++j) { mbar_init(bar(B_D1FULL + j), 1); mbar_init(bar(B_YFULL + j), NEPI); }
+        mbar_init(bar(B_D2FULL), 1);
+        mbar_init(bar(B_HAFULL), NEPI); mbar_init(bar(B_H1DFULL), 1);
+        mbar_init(bar(B_H2AFULL), NEPI); mbar_init(bar(B_H2DFULL), 1);
+        mbar_init(bar(B_HEADDONE), NEPI);
+        mbar_init(bar(B_EPISYNC), NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == W_MMA) tmem_alloc(smem_u32(s_tmem), 512);
+    {
+        uint2* st_s = reinterpret_cast<uint2*>(smem + SM_STAGES);
+        for (int i = tid; i < P.n_stages; i += NT) st_s[i] = make_uint2(P.stages[i].src16, P.stages[i].bytes);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<volatile unsigned*>(s_tmem);
+
+    unsigned char* ring_g = P.rings + (size_t)grp * P.ring_group_bytes;
+    const int n_layer_stages = 3 * n_ch;
+
+    if (warp == W_WP) {
+        // ===================== weight producer: the stage list of every step, in consumption order =====================
+        if (lane == 0) {
+            unsigned cnt = 0;
+            bool dead = false;
+            for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
+                const int n_st = L * n_layer_stages + (t >= P.t_head ? P.n_h1 + P.n_h2 : 0);
+                for (int i = 0; i < n_st; ++i, ++cnt) {
+                    const unsigned slot = cnt % NSLOT, use = cnt / NSLOT;
+                    if (!mbar_wait(bar(B_WEMPTY + slot), (use & 1u) ^ 1u, abort_flag)) { dead = true; break; }
+                    const uint2 r = reinterpret_cast<const uint2*>(smem + SM_STAGES)[i];
+                    mbar_expect_tx(bar(B_WFULL + slot), r.y);
+                    bulk_g2s(sb + SM_W + slot * SLOT_BYTES, P.wpack + (size_t)r.x * 16, r.y, bar(B_WFULL + slot));
+                }
+            }
+        }
+    } else if (warp == W_XP) {
+        // ===================== tap producer: h_l(t - d_l) from the ring of layer l =====================
+        if (lane == 0) {
+            unsigned n = 0;
+            bool dead = false;
+            for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
+                for (int l = 0; l < L; ++l, ++n) {
+                    if (!mbar_wait(bar(B_XOFREE), (n & 1u) ^ 1u, abort_flag)) { dead = true; break; }
+                    const unsigned slot = (unsigned)((t + 1) % (P.dil[l] + 1));   // d + 1 slots: holds h_l(t - d)
+                    mbar_expect_tx(bar(B_XOFULL), tile_bytes);
+                    bulk_g2s(sb + SM_XO, ring_g + P.ring_off[l] + (size_t)slot * tile_bytes, tile_bytes, bar(B_XOFULL));
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer: one thread =====================
+        if (lane == 0) {
+            unsigned wcnt = 0, n_lay = 0, n_xn = 0, n_head = 0;
+            bool dead = false;
+            const unsigned id64 = umma_idesc(64), idC = umma_idesc(C), idS = umma_idesc(S);
+            auto wslot_wait = [&](unsigned& slot) {
+                slot = wcnt % NSLOT;
+                if (!mbar_wait(bar(B_WFULL + slot), (wcnt / NSLOT) & 1u, abort_flag)) dead = true;
+                tc_fence_after();
+            };
+            for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
+                for (int l = 0; l < L && !dead; ++l, ++n_lay) {
+                    // ---- older tap: D1 = XO . W1o^T
+                    if (!mbar_wait(bar(B_XOFULL), n_lay & 1u, abort_flag)) { dead = true; break; }
+                    tc_fence_after();
+                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                        unsigned slot; wslot_wait(slot);
+                        if (dead) break;
+                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                        for (int kk = 0; kk < KC; ++kk)
+                            umma_bf16(tmem + TM_D1 + 64 * j, umma_desc(sb + SM_XO + kk * 256, C * 16),
+                                      umma_desc(wb + kk * 256, C * 16), id64, kk > 0);
+                        umma_commit(bar(B_WEMPTY + slot));
+                    }
+                    if (dead) break;
+                    umma_commit(bar(B_XOFREE));
+                    // ---- newer tap: D1 += XN . W1n^T, chunk by chunk
+                    if (!mbar_wait(bar(B_XNFULL), n_xn & 1u, abort_flag)) { dead = true; break; }
+                    ++n_xn;
+                    tc_fence_after();
+                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                        unsigned slot; wslot_wait(slot);
+                        if (dead) break;
+                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                        for (int kk = 0; kk < KC; ++kk)
+                            umma_bf16(tmem + TM_D1 + 64 * j, umma_desc(sb + SM_XN + kk * 256, C * 16),
+                                      umma_desc(wb + kk * 256, C * 16), id64, 1u);
+                        umma_commit(bar(B_WEMPTY + slot));
+                        umma_commit(bar(B_D1FULL + j));
+                    }
+                    if (dead) break;
+                    // ---- residual and skip 1x1 convs on y, K-chunk by K-chunk as the gate epilogue delivers them
+                    const bool has_res = P.has_res[l] != 0;
+                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                        if (!mbar_wait(bar(B_YFULL + j), n_lay & 1u, abort_flag)) { dead = true; break; }
+                        unsigned slot; wslot_wait(slot);
+                        if (dead) break;
+                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const unsigned long long a = umma_desc(sb + SM_Y + (2 * j + kk) * 256, C * 16);
+                            if (has_res) umma_bf16(tmem + TM_H, a, umma_desc(wb + kk * 256, 512), idC, 1u);
+                            umma_bf16(tmem + TM_SK, a, umma_desc(wb + C * 64 + kk * 256, 512), idS,
+                                      (l > 0 || j > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar(B_WEMPTY + slot));
+                    }
+                    if (dead) break;
+                    umma_commit(bar(B_D2FULL));
+                }
+                if (dead) break;
+                if (t >= P.t_head) {
+                    // ---- head: hidden = A(skip sum) . W1^T ; logits = A2(mish hidden) . W2^T
+                    if (!mbar_wait(bar(B_HAFULL), n_head & 1u, abort_flag)) break;
+                    tc_fence_after();
+                    for (int c = 0; c < P.n_h1 && !dead; ++c, ++wcnt) {
+                        unsigned slot; wslot_wait(slot);
+                        if (dead) break;
+                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                        const int rows = min(64, Hh - 64 * c);
+                        for (int kk = 0; kk < S / 16; ++kk)
+                            umma_bf16(tmem + TM_D1 + 64 * c, umma_desc(sb + SM_Y + kk * 256, S * 16),
+                                      umma_desc(wb + kk * 256, S * 16), umma_idesc(rows), kk > 0);
+                        umma_commit(bar(B_WEMPTY + slot));
+                    }
+                    if (dead) break;
+                    umma_commit(bar(B_H1DFULL));
+                    if (!mbar_wait(bar(B_H2AFULL), n_head & 1u, abort_flag)) break;
+                    tc_fence_after();
+                    for (int c = 0; c < P.n_h2 && !dead; ++c, ++wcnt) {
+                        unsigned slot; wslot_wait(slot);
+                        if (dead) break;
+                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                        const bool temp_chunk = (c == P.n_h2 - 1);        // the learned-temperature row, padded to 16
+                        const int rows = temp_chunk ? 16 : min(64, Q - 64 * c);
+                        const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 64 * c;
+                        for (int kk = 0; kk < Hh / 16; ++kk)
+                            umma_bf16(tmem + dcol, umma_desc(sb + SM_XN + kk * 256, Hh * 16),
+                                      umma_desc(wb + kk * 256, Hh * 16), umma_idesc(rows), kk > 0);
+                        umma_commit(bar(B_WEMPTY + slot));
+                    }
+                    if (dead) break;
+                    umma_commit(bar(B_H2DFULL));
+                    // D1 / H / SK are rewritten by the next step: wait until the epilogue has drained the logits
+                    if (!mbar_wait(bar(B_HEADDONE), n_head & 1u, abort_flag)) break;
+                    ++n_head;
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue warps: 2 threads per prompt row =====================
+        const int q4 = warp & 3, hf = warp >> 2;
+        const int m = 32 * q4 + lane;                    // prompt row = TMEM lane
+        const int b = grp * MROWS + m;
+        const bool live = b < P.B;
+        const unsigned tm_lane = tmem + ((unsigned)(32 * q4) << 16);
+        unsigned n_lay = 0, n_head = 0, n_sync = 0;
+        bool dead = false;
+        auto epi_sync = [&]() {      // barrier of the 256 epilogue threads (an mbarrier: the wait has the watchdog)
+            mbar_arrive(bar(B_EPISYNC));
+            dead |= !mbar_wait(bar(B_EPISYNC), n_sync & 1u, abort_flag);
+            ++n_sync;
+        };
+        const int half_c = C / 2, half_s = S / 2, half_h = Hh / 2, half_q = Q / 2;
+        float* zs = reinterpret_cast<float*>(smem + SM_XN);
+
+        for (long long t = P.t_begin; t < P.t_end; ++t) {
+            // ---------------- embedding: h_0(t) = E[q_t]  (EmbeddingIO, modules/io.py:148-154) ----------------
+            {
+                long long q = 0;
+                if (live) q = (!P.teacher_forced && t > P.t_head) ? (long long)s_idx[m] : __ldcg(P.seq + (size_t)b * P.seq_stride + t);
+                q = q < 0 ? 0 : (q >= Q ? Q - 1 : q);
+                const float* row = P.E + (size_t)q * C + hf * half_c;
+                unsigned char* rslot = ring_g + P.ring_off[0] + (size_t)(t % (P.dil[0] + 1)) * tile_bytes;
+                for (int i = 0; i < half_c / 16; ++i) {
+                    float v[16];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 e = __ldg(reinterpret_cast<const float4*>(row + 16 * i) + k4);
+                        v[4 * k4] = e.x; v[4 * k4 + 1] = e.y; v[4 * k4 + 2] = e.z; v[4 * k4 + 3] = e.w;
+                    }
+                    const int c0 = hf * half_c + 16 * i;
+                    tmem_st16(tm_lane + TM_H + c0, v);
+                    const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+                    const unsigned o0 = tile_off(m, c0 / 8, C), o1 = tile_off(m, c0 / 8 + 1, C);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + o0) = p0;
+                    *reinterpret_cast<uint4*>(smem + SM_XN + o1) = p1;
+                    __stcg(reinterpret_cast<uint4*>(rslot + o0), p0);
+                    __stcg(reinterpret_cast<uint4*>(rslot + o1), p1);
+                }
+                tmem_st_wait();
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar(B_XNFULL));
+            }
+            if (dead) break;
+            // ---------------- layers ----------------
+            for (int l = 0; l < L; ++l, ++n_lay) {
+                const float* bl = P.b1 + (size_t)l * 2 * C;
+                for (int j = 0; j < n_ch; ++j) {
+                    // gate epilogue of chunk j: channels 32 j + 16 hf + [0, 16)
+                    dead |= !mbar_wait(bar(B_D1FULL + j), n_lay & 1u, abort_flag);
+                    tc_fence_after();
+                    float f[16], g[16];
+                    tmem_ld16(tm_lane + TM_D1 + 64 * j + 16 * hf, f);
+                    tmem_ld16(tm_lane + TM_D1 + 64 * j + 32 + 16 * hf, g);
+                    tmem_ld_wait();
+                    const int ch0 = 32 * j + 16 * hf;
+                    float y[16];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
+                        y[4 * k4] = gate_fast(f[4 * k4] + bf.x, g[4 * k4] + bg.x);             // wavenet_v2.py:151
+                        y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf.y, g[4 * k4 + 1] + bg.y);
+                        y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf.z, g[4 * k4 + 2] + bg.z);
+                        y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf.w, g[4 * k4 + 3] + bg.w);
+                    }
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, C)) = pack8(y);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, C)) = pack8(y + 8);
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar(B_YFULL + j));
+                }
+                dead |= !mbar_wait(bar(B_D2FULL), n_lay & 1u, abort_flag);
+                tc_fence_after();
+                if (dead) break;
+                if (l < L - 1) {
+                    // h_{l+1}(t) = h_l + conv_res(y) (+ biases so far) -> next layer's A tile and its ring slot
+                    const float* cb = P.cbr + (size_t)(l + 1) * C;
+                    unsigned char* rslot = ring_g + P.ring_off[l + 1] + (size_t)(t % (P.dil[l + 1] + 1)) * tile_bytes;
+                    for (int i = 0; i < half_c / 16; ++i) {
+                        const int c0 = hf * half_c + 16 * i;
+                        float v[16];
+                        tmem_ld16(tm_lane + TM_H + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(cb + c0) + k4);
+                            v[4 * k4] += bb.x; v[4 * k4 + 1] += bb.y; v[4 * k4 + 2] += bb.z; v[4 * k4 + 3] += bb.w;
+                        }
+                        const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+                        const unsigned o0 = tile_off(m, c0 / 8, C), o1 = tile_off(m, c0 / 8 + 1, C);
+                        *reinterpret_cast<uint4*>(smem + SM_XN + o0) = p0;
+                        *reinterpret_cast<uint4*>(smem + SM_XN + o1) = p1;
+                        __stcg(reinterpret_cast<uint4*>(rslot + o0), p0);
+                        __stcg(reinterpret_cast<uint4*>(rslot + o1), p1);
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar(B_XNFULL));
+                }
+                if (dead) break;
+            }
+            if (dead) break;
+            // ---------------- head + sampler ----------------
+            if (t >= P.t_head) {
+                for (int i = 0; i < half_s / 16; ++i) {          // skip sum -> bf16 A tile (in the y buffer)
+                    const int c0 = hf * half_s + 16 * i;
+                    float v[16];
+                    tmem_ld16(tm_lane + TM_SK + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] += __ldg(P.cbs + c0 + k);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8, S)) = pack8(v);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8 + 1, S)) = pack8(v + 8);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar(B_HAFULL));
+                dead |= !mbar_wait(bar(B_H1DFULL), n_head & 1u, abort_flag);
+                tc_fence_after();
+                for (int i = 0; i < half_h / 16; ++i) {          // hidden = mish(. + b1) -> bf16 A tile (mlp.py:44-53)
+                    const int c0 = hf * half_h + 16 * i;
+                    float v[16];
+                    tmem_ld16(tm_lane + TM_D1 + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = mish_fast(v[k] + __ldg(P.hb1 + c0 + k));
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, Hh)) = pack8(v);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, Hh)) = pack8(v + 8);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar(B_H2AFULL));
+                dead |= !mbar_wait(bar(B_H2DFULL), n_head & 1u, abort_flag);
+                tc_fence_after();
+                if (dead) break;
+                // logits: two passes of 64 rows through the staging area, one warp decides one row at a time
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((q4 >> 1) == pass) {
+                        float* zr = zs + (size_t)(m - 64 * pass) * ZROW;
+                        for (int i = 0; i < half_q / 16; ++i) {
+                            const int c0 = hf * half_q + 16 * i;
+                            float v[16];
+                            tmem_ld16(tm_lane + TM_LOGIT + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.hb2 + c0) + k4);
+                                *reinterpret_cast<float4*>(zr + c0 + 4 * k4) =
+                                    make_float4(v[4 * k4] + bb.x, v[4 * k4 + 1] + bb.y, v[4 * k4 + 2] + bb.z, v[4 * k4 + 3] + bb.w);
+                            }
+                        }
+                        if (hf == 0) {
+                            float v[16];
+                            tmem_ld16(tm_lane + TM_TEMP, v);
+                            tmem_ld_wait();
+                            zr[Q] = v[0] + __ldg(P.hb2 + Q);
+                        }
+                    }
+                    if (pass == 1) { tc_fence_before(); mbar_arrive(bar(B_HEADDONE)); }   // every TMEM read of the step is done
+                    epi_sync();
+                    for (int r = 0; r < 8; ++r) {
+                        const int mr = 64 * pass + 8 * warp + r, br = grp * MROWS + mr;
+                        if (br < P.B) {
+                            const long long hstep = t - P.t_head, n_head_steps = P.t_end - P.t_head;
+                            float* lout = P.logits_out ? P.logits_out + ((size_t)br * n_head_steps + hstep) * Q : nullptr;
+                            const bool sample = P.temperature != nullptr;
+                            float Tt = 1.0f, u = 0.0f;
+                            if (sample) {
+                                Tt = P.temperature[P.n_temperature == 1 ? 0 : br];
+                                u = P.noise[(size_t)br * P.noise_stride + (t + 1 - P.noise_t0)];
+                            }
+                            const int choice = mmk::decide_warp(zs + (size_t)(8 * warp + r) * ZROW, Q, P.min_temp, lout, sample, Tt, u);
+                            if (lane == 0) {
+                                s_idx[mr] = choice;
+                                if (P.decisions) P.decisions[(size_t)br * n_head_steps + hstep] = choice;
+                                if (!P.teacher_forced) __stcg(P.seq + (size_t)br * P.seq_stride + t + 1, (long long)choice);
+                            }
+                        }
+                    }
+                    epi_sync();
+                }
+                ++n_head;
+                if (dead) break;
+            }
+            if (grp == 0 && tid == 0 && P.step_ts) P.step_ts[t - P.t_begin] = globaltimer();
+        }
+    }
+    __syncthreads();
+    if (warp == W_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Self-test kernel: D[128 x N] = A[128 x K] . B[N x K]^T through the same descriptors / TMEM path (N, K <= 128 ... 256).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tc_gemm_check_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                               float* __restrict__ D, int N, int K) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned sb = smem_u32(smem);
+    unsigned char* sA = smem;                       // 128 x K bf16
+    unsigned char* sB = smem + MROWS * K * 2;       // N x K bf16
+    unsigned* s_misc = reinterpret_cast<unsigned*>(sB + (size_t)N * K * 2);
+    const unsigned bar0 = smem_u32(s_misc), s_tm = smem_u32(s_misc + 4);
+    for (int i = tid; i < MROWS * K / 8; i += 128) {
+        const int m = i / (K / 8), kc = i % (K / 8);
+        float v[8];
+        for (int e = 0; e < 8; ++e) v[e] = A[(size_t)m * K + kc * 8 + e];
+        *reinterpret_cast<uint4*>(sA + tile_off(m, kc, K)) = pack8(v);
+    }
+    for (int i = tid; i < N * K / 8; i += 128) {
+        const int n = i / (K / 8), kc = i % (K / 8);
+        float v[8];
+        for (int e = 0; e < 8; ++e) v[e] = Bm[(size_t)n * K + kc * 8 + e];
+        *reinterpret_cast<uint4*>(sB + tile_off(n, kc, K)) = pack8(v);
+    }
+    if (tid == 0) { mbar_init(bar0, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(s_tm, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<volatile unsigned*>(s_misc + 4);
+    if (tid == 0) {
+        for (int kk = 0; kk < K / 16; ++kk)
+            umma_bf16(tmem, umma_desc(sb + kk * 256, K * 16), umma_desc(sb + MROWS * K * 2 + kk * 256, K * 16),
+                      umma_idesc(N), kk > 0);
+        umma_commit(bar0);
+    }
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar0, 0u)) { if (++spins > 100000000u) break; }
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((unsigned)(32 * warp) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int k = 0; k < 16; ++k) D[(size_t)(32 * warp + lane) * N + c0 + k] = v[k];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace mmk_tc
+
+using namespace mmk_tc;
+
+struct wn4_handle {
+    Params p{};
+    std::vector<void*> allocs;
+    int device = 0, max_groups = 0, smem_bytes = 0;
+};
+
+int wn4_destroy(wn4_handle* h) {
+    if (!h) return 0;
+    for (void* a : h->allocs) cudaFree(a);
+    delete h;
+    return 0;
+}
+
+static unsigned short f2bf(float f) {   // round to nearest even
+    unsigned u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+
+// Packs rows [r0, r0 + n) x K of a row-major fp32 matrix (row stride ld, element stride es) as a canonical bf16 tile.
+static void pack_tile(std::vector<unsigned char>& out, size_t at, int n_rows, int K, const float* src, size_t ld, size_t es,
+                      int valid_rows) {
+    for (int r = 0; r < n_rows; ++r)
+        for (int k = 0; k < K; ++k) {
+            const float v = r < valid_rows ? src[(size_t)r * ld + (size_t)k * es] : 0.0f;
+            const unsigned short bfv = f2bf(v);
+            memcpy(out.data() + at + tile_off(r, k / 8, K) + (k % 8) * 2, &bfv, 2);
+        }
+}
+
+int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* unsupported) {
+    *unsupported = 1;
+    const int L = d->n_layers, C = d->dilated_dim, S = d->skips_dim, Hh = d->head_hidden, Q = d->q_levels;
+    const char* why = nullptr;
+    if (L < 1 || L > MAXL) why = "n_layers out of range";
+    else if (C % 32 != 0 || C < 32 || C > 128) why = "dilated_dim must be 32, 64, 96 or 128";
+    else if (S % 32 != 0 || S < 32 || S > 128) why = "skips_dim must be 32, 64, 96 or 128";
+    else if (Hh % 32 != 0 || Hh < 32 || Hh > 128) why = "head hidden_dim must be 32, 64, 96 or 128";
+    else if (Q % 64 != 0 || Q < 64 || Q > 256) why = "q_levels must be 64, 128, 192 or 256";
+    if (!why)
+        for (int l = 0; l < L; ++l) {
+            if ((d->conv_res_w[l] != nullptr) != (l < L - 1)) why = "every layer but the last needs a residual conv";
+            if (!d->conv_skip_w || !d->conv_skip_w[l]) why = "every layer needs a skip conv";
+            if (d->dilations[l] < 1) why = "dilation must be >= 1";
+        }
+    if (why) {
+        mmk::set_error(std::string("bf16 tensor-core WaveNet kernel: unsupported configuration: ") + why);
+        return 1;
+    }
+    *unsupported = 0;
+    auto* h = new wn4_handle();
+    Params& p = h->p;
+    MMK_CUDA(cudaGetDevice(&h->device));
+    int cc_major = 0;
+    MMK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, h->device));
+    if (cc_major != 10) { delete h; MMK_FAIL("the bf16 tensor-core WaveNet kernel needs an sm_100 device (tcgen05)"); }
+    p.L = L; p.C = C; p.S = S; p.Hh = Hh; p.Q = Q; p.n_ch = C / 32;
+    p.n_h1 = (Hh + 63) / 64; p.n_h2 = Q / 64 + 1;
+    p.min_temp = d->min_temperature;
+    h->max_groups = (max_batch + MROWS - 1) / MROWS;
+    const size_t tile_bytes = (size_t)MROWS * C * 2;
+    long long ring = 0;
+    for (int l = 0; l < L; ++l) {
+        p.dil[l] = d->dilations[l];
+        p.has_res[l] = d->conv_res_w[l] ? 1 : 0;
+        p.ring_off[l] = ring;
+        ring += (long long)(d->dilations[l] + 1) * (long long)tile_bytes;   // d + 1 slots: the write of step t never
+                                                                            // lands on the slot the tap producer reads
+    }
+    p.ring_group_bytes = ring;
+
+    // ---- stage list + packed bf16 weights
+    std::vector<StageRec> stages;
+    std::vector<unsigned char> wpack;
+    auto new_stage = [&](size_t bytes) {
+        const size_t at = wpack.size();
+        wpack.resize(at + bytes, 0);
+        stages.push_back(StageRec{(unsigned)(at / 16), (unsigned)bytes});
+        return at;
+    };
+    for (int l = 0; l < L; ++l) {
+        const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample
+        for (int tap = 0; tap < 2; ++tap)      // stage order: older-tap chunks, then newer-tap chunks
+            for (int j = 0; j < p.n_ch; ++j) {
+                const size_t at = new_stage((size_t)64 * C * 2);
+                // rows 0..31: filter channels 32 j + r ; rows 32..63: gate channels 32 j + r
+                pack_tile(wpack, at, 32, C, wd + ((size_t)(32 * j) * C) * 2 + tap, (size_t)C * 2, 2, 32);
+                // the gate half starts at row 32 of the same tile: pack rows directly with a row offset
+                for (int r = 0; r < 32; ++r)
+                    for (int k = 0; k < C; ++k) {
+                        const unsigned short bfv = f2bf(wd[((size_t)(C + 32 * j + r) * C + k) * 2 + tap]);
+                        memcpy(wpack.data() + at + tile_off(32 + r, k / 8, C) + (k % 8) * 2, &bfv, 2);
+                    }
+            }
+        for (int j = 0; j < p.n_ch; ++j) {     // K-chunk j of [res rows | skip rows] x 32
+            const size_t at = new_stage((size_t)(C + S) * 64);
+            if (d->conv_res_w[l]) pack_tile(wpack, at, C, 32, d->conv_res_w[l] + 32 * j, (size_t)C, 1, C);
+            pack_tile(wpack, at + (size_t)C * 64, S, 32, d->conv_skip_w[l] + 32 * j, (size_t)C, 1, S);
+        }
+    }
+    for (int c = 0; c < p.n_h1; ++c) {
+        const int rows = std::min(64, Hh - 64 * c);
+        const size_t at = new_stage((size_t)rows * S * 2);
+        pack_tile(wpack, at, rows, S, d->head_w1 + (size_t)64 * c * S, (size_t)S, 1, rows);
+    }
+    for (int c = 0; c < p.n_h2; ++c) {
+        const bool temp_chunk = c == p.n_h2 - 1;
+        const int rows = temp_chunk ? 16 : 64, row0 = temp_chunk ? Q : 64 * c;
+        const size_t at = new_stage((size_t)rows * Hh * 2);
+        pack_tile(wpack, at, rows, Hh, d->head_w2 + (size_t)row0 * Hh, (size_t)Hh, 1, temp_chunk ? 1 : rows);
+    }
+    for (const StageRec& s : stages)
+        if (s.bytes > (unsigned)SLOT_BYTES || s.bytes % 16 != 0) { delete h; MMK_FAIL("internal: weight stage exceeds the ring slot"); }
+
+    std::vector<float> b1((size_t)L * 2 * C), cbr((size_t)(L + 1) * C, 0.0f), cbs(S, 0.0f);
+    for (int l = 0; l < L; ++l) {
+        for (int i = 0; i < 2 * C; ++i) b1[(size_t)l * 2 * C + i] = d->conv_dil_b[l][i];
+        for (int i = 0; i < C; ++i)
+            cbr[(size_t)(l + 1) * C + i] = cbr[(size_t)l * C + i] + (d->conv_res_w[l] ? d->conv_res_b[l][i] : 0.0f);
+        for (int i = 0; i < S; ++i) cbs[i] += d->conv_skip_b[l][i];
+    }
+    bool ok = true;
+    auto dev_alloc = [&](size_t bytes, const void* src) -> void* {
+        void* ptr = nullptr;
+        if (cudaMalloc(&ptr, bytes) != cudaSuccess) { ok = false; return nullptr; }
+        h->allocs.push_back(ptr);
+        if (src) cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); else cudaMemset(ptr, 0, bytes);
+        return ptr;
+    };
+    p.wpack = (const unsigned char*)dev_alloc(wpack.size(), wpack.data());
+    p.stages = (const StageRec*)dev_alloc(stages.size() * sizeof(StageRec), stages.data());
+    p.E = (const float*)dev_alloc((size_t)Q * C * 4, d->embedding);
+    p.b1 = (const float*)dev_alloc(b1.size() * 4, b1.data());
+    p.cbr = (const float*)dev_alloc(cbr.size() * 4, cbr.data());
+    p.cbs = (const float*)dev_alloc(cbs.size() * 4, cbs.data());
+    p.hb1 = (const float*)dev_alloc((size_t)Hh * 4, d->head_b1);
+    p.hb2 = (const float*)dev_alloc((size_t)(Q + 1) * 4, d->head_b2);
+    p.rings = (unsigned char*)dev_alloc((size_t)h->max_groups * (size_t)ring, nullptr);
+    p.abort_flag = (unsigned*)dev_alloc(16, nullptr);
+    if (!ok) { wn4_destroy(h); MMK_FAIL("cudaMalloc failed while creating the bf16 WaveNet handle"); }
+    p.n_stages = (int)stages.size();
+    h->smem_bytes = SM_FIXED + (int)stages.size() * 8;
+    if (h->smem_bytes > 232448) { wn4_destroy(h); MMK_FAIL("too many layers for the bf16 kernel's shared-memory stage list"); }
+    MMK_CUDA(cudaFuncSetAttribute(wavenet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    MMK_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+int wn4_launch_info(wn4_handle* h, mmk_launch_info* out) {
+    out->cluster_size = 1; out->n_stages = 1; out->group_size = MROWS; out->threads = NT;
+    out->smem_bytes = h->smem_bytes; out->sm_used = h->max_groups;
+    return 0;
+}
+
+int wn4_sync_check(wn4_handle* h, void* stream) {
+    unsigned aborted = 0;
+    MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    MMK_CHECK(aborted == 0, "bf16 WaveNet kernel watchdog fired: a pipeline wait timed out (results invalid)");
+    return 0;
+}
+
+int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
+            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream) {
+    Params p = h->p;
+    p.seq = reinterpret_cast<long long*>(d_seq) - seq_t0;
+    p.seq_stride = seq_stride; p.t_begin = t_begin; p.t_head = t_head; p.t_end = t_end;
+    p.B = B; p.teacher_forced = teacher_forced ? 1 : 0;
+    p.temperature = d_temperature; p.n_temperature = n_temperature;
+    p.noise = d_noise; p.noise_stride = noise_stride; p.noise_t0 = noise_t0;
+    p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
+    const int groups = (B + MROWS - 1) / MROWS;
+    MMK_CHECK(groups <= h->max_groups, "batch exceeds the max_batch the handle was created for");
+    MMK_CUDA(cudaMemsetAsync(p.abort_flag, 0, sizeof(unsigned), (cudaStream_t)stream));
+    wavenet_tc_kernel<<<groups, NT, h->smem_bytes, (cudaStream_t)stream>>>(p);
+    MMK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Diagnostic: D (128 x N) = A (128 x K) . B (N x K)^T with bf16 operands through the UMMA path used above.
+extern "C" int mmk_tc_gemm_check(const float* d_A, const float* d_B, float* d_D, int N, int K, void* stream) {
+    MMK_CHECK(d_A && d_B && d_D, "mmk_tc_gemm_check: null pointer");
+    MMK_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "need N, K multiples of 16 in [16, 256]");
+    const size_t smem = (size_t)MROWS * K * 2 + (size_t)N * K * 2 + 64;
+    MMK_CUDA(cudaFuncSetAttribute(tc_gemm_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_check_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_D, N, K);
+    MMK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -108,6 +108,31 @@ class WaveNet(NativeARM):
         self.has_residuals = config.residuals_dim is not None
         self._sd = self._init_state_dict()
         self._gen = None  # state of the step-wise protocol
+        self._compute_dtype = torch.float32
+
+    # ---- arithmetic ------------------------------------------------------------------------------
+    @property
+    def compute_dtype(self):
+        """torch.float32 (default): fp32 FFMA kernels, sequences bit-exact with the oracle.
+        torch.bfloat16: the tensor-core kernel (tcgen05.mma, TMEM accumulators; csrc/wavenet_tc.cu) — bf16 operands,
+        fp32 accumulation, logits within 5e-2 relative; one CTA per 128 prompts, meant for large batches."""
+        return self._compute_dtype
+
+    @compute_dtype.setter
+    def compute_dtype(self, dtype):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("compute_dtype must be torch.float32 or torch.bfloat16")
+        if dtype != self._compute_dtype:
+            self._release()
+            self._compute_dtype = dtype
+
+    def bfloat16(self):
+        self.compute_dtype = torch.bfloat16
+        return self
+
+    def float(self):
+        self.compute_dtype = torch.float32
+        return self
 
     # ---- geometry -------------------------------------------------------------------------------
     @property
@@ -204,7 +229,8 @@ class WaveNet(NativeARM):
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
         d.head_w2, d.head_b2 = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
         h = ctypes.c_void_p()
-        _capi.check(_capi.lib().mmk_wavenet_create(ctypes.byref(d), int(max_batch), ctypes.byref(h)))
+        mode = 1 if self._compute_dtype == torch.bfloat16 else 0      # MMK_COMPUTE_BF16_TC / MMK_COMPUTE_FP32
+        _capi.check(_capi.lib().mmk_wavenet_create_ex(ctypes.byref(d), int(max_batch), mode, ctypes.byref(h)))
         return h
 
     def _destroy_handle(self, h):

@@ -84,7 +84,7 @@ def test_generate_sharded_equals_single_process(world, B):
     procs = [ctx.Process(target=_worker, args=(r, world, port, B, P, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(world))
+    got = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

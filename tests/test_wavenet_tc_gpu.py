@@ -1,0 +1,111 @@
+"""GPU parity tests of the bf16 tensor-core WaveNet kernel (csrc/wavenet_tc.cu: tcgen05.mma + TMEM), through the C ABI.
+
+Bar (BASELINE.json north_star): teacher-forced logits within 5e-2 relative in bf16.  Sequences follow the bf16 logits, so
+they are checked for internal consistency (decisions == the oracle's sampler applied to the kernel's own logits; a
+generated sequence replays exactly when teacher-forced) rather than against the fp32 golden sequences."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from mimikit_b200 import _capi
+from oracle import restate
+from test_wavenet_gpu import _rel_err, make_net
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 5e-2
+
+
+@pytest.mark.parametrize("N,K", [(64, 128), (128, 128), (256, 64), (16, 128), (128, 32), (256, 128), (48, 96)])
+def test_umma_descriptor_path_is_a_gemm(N, K):
+    """D = A . B^T through the kernel's shared-memory descriptors, tcgen05.mma and TMEM loads."""
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    _capi.check(_capi.lib().mmk_tc_gemm_check(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, _capi.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.bfloat16().float() @ B.bfloat16().float().T
+    assert torch.isfinite(D).all()
+    assert float((D - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def _bf16_net(blocks, dims, skips, mlp, seed=0):
+    net = make_net(blocks, dims, dims, skips, mlp, seed=seed)
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    return net.bfloat16(), orc
+
+
+@pytest.mark.parametrize("blocks,dims,skips,mlp,B,n", [((3, 3), 64, 64, 64, 5, 40), ((4, 4), 128, 128, 128, 130, 24),
+                                                       ((2, 5), 32, 96, 32, 129, 33), ((8, 8, 7, 7), 128, 128, 128, 64, 24)])
+def test_teacher_forced_logits_within_bf16_tolerance(blocks, dims, skips, mlp, B, n):
+    net, orc = _bf16_net(blocks, dims, skips, mlp)
+    g = torch.Generator().manual_seed(7)
+    P = net.rf + 5
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    for temp in (None, 0.9):
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())          # fp32 oracle, its own feedback
+        logits, dec = net.teacher_forced(torch.from_numpy(ref_seq), P, temp, noise)           # same inputs, bf16 arithmetic
+        logits, dec = logits.cpu().numpy(), dec.cpu().numpy()
+        assert np.isfinite(logits).all()
+        assert _rel_err(logits, ref_logits) <= BF16_TOL, _rel_err(logits, ref_logits)
+        # the sampler contract holds on the kernel's own logits, bit for bit
+        if temp is None:
+            want = restate.argmax_first(logits)
+        else:
+            T = restate.normalize_temperature(temp, B)
+            want = np.stack([restate.sample_inverse_cdf(logits[:, i], T, noise.numpy()[:, i]) for i in range(n)], 1)
+        assert np.array_equal(dec, want)
+        assert (dec == ref_seq[:, P:]).mean() > 0.5      # and mostly agrees with the fp32 decisions
+
+
+def test_generation_replays_and_is_deterministic():
+    net, orc = _bf16_net((3, 3), 64, 64, 64)
+    g = torch.Generator().manual_seed(11)
+    B, n, P = 131, 50, net.rf + 9
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    tvec = torch.linspace(0.85, 0.999, B)
+    seq, logits = net.generate(prompts, n, temperature=tvec, noise=noise, return_logits=True)
+    seq2 = net.generate(prompts, n, temperature=tvec, noise=noise)
+    assert torch.equal(seq, seq2)
+    assert torch.equal(seq[:, :P].cpu(), prompts)
+    lg, dec = net.teacher_forced(seq, P, tvec, noise)
+    assert torch.equal(dec, seq[:, P:])
+    assert torch.equal(lg, logits)
+    # the fp32 oracle teacher-forced on this sequence stays within the bf16 tolerance
+    _, ref_logits = orc.generate(prompts.numpy(), n, None, None, forced=seq.cpu().numpy())
+    assert _rel_err(logits.cpu().numpy(), ref_logits) <= BF16_TOL
+    # permuting the prompts permutes the outputs (rows are independent inside the 128-row MMA tile)
+    perm = torch.randperm(B, generator=g)
+    seqp = net.generate(prompts[perm], n, temperature=tvec[perm], noise=noise[perm])
+    assert torch.equal(seqp.cpu(), seq.cpu()[perm])
+
+
+def test_stepwise_protocol_matches_whole_sequence_launch():
+    from mimikit_b200 import GenerateLoopV2
+    net, _ = _bf16_net((3, 3), 64, 64, 64)
+    g = torch.Generator().manual_seed(3)
+    B, n, P = 4, 12, net.rf + 3
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    want = net.generate(prompts, n)
+    seq = torch.cat([prompts, torch.zeros(B, n, dtype=torch.int64)], 1).cuda()
+    net.before_generate((prompts,), 0)
+    for t in range(P, P + n):
+        out, = net.generate_step((seq[:, t - net.rf:t],), t=t)
+        seq[:, t:t + 1] = out
+    net.after_generate((seq,), 0)
+    assert torch.equal(seq, want)
+
+
+def test_unsupported_configurations_fail_loudly():
+    net = make_net((3,), 128).bfloat16()           # no residual / skip convs: fp32 kernels only
+    with pytest.raises(RuntimeError, match="unsupported configuration"):
+        net.generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4)
+    net = make_net((3, 3), 48, 48, 48, 48).bfloat16()   # channel counts that are not multiples of 32
+    with pytest.raises(RuntimeError, match="unsupported configuration"):
+        net.generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4)
+    assert net.float().generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4).shape == (2, net.rf + 5)
