@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--seconds", type=float, default=10.0, help="generated audio per prompt")
     ap.add_argument("--prompt-seconds", type=float, default=1.0)
     ap.add_argument("--temperature", type=float, default=None, help="default: argmax (what GenerateLoopV2 does)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="wavenet only: f32 = FFMA kernels (bit-exact sequences, the default); bf16 = tcgen05 tensor-core "
+                         "kernel (logits within 5e-2), one CTA per 128 prompts: use with --batch >= 128")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -227,6 +230,10 @@ def run_b200(args):
     B = args.batch or (64 if wl == "wavenet" else max(1, 128 // world))
     P, n = int(SR * args.prompt_seconds), int(SR * args.seconds)
     net = make_network(wl, dev)
+    if args.dtype == "bf16":
+        if wl != "wavenet":
+            raise SystemExit("--dtype bf16 is implemented for the wavenet workload only")
+        net.bfloat16()
     prompts_host = synthetic_prompts(B, P, rank).pin_memory()
     prompts_dev = prompts_host.to(dev)
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
@@ -319,7 +326,7 @@ def run_b200(args):
             "metric": "generated audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (wl == "samplernn" and args.batch is None) else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(wl, B, P, n, world),
             "p50_step_latency_us": p50_us,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": B * P * 8,
@@ -330,8 +337,9 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
                          "fp32_fma": {"peak": fp32_peak, "frac": ach / fp32_peak,
-                                      "note": "the path computes in fp32 FFMA for bit-exact parity; per-step time is "
-                                              "bounded by the 31-stage dependency chain, see DESIGN.md"}},
+                                      "note": "the f32 path computes in fp32 FFMA for bit-exact parity (this is its "
+                                              "ceiling); the bf16 path runs on tcgen05 (the tensor peak is its ceiling); "
+                                              "per-step time is bounded by the 31-stage dependency chain, see DESIGN.md"}},
         }
         if not args.no_cpu_baseline:
             n_gen = cpu_sample_steps(wl)

@@ -30,6 +30,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -85,7 +87,10 @@ struct Params {
     const float* temperature; const float* noise;
     long long noise_stride, noise_t0;
     float* logits_out; long long* decisions; unsigned long long* step_ts;
+    int exp;                               // MMK_TC_EXP: timing experiments (bit 0: no weight copies, bit 1: no tap copies; results invalid)
+    long long* trace; long long trace_t;   // MMK_TC_TRACE_T: clock64 stamps of group 0 at that step, [role][layer][16]
 };
+constexpr int TRACE_EV = 16;
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -134,6 +139,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy st.shared -> async-proxy reads (tcgen05.mma operands): the cheap CTA-local form
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy st.global (ring slots) -> async-proxy bulk copies, once per step (the copies happen >= 1 step later)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     const unsigned slot = cnt % NSLOT, use = cnt / NSLOT;
                     if (!mbar_wait(bar(B_WEMPTY + slot), (use & 1u) ^ 1u, abort_flag)) { dead = true; break; }
                     const uint2 r = reinterpret_cast<const uint2*>(smem + SM_STAGES)[i];
+                    if ((P.exp & 1) && cnt >= NSLOT) { mbar_arrive(bar(B_WFULL + slot)); continue; }
                     mbar_expect_tx(bar(B_WFULL + slot), r.y);
                     bulk_g2s(sb + SM_W + slot * SLOT_BYTES, P.wpack + (size_t)r.x * 16, r.y, bar(B_WFULL + slot));
                 }
@@ -286,108 +296,150 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 for (int l = 0; l < L; ++l, ++n) {
                     if (!mbar_wait(bar(B_XOFREE), (n & 1u) ^ 1u, abort_flag)) { dead = true; break; }
                     const unsigned slot = (unsigned)((t + 1) % (P.dil[l] + 1));   // d + 1 slots: holds h_l(t - d)
+                    if ((P.exp & 2) && n >= 1) { mbar_arrive(bar(B_XOFULL)); continue; }
                     mbar_expect_tx(bar(B_XOFULL), tile_bytes);
                     bulk_g2s(sb + SM_XO, ring_g + P.ring_off[l] + (size_t)slot * tile_bytes, tile_bytes, bar(B_XOFULL));
                 }
             }
         }
     } else if (warp == W_MMA) {
-        // ===================== MMA issuer: one thread =====================
-        if (lane == 0) {
-            unsigned wcnt = 0, n_lay = 0, n_xn = 0, n_head = 0;
-            bool dead = false;
-            const unsigned id64 = umma_idesc(64), idC = umma_idesc(C), idS = umma_idesc(S);
-            auto wslot_wait = [&](unsigned& slot) {
-                slot = wcnt % NSLOT;
-                if (!mbar_wait(bar(B_WFULL + slot), (wcnt / NSLOT) & 1u, abort_flag)) dead = true;
+        // ===================== MMA issuer =====================
+        // The whole warp runs the control flow, so that every descriptor is a warp-uniform value (uniform registers,
+        // no per-instruction R2UR waterfall); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        auto wait_u = [&](unsigned b, unsigned parity) -> bool {    // warp-uniform result
+            return __all_sync(0xffffffffu, mbar_wait(b, parity, abort_flag) ? 1 : 0) != 0;
+        };
+        auto elect = [&]() -> bool {
+            unsigned pred;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+            return pred != 0;
+        };
+        unsigned wcnt = 0, n_lay = 0, n_xn = 0, n_head = 0;
+        bool dead = false;
+        long long* tr = nullptr;
+        int tn = 0;
+        auto stamp = [&]() { if (tr && lane == 0 && tn < TRACE_EV) tr[tn] = clock64(); ++tn; };
+        const unsigned id64 = umma_idesc(64), idC = umma_idesc(C), idS = umma_idesc(S);
+        // descriptors of the A tiles; a K-step of 16 elements advances the start-address field by 256 B >> 4 = 16
+        const unsigned long long dXO = umma_desc(sb + SM_XO, C * 16), dXN = umma_desc(sb + SM_XN, C * 16),
+                                 dY = umma_desc(sb + SM_Y, C * 16);
+        const unsigned long long dW0 = umma_desc(sb + SM_W, C * 16), dW0k = umma_desc(sb + SM_W, 512);
+        constexpr unsigned SLOT16 = SLOT_BYTES >> 4;
+        auto wslot_wait = [&](unsigned& slot) -> bool {
+            slot = wcnt % NSLOT;
+            const bool ok = wait_u(bar(B_WFULL + slot), (wcnt / NSLOT) & 1u);
+            tc_fence_after();
+            return ok;
+        };
+        for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
+            for (int l = 0; l < L && !dead; ++l, ++n_lay) {
+                tr = (P.trace && grp == 0 && t == P.trace_t) ? P.trace + (size_t)l * TRACE_EV : nullptr;
+                tn = 0;
+                stamp();                                                    // 0: layer start
+                // ---- older tap: D1 = XO . W1o^T
+                if (!wait_u(bar(B_XOFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
-            };
-            for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
-                for (int l = 0; l < L && !dead; ++l, ++n_lay) {
-                    // ---- older tap: D1 = XO . W1o^T
-                    if (!mbar_wait(bar(B_XOFULL), n_lay & 1u, abort_flag)) { dead = true; break; }
-                    tc_fence_after();
-                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
-                        unsigned slot; wslot_wait(slot);
-                        if (dead) break;
-                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                stamp();                                                    // 1: older tap tile landed
+                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                    unsigned slot;
+                    if (!wslot_wait(slot)) { dead = true; break; }
+                    stamp();                                                // 2..5: weights of older-tap chunk j landed
+                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
+                    if (elect()) {
                         for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem + TM_D1 + 64 * j, umma_desc(sb + SM_XO + kk * 256, C * 16),
-                                      umma_desc(wb + kk * 256, C * 16), id64, kk > 0);
+                            umma_bf16(tmem_u + TM_D1 + 64 * j, dXO + 16u * kk, dW + 16u * kk, id64, kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
+                        if (j == n_ch - 1) umma_commit(bar(B_XOFREE));
                     }
-                    if (dead) break;
-                    umma_commit(bar(B_XOFREE));
-                    // ---- newer tap: D1 += XN . W1n^T, chunk by chunk
-                    if (!mbar_wait(bar(B_XNFULL), n_xn & 1u, abort_flag)) { dead = true; break; }
-                    ++n_xn;
-                    tc_fence_after();
-                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
-                        unsigned slot; wslot_wait(slot);
-                        if (dead) break;
-                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                    __syncwarp();
+                }
+                if (dead) break;
+                stamp();                                                    // 2: older-tap MMAs issued
+                // ---- newer tap: D1 += XN . W1n^T, chunk by chunk
+                if (!wait_u(bar(B_XNFULL), n_xn & 1u)) { dead = true; break; }
+                ++n_xn;
+                tc_fence_after();
+                stamp();                                                    // 3: layer input tile ready
+                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                    unsigned slot;
+                    if (!wslot_wait(slot)) { dead = true; break; }
+                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
+                    if (elect()) {
                         for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem + TM_D1 + 64 * j, umma_desc(sb + SM_XN + kk * 256, C * 16),
-                                      umma_desc(wb + kk * 256, C * 16), id64, 1u);
+                            umma_bf16(tmem_u + TM_D1 + 64 * j, dXN + 16u * kk, dW + 16u * kk, id64, 1u);
                         umma_commit(bar(B_WEMPTY + slot));
                         umma_commit(bar(B_D1FULL + j));
                     }
-                    if (dead) break;
-                    // ---- residual and skip 1x1 convs on y, K-chunk by K-chunk as the gate epilogue delivers them
-                    const bool has_res = P.has_res[l] != 0;
-                    for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
-                        if (!mbar_wait(bar(B_YFULL + j), n_lay & 1u, abort_flag)) { dead = true; break; }
-                        unsigned slot; wslot_wait(slot);
-                        if (dead) break;
-                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const unsigned long long a = umma_desc(sb + SM_Y + (2 * j + kk) * 256, C * 16);
-                            if (has_res) umma_bf16(tmem + TM_H, a, umma_desc(wb + kk * 256, 512), idC, 1u);
-                            umma_bf16(tmem + TM_SK, a, umma_desc(wb + C * 64 + kk * 256, 512), idS,
-                                      (l > 0 || j > 0 || kk > 0) ? 1u : 0u);
-                        }
-                        umma_commit(bar(B_WEMPTY + slot));
-                    }
-                    if (dead) break;
-                    umma_commit(bar(B_D2FULL));
+                    __syncwarp();
                 }
                 if (dead) break;
-                if (t >= P.t_head) {
-                    // ---- head: hidden = A(skip sum) . W1^T ; logits = A2(mish hidden) . W2^T
-                    if (!mbar_wait(bar(B_HAFULL), n_head & 1u, abort_flag)) break;
-                    tc_fence_after();
-                    for (int c = 0; c < P.n_h1 && !dead; ++c, ++wcnt) {
-                        unsigned slot; wslot_wait(slot);
-                        if (dead) break;
-                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
-                        const int rows = min(64, Hh - 64 * c);
+                stamp();                                                    // 4: newer-tap MMAs issued
+                // ---- residual and skip 1x1 convs on y, K-chunk by K-chunk as the gate epilogue delivers them
+                const bool has_res = P.has_res[l] != 0;
+                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                    if (!wait_u(bar(B_YFULL + j), n_lay & 1u)) { dead = true; break; }
+                    if (j == n_ch - 1) stamp();                              // last y chunk ready
+                    unsigned slot;
+                    if (!wslot_wait(slot)) { dead = true; break; }
+                    const unsigned long long dWr = dW0k + (unsigned long long)(slot * SLOT16);
+                    const unsigned long long dWs = dWr + (unsigned long long)((C * 64) >> 4);
+                    if (elect()) {
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const unsigned long long a = dY + 16u * (2 * j + kk);
+                            if (has_res) umma_bf16(tmem_u + TM_H, a, dWr + 16u * kk, idC, 1u);
+                            umma_bf16(tmem_u + TM_SK, a, dWs + 16u * kk, idS, (l > 0 || j > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar(B_WEMPTY + slot));
+                        if (j == n_ch - 1) umma_commit(bar(B_D2FULL));
+                    }
+                    __syncwarp();
+                }
+                if (dead) break;
+                stamp();                                                    // 13: layer issued
+            }
+            if (dead) break;
+            if (t >= P.t_head) {
+                // ---- head: hidden = A(skip sum) . W1^T ; logits = A2(mish hidden) . W2^T
+                if (!wait_u(bar(B_HAFULL), n_head & 1u)) break;
+                tc_fence_after();
+                for (int c = 0; c < P.n_h1 && !dead; ++c, ++wcnt) {
+                    unsigned slot;
+                    if (!wslot_wait(slot)) { dead = true; break; }
+                    const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                    const int rows = min(64, Hh - 64 * c);
+                    if (elect()) {
                         for (int kk = 0; kk < S / 16; ++kk)
-                            umma_bf16(tmem + TM_D1 + 64 * c, umma_desc(sb + SM_Y + kk * 256, S * 16),
+                            umma_bf16(tmem_u + TM_D1 + 64 * c, umma_desc(sb + SM_Y + kk * 256, S * 16),
                                       umma_desc(wb + kk * 256, S * 16), umma_idesc(rows), kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
+                        if (c == P.n_h1 - 1) umma_commit(bar(B_H1DFULL));
                     }
-                    if (dead) break;
-                    umma_commit(bar(B_H1DFULL));
-                    if (!mbar_wait(bar(B_H2AFULL), n_head & 1u, abort_flag)) break;
-                    tc_fence_after();
-                    for (int c = 0; c < P.n_h2 && !dead; ++c, ++wcnt) {
-                        unsigned slot; wslot_wait(slot);
-                        if (dead) break;
-                        const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
-                        const bool temp_chunk = (c == P.n_h2 - 1);        // the learned-temperature row, padded to 16
-                        const int rows = temp_chunk ? 16 : min(64, Q - 64 * c);
-                        const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 64 * c;
+                    __syncwarp();
+                }
+                if (dead) break;
+                if (!wait_u(bar(B_H2AFULL), n_head & 1u)) break;
+                tc_fence_after();
+                for (int c = 0; c < P.n_h2 && !dead; ++c, ++wcnt) {
+                    unsigned slot;
+                    if (!wslot_wait(slot)) { dead = true; break; }
+                    const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                    const bool temp_chunk = (c == P.n_h2 - 1);        // the learned-temperature row, padded to 16
+                    const int rows = temp_chunk ? 16 : min(64, Q - 64 * c);
+                    const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 64 * c;
+                    if (elect()) {
                         for (int kk = 0; kk < Hh / 16; ++kk)
-                            umma_bf16(tmem + dcol, umma_desc(sb + SM_XN + kk * 256, Hh * 16),
+                            umma_bf16(tmem_u + dcol, umma_desc(sb + SM_XN + kk * 256, Hh * 16),
                                       umma_desc(wb + kk * 256, Hh * 16), umma_idesc(rows), kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
+                        if (temp_chunk) umma_commit(bar(B_H2DFULL));
                     }
-                    if (dead) break;
-                    umma_commit(bar(B_H2DFULL));
-                    // D1 / H / SK are rewritten by the next step: wait until the epilogue has drained the logits
-                    if (!mbar_wait(bar(B_HEADDONE), n_head & 1u, abort_flag)) break;
-                    ++n_head;
+                    __syncwarp();
                 }
+                if (dead) break;
+                // D1 / H / SK are rewritten by the next step: wait until the epilogue has drained the logits
+                if (!wait_u(bar(B_HEADDONE), n_head & 1u)) break;
+                ++n_head;
             }
         }
     } else if (warp < 8) {
@@ -399,6 +451,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         const unsigned tm_lane = tmem + ((unsigned)(32 * q4) << 16);
         unsigned n_lay = 0, n_head = 0, n_sync = 0;
         bool dead = false;
+        long long* tr = nullptr;
+        int tn = 0;
+        auto stamp = [&]() { if (tr && tn < TRACE_EV) tr[tn++] = clock64(); };
         auto epi_sync = [&]() {      // barrier of the 256 epilogue threads (an mbarrier: the wait has the watchdog)
             mbar_arrive(bar(B_EPISYNC));
             dead |= !mbar_wait(bar(B_EPISYNC), n_sync & 1u, abort_flag);
@@ -432,7 +487,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     __stcg(reinterpret_cast<uint4*>(rslot + o1), p1);
                 }
                 tmem_st_wait();
-                fence_proxy_async();
+                fence_proxy_async_smem();
+                fence_proxy_async_global();
                 tc_fence_before();
                 mbar_arrive(bar(B_XNFULL));
             }
@@ -440,58 +496,73 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             // ---------------- layers ----------------
             for (int l = 0; l < L; ++l, ++n_lay) {
                 const float* bl = P.b1 + (size_t)l * 2 * C;
+                tr = (P.trace && grp == 0 && tid == 0 && t == P.trace_t) ? P.trace + (size_t)(MAXL + l) * TRACE_EV : nullptr;
+                tn = 0;
+                stamp();                                                        // 0: layer start
                 for (int j = 0; j < n_ch; ++j) {
                     // gate epilogue of chunk j: channels 32 j + 16 hf + [0, 16)
+                    const int ch0 = 32 * j + 16 * hf;
+                    float4 bf[4], bg[4];                     // this chunk's biases, fetched before the wait
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
+                        bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
+                    }
                     dead |= !mbar_wait(bar(B_D1FULL + j), n_lay & 1u, abort_flag);
                     tc_fence_after();
+                    stamp();                                                    // 1,3,5,7: D1 chunk j complete
                     float f[16], g[16];
                     tmem_ld16(tm_lane + TM_D1 + 64 * j + 16 * hf, f);
                     tmem_ld16(tm_lane + TM_D1 + 64 * j + 32 + 16 * hf, g);
                     tmem_ld_wait();
-                    const int ch0 = 32 * j + 16 * hf;
                     float y[16];
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
-                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
-                        y[4 * k4] = gate_fast(f[4 * k4] + bf.x, g[4 * k4] + bg.x);             // wavenet_v2.py:151
-                        y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf.y, g[4 * k4 + 1] + bg.y);
-                        y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf.z, g[4 * k4 + 2] + bg.z);
-                        y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf.w, g[4 * k4 + 3] + bg.w);
+                        y[4 * k4] = gate_fast(f[4 * k4] + bf[k4].x, g[4 * k4] + bg[k4].x);     // wavenet_v2.py:151
+                        y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf[k4].y, g[4 * k4 + 1] + bg[k4].y);
+                        y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
+                        y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
                     }
                     *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, C)) = pack8(y);
                     *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, C)) = pack8(y + 8);
-                    fence_proxy_async();
+                    fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_YFULL + j));
+                    stamp();                                                    // 2,4,6,8: y chunk j written
                 }
                 dead |= !mbar_wait(bar(B_D2FULL), n_lay & 1u, abort_flag);
                 tc_fence_after();
+                stamp();                                                        // 9: res/skip MMAs complete
                 if (dead) break;
                 if (l < L - 1) {
-                    // h_{l+1}(t) = h_l + conv_res(y) (+ biases so far) -> next layer's A tile and its ring slot
-                    const float* cb = P.cbr + (size_t)(l + 1) * C;
+                    // h_{l+1}(t) = h_l + conv_res(y) -> next layer's A tile and its ring slot.  The residual-conv biases
+                    // are not in the stream: their effect on the next gates is folded into the gate biases (host).
                     unsigned char* rslot = ring_g + P.ring_off[l + 1] + (size_t)(t % (P.dil[l + 1] + 1)) * tile_bytes;
-                    for (int i = 0; i < half_c / 16; ++i) {
+                    for (int i = 0; i < half_c / 16; i += 2) {
                         const int c0 = hf * half_c + 16 * i;
-                        float v[16];
+                        const bool two = i + 1 < half_c / 16;
+                        float v[16], w[16];
                         tmem_ld16(tm_lane + TM_H + c0, v);
+                        if (two) tmem_ld16(tm_lane + TM_H + c0 + 16, w);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(cb + c0) + k4);
-                            v[4 * k4] += bb.x; v[4 * k4 + 1] += bb.y; v[4 * k4 + 2] += bb.z; v[4 * k4 + 3] += bb.w;
-                        }
+                        const unsigned o0 = tile_off(m, c0 / 8, C);      // consecutive 8-channel chunks are 128 B apart
                         const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-                        const unsigned o0 = tile_off(m, c0 / 8, C), o1 = tile_off(m, c0 / 8 + 1, C);
                         *reinterpret_cast<uint4*>(smem + SM_XN + o0) = p0;
-                        *reinterpret_cast<uint4*>(smem + SM_XN + o1) = p1;
+                        *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 128) = p1;
                         __stcg(reinterpret_cast<uint4*>(rslot + o0), p0);
-                        __stcg(reinterpret_cast<uint4*>(rslot + o1), p1);
+                        __stcg(reinterpret_cast<uint4*>(rslot + o0 + 128), p1);
+                        if (two) {
+                            const uint4 p2 = pack8(w), p3 = pack8(w + 8);
+                            *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 256) = p2;
+                            *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 384) = p3;
+                            __stcg(reinterpret_cast<uint4*>(rslot + o0 + 256), p2);
+                            __stcg(reinterpret_cast<uint4*>(rslot + o0 + 384), p3);
+                        }
                     }
-                    fence_proxy_async();
+                    fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_XNFULL));
+                    stamp();                                                    // 10: next layer input written
                 }
                 if (dead) break;
             }
@@ -508,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8, S)) = pack8(v);
                     *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8 + 1, S)) = pack8(v + 8);
                 }
-                fence_proxy_async();
+                fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(bar(B_HAFULL));
                 dead |= !mbar_wait(bar(B_H1DFULL), n_head & 1u, abort_flag);
@@ -523,7 +594,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, Hh)) = pack8(v);
                     *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, Hh)) = pack8(v + 8);
                 }
-                fence_proxy_async();
+                fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(bar(B_H2AFULL));
                 dead |= !mbar_wait(bar(B_H2DFULL), n_head & 1u, abort_flag);
@@ -644,6 +715,7 @@ struct wn4_handle {
     Params p{};
     std::vector<void*> allocs;
     int device = 0, max_groups = 0, smem_bytes = 0;
+    long long* d_trace = nullptr; long long trace_t = 0;
 };
 
 int wn4_destroy(wn4_handle* h) {
@@ -758,7 +830,16 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
 
     std::vector<float> b1((size_t)L * 2 * C), cbr((size_t)(L + 1) * C, 0.0f), cbs(S, 0.0f);
     for (int l = 0; l < L; ++l) {
-        for (int i = 0; i < 2 * C; ++i) b1[(size_t)l * 2 * C + i] = d->conv_dil_b[l][i];
+        // The residual stream is kept WITHOUT the residual-conv biases (TMEM accumulates only the MMAs); layer l's input
+        // is therefore short of cbr_l = sum_{j<l} b_res_j, a constant: both taps of W1_l see it, so W1_l . cbr_l (fp64,
+        // fp32 weights) is added to the gate biases instead.
+        for (int i = 0; i < 2 * C; ++i) {
+            double acc = d->conv_dil_b[l][i];
+            for (int c = 0; c < C; ++c)
+                acc += ((double)d->conv_dil_w[l][((size_t)i * C + c) * 2] + (double)d->conv_dil_w[l][((size_t)i * C + c) * 2 + 1]) *
+                       (double)cbr[(size_t)l * C + c];
+            b1[(size_t)l * 2 * C + i] = (float)acc;
+        }
         for (int i = 0; i < C; ++i)
             cbr[(size_t)(l + 1) * C + i] = cbr[(size_t)l * C + i] + (d->conv_res_w[l] ? d->conv_res_b[l][i] : 0.0f);
         for (int i = 0; i < S; ++i) cbs[i] += d->conv_skip_b[l][i];
@@ -781,6 +862,10 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     p.hb2 = (const float*)dev_alloc((size_t)(Q + 1) * 4, d->head_b2);
     p.rings = (unsigned char*)dev_alloc((size_t)h->max_groups * (size_t)ring, nullptr);
     p.abort_flag = (unsigned*)dev_alloc(16, nullptr);
+    if (const char* e = getenv("MMK_TC_TRACE_T")) {   // debug timeline of one step (see wn4_sync_check)
+        h->trace_t = atoll(e);
+        h->d_trace = (long long*)dev_alloc((size_t)2 * MAXL * TRACE_EV * sizeof(long long), nullptr);
+    }
     if (!ok) { wn4_destroy(h); MMK_FAIL("cudaMalloc failed while creating the bf16 WaveNet handle"); }
     p.n_stages = (int)stages.size();
     h->smem_bytes = SM_FIXED + (int)stages.size() * 8;
@@ -802,6 +887,20 @@ int wn4_sync_check(wn4_handle* h, void* stream) {
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MMK_CHECK(aborted == 0, "bf16 WaveNet kernel watchdog fired: a pipeline wait timed out (results invalid)");
+    if (h->d_trace) {   // debug: dump the stamps of step MMK_TC_TRACE_T (role 0 = MMA issuer, 1 = epilogue thread 0)
+        std::vector<long long> tr((size_t)2 * MAXL * TRACE_EV);
+        MMK_CUDA(cudaMemcpy(tr.data(), h->d_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const char* path = getenv("MMK_TC_TRACE_FILE");
+        if (FILE* f = fopen(path ? path : "tc_trace.txt", "w")) {
+            for (int r = 0; r < 2; ++r)
+                for (int l = 0; l < h->p.L; ++l) {
+                    fprintf(f, "%d %d", r, l);
+                    for (int e = 0; e < TRACE_EV; ++e) fprintf(f, " %lld", tr[((size_t)r * MAXL + l) * TRACE_EV + e]);
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
+    }
     return 0;
 }
 
@@ -816,6 +915,8 @@ int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     p.temperature = d_temperature; p.n_temperature = n_temperature;
     p.noise = d_noise; p.noise_stride = noise_stride; p.noise_t0 = noise_t0;
     p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
+    p.trace = h->d_trace; p.trace_t = h->trace_t;
+    if (const char* e = getenv("MMK_TC_EXP")) p.exp = atoi(e);
     const int groups = (B + MROWS - 1) / MROWS;
     MMK_CHECK(groups <= h->max_groups, "batch exceeds the max_batch the handle was created for");
     MMK_CUDA(cudaMemsetAsync(p.abort_flag, 0, sizeof(unsigned), (cudaStream_t)stream));
