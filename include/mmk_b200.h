@@ -116,14 +116,16 @@ int mmk_wavenet_create(const mmk_wavenet_desc* desc, int max_batch, mmk_wavenet_
  *                        streamed by cp.async.bulk): the batch is the MMA M dimension, one CTA per 128 prompts, for the
  *                        large-batch regime (BASELINE.json configs[3]).  Logits within 5e-2 relative (the north star's
  *                        bf16 tolerance); sequences follow the bf16 logits.  Needs residual and skip convs, channel
- *                        counts that are multiples of 32 up to 128 and q_levels a multiple of 64 up to 256; any other
+ *                        counts of 64 or 128 and q_levels a multiple of 64 up to 256; any other
  *                        configuration is an error (no silent change of precision). */
 #define MMK_COMPUTE_FP32 0
 #define MMK_COMPUTE_BF16_TC 1
 int mmk_wavenet_create_ex(const mmk_wavenet_desc* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
 /* Diagnostic for the tensor-core path: d_D (128, N) fp32 = d_A (128, K) . d_B (N, K)^T with operands rounded to bf16,
- * through the same shared-memory descriptors, tcgen05.mma and TMEM loads as the bf16 kernel.  N, K multiples of 16 <= 256. */
-int mmk_tc_gemm_check(const float* d_A, const float* d_B, float* d_D, int N, int K, void* stream);
+ * through the same shared-memory descriptors (K-major SWIZZLE_128B), tcgen05.mma and TMEM loads as the bf16 kernel.
+ * N a multiple of 16 <= 256, K a multiple of 64 <= 256.  h_cycles: nullable HOST pointer; receives the clock cycles of 8
+ * back-to-back passes of the K / 16 instructions (the call then synchronises the stream). */
+int mmk_tc_gemm_check(const float* d_A, const float* d_B, float* d_D, int N, int K, long long* h_cycles, void* stream);
 int mmk_wavenet_destroy(mmk_wavenet_t h);
 int mmk_wavenet_rf(mmk_wavenet_t h);   /* WaveNet.rf, wavenet_v2.py:337-339 */
 

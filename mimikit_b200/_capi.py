@@ -65,7 +65,7 @@ PROTOTYPES = {
     "mmk_mel_filterbank": (c_int, [c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "mmk_wavenet_create": (c_int, [POINTER(WaveNetDesc), c_int, POINTER(c_void_p)]),
     "mmk_wavenet_create_ex": (c_int, [POINTER(WaveNetDesc), c_int, c_int, POINTER(c_void_p)]),
-    "mmk_tc_gemm_check": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmk_tc_gemm_check": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mmk_wavenet_destroy": (c_int, [c_void_p]),
     "mmk_wavenet_rf": (c_int, [c_void_p]),
     "mmk_wavenet_sync_check": (c_int, [c_void_p, c_void_p]),

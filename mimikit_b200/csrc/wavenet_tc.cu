@@ -10,17 +10,22 @@
 //       H [128 x C]  += y . Wres^T                      (the residual stream stays in TMEM across the 30 layers)
 //       SK[128 x S]  += y . Wskip^T                     (so does the running skip sum)
 //     TMEM columns: D1 [0,256) | H [256,384) | SK [384,512); the head reuses them (hidden -> D1, logits -> H|SK).
-//   * weights (bf16, pre-packed on the host in the UMMA canonical K-major no-swizzle layout) are streamed from L2 through
-//     a 7-slot x 16 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx by a producer warp; slots are
+//   * weights (bf16, pre-packed on the host in the UMMA canonical K-major SWIZZLE_128B layout) are streamed from L2 through
+//     a 3-slot x 32 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx by a producer warp; slots are
 //     released by tcgen05.commit.  Nothing is resident: 5.8 MB per step per group, all L2 hits.
-//   * the older conv tap h_l(t-d) comes from a per-layer ring in global memory (L2), written by the epilogue in the same
-//     canonical layout and fetched d steps later with one bulk copy by a second producer warp.
-//   * 8 epilogue warps (2 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (one MUFU
-//     tanh.approx.f16x2 per gate), bf16 pack straight into the next MMA's A tile, per 32-channel chunk so that the
-//     res/skip MMAs of a chunk start while the gate MMAs of the next chunk run.
+//   * MMAs are issued with N >= 128 (a 64-channel chunk of filter + gate rows; res and skip rows together): the tensor
+//     core fetches its A tile from shared memory once per instruction, so narrow N multiplies the operand traffic (measured:
+//     N = 64 instructions in the no-swizzle layout ran at 64 B/clk of operand fetch, 3x over the tensor floor).
+//   * the older conv tap h_l(t-d) comes from a per-layer ring in global memory (L2): a producer warp copies every layer
+//     input tile shared -> global with one cp.async.bulk (the epilogue threads never store to global) and fetches it d
+//     steps later with one bulk copy into the tap tile.
+//   * 8 epilogue warps (2 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (tanh.approx.f16x2),
+//     bf16 pack straight into the next MMA's A tile, per 64-channel chunk so that the res/skip MMAs of a chunk start
+//     while the gate MMAs of the next chunk run.  The residual-conv biases never enter the stream (folded into the gate
+//     biases on the host); the skip sum is zeroed by the epilogue at the start of a step and only ever accumulated.
 //   * head: skip sum -> bf16 -> MMA (W1) -> Mish -> MMA (W2, + learned-temperature row) -> logits staged in shared
 //     memory -> the same decide_warp sampler as the fp32 kernels (argmax or inverse-CDF on external noise).
-// Work per step per group: 30 x (16 + 8) MMAs of 128 x 256 x 16: ~3 070 tensor cycles per layer (the floor of this
+// Work per step per group: 30 x (16 + 8) K-steps of 128 x 256 x 16: ~3 070 tensor cycles per layer (the floor of this
 // design); algorithmic FLOPs 2 x 2 982 016 per sample per prompt.
 #include "common.cuh"
 #include "sampler.cuh"
@@ -41,10 +46,10 @@ constexpr int NT = 384;            // 8 epilogue warps, MMA warp, weight produce
 constexpr int NEPI = 256;
 constexpr int W_MMA = 8, W_WP = 9, W_XP = 10;
 constexpr int MROWS = 128;         // prompts per group = MMA M
-constexpr int NSLOT = 7;
-constexpr int SLOT_BYTES = 16384;
+constexpr int NSLOT = 3;
+constexpr int SLOT_BYTES = 32768;
 constexpr int MAXL = 96;
-constexpr int TM_D1 = 0, TM_H = 256, TM_SK = 384, TM_TEMP = 128, TM_LOGIT = 256;
+constexpr int TM_D1 = 0, TM_H = 256, TM_TEMP = 128, TM_LOGIT = 256;   // the skip sum sits right after H: TM_H + C
 
 // shared-memory map (bytes)
 constexpr int SM_XN = 0;                         // A tile: h_l(t) bf16 [128 x C]; head: hidden
@@ -58,14 +63,14 @@ constexpr int SM_FIXED = SM_STAGES;
 constexpr int ZROW = 260;
 
 enum {
-    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_D1FULL, B_YFULL = B_D1FULL + 4,
+    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_XNSAVED, B_D1FULL, B_YFULL = B_D1FULL + 4,
     B_D2FULL = B_YFULL + 4, B_HAFULL, B_H1DFULL, B_H2AFULL, B_H2DFULL, B_HEADDONE, B_EPISYNC, B_COUNT
 };
 
 struct StageRec { unsigned src16, bytes; };   // src16: offset into wpack in 16-byte units
 
 struct Params {
-    int L, C, S, Hh, Q, n_ch, n_h1, n_h2, n_stages;
+    int L, C, S, Hh, Q, cw, n_ch, n_h1, n_h2, n_stages;   // cw = channels per chunk (64), n_ch = C / cw
     float min_temp;
     int dil[MAXL];
     unsigned char has_res[MAXL];
@@ -75,7 +80,6 @@ struct Params {
     const StageRec* stages;        // [L * 3 n_ch + n_h1 + n_h2]
     const float* E;                // (Q, C)
     const float* b1;               // [L][2C] gate biases (filter rows then gate rows)
-    const float* cbr;              // [L + 1][C] cumulative residual-conv biases (sum over layers < l)
     const float* cbs;              // [S] sum of the skip-conv biases
     const float* hb1; const float* hb2;
     unsigned char* rings;
@@ -184,23 +188,28 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
-// LBO (K direction) = 128 B; SBO (next 8 rows) = row_bytes * 8.  (cute::UMMA::SmemDescriptor, version 1.)
-__host__ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned sbo_bytes) {
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor, version 1, layout_type 2): a tile of
+// R rows x K bf16 is a sequence of K/64 "atoms"; an atom holds 64 K-elements of every row as 128-byte lines, 8 rows =
+// 1024 bytes (SBO), line r of a group stores its 16-byte chunk c at position c ^ (r & 7).  Atoms are R * 128 bytes apart.
+// A K-step of 16 elements advances the start address by 32 bytes inside an atom.  Tile bases are 1024-byte aligned.
+__host__ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) {
     unsigned long long d = 0;
     d |= (unsigned long long)((saddr & 0x3ffffu) >> 4);
-    d |= (unsigned long long)(128u >> 4) << 16;
-    d |= (unsigned long long)(sbo_bytes >> 4) << 32;
-    d |= 1ull << 46;
+    d |= (unsigned long long)1u << 16;                 // LBO: unused for swizzled K-major layouts (CUTLASS writes 1)
+    d |= (unsigned long long)(1024u >> 4) << 32;       // SBO
+    d |= 1ull << 46;                                   // descriptor version (sm_100)
+    d |= 2ull << 61;                                   // SWIZZLE_128B
     return d;
 }
+// start-address advance (16-byte units) of K-step kk in a tile of R rows
+__host__ __device__ __forceinline__ unsigned kstep16(int kk, int R) { return (unsigned)((kk >> 2) * (R * 8) + (kk & 3) * 2); }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
 __host__ __device__ __forceinline__ unsigned umma_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(MROWS >> 4) << 24);
 }
-// byte offset of (row m, 8-element chunk kc) in a canonical tile with K elements per row
-__host__ __device__ __forceinline__ unsigned tile_off(int m, int kc, int K) {
-    return (unsigned)((m >> 3) * (K * 16) + kc * 128 + (m & 7) * 16);
+// byte offset of (row m, 8-element chunk kc) in a swizzled tile of R rows
+__host__ __device__ __forceinline__ unsigned tile_off(int m, int kc, int R) {
+    return (unsigned)((kc >> 3) * (R * 128) + (m >> 3) * 1024 + (m & 7) * 128 + (((kc & 7) ^ (m & 7)) << 4));
 }
 __device__ __forceinline__ unsigned pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -227,6 +236,13 @@ __device__ __forceinline__ float mish_fast(float x) {   // x * tanh(softplus(x))
     return x * tanh_fast(sp);
 }
 
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------
 // The kernel: one CTA per group of 128 prompts.
 // ------------------------------------------------------------------------------------------------------------
@@ -240,14 +256,17 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
     unsigned* s_tmem = reinterpret_cast<unsigned*>(smem + SM_BAR + 8 * B_COUNT);
     int* s_idx = reinterpret_cast<int*>(smem + SM_BAR + 8 * B_COUNT + 16);
     unsigned* abort_flag = P.abort_flag;
-    const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q, n_ch = P.n_ch;
-    const int KC = C / 16;                                // k-steps of a C-deep contraction
+    const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q, CW = P.cw, n_ch = P.n_ch;
+    const int KC = C / 16;                                // K-steps of one conv tap
+    const int KW = CW / 16;                               // K-steps of one y chunk
     const unsigned tile_bytes = (unsigned)(MROWS * C * 2);
+    const unsigned TM_SK = TM_H + C;
 
     if (tid == 0) {
+        if (sb & 1023u) atomicExch(abort_flag, 2u);       // the swizzled tiles need a 1024-byte aligned window
         for (int i = 0; i < NSLOT; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         mbar_init(bar(B_XOFULL), 1); mbar_init(bar(B_XOFREE), 1);
-        mbar_init(bar(B_XNFULL), NEPI);
+        mbar_init(bar(B_XNFULL), NEPI); mbar_init(bar(B_XNSAVED), 1);
         for (int j = 0; j < 4; ++j) { mbar_init(bar(B_D1FULL + j), 1); mbar_init(bar(B_YFULL + j), NEPI); }
         mbar_init(bar(B_D2FULL), 1);
         mbar_init(bar(B_HAFULL), NEPI); mbar_init(bar(B_H1DFULL), 1);
@@ -288,19 +307,32 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             }
         }
     } else if (warp == W_XP) {
-        // ===================== tap producer: h_l(t - d_l) from the ring of layer l =====================
+        // ===================== tap producer: ring traffic of the older conv tap =====================
+        // per layer: fetch h_l(t - d_l) into the tap tile; then copy the layer's input tile h_l(t) to its ring slot.
+        // The ring of layer l has d_l + 1 slots, so the slot written at step t is never the one read at step t.
         if (lane == 0) {
             unsigned n = 0;
             bool dead = false;
             for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
                 for (int l = 0; l < L; ++l, ++n) {
                     if (!mbar_wait(bar(B_XOFREE), (n & 1u) ^ 1u, abort_flag)) { dead = true; break; }
-                    const unsigned slot = (unsigned)((t + 1) % (P.dil[l] + 1));   // d + 1 slots: holds h_l(t - d)
-                    if ((P.exp & 2) && n >= 1) { mbar_arrive(bar(B_XOFULL)); continue; }
-                    mbar_expect_tx(bar(B_XOFULL), tile_bytes);
-                    bulk_g2s(sb + SM_XO, ring_g + P.ring_off[l] + (size_t)slot * tile_bytes, tile_bytes, bar(B_XOFULL));
+                    if (l == 0) bulk_wait_all();          // every ring store of the previous steps has landed
+                    const unsigned slots = (unsigned)P.dil[l] + 1u;
+                    if ((P.exp & 2) && n >= 1) {
+                        mbar_arrive(bar(B_XOFULL));
+                    } else {
+                        mbar_expect_tx(bar(B_XOFULL), tile_bytes);
+                        bulk_g2s(sb + SM_XO, ring_g + P.ring_off[l] + (size_t)((t + 1) % slots) * tile_bytes, tile_bytes,
+                                 bar(B_XOFULL));
+                    }
+                    if (!mbar_wait(bar(B_XNFULL), n & 1u, abort_flag)) { dead = true; break; }
+                    bulk_s2g(ring_g + P.ring_off[l] + (size_t)(t % slots) * tile_bytes, sb + SM_XN, tile_bytes);
+                    bulk_commit();
+                    bulk_wait_read();                     // the tile has been read: the epilogue may overwrite it
+                    mbar_arrive(bar(B_XNSAVED));
                 }
             }
+            bulk_wait_all();
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
@@ -315,16 +347,14 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
             return pred != 0;
         };
-        unsigned wcnt = 0, n_lay = 0, n_xn = 0, n_head = 0;
+        unsigned wcnt = 0, n_lay = 0, n_head = 0;
         bool dead = false;
         long long* tr = nullptr;
         int tn = 0;
         auto stamp = [&]() { if (tr && lane == 0 && tn < TRACE_EV) tr[tn] = clock64(); ++tn; };
-        const unsigned id64 = umma_idesc(64), idC = umma_idesc(C), idS = umma_idesc(S);
-        // descriptors of the A tiles; a K-step of 16 elements advances the start-address field by 256 B >> 4 = 16
-        const unsigned long long dXO = umma_desc(sb + SM_XO, C * 16), dXN = umma_desc(sb + SM_XN, C * 16),
-                                 dY = umma_desc(sb + SM_Y, C * 16);
-        const unsigned long long dW0 = umma_desc(sb + SM_W, C * 16), dW0k = umma_desc(sb + SM_W, 512);
+        const unsigned idG = umma_idesc(2 * CW), idRS = umma_idesc(C + S), idS = umma_idesc(S);
+        const unsigned long long dXO = umma_desc(sb + SM_XO), dXN = umma_desc(sb + SM_XN), dY = umma_desc(sb + SM_Y);
+        const unsigned long long dW0 = umma_desc(sb + SM_W);
         constexpr unsigned SLOT16 = SLOT_BYTES >> 4;
         auto wslot_wait = [&](unsigned& slot) -> bool {
             slot = wcnt % NSLOT;
@@ -337,58 +367,58 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 tr = (P.trace && grp == 0 && t == P.trace_t) ? P.trace + (size_t)l * TRACE_EV : nullptr;
                 tn = 0;
                 stamp();                                                    // 0: layer start
-                // ---- older tap: D1 = XO . W1o^T
+                // ---- older tap: D1 = XO . W1o^T (independent of this step's activations: issued first)
                 if (!wait_u(bar(B_XOFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
                 stamp();                                                    // 1: older tap tile landed
                 for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
-                    stamp();                                                // 2..5: weights of older-tap chunk j landed
+                    stamp();                                                // 2..: weights of older-tap chunk j landed
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
                         for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem_u + TM_D1 + 64 * j, dXO + 16u * kk, dW + 16u * kk, id64, kk > 0);
+                            umma_bf16(tmem_u + TM_D1 + 2 * CW * j, dXO + kstep16(kk, MROWS), dW + kstep16(kk, 2 * CW), idG, kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
                         if (j == n_ch - 1) umma_commit(bar(B_XOFREE));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
-                stamp();                                                    // 2: older-tap MMAs issued
+                stamp();                                                    // older-tap MMAs issued
                 // ---- newer tap: D1 += XN . W1n^T, chunk by chunk
-                if (!wait_u(bar(B_XNFULL), n_xn & 1u)) { dead = true; break; }
-                ++n_xn;
+                if (!wait_u(bar(B_XNFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
-                stamp();                                                    // 3: layer input tile ready
+                stamp();                                                    // layer input tile ready
                 for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
                         for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem_u + TM_D1 + 64 * j, dXN + 16u * kk, dW + 16u * kk, id64, 1u);
+                            umma_bf16(tmem_u + TM_D1 + 2 * CW * j, dXN + kstep16(kk, MROWS), dW + kstep16(kk, 2 * CW), idG, 1u);
                         umma_commit(bar(B_WEMPTY + slot));
                         umma_commit(bar(B_D1FULL + j));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
-                stamp();                                                    // 4: newer-tap MMAs issued
-                // ---- residual and skip 1x1 convs on y, K-chunk by K-chunk as the gate epilogue delivers them
+                stamp();                                                    // newer-tap MMAs issued
+                // ---- residual and skip 1x1 convs on y (one MMA of N = C + S: H and the skip sum are adjacent in TMEM),
+                //      K-chunk by K-chunk as the gate epilogue delivers them
                 const bool has_res = P.has_res[l] != 0;
                 for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
                     if (!wait_u(bar(B_YFULL + j), n_lay & 1u)) { dead = true; break; }
+                    tc_fence_after();
                     if (j == n_ch - 1) stamp();                              // last y chunk ready
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
-                    const unsigned long long dWr = dW0k + (unsigned long long)(slot * SLOT16);
-                    const unsigned long long dWs = dWr + (unsigned long long)((C * 64) >> 4);
+                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const unsigned long long a = dY + 16u * (2 * j + kk);
-                            if (has_res) umma_bf16(tmem_u + TM_H, a, dWr + 16u * kk, idC, 1u);
-                            umma_bf16(tmem_u + TM_SK, a, dWs + 16u * kk, idS, (l > 0 || j > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < KW; ++kk) {
+                            const unsigned long long a = dY + kstep16(KW * j + kk, MROWS);
+                            if (has_res) umma_bf16(tmem_u + TM_H, a, dW + kstep16(kk, C + S), idRS, 1u);
+                            else umma_bf16(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + kstep16(kk, C + S), idS, 1u);
                         }
                         umma_commit(bar(B_WEMPTY + slot));
                         if (j == n_ch - 1) umma_commit(bar(B_D2FULL));
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     __syncwarp();
                 }
                 if (dead) break;
-                stamp();                                                    // 13: layer issued
+                stamp();                                                    // layer issued
             }
             if (dead) break;
             if (t >= P.t_head) {
@@ -406,14 +436,12 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 for (int c = 0; c < P.n_h1 && !dead; ++c, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
-                    const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
-                    const int rows = min(64, Hh - 64 * c);
+                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
                         for (int kk = 0; kk < S / 16; ++kk)
-                            umma_bf16(tmem_u + TM_D1 + 64 * c, umma_desc(sb + SM_Y + kk * 256, S * 16),
-                                      umma_desc(wb + kk * 256, S * 16), umma_idesc(rows), kk > 0);
+                            umma_bf16(tmem_u + TM_D1, dY + kstep16(kk, MROWS), dW + kstep16(kk, Hh), umma_idesc(Hh), kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (c == P.n_h1 - 1) umma_commit(bar(B_H1DFULL));
+                        umma_commit(bar(B_H1DFULL));
                     }
                     __syncwarp();
                 }
@@ -423,14 +451,13 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 for (int c = 0; c < P.n_h2 && !dead; ++c, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
-                    const unsigned wb = sb + SM_W + slot * SLOT_BYTES;
+                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     const bool temp_chunk = (c == P.n_h2 - 1);        // the learned-temperature row, padded to 16
-                    const int rows = temp_chunk ? 16 : min(64, Q - 64 * c);
-                    const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 64 * c;
+                    const int rows = temp_chunk ? 16 : min(128, Q - 128 * c);
+                    const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 128 * c;
                     if (elect()) {
                         for (int kk = 0; kk < Hh / 16; ++kk)
-                            umma_bf16(tmem_u + dcol, umma_desc(sb + SM_XN + kk * 256, Hh * 16),
-                                      umma_desc(wb + kk * 256, Hh * 16), umma_idesc(rows), kk > 0);
+                            umma_bf16(tmem_u + dcol, dXN + kstep16(kk, MROWS), dW + kstep16(kk, rows), umma_idesc(rows), kk > 0);
                         umma_commit(bar(B_WEMPTY + slot));
                         if (temp_chunk) umma_commit(bar(B_H2DFULL));
                     }
@@ -449,7 +476,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         const int b = grp * MROWS + m;
         const bool live = b < P.B;
         const unsigned tm_lane = tmem + ((unsigned)(32 * q4) << 16);
-        unsigned n_lay = 0, n_head = 0, n_sync = 0;
+        unsigned n_lay = 0, n_head = 0, n_sync = 0, n_saved = 0;
         bool dead = false;
         long long* tr = nullptr;
         int tn = 0;
@@ -459,7 +486,11 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             dead |= !mbar_wait(bar(B_EPISYNC), n_sync & 1u, abort_flag);
             ++n_sync;
         };
-        const int half_c = C / 2, half_s = S / 2, half_h = Hh / 2, half_q = Q / 2;
+        auto wait_saved = [&]() {    // the tap producer has copied the current layer-input tile out: it may be rewritten
+            dead |= !mbar_wait(bar(B_XNSAVED), n_saved & 1u, abort_flag);
+            ++n_saved;
+        };
+        const int half_c = C / 2, half_s = S / 2, half_h = Hh / 2, half_q = Q / 2, half_w = CW / 2;
         float* zs = reinterpret_cast<float*>(smem + SM_XN);
 
         for (long long t = P.t_begin; t < P.t_end; ++t) {
@@ -469,7 +500,6 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 if (live) q = (!P.teacher_forced && t > P.t_head) ? (long long)s_idx[m] : __ldcg(P.seq + (size_t)b * P.seq_stride + t);
                 q = q < 0 ? 0 : (q >= Q ? Q - 1 : q);
                 const float* row = P.E + (size_t)q * C + hf * half_c;
-                unsigned char* rslot = ring_g + P.ring_off[0] + (size_t)(t % (P.dil[0] + 1)) * tile_bytes;
                 for (int i = 0; i < half_c / 16; ++i) {
                     float v[16];
 #pragma unroll
@@ -479,20 +509,20 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     }
                     const int c0 = hf * half_c + 16 * i;
                     tmem_st16(tm_lane + TM_H + c0, v);
-                    const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-                    const unsigned o0 = tile_off(m, c0 / 8, C), o1 = tile_off(m, c0 / 8 + 1, C);
-                    *reinterpret_cast<uint4*>(smem + SM_XN + o0) = p0;
-                    *reinterpret_cast<uint4*>(smem + SM_XN + o1) = p1;
-                    __stcg(reinterpret_cast<uint4*>(rslot + o0), p0);
-                    __stcg(reinterpret_cast<uint4*>(rslot + o1), p1);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, MROWS)) = pack8(v);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, MROWS)) = pack8(v + 8);
+                }
+                {
+                    float z[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) z[k] = 0.0f;
+                    for (int i = 0; i < half_s / 16; ++i) tmem_st16(tm_lane + TM_SK + hf * half_s + 16 * i, z);   // skip sum = 0
                 }
                 tmem_st_wait();
                 fence_proxy_async_smem();
-                fence_proxy_async_global();
                 tc_fence_before();
                 mbar_arrive(bar(B_XNFULL));
             }
-            if (dead) break;
             // ---------------- layers ----------------
             for (int l = 0; l < L; ++l, ++n_lay) {
                 const float* bl = P.b1 + (size_t)l * 2 * C;
@@ -500,44 +530,54 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 tn = 0;
                 stamp();                                                        // 0: layer start
                 for (int j = 0; j < n_ch; ++j) {
-                    // gate epilogue of chunk j: channels 32 j + 16 hf + [0, 16)
-                    const int ch0 = 32 * j + 16 * hf;
-                    float4 bf[4], bg[4];                     // this chunk's biases, fetched before the wait
+                    // gate epilogue of chunk j: channels cw j + (cw / 2) hf + [0, cw / 2), 16 at a time
+                    const int chb = CW * j + half_w * hf;
+                    float4 bf[4], bg[4];                     // the first 16 channels' biases, fetched before the wait
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
-                        bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
+                        bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + chb) + k4);
+                        bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + chb) + k4);
                     }
                     dead |= !mbar_wait(bar(B_D1FULL + j), n_lay & 1u, abort_flag);
                     tc_fence_after();
-                    stamp();                                                    // 1,3,5,7: D1 chunk j complete
-                    float f[16], g[16];
-                    tmem_ld16(tm_lane + TM_D1 + 64 * j + 16 * hf, f);
-                    tmem_ld16(tm_lane + TM_D1 + 64 * j + 32 + 16 * hf, g);
-                    tmem_ld_wait();
-                    float y[16];
+                    stamp();                                                    // D1 chunk j complete
+                    for (int sub = 0; sub < half_w / 16; ++sub) {
+                        const int ch0 = chb + 16 * sub;
+                        float f[16], g[16];
+                        tmem_ld16(tm_lane + TM_D1 + 2 * CW * j + half_w * hf + 16 * sub, f);
+                        tmem_ld16(tm_lane + TM_D1 + 2 * CW * j + CW + half_w * hf + 16 * sub, g);
+                        if (sub > 0) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        y[4 * k4] = gate_fast(f[4 * k4] + bf[k4].x, g[4 * k4] + bg[k4].x);     // wavenet_v2.py:151
-                        y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf[k4].y, g[4 * k4 + 1] + bg[k4].y);
-                        y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
-                        y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
+                                bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
+                            }
+                        }
+                        tmem_ld_wait();
+                        float y[16];
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            y[4 * k4] = gate_fast(f[4 * k4] + bf[k4].x, g[4 * k4] + bg[k4].x);     // wavenet_v2.py:151
+                            y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf[k4].y, g[4 * k4 + 1] + bg[k4].y);
+                            y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
+                            y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
+                        }
+                        *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, MROWS)) = pack8(y);
+                        *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, MROWS)) = pack8(y + 8);
                     }
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, C)) = pack8(y);
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, C)) = pack8(y + 8);
                     fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_YFULL + j));
-                    stamp();                                                    // 2,4,6,8: y chunk j written
+                    stamp();                                                    // y chunk j written
                 }
                 dead |= !mbar_wait(bar(B_D2FULL), n_lay & 1u, abort_flag);
                 tc_fence_after();
-                stamp();                                                        // 9: res/skip MMAs complete
+                stamp();                                                        // res/skip MMAs complete
+                wait_saved();                                                   // this layer's input tile is in its ring slot
                 if (dead) break;
                 if (l < L - 1) {
-                    // h_{l+1}(t) = h_l + conv_res(y) -> next layer's A tile and its ring slot.  The residual-conv biases
-                    // are not in the stream: their effect on the next gates is folded into the gate biases (host).
-                    unsigned char* rslot = ring_g + P.ring_off[l + 1] + (size_t)(t % (P.dil[l + 1] + 1)) * tile_bytes;
+                    // h_{l+1}(t) = h_l + conv_res(y) -> next layer's A tile.  The residual-conv biases are not in the
+                    // stream: their effect on the next gates is folded into the gate biases (host).
                     for (int i = 0; i < half_c / 16; i += 2) {
                         const int c0 = hf * half_c + 16 * i;
                         const bool two = i + 1 < half_c / 16;
@@ -545,26 +585,18 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                         tmem_ld16(tm_lane + TM_H + c0, v);
                         if (two) tmem_ld16(tm_lane + TM_H + c0 + 16, w);
                         tmem_ld_wait();
-                        const unsigned o0 = tile_off(m, c0 / 8, C);      // consecutive 8-channel chunks are 128 B apart
-                        const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-                        *reinterpret_cast<uint4*>(smem + SM_XN + o0) = p0;
-                        *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 128) = p1;
-                        __stcg(reinterpret_cast<uint4*>(rslot + o0), p0);
-                        __stcg(reinterpret_cast<uint4*>(rslot + o0 + 128), p1);
+                        *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, MROWS)) = pack8(v);
+                        *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, MROWS)) = pack8(v + 8);
                         if (two) {
-                            const uint4 p2 = pack8(w), p3 = pack8(w + 8);
-                            *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 256) = p2;
-                            *reinterpret_cast<uint4*>(smem + SM_XN + o0 + 384) = p3;
-                            __stcg(reinterpret_cast<uint4*>(rslot + o0 + 256), p2);
-                            __stcg(reinterpret_cast<uint4*>(rslot + o0 + 384), p3);
+                            *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 2, MROWS)) = pack8(w);
+                            *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 3, MROWS)) = pack8(w + 8);
                         }
                     }
                     fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_XNFULL));
-                    stamp();                                                    // 10: next layer input written
+                    stamp();                                                    // next layer input written
                 }
-                if (dead) break;
             }
             if (dead) break;
             // ---------------- head + sampler ----------------
@@ -576,8 +608,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] += __ldg(P.cbs + c0 + k);
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8, S)) = pack8(v);
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8 + 1, S)) = pack8(v + 8);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8, MROWS)) = pack8(v);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, c0 / 8 + 1, MROWS)) = pack8(v + 8);
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
@@ -591,8 +623,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] = mish_fast(v[k] + __ldg(P.hb1 + c0 + k));
-                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, Hh)) = pack8(v);
-                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, Hh)) = pack8(v + 8);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8, MROWS)) = pack8(v);
+                    *reinterpret_cast<uint4*>(smem + SM_XN + tile_off(m, c0 / 8 + 1, MROWS)) = pack8(v + 8);
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
@@ -657,28 +689,29 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Self-test kernel: D[128 x N] = A[128 x K] . B[N x K]^T through the same descriptors / TMEM path (N, K <= 128 ... 256).
+// Self-test kernel: D[128 x N] = A[128 x K] . B[N x K]^T through the same descriptors / TMEM path (K a multiple of 64).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) tc_gemm_check_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                                               float* __restrict__ D, int N, int K) {
+                                                               float* __restrict__ D, int N, int K, long long* cycles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned sb = smem_u32(smem);
+    const int a_bytes = MROWS * K * 2, b_bytes = ((N * K * 2 + 1023) / 1024) * 1024;
     unsigned char* sA = smem;                       // 128 x K bf16
-    unsigned char* sB = smem + MROWS * K * 2;       // N x K bf16
-    unsigned* s_misc = reinterpret_cast<unsigned*>(sB + (size_t)N * K * 2);
+    unsigned char* sB = smem + a_bytes;             // N x K bf16
+    unsigned* s_misc = reinterpret_cast<unsigned*>(sB + b_bytes);
     const unsigned bar0 = smem_u32(s_misc), s_tm = smem_u32(s_misc + 4);
     for (int i = tid; i < MROWS * K / 8; i += 128) {
         const int m = i / (K / 8), kc = i % (K / 8);
         float v[8];
         for (int e = 0; e < 8; ++e) v[e] = A[(size_t)m * K + kc * 8 + e];
-        *reinterpret_cast<uint4*>(sA + tile_off(m, kc, K)) = pack8(v);
+        *reinterpret_cast<uint4*>(sA + tile_off(m, kc, MROWS)) = pack8(v);
     }
     for (int i = tid; i < N * K / 8; i += 128) {
         const int n = i / (K / 8), kc = i % (K / 8);
         float v[8];
         for (int e = 0; e < 8; ++e) v[e] = Bm[(size_t)n * K + kc * 8 + e];
-        *reinterpret_cast<uint4*>(sB + tile_off(n, kc, K)) = pack8(v);
+        *reinterpret_cast<uint4*>(sB + tile_off(n, kc, N)) = pack8(v);
     }
     if (tid == 0) { mbar_init(bar0, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc(s_tm, 256);
@@ -687,20 +720,23 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_check_kernel(const float* __re
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *reinterpret_cast<volatile unsigned*>(s_misc + 4);
+    long long c0 = 0;
     if (tid == 0) {
-        for (int kk = 0; kk < K / 16; ++kk)
-            umma_bf16(tmem, umma_desc(sb + kk * 256, K * 16), umma_desc(sb + MROWS * K * 2 + kk * 256, K * 16),
-                      umma_idesc(N), kk > 0);
+        c0 = clock64();
+        for (int rep = 0; rep < 8; ++rep)           // the same product 8 times (timing); the last pass is the result
+            for (int kk = 0; kk < K / 16; ++kk)
+                umma_bf16(tmem, umma_desc(sb) + kstep16(kk, MROWS), umma_desc(sb + a_bytes) + kstep16(kk, N), umma_idesc(N), kk > 0);
         umma_commit(bar0);
     }
     unsigned spins = 0;
     while (!mbar_try_wait(bar0, 0u)) { if (++spins > 100000000u) break; }
+    if (tid == 0 && cycles) *cycles = clock64() - c0;
     tc_fence_after();
-    for (int c0 = 0; c0 < N; c0 += 16) {
+    for (int c = 0; c < N; c += 16) {
         float v[16];
-        tmem_ld16(tmem + ((unsigned)(32 * warp) << 16) + c0, v);
+        tmem_ld16(tmem + ((unsigned)(32 * warp) << 16) + c, v);
         tmem_ld_wait();
-        for (int k = 0; k < 16; ++k) D[(size_t)(32 * warp + lane) * N + c0 + k] = v[k];
+        for (int k = 0; k < 16; ++k) D[(size_t)(32 * warp + lane) * N + c + k] = v[k];
     }
     tc_fence_before();
     __syncthreads();
@@ -733,14 +769,14 @@ static unsigned short f2bf(float f) {   // round to nearest even
     return (unsigned short)(u >> 16);
 }
 
-// Packs rows [r0, r0 + n) x K of a row-major fp32 matrix (row stride ld, element stride es) as a canonical bf16 tile.
-static void pack_tile(std::vector<unsigned char>& out, size_t at, int n_rows, int K, const float* src, size_t ld, size_t es,
-                      int valid_rows) {
-    for (int r = 0; r < n_rows; ++r)
+// Writes rows [row_at, row_at + n) of a canonical bf16 tile of R rows x K from a strided fp32 matrix
+// (src[r * ld + k * es]); rows >= valid are zero.
+static void pack_rows(std::vector<unsigned char>& out, size_t at, int R, int K, int row_at, int n, const float* src,
+                      size_t ld, size_t es, int valid) {
+    for (int r = 0; r < n; ++r)
         for (int k = 0; k < K; ++k) {
-            const float v = r < valid_rows ? src[(size_t)r * ld + (size_t)k * es] : 0.0f;
-            const unsigned short bfv = f2bf(v);
-            memcpy(out.data() + at + tile_off(r, k / 8, K) + (k % 8) * 2, &bfv, 2);
+            const unsigned short bfv = f2bf((src && r < valid) ? src[(size_t)r * ld + (size_t)k * es] : 0.0f);
+            memcpy(out.data() + at + tile_off(row_at + r, k / 8, R) + (k % 8) * 2, &bfv, 2);
         }
 }
 
@@ -749,9 +785,9 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     const int L = d->n_layers, C = d->dilated_dim, S = d->skips_dim, Hh = d->head_hidden, Q = d->q_levels;
     const char* why = nullptr;
     if (L < 1 || L > MAXL) why = "n_layers out of range";
-    else if (C % 32 != 0 || C < 32 || C > 128) why = "dilated_dim must be 32, 64, 96 or 128";
-    else if (S % 32 != 0 || S < 32 || S > 128) why = "skips_dim must be 32, 64, 96 or 128";
-    else if (Hh % 32 != 0 || Hh < 32 || Hh > 128) why = "head hidden_dim must be 32, 64, 96 or 128";
+    else if (C != 64 && C != 128) why = "dilated_dim must be 64 or 128";
+    else if (S != 64 && S != 128) why = "skips_dim must be 64 or 128";
+    else if (Hh != 64 && Hh != 128) why = "head hidden_dim must be 64 or 128";
     else if (Q % 64 != 0 || Q < 64 || Q > 256) why = "q_levels must be 64, 128, 192 or 256";
     if (!why)
         for (int l = 0; l < L; ++l) {
@@ -770,8 +806,9 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     int cc_major = 0;
     MMK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, h->device));
     if (cc_major != 10) { delete h; MMK_FAIL("the bf16 tensor-core WaveNet kernel needs an sm_100 device (tcgen05)"); }
-    p.L = L; p.C = C; p.S = S; p.Hh = Hh; p.Q = Q; p.n_ch = C / 32;
-    p.n_h1 = (Hh + 63) / 64; p.n_h2 = Q / 64 + 1;
+    const int CW = 64;
+    p.L = L; p.C = C; p.S = S; p.Hh = Hh; p.Q = Q; p.cw = CW; p.n_ch = C / CW;
+    p.n_h1 = 1; p.n_h2 = (Q + 127) / 128 + 1;
     p.min_temp = d->min_temperature;
     h->max_groups = (max_batch + MROWS - 1) / MROWS;
     const size_t tile_bytes = (size_t)MROWS * C * 2;
@@ -785,11 +822,11 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     }
     p.ring_group_bytes = ring;
 
-    // ---- stage list + packed bf16 weights
+    // ---- stage list + packed bf16 weights (every stage is one canonical swizzled tile, <= 32 KB)
     std::vector<StageRec> stages;
     std::vector<unsigned char> wpack;
     auto new_stage = [&](size_t bytes) {
-        const size_t at = wpack.size();
+        const size_t at = (wpack.size() + 1023) / 1024 * 1024;
         wpack.resize(at + bytes, 0);
         stages.push_back(StageRec{(unsigned)(at / 16), (unsigned)bytes});
         return at;
@@ -798,32 +835,26 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
         const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample
         for (int tap = 0; tap < 2; ++tap)      // stage order: older-tap chunks, then newer-tap chunks
             for (int j = 0; j < p.n_ch; ++j) {
-                const size_t at = new_stage((size_t)64 * C * 2);
-                // rows 0..31: filter channels 32 j + r ; rows 32..63: gate channels 32 j + r
-                pack_tile(wpack, at, 32, C, wd + ((size_t)(32 * j) * C) * 2 + tap, (size_t)C * 2, 2, 32);
-                // the gate half starts at row 32 of the same tile: pack rows directly with a row offset
-                for (int r = 0; r < 32; ++r)
-                    for (int k = 0; k < C; ++k) {
-                        const unsigned short bfv = f2bf(wd[((size_t)(C + 32 * j + r) * C + k) * 2 + tap]);
-                        memcpy(wpack.data() + at + tile_off(32 + r, k / 8, C) + (k % 8) * 2, &bfv, 2);
-                    }
+                // rows 0..cw-1: filter channels cw j + r ; rows cw..2cw-1: gate channels cw j + r ; K = C input channels
+                const size_t at = new_stage((size_t)2 * CW * C * 2);
+                pack_rows(wpack, at, 2 * CW, C, 0, CW, wd + ((size_t)(CW * j) * C) * 2 + tap, (size_t)C * 2, 2, CW);
+                pack_rows(wpack, at, 2 * CW, C, CW, CW, wd + ((size_t)(C + CW * j) * C) * 2 + tap, (size_t)C * 2, 2, CW);
             }
-        for (int j = 0; j < p.n_ch; ++j) {     // K-chunk j of [res rows | skip rows] x 32
-            const size_t at = new_stage((size_t)(C + S) * 64);
-            if (d->conv_res_w[l]) pack_tile(wpack, at, C, 32, d->conv_res_w[l] + 32 * j, (size_t)C, 1, C);
-            pack_tile(wpack, at + (size_t)C * 64, S, 32, d->conv_skip_w[l] + 32 * j, (size_t)C, 1, S);
+        for (int j = 0; j < p.n_ch; ++j) {     // K-chunk j (cw input channels) of [res rows | skip rows]
+            const size_t at = new_stage((size_t)(C + S) * CW * 2);
+            pack_rows(wpack, at, C + S, CW, 0, C, d->conv_res_w[l] ? d->conv_res_w[l] + CW * j : nullptr, (size_t)C, 1, C);
+            pack_rows(wpack, at, C + S, CW, C, S, d->conv_skip_w[l] + CW * j, (size_t)C, 1, S);
         }
     }
-    for (int c = 0; c < p.n_h1; ++c) {
-        const int rows = std::min(64, Hh - 64 * c);
-        const size_t at = new_stage((size_t)rows * S * 2);
-        pack_tile(wpack, at, rows, S, d->head_w1 + (size_t)64 * c * S, (size_t)S, 1, rows);
+    {
+        const size_t at = new_stage((size_t)Hh * S * 2);
+        pack_rows(wpack, at, Hh, S, 0, Hh, d->head_w1, (size_t)S, 1, Hh);
     }
     for (int c = 0; c < p.n_h2; ++c) {
         const bool temp_chunk = c == p.n_h2 - 1;
-        const int rows = temp_chunk ? 16 : 64, row0 = temp_chunk ? Q : 64 * c;
+        const int rows = temp_chunk ? 16 : std::min(128, Q - 128 * c), row0 = temp_chunk ? Q : 128 * c;
         const size_t at = new_stage((size_t)rows * Hh * 2);
-        pack_tile(wpack, at, rows, Hh, d->head_w2 + (size_t)row0 * Hh, (size_t)Hh, 1, temp_chunk ? 1 : rows);
+        pack_rows(wpack, at, rows, Hh, 0, rows, d->head_w2 + (size_t)row0 * Hh, (size_t)Hh, 1, temp_chunk ? 1 : rows);
     }
     for (const StageRec& s : stages)
         if (s.bytes > (unsigned)SLOT_BYTES || s.bytes % 16 != 0) { delete h; MMK_FAIL("internal: weight stage exceeds the ring slot"); }
@@ -856,7 +887,6 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     p.stages = (const StageRec*)dev_alloc(stages.size() * sizeof(StageRec), stages.data());
     p.E = (const float*)dev_alloc((size_t)Q * C * 4, d->embedding);
     p.b1 = (const float*)dev_alloc(b1.size() * 4, b1.data());
-    p.cbr = (const float*)dev_alloc(cbr.size() * 4, cbr.data());
     p.cbs = (const float*)dev_alloc(cbs.size() * 4, cbs.data());
     p.hb1 = (const float*)dev_alloc((size_t)Hh * 4, d->head_b1);
     p.hb2 = (const float*)dev_alloc((size_t)(Q + 1) * 4, d->head_b2);
@@ -926,12 +956,20 @@ int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
 }
 
 // Diagnostic: D (128 x N) = A (128 x K) . B (N x K)^T with bf16 operands through the UMMA path used above.
-extern "C" int mmk_tc_gemm_check(const float* d_A, const float* d_B, float* d_D, int N, int K, void* stream) {
+// h_cycles (nullable, host): clock cycles of 8 back-to-back passes of the K / 16 instructions (synchronises the stream).
+extern "C" int mmk_tc_gemm_check(const float* d_A, const float* d_B, float* d_D, int N, int K, long long* h_cycles, void* stream) {
     MMK_CHECK(d_A && d_B && d_D, "mmk_tc_gemm_check: null pointer");
-    MMK_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "need N, K multiples of 16 in [16, 256]");
-    const size_t smem = (size_t)MROWS * K * 2 + (size_t)N * K * 2 + 64;
+    MMK_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, "need N a multiple of 16 in [16, 256], K of 64 in [64, 256]");
+    const size_t smem = (size_t)MROWS * K * 2 + ((size_t)N * K * 2 + 1023) / 1024 * 1024 + 64;
     MMK_CUDA(cudaFuncSetAttribute(tc_gemm_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_gemm_check_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_D, N, K);
+    long long* d_cycles = nullptr;
+    if (h_cycles) MMK_CUDA(cudaMalloc(&d_cycles, sizeof(long long)));
+    tc_gemm_check_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_D, N, K, d_cycles);
     MMK_CUDA(cudaGetLastError());
+    if (h_cycles) {
+        MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        MMK_CUDA(cudaMemcpy(h_cycles, d_cycles, sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_cycles);
+    }
     return 0;
 }

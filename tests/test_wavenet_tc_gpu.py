@@ -18,18 +18,21 @@ pytestmark = pytest.mark.gpu
 BF16_TOL = 5e-2
 
 
-@pytest.mark.parametrize("N,K", [(64, 128), (128, 128), (256, 64), (16, 128), (128, 32), (256, 128), (48, 96)])
+@pytest.mark.parametrize("N,K", [(64, 128), (128, 128), (256, 64), (16, 128), (128, 64), (256, 128), (48, 64), (256, 256)])
 def test_umma_descriptor_path_is_a_gemm(N, K):
-    """D = A . B^T through the kernel's shared-memory descriptors, tcgen05.mma and TMEM loads."""
+    """D = A . B^T through the kernel's shared-memory descriptors (K-major SWIZZLE_128B), tcgen05.mma and TMEM loads."""
     g = torch.Generator().manual_seed(N * 1000 + K)
     A = torch.randn(128, K, generator=g).cuda()
     B = torch.randn(N, K, generator=g).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
-    _capi.check(_capi.lib().mmk_tc_gemm_check(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, _capi.stream_ptr()))
+    cycles = ctypes.c_longlong(0)
+    _capi.check(_capi.lib().mmk_tc_gemm_check(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, ctypes.byref(cycles),
+                                              _capi.stream_ptr()))
     torch.cuda.synchronize()
     ref = A.bfloat16().float() @ B.bfloat16().float().T
     assert torch.isfinite(D).all()
     assert float((D - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+    print(f"tcgen05.mma 128x{N}x16: {cycles.value / (8 * K / 16):.0f} cycles per instruction (issue to commit, 8 x {K // 16})")
 
 
 def _bf16_net(blocks, dims, skips, mlp, seed=0):
@@ -39,7 +42,7 @@ def _bf16_net(blocks, dims, skips, mlp, seed=0):
 
 
 @pytest.mark.parametrize("blocks,dims,skips,mlp,B,n", [((3, 3), 64, 64, 64, 5, 40), ((4, 4), 128, 128, 128, 130, 24),
-                                                       ((2, 5), 32, 96, 32, 129, 33), ((8, 8, 7, 7), 128, 128, 128, 64, 24)])
+                                                       ((2, 5), 64, 128, 64, 129, 33), ((8, 8, 7, 7), 128, 128, 128, 64, 24)])
 def test_teacher_forced_logits_within_bf16_tolerance(blocks, dims, skips, mlp, B, n):
     net, orc = _bf16_net(blocks, dims, skips, mlp)
     g = torch.Generator().manual_seed(7)
@@ -105,7 +108,7 @@ def test_unsupported_configurations_fail_loudly():
     net = make_net((3,), 128).bfloat16()           # no residual / skip convs: fp32 kernels only
     with pytest.raises(RuntimeError, match="unsupported configuration"):
         net.generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4)
-    net = make_net((3, 3), 48, 48, 48, 48).bfloat16()   # channel counts that are not multiples of 32
+    net = make_net((3, 3), 32, 32, 32, 32).bfloat16()   # channel counts other than 64 / 128
     with pytest.raises(RuntimeError, match="unsupported configuration"):
         net.generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4)
     assert net.float().generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4).shape == (2, net.rf + 5)
