@@ -19,7 +19,7 @@
 //   * the older conv tap h_l(t-d) comes from a per-layer ring in global memory (L2): a producer warp copies every layer
 //     input tile shared -> global with one cp.async.bulk (the epilogue threads never store to global) and fetches it d
 //     steps later with one bulk copy into the tap tile.
-//   * 8 epilogue warps (2 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (tanh.approx.f16x2),
+//   * 16 epilogue warps (4 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (2 MUFU.TANH per gate),
 //     bf16 pack straight into the next MMA's A tile, per 64-channel chunk so that the res/skip MMAs of a chunk start
 //     while the gate MMAs of the next chunk run.  The residual-conv biases never enter the stream (folded into the gate
 //     biases on the host); the skip sum is zeroed by the epilogue at the start of a step and only ever accumulated.
@@ -42,12 +42,14 @@
 
 namespace mmk_tc {
 
-constexpr int NT = 384;            // 8 epilogue warps, MMA warp, weight producer, tap producer, one spare
-constexpr int NEPI = 256;
-constexpr int W_MMA = 8, W_WP = 9, W_XP = 10;
+constexpr int NEW = 16;            // epilogue warps: 4 threads per prompt row
+constexpr int QT = NEW / 4;        // column quarters
+constexpr int NT = 32 * (NEW + 3); // + MMA warp, weight producer, tap producer
+constexpr int NEPI = 32 * NEW;
+constexpr int W_MMA = NEW, W_WP = NEW + 1, W_XP = NEW + 2;
 constexpr int MROWS = 128;         // prompts per group = MMA M
-constexpr int NSLOT = 3;
-constexpr int SLOT_BYTES = 32768;
+constexpr int NSLOT = 4;
+constexpr int SLOT_BYTES = 32768;      // one 64-deep K atom of up to 256 rows (loaded as two 16 KB bulk copies)
 constexpr int MAXL = 96;
 constexpr int TM_D1 = 0, TM_H = 256, TM_TEMP = 128, TM_LOGIT = 256;   // the skip sum sits right after H: TM_H + C
 
@@ -58,26 +60,29 @@ constexpr int SM_ZX = 65536;                     // + 2 KB: with XN|Y the logits
 constexpr int SM_XO = 67584;                     // A tile: h_l(t-d) from the ring
 constexpr int SM_W = 100352;                     // weight ring
 constexpr int SM_BAR = SM_W + NSLOT * SLOT_BYTES;
-constexpr int SM_STAGES = SM_BAR + 1024;      // uint2 {src / 16, bytes} per stage of a step
-constexpr int SM_FIXED = SM_STAGES;
+constexpr int SM_TOTAL = SM_BAR + 1024;
 constexpr int ZROW = 260;
 
 enum {
-    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_XNSAVED, B_D1FULL, B_YFULL = B_D1FULL + 4,
-    B_D2FULL = B_YFULL + 4, B_HAFULL, B_H1DFULL, B_H2AFULL, B_H2DFULL, B_HEADDONE, B_EPISYNC, B_COUNT
+    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_XNSAVED, B_D1FULL, B_YFULL,
+    B_D2FULL = B_YFULL + 2, B_HAFULL, B_H1DFULL, B_H2AFULL, B_H2DFULL, B_HEADDONE, B_EPISYNC, B_COUNT
 };
 
-struct StageRec { unsigned src16, bytes; };   // src16: offset into wpack in 16-byte units
+constexpr int MAX_LS = 8, MAX_HS = 12;        // weight stages of one layer / of the head
 
 struct Params {
-    int L, C, S, Hh, Q, cw, n_ch, n_h1, n_h2, n_stages;   // cw = channels per chunk (64), n_ch = C / cw
+    int L, C, S, Hh, Q, n_h2;
+    // weight stages (each = one 64-deep K atom of a B tile, <= 32 KB): every layer has the same n_ls stages, layer l's
+    // stage i starts at byte l * layer_bytes + ls_off[i] of wpack; the head's n_hs stages start at head_off + hs_off[i]
+    int n_ls, n_hs;
+    unsigned ls_off[MAX_LS], ls_bytes[MAX_LS], hs_off[MAX_HS], hs_bytes[MAX_HS];
+    unsigned long long layer_bytes, head_off;
     float min_temp;
     int dil[MAXL];
     unsigned char has_res[MAXL];
     long long ring_off[MAXL];      // byte offset of layer l's ring inside a group's block
     long long ring_group_bytes;
     const unsigned char* wpack;
-    const StageRec* stages;        // [L * 3 n_ch + n_h1 + n_h2]
     const float* E;                // (Q, C)
     const float* b1;               // [L][2C] gate biases (filter rows then gate rows)
     const float* cbs;              // [S] sum of the skip-conv biases
@@ -218,18 +223,15 @@ __device__ __forceinline__ unsigned pack_bf16(float a, float b) {
 __device__ __forceinline__ uint4 pack8(const float* v) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
-// tanh(f) * sigmoid(g) with ONE MUFU op: tanh.approx.f16x2 on (f, g / 2); sigmoid(g) = 0.5 tanh(g / 2) + 0.5
-__device__ __forceinline__ float gate_fast(float f, float g) {
-    const __half2 in = __floats2half2_rn(f, 0.5f * g);
-    unsigned o;
-    asm("tanh.approx.f16x2 %0, %1;" : "=r"(o) : "r"(*reinterpret_cast<const unsigned*>(&in)));
-    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&o));
-    return t.x * fmaf(0.5f, t.y, 0.5f);
-}
 __device__ __forceinline__ float tanh_fast(float x) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+// tanh(f) * sigmoid(g), sigmoid(g) = 0.5 tanh(g / 2) + 0.5: two MUFU.TANH and four FP32 ops per gate.  (A packed
+// tanh.approx.f16x2 does not help: it is issued as two MUFU.TANH.F16, plus the conversions.)
+__device__ __forceinline__ float gate_fast(float f, float g) {
+    return tanh_fast(f) * fmaf(0.5f, tanh_fast(0.5f * g), 0.5f);
 }
 __device__ __forceinline__ float mish_fast(float x) {   // x * tanh(softplus(x)), softplus threshold 20 (F.softplus)
     const float sp = x > 20.0f ? x : __logf(1.0f + __expf(x));
@@ -256,9 +258,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
     unsigned* s_tmem = reinterpret_cast<unsigned*>(smem + SM_BAR + 8 * B_COUNT);
     int* s_idx = reinterpret_cast<int*>(smem + SM_BAR + 8 * B_COUNT + 16);
     unsigned* abort_flag = P.abort_flag;
-    const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q, CW = P.cw, n_ch = P.n_ch;
-    const int KC = C / 16;                                // K-steps of one conv tap
-    const int KW = CW / 16;                               // K-steps of one y chunk
+    const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q;
+    const int KA = C / 64;                                // 64-deep K atoms per conv tap = 64-channel chunks of y
     const unsigned tile_bytes = (unsigned)(MROWS * C * 2);
     const unsigned TM_SK = TM_H + C;
 
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         for (int i = 0; i < NSLOT; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         mbar_init(bar(B_XOFULL), 1); mbar_init(bar(B_XOFREE), 1);
         mbar_init(bar(B_XNFULL), NEPI); mbar_init(bar(B_XNSAVED), 1);
-        for (int j = 0; j < 4; ++j) { mbar_init(bar(B_D1FULL + j), 1); mbar_init(bar(B_YFULL + j), NEPI); }
+        mbar_init(bar(B_D1FULL), 1);
+        for (int j = 0; j < 2; ++j) mbar_init(bar(B_YFULL + j), NEPI);
         mbar_init(bar(B_D2FULL), 1);
         mbar_init(bar(B_HAFULL), NEPI); mbar_init(bar(B_H1DFULL), 1);
         mbar_init(bar(B_H2AFULL), NEPI); mbar_init(bar(B_H2DFULL), 1);
@@ -277,33 +279,36 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         fence_proxy_async();
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(s_tmem), 512);
-    {
-        uint2* st_s = reinterpret_cast<uint2*>(smem + SM_STAGES);
-        for (int i = tid; i < P.n_stages; i += NT) st_s[i] = make_uint2(P.stages[i].src16, P.stages[i].bytes);
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *reinterpret_cast<volatile unsigned*>(s_tmem);
 
     unsigned char* ring_g = P.rings + (size_t)grp * P.ring_group_bytes;
-    const int n_layer_stages = 3 * n_ch;
 
     if (warp == W_WP) {
         // ===================== weight producer: the stage list of every step, in consumption order =====================
         if (lane == 0) {
             unsigned cnt = 0;
             bool dead = false;
+            auto load = [&](const unsigned char* src, unsigned bytes) -> bool {
+                const unsigned slot = cnt % NSLOT, use = cnt / NSLOT;
+                if (!mbar_wait(bar(B_WEMPTY + slot), (use & 1u) ^ 1u, abort_flag)) return false;
+                if ((P.exp & 1) && cnt >= NSLOT) { mbar_arrive(bar(B_WFULL + slot)); ++cnt; return true; }
+                mbar_expect_tx(bar(B_WFULL + slot), bytes);
+                const unsigned dst = sb + SM_W + slot * SLOT_BYTES, half = bytes > 16384u ? 16384u : bytes;
+                bulk_g2s(dst, src, half, bar(B_WFULL + slot));            // two requests in flight per slot
+                if (bytes > half) bulk_g2s(dst + half, src + half, bytes - half, bar(B_WFULL + slot));
+                ++cnt;
+                return true;
+            };
             for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
-                const int n_st = L * n_layer_stages + (t >= P.t_head ? P.n_h1 + P.n_h2 : 0);
-                for (int i = 0; i < n_st; ++i, ++cnt) {
-                    const unsigned slot = cnt % NSLOT, use = cnt / NSLOT;
-                    if (!mbar_wait(bar(B_WEMPTY + slot), (use & 1u) ^ 1u, abort_flag)) { dead = true; break; }
-                    const uint2 r = reinterpret_cast<const uint2*>(smem + SM_STAGES)[i];
-                    if ((P.exp & 1) && cnt >= NSLOT) { mbar_arrive(bar(B_WFULL + slot)); continue; }
-                    mbar_expect_tx(bar(B_WFULL + slot), r.y);
-                    bulk_g2s(sb + SM_W + slot * SLOT_BYTES, P.wpack + (size_t)r.x * 16, r.y, bar(B_WFULL + slot));
-                }
+                for (int l = 0; l < L && !dead; ++l)
+                    for (int i = 0; i < P.n_ls; ++i)
+                        if (!load(P.wpack + (size_t)l * P.layer_bytes + P.ls_off[i], P.ls_bytes[i])) { dead = true; break; }
+                if (t >= P.t_head)
+                    for (int i = 0; i < P.n_hs && !dead; ++i)
+                        if (!load(P.wpack + P.head_off + P.hs_off[i], P.hs_bytes[i])) dead = true;
             }
         }
     } else if (warp == W_XP) {
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         long long* tr = nullptr;
         int tn = 0;
         auto stamp = [&]() { if (tr && lane == 0 && tn < TRACE_EV) tr[tn] = clock64(); ++tn; };
-        const unsigned idG = umma_idesc(2 * CW), idRS = umma_idesc(C + S), idS = umma_idesc(S);
+        const unsigned idG = umma_idesc(2 * C), idRS = umma_idesc(C + S), idS = umma_idesc(S);
         const unsigned long long dXO = umma_desc(sb + SM_XO), dXN = umma_desc(sb + SM_XN), dY = umma_desc(sb + SM_Y);
         const unsigned long long dW0 = umma_desc(sb + SM_W);
         constexpr unsigned SLOT16 = SLOT_BYTES >> 4;
@@ -367,61 +372,61 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 tr = (P.trace && grp == 0 && t == P.trace_t) ? P.trace + (size_t)l * TRACE_EV : nullptr;
                 tn = 0;
                 stamp();                                                    // 0: layer start
-                // ---- older tap: D1 = XO . W1o^T (independent of this step's activations: issued first)
+                // ---- older tap: D1[128 x 2C] = XO . W1o^T (independent of this step's activations: issued first)
                 if (!wait_u(bar(B_XOFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
                 stamp();                                                    // 1: older tap tile landed
-                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                for (int a = 0; a < KA && !dead; ++a, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
-                    stamp();                                                // 2..: weights of older-tap chunk j landed
+                    stamp();                                                // 2..: weights of an older-tap atom landed
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem_u + TM_D1 + 2 * CW * j, dXO + kstep16(kk, MROWS), dW + kstep16(kk, 2 * CW), idG, kk > 0);
+                        for (int kq = 0; kq < 4; ++kq)
+                            umma_bf16(tmem_u + TM_D1, dXO + kstep16(4 * a + kq, MROWS), dW + 2u * kq, idG, (a | kq) != 0);
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (j == n_ch - 1) umma_commit(bar(B_XOFREE));
+                        if (a == KA - 1) umma_commit(bar(B_XOFREE));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
                 stamp();                                                    // older-tap MMAs issued
-                // ---- newer tap: D1 += XN . W1n^T, chunk by chunk
+                // ---- newer tap: D1 += XN . W1n^T
                 if (!wait_u(bar(B_XNFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
                 stamp();                                                    // layer input tile ready
-                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                for (int a = 0; a < KA && !dead; ++a, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kk = 0; kk < KC; ++kk)
-                            umma_bf16(tmem_u + TM_D1 + 2 * CW * j, dXN + kstep16(kk, MROWS), dW + kstep16(kk, 2 * CW), idG, 1u);
+                        for (int kq = 0; kq < 4; ++kq)
+                            umma_bf16(tmem_u + TM_D1, dXN + kstep16(4 * a + kq, MROWS), dW + 2u * kq, idG, 1u);
                         umma_commit(bar(B_WEMPTY + slot));
-                        umma_commit(bar(B_D1FULL + j));
+                        if (a == KA - 1) umma_commit(bar(B_D1FULL));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
                 stamp();                                                    // newer-tap MMAs issued
-                // ---- residual and skip 1x1 convs on y (one MMA of N = C + S: H and the skip sum are adjacent in TMEM),
-                //      K-chunk by K-chunk as the gate epilogue delivers them
+                // ---- residual and skip 1x1 convs on y: ONE instruction of N = C + S per K-step (H and the skip sum are
+                //      adjacent in TMEM), a 64-channel K atom at a time as the gate epilogue delivers them
                 const bool has_res = P.has_res[l] != 0;
-                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
+                for (int j = 0; j < KA && !dead; ++j, ++wcnt) {
                     if (!wait_u(bar(B_YFULL + j), n_lay & 1u)) { dead = true; break; }
                     tc_fence_after();
-                    if (j == n_ch - 1) stamp();                              // last y chunk ready
+                    if (j == KA - 1) stamp();                               // last y chunk ready
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kk = 0; kk < KW; ++kk) {
-                            const unsigned long long a = dY + kstep16(KW * j + kk, MROWS);
-                            if (has_res) umma_bf16(tmem_u + TM_H, a, dW + kstep16(kk, C + S), idRS, 1u);
-                            else umma_bf16(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + kstep16(kk, C + S), idS, 1u);
+                        for (int kq = 0; kq < 4; ++kq) {
+                            const unsigned long long a = dY + kstep16(4 * j + kq, MROWS);
+                            if (has_res) umma_bf16(tmem_u + TM_H, a, dW + 2u * kq, idRS, 1u);
+                            else umma_bf16(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + 2u * kq, idS, 1u);
                         }
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (j == n_ch - 1) umma_commit(bar(B_D2FULL));
+                        if (j == KA - 1) umma_commit(bar(B_D2FULL));
                     }
                     __syncwarp();
                 }
@@ -433,33 +438,34 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 // ---- head: hidden = A(skip sum) . W1^T ; logits = A2(mish hidden) . W2^T
                 if (!wait_u(bar(B_HAFULL), n_head & 1u)) break;
                 tc_fence_after();
-                for (int c = 0; c < P.n_h1 && !dead; ++c, ++wcnt) {
+                for (int a = 0; a < S / 64 && !dead; ++a, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kk = 0; kk < S / 16; ++kk)
-                            umma_bf16(tmem_u + TM_D1, dY + kstep16(kk, MROWS), dW + kstep16(kk, Hh), umma_idesc(Hh), kk > 0);
+                        for (int kq = 0; kq < 4; ++kq)
+                            umma_bf16(tmem_u + TM_D1, dY + kstep16(4 * a + kq, MROWS), dW + 2u * kq, umma_idesc(Hh), (a | kq) != 0);
                         umma_commit(bar(B_WEMPTY + slot));
-                        umma_commit(bar(B_H1DFULL));
+                        if (a == S / 64 - 1) umma_commit(bar(B_H1DFULL));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
                 if (!wait_u(bar(B_H2AFULL), n_head & 1u)) break;
                 tc_fence_after();
-                for (int c = 0; c < P.n_h2 && !dead; ++c, ++wcnt) {
+                for (int ca = 0; ca < P.n_h2 * (Hh / 64) && !dead; ++ca, ++wcnt) {   // row chunk c, K atom a
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
+                    const int c = ca / (Hh / 64), a = ca - c * (Hh / 64);
                     const bool temp_chunk = (c == P.n_h2 - 1);        // the learned-temperature row, padded to 16
                     const int rows = temp_chunk ? 16 : min(128, Q - 128 * c);
                     const unsigned dcol = temp_chunk ? TM_TEMP : TM_LOGIT + 128 * c;
                     if (elect()) {
-                        for (int kk = 0; kk < Hh / 16; ++kk)
-                            umma_bf16(tmem_u + dcol, dXN + kstep16(kk, MROWS), dW + kstep16(kk, rows), umma_idesc(rows), kk > 0);
+                        for (int kq = 0; kq < 4; ++kq)
+                            umma_bf16(tmem_u + dcol, dXN + kstep16(4 * a + kq, MROWS), dW + 2u * kq, umma_idesc(rows), (a | kq) != 0);
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (temp_chunk) umma_commit(bar(B_H2DFULL));
+                        if (ca == P.n_h2 * (Hh / 64) - 1) umma_commit(bar(B_H2DFULL));
                     }
                     __syncwarp();
                 }
@@ -469,9 +475,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 ++n_head;
             }
         }
-    } else if (warp < 8) {
-        // ===================== epilogue warps: 2 threads per prompt row =====================
-        const int q4 = warp & 3, hf = warp >> 2;
+    } else if (warp < NEW) {
+        // ===================== epilogue warps: QT threads per prompt row, each owns 1/QT of every column range =====================
+        const int q4 = warp & 3, hf = warp >> 2;         // TMEM lane quarter (fixed by the warp id), column part
         const int m = 32 * q4 + lane;                    // prompt row = TMEM lane
         const int b = grp * MROWS + m;
         const bool live = b < P.B;
@@ -490,7 +496,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             dead |= !mbar_wait(bar(B_XNSAVED), n_saved & 1u, abort_flag);
             ++n_saved;
         };
-        const int half_c = C / 2, half_s = S / 2, half_h = Hh / 2, half_q = Q / 2, half_w = CW / 2;
+        const int half_c = C / QT, half_s = S / QT, half_h = Hh / QT, half_q = Q / QT;   // per-thread widths
         float* zs = reinterpret_cast<float*>(smem + SM_XN);
 
         for (long long t = P.t_begin; t < P.t_end; ++t) {
@@ -529,42 +535,34 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 tr = (P.trace && grp == 0 && tid == 0 && t == P.trace_t) ? P.trace + (size_t)(MAXL + l) * TRACE_EV : nullptr;
                 tn = 0;
                 stamp();                                                        // 0: layer start
-                for (int j = 0; j < n_ch; ++j) {
-                    // gate epilogue of chunk j: channels cw j + (cw / 2) hf + [0, cw / 2), 16 at a time
-                    const int chb = CW * j + half_w * hf;
-                    float4 bf[4], bg[4];                     // the first 16 channels' biases, fetched before the wait
+                for (int j = 0; j < KA; ++j) {
+                    // gate epilogue of the 64-channel chunk j: this thread's 16 channels 64 j + 16 hf + [0, 16)
+                    const int ch0 = 64 * j + 16 * hf;
+                    float4 bf[4], bg[4];                     // biases, fetched before the wait
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + chb) + k4);
-                        bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + chb) + k4);
+                        bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
+                        bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
                     }
-                    dead |= !mbar_wait(bar(B_D1FULL + j), n_lay & 1u, abort_flag);
-                    tc_fence_after();
-                    stamp();                                                    // D1 chunk j complete
-                    for (int sub = 0; sub < half_w / 16; ++sub) {
-                        const int ch0 = chb + 16 * sub;
-                        float f[16], g[16];
-                        tmem_ld16(tm_lane + TM_D1 + 2 * CW * j + half_w * hf + 16 * sub, f);
-                        tmem_ld16(tm_lane + TM_D1 + 2 * CW * j + CW + half_w * hf + 16 * sub, g);
-                        if (sub > 0) {
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
-                                bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
-                            }
-                        }
-                        tmem_ld_wait();
-                        float y[16];
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            y[4 * k4] = gate_fast(f[4 * k4] + bf[k4].x, g[4 * k4] + bg[k4].x);     // wavenet_v2.py:151
-                            y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf[k4].y, g[4 * k4 + 1] + bg[k4].y);
-                            y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
-                            y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
-                        }
-                        *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, MROWS)) = pack8(y);
-                        *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, MROWS)) = pack8(y + 8);
+                    if (j == 0) {
+                        dead |= !mbar_wait(bar(B_D1FULL), n_lay & 1u, abort_flag);
+                        tc_fence_after();
+                        stamp();                                                // gate pre-activations complete
                     }
+                    float f[16], g[16];
+                    tmem_ld16(tm_lane + TM_D1 + ch0, f);
+                    tmem_ld16(tm_lane + TM_D1 + C + ch0, g);
+                    tmem_ld_wait();
+                    float y[16];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        y[4 * k4] = gate_fast(f[4 * k4] + bf[k4].x, g[4 * k4] + bg[k4].x);     // wavenet_v2.py:151
+                        y[4 * k4 + 1] = gate_fast(f[4 * k4 + 1] + bf[k4].y, g[4 * k4 + 1] + bg[k4].y);
+                        y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
+                        y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
+                    }
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, MROWS)) = pack8(y);
+                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, MROWS)) = pack8(y + 8);
                     fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_YFULL + j));
@@ -657,8 +655,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     }
                     if (pass == 1) { tc_fence_before(); mbar_arrive(bar(B_HEADDONE)); }   // every TMEM read of the step is done
                     epi_sync();
-                    for (int r = 0; r < 8; ++r) {
-                        const int mr = 64 * pass + 8 * warp + r, br = grp * MROWS + mr;
+                    for (int r = 0; r < 64 / NEW; ++r) {
+                        const int mr = 64 * pass + (64 / NEW) * warp + r, br = grp * MROWS + mr;
                         if (br < P.B) {
                             const long long hstep = t - P.t_head, n_head_steps = P.t_end - P.t_head;
                             float* lout = P.logits_out ? P.logits_out + ((size_t)br * n_head_steps + hstep) * Q : nullptr;
@@ -668,7 +666,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                                 Tt = P.temperature[P.n_temperature == 1 ? 0 : br];
                                 u = P.noise[(size_t)br * P.noise_stride + (t + 1 - P.noise_t0)];
                             }
-                            const int choice = mmk::decide_warp(zs + (size_t)(8 * warp + r) * ZROW, Q, P.min_temp, lout, sample, Tt, u);
+                            const int choice = mmk::decide_warp(zs + (size_t)((64 / NEW) * warp + r) * ZROW, Q, P.min_temp, lout, sample, Tt, u);
                             if (lane == 0) {
                                 s_idx[mr] = choice;
                                 if (P.decisions) P.decisions[(size_t)br * n_head_steps + hstep] = choice;
@@ -806,9 +804,8 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     int cc_major = 0;
     MMK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, h->device));
     if (cc_major != 10) { delete h; MMK_FAIL("the bf16 tensor-core WaveNet kernel needs an sm_100 device (tcgen05)"); }
-    const int CW = 64;
-    p.L = L; p.C = C; p.S = S; p.Hh = Hh; p.Q = Q; p.cw = CW; p.n_ch = C / CW;
-    p.n_h1 = 1; p.n_h2 = (Q + 127) / 128 + 1;
+    p.L = L; p.C = C; p.S = S; p.Hh = Hh; p.Q = Q;
+    p.n_h2 = (Q + 127) / 128 + 1;
     p.min_temp = d->min_temperature;
     h->max_groups = (max_batch + MROWS - 1) / MROWS;
     const size_t tile_bytes = (size_t)MROWS * C * 2;
@@ -822,42 +819,50 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
     }
     p.ring_group_bytes = ring;
 
-    // ---- stage list + packed bf16 weights (every stage is one canonical swizzled tile, <= 32 KB)
-    std::vector<StageRec> stages;
+    // ---- packed bf16 weights + stage tables
     std::vector<unsigned char> wpack;
-    auto new_stage = [&](size_t bytes) {
-        const size_t at = (wpack.size() + 1023) / 1024 * 1024;
+    // every stage is one 64-deep K atom of a B tile: [rows x 64] bf16, rows * 128 bytes <= 32 KB.  All layers share one
+    // stage sequence (the last layer's residual rows are zero and its MMA skips them).
+    auto add_ls = [&](int l, size_t bytes) {
+        if (l == 0) { p.ls_off[p.n_ls] = (unsigned)wpack.size(); p.ls_bytes[p.n_ls] = (unsigned)bytes; ++p.n_ls; }
+        const size_t at = wpack.size();
         wpack.resize(at + bytes, 0);
-        stages.push_back(StageRec{(unsigned)(at / 16), (unsigned)bytes});
         return at;
     };
     for (int l = 0; l < L; ++l) {
-        const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample
-        for (int tap = 0; tap < 2; ++tap)      // stage order: older-tap chunks, then newer-tap chunks
-            for (int j = 0; j < p.n_ch; ++j) {
-                // rows 0..cw-1: filter channels cw j + r ; rows cw..2cw-1: gate channels cw j + r ; K = C input channels
-                const size_t at = new_stage((size_t)2 * CW * C * 2);
-                pack_rows(wpack, at, 2 * CW, C, 0, CW, wd + ((size_t)(CW * j) * C) * 2 + tap, (size_t)C * 2, 2, CW);
-                pack_rows(wpack, at, 2 * CW, C, CW, CW, wd + ((size_t)(C + CW * j) * C) * 2 + tap, (size_t)C * 2, 2, CW);
+        const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample; rows o < C filter, o >= C gate
+        for (int tap = 0; tap < 2; ++tap)      // stage order: older-tap atoms, then newer-tap atoms
+            for (int a = 0; a < C / 64; ++a) {
+                const size_t at = add_ls(l, (size_t)2 * C * 128);
+                pack_rows(wpack, at, 2 * C, 64, 0, 2 * C, wd + (size_t)(64 * a) * 2 + tap, (size_t)C * 2, 2, 2 * C);
             }
-        for (int j = 0; j < p.n_ch; ++j) {     // K-chunk j (cw input channels) of [res rows | skip rows]
-            const size_t at = new_stage((size_t)(C + S) * CW * 2);
-            pack_rows(wpack, at, C + S, CW, 0, C, d->conv_res_w[l] ? d->conv_res_w[l] + CW * j : nullptr, (size_t)C, 1, C);
-            pack_rows(wpack, at, C + S, CW, C, S, d->conv_skip_w[l] + CW * j, (size_t)C, 1, S);
+        for (int j = 0; j < C / 64; ++j) {     // K atom j (64 gated channels) of [residual rows | skip rows]
+            const size_t at = add_ls(l, (size_t)(C + S) * 128);
+            pack_rows(wpack, at, C + S, 64, 0, C, d->conv_res_w[l] ? d->conv_res_w[l] + 64 * j : nullptr, (size_t)C, 1, C);
+            pack_rows(wpack, at, C + S, 64, C, S, d->conv_skip_w[l] + 64 * j, (size_t)C, 1, S);
         }
+        if (l == 0) p.layer_bytes = wpack.size();
     }
-    {
-        const size_t at = new_stage((size_t)Hh * S * 2);
-        pack_rows(wpack, at, Hh, S, 0, Hh, d->head_w1, (size_t)S, 1, Hh);
+    p.head_off = wpack.size();
+    auto add_hs = [&](size_t bytes) {
+        const size_t at = wpack.size();
+        p.hs_off[p.n_hs] = (unsigned)(at - p.head_off); p.hs_bytes[p.n_hs] = (unsigned)bytes; ++p.n_hs;
+        wpack.resize(at + ((bytes + 1023) / 1024) * 1024, 0);
+        return at;
+    };
+    for (int a = 0; a < S / 64; ++a) {
+        const size_t at = add_hs((size_t)Hh * 128);
+        pack_rows(wpack, at, Hh, 64, 0, Hh, d->head_w1 + 64 * a, (size_t)S, 1, Hh);
     }
     for (int c = 0; c < p.n_h2; ++c) {
         const bool temp_chunk = c == p.n_h2 - 1;
         const int rows = temp_chunk ? 16 : std::min(128, Q - 128 * c), row0 = temp_chunk ? Q : 128 * c;
-        const size_t at = new_stage((size_t)rows * Hh * 2);
-        pack_rows(wpack, at, rows, Hh, 0, rows, d->head_w2 + (size_t)row0 * Hh, (size_t)Hh, 1, temp_chunk ? 1 : rows);
+        for (int a = 0; a < Hh / 64; ++a) {
+            const size_t at = add_hs((size_t)rows * 128);
+            pack_rows(wpack, at, rows, 64, 0, rows, d->head_w2 + (size_t)row0 * Hh + 64 * a, (size_t)Hh, 1, temp_chunk ? 1 : rows);
+        }
     }
-    for (const StageRec& s : stages)
-        if (s.bytes > (unsigned)SLOT_BYTES || s.bytes % 16 != 0) { delete h; MMK_FAIL("internal: weight stage exceeds the ring slot"); }
+    if (p.n_ls > MAX_LS || p.n_hs > MAX_HS) { delete h; MMK_FAIL("internal: stage table overflow"); }
 
     std::vector<float> b1((size_t)L * 2 * C), cbr((size_t)(L + 1) * C, 0.0f), cbs(S, 0.0f);
     for (int l = 0; l < L; ++l) {
@@ -884,7 +889,6 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
         return ptr;
     };
     p.wpack = (const unsigned char*)dev_alloc(wpack.size(), wpack.data());
-    p.stages = (const StageRec*)dev_alloc(stages.size() * sizeof(StageRec), stages.data());
     p.E = (const float*)dev_alloc((size_t)Q * C * 4, d->embedding);
     p.b1 = (const float*)dev_alloc(b1.size() * 4, b1.data());
     p.cbs = (const float*)dev_alloc(cbs.size() * 4, cbs.data());
@@ -897,9 +901,7 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
         h->d_trace = (long long*)dev_alloc((size_t)2 * MAXL * TRACE_EV * sizeof(long long), nullptr);
     }
     if (!ok) { wn4_destroy(h); MMK_FAIL("cudaMalloc failed while creating the bf16 WaveNet handle"); }
-    p.n_stages = (int)stages.size();
-    h->smem_bytes = SM_FIXED + (int)stages.size() * 8;
-    if (h->smem_bytes > 232448) { wn4_destroy(h); MMK_FAIL("too many layers for the bf16 kernel's shared-memory stage list"); }
+    h->smem_bytes = SM_TOTAL;
     MMK_CUDA(cudaFuncSetAttribute(wavenet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     MMK_CUDA(cudaDeviceSynchronize());
     *out = h;
