@@ -175,8 +175,7 @@ __global__ void __launch_bounds__(256, 8) mulaw_compress_table_kernel(const floa
     };
     const size_t n4 = n / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+    auto store4 = [&](size_t i, const float4& v) {
         long long r0 = one(v.x), r1 = one(v.y), r2 = one(v.z), r3 = one(v.w);
         if constexpr (sizeof(OutT) == 8) {
             longlong2* o = reinterpret_cast<longlong2*>(q) + 2 * i;
@@ -186,7 +185,16 @@ __global__ void __launch_bounds__(256, 8) mulaw_compress_table_kernel(const floa
             reinterpret_cast<uchar4*>(q)[i] =
                 make_uchar4((unsigned char)r0, (unsigned char)r1, (unsigned char)r2, (unsigned char)r3);
         }
+    };
+    // two 16-byte loads in flight per thread (the kernel is latency-bound on HBM with one)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(x) + i);
+        const float4 v1 = __ldcs(reinterpret_cast<const float4*>(x) + i + stride);
+        store4(i, v0);
+        store4(i + stride, v1);
     }
+    if (i < n4) store4(i, __ldcs(reinterpret_cast<const float4*>(x) + i));
     size_t t = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) q[t] = (OutT)one(x[t]);
 }
