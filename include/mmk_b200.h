@@ -56,6 +56,18 @@ int mmk_mulaw_prepare(int q_levels, float compression, int* table_in_use, uint64
  * GenerateLoopV2.process_outputs applies, mimikit/loops/generate.py:245).  d_q int64 (n) -> d_x fp32 (n). */
 int mmk_mulaw_expand(const int64_t* d_q, float* d_x, size_t n, int q_levels, float compression, void* stream);
 
+/* Normalize(p=inf, dim=-1).torch_func — mimikit/features/functionals.py:236-253: F.normalize(x, p=inf, dim=-1) =
+ * x / max(max|x|, 1e-12) per row (one IEEE division per sample; NaN rows stay NaN).  d_x fp32 (n_rows, row_len) with row
+ * stride `row_stride` elements; d_out fp32 (n_rows, row_len) contiguous (may alias a contiguous d_x); d_norms fp32 (n_rows)
+ * receives the row maxima (it is also the scratch of the first pass).  n_rows <= 65535 per call. */
+int mmk_normalize_inf(const float* d_x, float* d_out, float* d_norms, int64_t n_rows, int64_t row_len, int64_t row_stride,
+                      void* stream);
+/* Compose(Normalize(), MuLawCompress(q_levels, compression)) — functionals.py:196-213, 236-253, 313-342 — in two passes
+ * over the waveform (16 B per sample) instead of four (24 B): row maxima, then x / max -> mu-law level.  d_q int64
+ * (n_rows, row_len) contiguous.  Bit-exact with the reference's composition evaluated by torch on CPU. */
+int mmk_normalize_mulaw_compress(const float* d_x, int64_t* d_q, float* d_norms, int64_t n_rows, int64_t row_len,
+                                 int64_t row_stride, int q_levels, float compression, void* stream);
+
 /* MagSpec.torch_func -> STFT(coordinate="mag").torch_func — mimikit/features/functionals.py:468-524, 576-606,
  * fused with MelSpec.np_func — functionals.py:649-668 (librosa mel filterbank @ magnitudes).
  *   d_x        fp32 (n_clips, clip_len), row stride `clip_stride` elements

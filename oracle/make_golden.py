@@ -41,9 +41,27 @@ def gen_network(name, net, prompts, n_steps, meta):
     print(name, {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
 
 
+def gen_normalize(ref):
+    """Normalize (functionals.py:236-253) and Compose(Normalize(), MuLawCompress()) (:196-213) of the live reference."""
+    g = torch.Generator().manual_seed(99)
+    x = (torch.randn(7, 4099, generator=g) * torch.tensor([1e-3, .1, .5, 1., 3., 1e-20, 1.])[:, None]).float()
+    x[5] = 0.                                 # an all-zero clip: x / eps
+    x[6, 17] = -7.5                           # the peak is a negative sample
+    x1 = torch.rand(5, generator=g) * 2 - 1   # 1-D input
+    F = ref.functionals
+    d = dict(x=x.numpy(), x1=x1.numpy(), norm=F.Normalize().torch_func(x).numpy(), norm1=F.Normalize().torch_func(x1).numpy())
+    for q, C in [(256, 1.), (64, 2.)]:
+        d[f"compose_q{q}_c{C}"] = F.Compose(F.Normalize(), F.MuLawCompress(q, C))(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "normalize.npz"), **d)
+    print("normalize", {k: v.shape for k, v in d.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "normalize":   # only this fixture (the others are unchanged)
+        return gen_normalize(ref)
+    gen_normalize(ref)
     g = torch.Generator().manual_seed(1234)
 
     # ---- mu-law (functionals.py:313-373)

@@ -69,6 +69,16 @@ def mulaw_expand(idx, q_levels=256, compression=1.0):
     return out
 
 
+def normalize_inf(x, eps=1e-12):
+    """Normalize(p=inf, dim=-1).torch_func = F.normalize(x, p=inf, dim=-1) (features/functionals.py:236-253; torch:
+    x / clamp_min(vector_norm(x, inf, dim, keepdim), eps)) in fp32: one IEEE division per sample."""
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        n = np.abs(x).max(axis=-1, keepdims=True)
+        d = np.where(np.isnan(n), n, np.maximum(n, f32(eps))).astype(f32)
+        return (x / d).astype(f32)
+
+
 def expf_portable(x):
     x = np.ascontiguousarray(x, dtype=f32)
     out = np.empty_like(x)

@@ -31,3 +31,13 @@ for clips in (36, 360, 1800, 3600):
         del q
     os.environ.pop("MMK_MULAW_EXACT")
     del x
+
+# Normalize and the fused Normalize -> mu-law pipeline
+from mimikit_b200 import Compose, Normalize
+x = torch.rand((3600, L), device="cuda") * 2 - 1
+t = timeit(lambda: Normalize()(x))
+print(f"normalize 3600 clips: ms {['%.3f' % v for v in t]} -> {12*3600*L/min(t)/1e6:.1f} GB/s (12 B/sample)")
+t = timeit(lambda: Compose(Normalize(), MuLawCompress())(x))
+print(f"fused normalize+mulaw: ms {['%.3f' % v for v in t]} -> {16*3600*L/min(t)/1e6:.1f} GB/s (16 B/sample)")
+t = timeit(lambda: MuLawCompress()(Normalize()(x)))
+print(f"unfused normalize, mulaw: ms {['%.3f' % v for v in t]}")

@@ -169,3 +169,44 @@ def test_stft_linearity_and_too_short():
     assert float((a * 0.5 - b).abs().max()) <= 1e-5 * float(a.max())
     with pytest.raises(_capi.MmkError):
         MagSpec(2048, 512, center=False)(torch.zeros(1000, device="cuda"))
+
+
+def test_normalize_and_fused_compose_golden_bit_exact():
+    """Normalize(p=inf, dim=-1) and Compose(Normalize(), MuLawCompress()) against the live reference's outputs
+    (tests/golden/normalize.npz): bit-exact, fused and unfused, device / host / 1-D inputs."""
+    from mimikit_b200 import Compose, MuLawCompress, Normalize
+    d = load_golden("normalize")
+    x = torch.from_numpy(d["x"]).cuda()
+    nz = Normalize()
+    got = nz(x)
+    assert got.dtype == torch.float32 and got.is_cuda
+    assert np.array_equal(got.cpu().numpy().view(np.int32), d["norm"].view(np.int32))
+    assert np.array_equal(nz.norms.cpu().numpy(), np.abs(d["x"]).max(-1))
+    assert np.array_equal(Normalize()(d["x1"]).view(np.int32), d["norm1"].view(np.int32))          # numpy, 1-D
+    xs = torch.from_numpy(d["x"]).cuda()[:, 3:]                                                       # unaligned rows
+    assert np.array_equal(Normalize()(xs).cpu().numpy(), restate.normalize_inf(d["x"][:, 3:]))
+    for q, C in [(256, 1.), (64, 2.)]:
+        fused = Compose(Normalize(), MuLawCompress(q, C))(x)
+        assert fused.dtype == torch.int64 and np.array_equal(fused.cpu().numpy(), d[f"compose_q{q}_c{C}"])
+        assert torch.equal(MuLawCompress(q, C)(Normalize()(x)), fused)                                 # unfused == fused
+        assert np.array_equal(Compose(Normalize(), MuLawCompress(q, C))(d["x"]), d[f"compose_q{q}_c{C}"])   # host buffers
+    with pytest.raises(NotImplementedError):
+        Normalize(p=2.)(x)
+    xn = x.clone(); xn[1, 5] = float("nan")
+    assert torch.isnan(Normalize()(xn)[1]).all() and not torch.isnan(Normalize()(xn)[0]).any()         # F.normalize semantics
+
+
+def test_normalize_full_size_properties():
+    """One hour of 22.05 kHz clips: every clip peaks at exactly 1, idempotent, and the fused compressor agrees with the
+    oracle on a strided sample."""
+    from mimikit_b200 import Compose, MuLawCompress, Normalize
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.rand((360, 220500), generator=g, device="cuda") * 2 - 1) * torch.rand((360, 1), generator=g, device="cuda")
+    y = Normalize()(x)
+    assert torch.equal(y.abs().amax(dim=1), torch.ones(360, device="cuda"))
+    assert torch.equal(Normalize()(y), y)
+    q = Compose(Normalize(), MuLawCompress())(x)
+    assert int(q.min()) == 0 and int(q.max()) == 255
+    sub = x[::37, :20000].contiguous()
+    want = restate.mulaw_compress(restate.normalize_inf(x[::37].cpu().numpy())[:, :20000])
+    assert np.array_equal(q[::37, :20000].cpu().numpy(), want) and sub.shape[0] == 10

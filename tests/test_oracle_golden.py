@@ -128,3 +128,14 @@ def test_sampling_contract_properties():
     p = np.exp(lg[0] - lg[0].max()); p /= p.sum()
     freq = np.bincount(s, minlength=256) / 20000
     assert np.abs(freq - p).max() < 0.02
+
+
+def test_normalize_and_compose_oracle_vs_reference():
+    """Normalize(p=inf) and Compose(Normalize(), MuLawCompress()) of the live reference (tests/golden/normalize.npz)."""
+    d = load_golden("normalize")
+    got = restate.normalize_inf(d["x"])
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.int32), d["norm"].view(np.int32))   # bit-exact
+    assert np.array_equal(restate.normalize_inf(d["x1"]).view(np.int32), d["norm1"].view(np.int32))
+    assert np.abs(got[6]).max() == 1.0 and got[6, 17] == -1.0 and not got[5].any()
+    for q, C in [(256, 1.), (64, 2.)]:
+        assert np.array_equal(restate.mulaw_compress(got, q, C), d[f"compose_q{q}_c{C}"])
