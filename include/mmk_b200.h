@@ -68,6 +68,13 @@ int mmk_normalize_inf(const float* d_x, float* d_out, float* d_norms, int64_t n_
 int mmk_normalize_mulaw_compress(const float* d_x, int64_t* d_q, float* d_norms, int64_t n_rows, int64_t row_len,
                                  int64_t row_stride, int q_levels, float compression, void* stream);
 
+/* RemoveDC.np_func — mimikit/features/functionals.py:216-233: scipy.signal.lfilter([1, -1], [1, -0.99], x, axis=-1) in
+ * float64 (scipy's direct-form-II-transposed loop, zero initial state), cast back to float32.  Bit-exact: one lane per
+ * row evaluates scipy's chain; rows are the parallel dimension.  d_x fp32 (n_rows, row_len) with row stride; d_out fp32
+ * (n_rows, row_len) contiguous, must not alias d_x.  (RemoveDC.torch_func cannot run in the reference: it passes
+ * lfilter's arguments in the wrong order.) */
+int mmk_remove_dc(const float* d_x, float* d_out, int64_t n_rows, int64_t row_len, int64_t row_stride, void* stream);
+
 /* MagSpec.torch_func -> STFT(coordinate="mag").torch_func — mimikit/features/functionals.py:468-524, 576-606,
  * fused with MelSpec.np_func — functionals.py:649-668 (librosa mel filterbank @ magnitudes).
  *   d_x        fp32 (n_clips, clip_len), row stride `clip_stride` elements

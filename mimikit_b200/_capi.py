@@ -58,6 +58,7 @@ PROTOTYPES = {
     "mmk_mulaw_compress": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_mulaw_compress_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_mulaw_prepare": (c_int, [c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmk_remove_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "mmk_normalize_inf": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "mmk_normalize_mulaw_compress": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_float,
                                              c_void_p]),

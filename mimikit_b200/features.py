@@ -14,7 +14,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["Continuous", "Discrete", "Sample", "Frame", "Functional", "Identity", "Compose", "Normalize",
+__all__ = ["Continuous", "Discrete", "Sample", "Frame", "Functional", "Identity", "Compose", "Normalize", "RemoveDC",
            "MuLawCompress", "MuLawExpand", "STFT", "MagSpec", "MelSpec", "mel_filterbank", "stft_n_frames"]
 
 N_FFT = 2048
@@ -135,6 +135,31 @@ class Normalize(Functional):
                 _capi.check(_capi.lib().mmk_normalize_inf(x2[r0:].data_ptr(), out[r0:].data_ptr(), norms[r0:].data_ptr(),
                                                           r1 - r0, L, x2.stride(0), _capi.stream_ptr()))
         self.norms = norms.reshape(x.shape[:-1])
+        return restore(out.reshape(x.shape))
+
+    @property
+    def inv(self):
+        return Identity()
+
+
+@dtc.dataclass
+class RemoveDC(Functional):
+    """functionals.py:216-233 — np_func semantics (scipy.signal.lfilter([1, -1], [1, -0.99], x) in float64, cast back),
+    for numpy AND torch inputs: the reference's torch_func passes lfilter's arguments in the wrong order and cannot run
+    (documented deviation).  Bit-exact with the reference's np_func: one lane per clip evaluates scipy's chain."""
+
+    @property
+    def elem_type(self):
+        return None
+
+    def torch_func(self, inputs):
+        x, restore = _to_device(inputs)
+        if x.dtype != torch.float32:
+            raise TypeError("RemoveDC: the B200 path takes fp32 audio (the filter itself runs in fp64, as scipy's does)")
+        x2, n_rows, L = _rows(x)
+        out = torch.empty_like(x2)
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.lib().mmk_remove_dc(x2.data_ptr(), out.data_ptr(), n_rows, L, x2.stride(0), _capi.stream_ptr()))
         return restore(out.reshape(x.shape))
 
     @property

@@ -128,3 +128,19 @@ void orc_mulaw_expand(const int64_t* idx, float* out, int64_t n, int q_levels, f
 
 void orc_log1pf_arr(const float* in, float* out, int64_t n) { for (int64_t i = 0; i < n; ++i) out[i] = orc_log1pf(in[i]); }
 void orc_expf_arr(const float* in, float* out, int64_t n) { for (int64_t i = 0; i < n; ++i) out[i] = orc_expf(in[i]); }
+
+/* RemoveDC.np_func — mimikit/features/functionals.py:216-233: scipy.signal.lfilter([1, -1], [1, -0.99], x, axis=-1) on a
+ * float32 signal: scipy promotes to float64 and runs its direct-form-II-transposed loop (scipy/signal/_lfilter.c.in,
+ * @NAME@_filt: y = Z[0] + b[0] x ; Z[last] = x b[last] - y a[last]), zero initial state; the caller casts back to float32. */
+void orc_remove_dc(const float* x, float* y, int64_t n_rows, int64_t row_len) {
+    const double b1 = -1.0, a1 = -0.99;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        double z = 0.0;
+        for (int64_t n = 0; n < row_len; ++n) {
+            const double xn = (double)x[r * row_len + n];
+            const double yn = z + 1.0 * xn;
+            z = xn * b1 - yn * a1;
+            y[r * row_len + n] = (float)yn;
+        }
+    }
+}

@@ -41,6 +41,15 @@ def gen_network(name, net, prompts, n_steps, meta):
     print(name, {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
 
 
+def restate_like_signal(g):
+    """(5, 6007) fp32: sines with a DC offset + noise, one silent row, one constant row."""
+    t = torch.arange(6007, dtype=torch.float64) / 16000
+    x = torch.stack([0.4 * torch.sin(2 * np.pi * f * t) + dc for f, dc in [(220., .3), (659., -.2), (50., .05)]])
+    x = x + 0.01 * torch.randn(3, 6007, generator=g, dtype=torch.float64)
+    x = torch.cat([x, torch.zeros(1, 6007, dtype=torch.float64), torch.full((1, 6007), 0.25, dtype=torch.float64)])
+    return x.float().numpy()
+
+
 def gen_normalize(ref):
     """Normalize (functionals.py:236-253) and Compose(Normalize(), MuLawCompress()) (:196-213) of the live reference."""
     g = torch.Generator().manual_seed(99)
@@ -52,6 +61,11 @@ def gen_normalize(ref):
     d = dict(x=x.numpy(), x1=x1.numpy(), norm=F.Normalize().torch_func(x).numpy(), norm1=F.Normalize().torch_func(x1).numpy())
     for q, C in [(256, 1.), (64, 2.)]:
         d[f"compose_q{q}_c{C}"] = F.Compose(F.Normalize(), F.MuLawCompress(q, C))(x).numpy()
+    # RemoveDC.np_func (functionals.py:216-233; the path used at extraction — torch_func passes lfilter's arguments in
+    # the wrong order and cannot run): scipy fp64 IIR, cast back to fp32
+    xs = restate_like_signal(g)
+    d["dc_x"], d["dc_y"] = xs, F.RemoveDC().np_func(xs)
+    d["dc_norm_y"] = F.RemoveDC().np_func(F.Normalize().torch_func(torch.from_numpy(xs)).numpy())
     np.savez_compressed(os.path.join(OUT, "normalize.npz"), **d)
     print("normalize", {k: v.shape for k, v in d.items()})
 

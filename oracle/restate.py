@@ -79,6 +79,16 @@ def normalize_inf(x, eps=1e-12):
         return (x / d).astype(f32)
 
 
+def remove_dc(x):
+    """RemoveDC.np_func (features/functionals.py:216-233): scipy.signal.lfilter([1, -1], [1, -0.99], x, axis=-1) —
+    scipy's fp64 direct-form-II-transposed loop restated in C — cast back to fp32."""
+    x = np.ascontiguousarray(x, dtype=f32)
+    out = np.empty_like(x)
+    L = x.shape[-1] if x.ndim else 1
+    clib().orc_remove_dc(_ptr(x), _ptr(out), ctypes.c_int64(x.size // max(L, 1)), ctypes.c_int64(L))
+    return out
+
+
 def expf_portable(x):
     x = np.ascontiguousarray(x, dtype=f32)
     out = np.empty_like(x)

@@ -41,3 +41,9 @@ t = timeit(lambda: Compose(Normalize(), MuLawCompress())(x))
 print(f"fused normalize+mulaw: ms {['%.3f' % v for v in t]} -> {16*3600*L/min(t)/1e6:.1f} GB/s (16 B/sample)")
 t = timeit(lambda: MuLawCompress()(Normalize()(x)))
 print(f"unfused normalize, mulaw: ms {['%.3f' % v for v in t]}")
+from mimikit_b200 import RemoveDC
+t = timeit(lambda: RemoveDC()(x))
+print(f"remove_dc 3600 clips: ms {['%.3f' % v for v in t]} -> {8*3600*L/min(t)/1e6:.1f} GB/s (8 B/sample)")
+xx = torch.rand((36000, 22050), device="cuda") * 2 - 1
+t = timeit(lambda: RemoveDC()(xx))
+print(f"remove_dc 36000 x 1 s clips: ms {['%.3f' % v for v in t]} -> {8*36000*22050/min(t)/1e6:.1f} GB/s")

@@ -210,3 +210,22 @@ def test_normalize_full_size_properties():
     sub = x[::37, :20000].contiguous()
     want = restate.mulaw_compress(restate.normalize_inf(x[::37].cpu().numpy())[:, :20000])
     assert np.array_equal(q[::37, :20000].cpu().numpy(), want) and sub.shape[0] == 10
+
+
+def test_remove_dc_golden_bit_exact_and_full_size():
+    """RemoveDC against the live reference's np_func (tests/golden/normalize.npz) and, at one hour of audio, against the
+    oracle: bit-exact (the kernel evaluates scipy's fp64 chain per clip)."""
+    from mimikit_b200 import Compose, Normalize, RemoveDC
+    d = load_golden("normalize")
+    got = RemoveDC()(torch.from_numpy(d["dc_x"]).cuda())
+    assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy().view(np.int32), d["dc_y"].view(np.int32))
+    assert np.array_equal(RemoveDC()(d["dc_x"]).view(np.int32), d["dc_y"].view(np.int32))            # numpy in, numpy out
+    chain = Compose(Normalize(), RemoveDC())(torch.from_numpy(d["dc_x"]).cuda())                         # the extractor's order
+    assert np.array_equal(chain.cpu().numpy().view(np.int32), d["dc_norm_y"].view(np.int32))
+    assert np.array_equal(RemoveDC()(d["dc_x"][0, :77]).view(np.int32), restate.remove_dc(d["dc_x"][0, :77]).view(np.int32))  # 1-D, ragged
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand((361, 220500), generator=g, device="cuda") * 2 - 1 + 0.1      # 361 clips: a ragged last warp
+    y = RemoveDC()(x)
+    sel = [0, 31, 32, 200, 359, 360]
+    assert np.array_equal(y[sel].cpu().numpy().view(np.int32), restate.remove_dc(x[sel].cpu().numpy()).view(np.int32))
+    assert float(y[:, 5000:].mean().abs()) < 1e-3                                  # the offset is gone

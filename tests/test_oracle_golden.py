@@ -139,3 +139,12 @@ def test_normalize_and_compose_oracle_vs_reference():
     assert np.abs(got[6]).max() == 1.0 and got[6, 17] == -1.0 and not got[5].any()
     for q, C in [(256, 1.), (64, 2.)]:
         assert np.array_equal(restate.mulaw_compress(got, q, C), d[f"compose_q{q}_c{C}"])
+
+
+def test_remove_dc_oracle_vs_reference():
+    """RemoveDC.np_func of the live reference (scipy fp64 IIR): the C restatement is bit-exact, alone and after Normalize."""
+    d = load_golden("normalize")
+    assert np.array_equal(restate.remove_dc(d["dc_x"]).view(np.int32), d["dc_y"].view(np.int32))
+    assert np.array_equal(restate.remove_dc(restate.normalize_inf(d["dc_x"])).view(np.int32), d["dc_norm_y"].view(np.int32))
+    y = restate.remove_dc(d["dc_x"])
+    assert not y[3].any() and abs(float(y[4, -1])) < 1e-6 and abs(float(y[0, 2000:].mean())) < 1e-3   # silence, constant, DC gone
