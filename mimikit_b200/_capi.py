@@ -58,7 +58,9 @@ PROTOTYPES = {
     "mmk_mulaw_compress": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_mulaw_compress_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]),
     "mmk_mulaw_prepare": (c_int, [c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "mmk_remove_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "mmk_remove_dc_scratch_bytes": (c_size_t, [c_int64, c_int64]),
+    "mmk_remove_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "mmk_remove_dc_recomputed_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mmk_normalize_inf": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "mmk_normalize_mulaw_compress": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_float,
                                              c_void_p]),

@@ -148,6 +148,9 @@ class RemoveDC(Functional):
     for numpy AND torch inputs: the reference's torch_func passes lfilter's arguments in the wrong order and cannot run
     (documented deviation).  Bit-exact with the reference's np_func: one lane per clip evaluates scipy's chain."""
 
+    count_recomputed = False      # diagnostic: when set, `recomputed_rows` is filled after each call (synchronises)
+    recomputed_rows = 0
+
     @property
     def elem_type(self):
         return None
@@ -158,8 +161,16 @@ class RemoveDC(Functional):
             raise TypeError("RemoveDC: the B200 path takes fp32 audio (the filter itself runs in fp64, as scipy's does)")
         x2, n_rows, L = _rows(x)
         out = torch.empty_like(x2)
+        lib = _capi.lib()
+        nbytes = int(lib.mmk_remove_dc_scratch_bytes(n_rows, L))      # > 0: rows are long enough to be split in time
+        scratch = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=x.device) if nbytes else None
         with torch.cuda.device(x.device):
-            _capi.check(_capi.lib().mmk_remove_dc(x2.data_ptr(), out.data_ptr(), n_rows, L, x2.stride(0), _capi.stream_ptr()))
+            _capi.check(lib.mmk_remove_dc(x2.data_ptr(), out.data_ptr(), n_rows, L, x2.stride(0),
+                                          scratch.data_ptr() if nbytes else None, nbytes, _capi.stream_ptr()))
+            if self.count_recomputed and nbytes:
+                n = ctypes.c_int64(0)
+                _capi.check(lib.mmk_remove_dc_recomputed_rows(scratch.data_ptr(), n_rows, L, ctypes.byref(n), _capi.stream_ptr()))
+                self.recomputed_rows = n.value
         return restore(out.reshape(x.shape))
 
     @property

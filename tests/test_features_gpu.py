@@ -229,3 +229,24 @@ def test_remove_dc_golden_bit_exact_and_full_size():
     sel = [0, 31, 32, 200, 359, 360]
     assert np.array_equal(y[sel].cpu().numpy().view(np.int32), restate.remove_dc(x[sel].cpu().numpy()).view(np.int32))
     assert float(y[:, 5000:].mean().abs()) < 1e-3                                  # the offset is gone
+
+
+@pytest.mark.parametrize("chunk,warmup,expect_recompute", [(None, None, False), ("256", "32", True), ("64", "0", True),
+                                                           ("4096", "8192", False)])
+def test_remove_dc_time_split_is_always_exact(monkeypatch, chunk, warmup, expect_recompute):
+    """The speculative split in time (chunks filtered after a warm-up from a zero state, seams verified bitwise, failed
+    rows recomputed sequentially) returns the exact chain whatever the geometry: default (no row should need the
+    fallback), and warm-ups far too short to converge (the fallback must catch every such row)."""
+    from mimikit_b200 import RemoveDC
+    if chunk is not None:
+        monkeypatch.setenv("MMK_DC_CHUNK", chunk)
+        monkeypatch.setenv("MMK_DC_WARMUP", warmup)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.rand((67, 70001), generator=g, device="cuda") * 2 - 1 + 0.2       # >= 4 (W + CH): split by default
+    x[5] = 0.                                   # silence: every state is +0
+    x[6, :30000] = 0.                           # sound after a long silence
+    f = RemoveDC()
+    f.count_recomputed = True
+    y = f(x)
+    assert np.array_equal(y.cpu().numpy().view(np.int32), restate.remove_dc(x.cpu().numpy()).view(np.int32))
+    assert (f.recomputed_rows > 0) == expect_recompute, f.recomputed_rows
