@@ -64,18 +64,22 @@ constexpr int SM_TOTAL = SM_BAR + 1024;
 constexpr int ZROW = 260;
 
 enum {
-    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_XNSAVED, B_D1FULL, B_YFULL,
+    B_WFULL = 0, B_WEMPTY = NSLOT, B_XOFULL = 2 * NSLOT, B_XOFREE, B_XNFULL, B_XNSAVED, B_D1FULL, B_YFULL = B_D1FULL + 2,
     B_D2FULL = B_YFULL + 2, B_HAFULL, B_H1DFULL, B_H2AFULL, B_H2DFULL, B_HEADDONE, B_EPISYNC, B_COUNT
 };
 
-constexpr int MAX_LS = 8, MAX_HS = 12;        // weight stages of one layer / of the head
+constexpr int MAX_HS = 12;                    // weight stages of the head
 
 struct Params {
     int L, C, S, Hh, Q, n_h2;
-    // weight stages (each = one 64-deep K atom of a B tile, <= 32 KB): every layer has the same n_ls stages, layer l's
-    // stage i starts at byte l * layer_bytes + ls_off[i] of wpack; the head's n_hs stages start at head_off + hs_off[i]
-    int n_ls, n_hs;
-    unsigned ls_off[MAX_LS], ls_bytes[MAX_LS], hs_off[MAX_HS], hs_bytes[MAX_HS];
+    // weight stages (<= 32 KB each).  Layer l's block of wpack (layer_bytes each) holds, per 64-channel chunk j < n_ch:
+    //   older-tap tile  [f rows | g rows of chunk j] x C   at  j * cb              (cb bytes)
+    //   newer-tap tile                                      at  (n_ch + j) * cb
+    //   res|skip K atom [C res rows | S skip rows] x 64     at  2 n_ch cb + j * wb  (wb bytes)
+    // streamed per step as: older(0) ; then per layer l: newer(l), { res|skip(l, j), older(l + 1, j) } for every j.
+    // The head's n_hs stages start at head_off + hs_off[i].
+    int n_ch, n_hs;
+    unsigned cb, wb, hs_off[MAX_HS], hs_bytes[MAX_HS];
     unsigned long long layer_bytes, head_off;
     float min_temp;
     int dil[MAXL];
@@ -268,8 +272,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         for (int i = 0; i < NSLOT; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         mbar_init(bar(B_XOFULL), 1); mbar_init(bar(B_XOFREE), 1);
         mbar_init(bar(B_XNFULL), NEPI); mbar_init(bar(B_XNSAVED), 1);
-        mbar_init(bar(B_D1FULL), 1);
-        for (int j = 0; j < 2; ++j) mbar_init(bar(B_YFULL + j), NEPI);
+        for (int j = 0; j < 2; ++j) { mbar_init(bar(B_D1FULL + j), 1); mbar_init(bar(B_YFULL + j), NEPI); }
         mbar_init(bar(B_D2FULL), 1);
         mbar_init(bar(B_HAFULL), NEPI); mbar_init(bar(B_H1DFULL), 1);
         mbar_init(bar(B_H2AFULL), NEPI); mbar_init(bar(B_H2DFULL), 1);
@@ -303,9 +306,18 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 return true;
             };
             for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
-                for (int l = 0; l < L && !dead; ++l)
-                    for (int i = 0; i < P.n_ls; ++i)
-                        if (!load(P.wpack + (size_t)l * P.layer_bytes + P.ls_off[i], P.ls_bytes[i])) { dead = true; break; }
+                const int n_ch = P.n_ch;
+                for (int j = 0; j < n_ch && !dead; ++j)                       // older tap of layer 0
+                    if (!load(P.wpack + (size_t)j * P.cb, P.cb)) dead = true;
+                for (int l = 0; l < L && !dead; ++l) {
+                    const unsigned char* wl = P.wpack + (size_t)l * P.layer_bytes;
+                    for (int j = 0; j < n_ch && !dead; ++j)                   // newer tap
+                        if (!load(wl + (size_t)(n_ch + j) * P.cb, P.cb)) dead = true;
+                    for (int j = 0; j < n_ch && !dead; ++j) {                 // res|skip atom j, then the next layer's older tap
+                        if (!load(wl + (size_t)2 * n_ch * P.cb + (size_t)j * P.wb, P.wb)) { dead = true; break; }
+                        if (l + 1 < L && !load(wl + P.layer_bytes + (size_t)j * P.cb, P.cb)) dead = true;
+                    }
+                }
                 if (t >= P.t_head)
                     for (int i = 0; i < P.n_hs && !dead; ++i)
                         if (!load(P.wpack + P.head_off + P.hs_off[i], P.hs_bytes[i])) dead = true;
@@ -357,7 +369,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
         long long* tr = nullptr;
         int tn = 0;
         auto stamp = [&]() { if (tr && lane == 0 && tn < TRACE_EV) tr[tn] = clock64(); ++tn; };
-        const unsigned idG = umma_idesc(2 * C), idRS = umma_idesc(C + S), idS = umma_idesc(S);
+        const unsigned id128 = umma_idesc(128), idRS = umma_idesc(C + S), idS = umma_idesc(S);
+        const int n_ch = P.n_ch, KC = C / 16;
         const unsigned long long dXO = umma_desc(sb + SM_XO), dXN = umma_desc(sb + SM_XN), dY = umma_desc(sb + SM_Y);
         const unsigned long long dW0 = umma_desc(sb + SM_W);
         constexpr unsigned SLOT16 = SLOT_BYTES >> 4;
@@ -367,55 +380,60 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
             tc_fence_after();
             return ok;
         };
+        // older tap of global layer n (chunk j): D1[:, 128 j ..] = XO . W1o_j^T.  Independent of this step's activations,
+        // it is issued early — right after the previous layer's res/skip MMAs of the same chunk, whose wait on the gated
+        // output also guarantees that the gate epilogue has drained that half of D1.
+        auto issue_old = [&](unsigned n, int j) -> bool {
+            if (j == 0) {
+                if (!wait_u(bar(B_XOFULL), n & 1u)) return false;
+                tc_fence_after();
+            }
+            unsigned slot;
+            if (!wslot_wait(slot)) return false;
+            const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
+            if (elect()) {
+                for (int kk = 0; kk < KC; ++kk)
+                    umma_bf16(tmem_u + TM_D1 + 128 * j, dXO + kstep16(kk, MROWS), dW + kstep16(kk, 128), id128, kk > 0);
+                umma_commit(bar(B_WEMPTY + slot));
+                if (j == n_ch - 1) umma_commit(bar(B_XOFREE));
+            }
+            __syncwarp();
+            ++wcnt;
+            return true;
+        };
         for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
+            for (int j = 0; j < n_ch && !dead; ++j) dead = !issue_old(n_lay, j);           // layer 0 of this step
             for (int l = 0; l < L && !dead; ++l, ++n_lay) {
                 tr = (P.trace && grp == 0 && t == P.trace_t) ? P.trace + (size_t)l * TRACE_EV : nullptr;
                 tn = 0;
                 stamp();                                                    // 0: layer start
-                // ---- older tap: D1[128 x 2C] = XO . W1o^T (independent of this step's activations: issued first)
-                if (!wait_u(bar(B_XOFULL), n_lay & 1u)) { dead = true; break; }
-                tc_fence_after();
-                stamp();                                                    // 1: older tap tile landed
-                for (int a = 0; a < KA && !dead; ++a, ++wcnt) {
-                    unsigned slot;
-                    if (!wslot_wait(slot)) { dead = true; break; }
-                    stamp();                                                // 2..: weights of an older-tap atom landed
-                    const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
-                    if (elect()) {
-                        for (int kq = 0; kq < 4; ++kq)
-                            umma_bf16(tmem_u + TM_D1, dXO + kstep16(4 * a + kq, MROWS), dW + 2u * kq, idG, (a | kq) != 0);
-                        umma_commit(bar(B_WEMPTY + slot));
-                        if (a == KA - 1) umma_commit(bar(B_XOFREE));
-                    }
-                    __syncwarp();
-                }
-                if (dead) break;
-                stamp();                                                    // older-tap MMAs issued
-                // ---- newer tap: D1 += XN . W1n^T
+                // ---- newer tap: D1 += XN . W1n^T, 64-channel chunk by chunk (the gate epilogue follows chunk by chunk)
                 if (!wait_u(bar(B_XNFULL), n_lay & 1u)) { dead = true; break; }
                 tc_fence_after();
-                stamp();                                                    // layer input tile ready
-                for (int a = 0; a < KA && !dead; ++a, ++wcnt) {
+                stamp();                                                    // 1: layer input tile ready
+                for (int j = 0; j < n_ch && !dead; ++j, ++wcnt) {
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
-                        for (int kq = 0; kq < 4; ++kq)
-                            umma_bf16(tmem_u + TM_D1, dXN + kstep16(4 * a + kq, MROWS), dW + 2u * kq, idG, 1u);
+                        for (int kk = 0; kk < KC; ++kk)
+                            umma_bf16(tmem_u + TM_D1 + 128 * j, dXN + kstep16(kk, MROWS), dW + kstep16(kk, 128), id128, 1u);
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (a == KA - 1) umma_commit(bar(B_D1FULL));
+                        umma_commit(bar(B_D1FULL + j));
                     }
                     __syncwarp();
                 }
                 if (dead) break;
-                stamp();                                                    // newer-tap MMAs issued
+                stamp();                                                    // 2: newer-tap MMAs issued
                 // ---- residual and skip 1x1 convs on y: ONE instruction of N = C + S per K-step (H and the skip sum are
-                //      adjacent in TMEM), a 64-channel K atom at a time as the gate epilogue delivers them
+                //      adjacent in TMEM), a 64-channel K atom at a time as the gate epilogue delivers them; each is
+                //      followed by the NEXT layer's older-tap MMAs of the same chunk (they run under the gate epilogue
+                //      of the other chunk and under the next-input epilogue)
                 const bool has_res = P.has_res[l] != 0;
-                for (int j = 0; j < KA && !dead; ++j, ++wcnt) {
+                for (int j = 0; j < n_ch && !dead; ++j) {
                     if (!wait_u(bar(B_YFULL + j), n_lay & 1u)) { dead = true; break; }
                     tc_fence_after();
-                    if (j == KA - 1) stamp();                               // last y chunk ready
+                    stamp();                                                // 3, 5: y chunk j ready
                     unsigned slot;
                     if (!wslot_wait(slot)) { dead = true; break; }
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
@@ -426,12 +444,14 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                             else umma_bf16(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + 2u * kq, idS, 1u);
                         }
                         umma_commit(bar(B_WEMPTY + slot));
-                        if (j == KA - 1) umma_commit(bar(B_D2FULL));
+                        if (j == n_ch - 1) umma_commit(bar(B_D2FULL));
                     }
                     __syncwarp();
+                    ++wcnt;
+                    if (l + 1 < L && !issue_old(n_lay + 1u, j)) { dead = true; break; }
+                    stamp();                                                // 4, 6: next layer's older tap issued
                 }
                 if (dead) break;
-                stamp();                                                    // layer issued
             }
             if (dead) break;
             if (t >= P.t_head) {
@@ -535,8 +555,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                 tr = (P.trace && grp == 0 && tid == 0 && t == P.trace_t) ? P.trace + (size_t)(MAXL + l) * TRACE_EV : nullptr;
                 tn = 0;
                 stamp();                                                        // 0: layer start
-                for (int j = 0; j < KA; ++j) {
-                    // gate epilogue of the 64-channel chunk j: this thread's 16 channels 64 j + 16 hf + [0, 16)
+                for (int j = 0; j < P.n_ch; ++j) {
+                    // gate epilogue of the 64-channel chunk j: this thread's 16 channels 64 j + 16 hf + [0, 16);
+                    // D1 columns of chunk j: filter rows at 128 j + [0, 64), gate rows at 128 j + 64 + [0, 64)
                     const int ch0 = 64 * j + 16 * hf;
                     float4 bf[4], bg[4];                     // biases, fetched before the wait
 #pragma unroll
@@ -544,14 +565,12 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                         bf[k4] = __ldg(reinterpret_cast<const float4*>(bl + ch0) + k4);
                         bg[k4] = __ldg(reinterpret_cast<const float4*>(bl + C + ch0) + k4);
                     }
-                    if (j == 0) {
-                        dead |= !mbar_wait(bar(B_D1FULL), n_lay & 1u, abort_flag);
-                        tc_fence_after();
-                        stamp();                                                // gate pre-activations complete
-                    }
+                    dead |= !mbar_wait(bar(B_D1FULL + j), n_lay & 1u, abort_flag);
+                    tc_fence_after();
+                    stamp();                                                    // gate pre-activations of chunk j complete
                     float f[16], g[16];
-                    tmem_ld16(tm_lane + TM_D1 + ch0, f);
-                    tmem_ld16(tm_lane + TM_D1 + C + ch0, g);
+                    tmem_ld16(tm_lane + TM_D1 + 128 * j + 16 * hf, f);
+                    tmem_ld16(tm_lane + TM_D1 + 128 * j + 64 + 16 * hf, g);
                     tmem_ld_wait();
                     float y[16];
 #pragma unroll
@@ -821,27 +840,25 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
 
     // ---- packed bf16 weights + stage tables
     std::vector<unsigned char> wpack;
-    // every stage is one 64-deep K atom of a B tile: [rows x 64] bf16, rows * 128 bytes <= 32 KB.  All layers share one
-    // stage sequence (the last layer's residual rows are zero and its MMA skips them).
-    auto add_ls = [&](int l, size_t bytes) {
-        if (l == 0) { p.ls_off[p.n_ls] = (unsigned)wpack.size(); p.ls_bytes[p.n_ls] = (unsigned)bytes; ++p.n_ls; }
-        const size_t at = wpack.size();
-        wpack.resize(at + bytes, 0);
-        return at;
-    };
+    const int n_ch = C / 64;
+    p.n_ch = n_ch; p.cb = (unsigned)(128 * C * 2); p.wb = (unsigned)((C + S) * 128);
+    p.layer_bytes = (unsigned long long)2 * n_ch * p.cb + (unsigned long long)n_ch * p.wb;
+    wpack.assign((size_t)L * p.layer_bytes, 0);
     for (int l = 0; l < L; ++l) {
         const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample; rows o < C filter, o >= C gate
-        for (int tap = 0; tap < 2; ++tap)      // stage order: older-tap atoms, then newer-tap atoms
-            for (int a = 0; a < C / 64; ++a) {
-                const size_t at = add_ls(l, (size_t)2 * C * 128);
-                pack_rows(wpack, at, 2 * C, 64, 0, 2 * C, wd + (size_t)(64 * a) * 2 + tap, (size_t)C * 2, 2, 2 * C);
+        const size_t base = (size_t)l * p.layer_bytes;
+        for (int tap = 0; tap < 2; ++tap)      // block order: older-tap chunk tiles, then newer-tap chunk tiles
+            for (int j = 0; j < n_ch; ++j) {
+                // tile of 128 rows x C: rows 0..63 filter channels 64 j + r ; rows 64..127 gate channels 64 j + r
+                const size_t at = base + (size_t)(tap * n_ch + j) * p.cb;
+                pack_rows(wpack, at, 128, C, 0, 64, wd + ((size_t)(64 * j) * C) * 2 + tap, (size_t)C * 2, 2, 64);
+                pack_rows(wpack, at, 128, C, 64, 64, wd + ((size_t)(C + 64 * j) * C) * 2 + tap, (size_t)C * 2, 2, 64);
             }
-        for (int j = 0; j < C / 64; ++j) {     // K atom j (64 gated channels) of [residual rows | skip rows]
-            const size_t at = add_ls(l, (size_t)(C + S) * 128);
+        for (int j = 0; j < n_ch; ++j) {       // K atom j (64 gated channels) of [residual rows | skip rows]
+            const size_t at = base + (size_t)2 * n_ch * p.cb + (size_t)j * p.wb;
             pack_rows(wpack, at, C + S, 64, 0, C, d->conv_res_w[l] ? d->conv_res_w[l] + 64 * j : nullptr, (size_t)C, 1, C);
             pack_rows(wpack, at, C + S, 64, C, S, d->conv_skip_w[l] + 64 * j, (size_t)C, 1, S);
         }
-        if (l == 0) p.layer_bytes = wpack.size();
     }
     p.head_off = wpack.size();
     auto add_hs = [&](size_t bytes) {
@@ -862,7 +879,7 @@ int wn4_create(const mmk_wavenet_desc* d, int max_batch, wn4_handle** out, int* 
             pack_rows(wpack, at, rows, 64, 0, rows, d->head_w2 + (size_t)row0 * Hh + 64 * a, (size_t)Hh, 1, temp_chunk ? 1 : rows);
         }
     }
-    if (p.n_ls > MAX_LS || p.n_hs > MAX_HS) { delete h; MMK_FAIL("internal: stage table overflow"); }
+    if (p.n_hs > MAX_HS) { delete h; MMK_FAIL("internal: stage table overflow"); }
 
     std::vector<float> b1((size_t)L * 2 * C), cbr((size_t)(L + 1) * C, 0.0f), cbs(S, 0.0f);
     for (int l = 0; l < L; ++l) {
