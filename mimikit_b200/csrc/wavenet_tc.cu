@@ -173,6 +173,14 @@ __device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a_
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in TMEM: row i in lane i, 16 bf16 K-elements packed two per 32-bit column (8 columns)
+__device__ __forceinline__ void umma_bf16_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc, unsigned idesc,
+                                             unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -194,6 +202,10 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) 
                    "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
                    "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -439,9 +451,11 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                     const unsigned long long dW = dW0 + (unsigned long long)(slot * SLOT16);
                     if (elect()) {
                         for (int kq = 0; kq < 4; ++kq) {
-                            const unsigned long long a = dY + kstep16(4 * j + kq, MROWS);
-                            if (has_res) umma_bf16(tmem_u + TM_H, a, dW + 2u * kq, idRS, 1u);
-                            else umma_bf16(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + 2u * kq, idS, 1u);
+                            // A = y (chunk j, channels 16 kq ..) straight from TMEM: the gate epilogue wrote it, packed, over
+                            // the first 8 of the 16 filter columns it had just read (D1 column 128 j + 16 kq)
+                            const unsigned a = tmem_u + TM_D1 + 128 * j + 16 * kq;
+                            if (has_res) umma_bf16_ts(tmem_u + TM_H, a, dW + 2u * kq, idRS, 1u);
+                            else umma_bf16_ts(tmem_u + TM_SK, a, dW + (unsigned long long)(C * 8) + 2u * kq, idS, 1u);
                         }
                         umma_commit(bar(B_WEMPTY + slot));
                         if (j == n_ch - 1) umma_commit(bar(B_D2FULL));
@@ -580,9 +594,13 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
                         y[4 * k4 + 2] = gate_fast(f[4 * k4 + 2] + bf[k4].z, g[4 * k4 + 2] + bg[k4].z);
                         y[4 * k4 + 3] = gate_fast(f[4 * k4 + 3] + bf[k4].w, g[4 * k4 + 3] + bg[k4].w);
                     }
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8, MROWS)) = pack8(y);
-                    *reinterpret_cast<uint4*>(smem + SM_Y + tile_off(m, ch0 / 8 + 1, MROWS)) = pack8(y + 8);
-                    fence_proxy_async_smem();
+                    {   // y (bf16, two channels per 32-bit column) into TMEM, over this thread's own drained filter columns
+                        unsigned yp[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) yp[k] = pack_bf16(y[2 * k], y[2 * k + 1]);
+                        tmem_st8(tm_lane + TM_D1 + 128 * j + 16 * hf, yp);
+                        tmem_st_wait();
+                    }
                     tc_fence_before();
                     mbar_arrive(bar(B_YFULL + j));
                     stamp();                                                    // y chunk j written
