@@ -6,27 +6,34 @@
 // Design: the PROMPT BATCH is the MMA M dimension.  One CTA owns a group of up to 128 prompts for the whole launch
 // (prefill + every generated sample) and never talks to another CTA: no collective, no grid or cluster barrier.
 //   * every 1x1 / 2-tap contraction of a layer is a tcgen05.mma with M = 128 (prompts), fp32 accumulators in TMEM:
-//       D1[128 x 2C]  = [h_l(t) | h_l(t-d)] . W1^T      (gate pre-activations; N-chunks of 32 channels: f and g side by side)
-//       H [128 x C]  += y . Wres^T                      (the residual stream stays in TMEM across the 30 layers)
-//       SK[128 x S]  += y . Wskip^T                     (so does the running skip sum)
-//     TMEM columns: D1 [0,256) | H [256,384) | SK [384,512); the head reuses them (hidden -> D1, logits -> H|SK).
+//       D1[128 x 2C]  = [h_l(t) | h_l(t-d)] . W1^T      (gate pre-activations, in 64-channel chunks: columns 128 j + [0, 64)
+//                                                        hold the filter rows of chunk j, 128 j + 64 + [0, 64) its gate rows)
+//       [H | SK][128 x (C + S)] += y . [Wres | Wskip]^T (ONE instruction of N = C + S per K-step: the residual stream H and
+//                                                        the running skip sum SK stay in TMEM across all layers)
+//     TMEM columns: D1 [0, 256) | H [256, 256 + C) | SK right after; the head reuses them (hidden -> D1, logits -> H | SK).
 //   * weights (bf16, pre-packed on the host in the UMMA canonical K-major SWIZZLE_128B layout) are streamed from L2 through
-//     a 3-slot x 32 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx by a producer warp; slots are
-//     released by tcgen05.commit.  Nothing is resident: 5.8 MB per step per group, all L2 hits.
-//   * MMAs are issued with N >= 128 (a 64-channel chunk of filter + gate rows; res and skip rows together): the tensor
-//     core fetches its A tile from shared memory once per instruction, so narrow N multiplies the operand traffic (measured:
-//     N = 64 instructions in the no-swizzle layout ran at 64 B/clk of operand fetch, 3x over the tensor floor).
-//   * the older conv tap h_l(t-d) comes from a per-layer ring in global memory (L2): a producer warp copies every layer
-//     input tile shared -> global with one cp.async.bulk (the epilogue threads never store to global) and fetches it d
-//     steps later with one bulk copy into the tap tile.
-//   * 16 epilogue warps (4 threads per prompt row) move TMEM -> registers: bias, tanh * sigmoid (2 MUFU.TANH per gate),
-//     bf16 pack straight into the next MMA's A tile, per 64-channel chunk so that the res/skip MMAs of a chunk start
-//     while the gate MMAs of the next chunk run.  The residual-conv biases never enter the stream (folded into the gate
-//     biases on the host); the skip sum is zeroed by the epilogue at the start of a step and only ever accumulated.
+//     a 4-slot x 32 KB shared-memory ring with cp.async.bulk + mbarrier complete_tx (two requests per slot) by a producer
+//     warp; slots are released by tcgen05.commit.  Nothing is resident: 5.8 MB per step per group, all L2 hits.
+//   * the tensor core fetches its shared-memory operands once per instruction, so narrow N multiplies the traffic and the
+//     MMAs become fetch-bound (measured: N = 64 in a no-swizzle layout ran 3x over the tensor floor): instructions are
+//     N = 128 (a gate chunk) or N = C + S, and the gated output y is handed to the res/skip MMAs as a TMEM A operand — the
+//     epilogue packs it over filter columns of D1 it has just drained; y never touches shared memory.
+//   * issue order (one elected lane of a warp whose control flow is warp-uniform, so descriptors sit in uniform registers):
+//     newer-tap chunks of layer l; then per chunk j: res/skip atom j (waits for y_j, which also proves D1 half j drained)
+//     followed by the OLDER-tap MMAs of layer l + 1, chunk j — they do not depend on this step's activations and run
+//     under the epilogues.
+//   * the older conv tap h_l(t-d) comes from a per-layer ring of d + 1 slots in global memory (L2): a producer warp copies
+//     every layer-input tile shared -> global with one cp.async.bulk (the epilogue threads never store to global) and
+//     fetches it d steps later with one bulk copy into the tap tile.
+//   * 16 epilogue warps (4 threads per prompt row = TMEM lane) move TMEM -> registers: bias, tanh * sigmoid (2 MUFU.TANH per
+//     gate), bf16 pack; the next layer's input goes straight into its swizzled A tile.  The residual-conv biases never
+//     enter the stream (folded into the gate biases on the host); the skip sum is zeroed by the epilogue at the start of
+//     a step and only ever accumulated.
 //   * head: skip sum -> bf16 -> MMA (W1) -> Mish -> MMA (W2, + learned-temperature row) -> logits staged in shared
 //     memory -> the same decide_warp sampler as the fp32 kernels (argmax or inverse-CDF on external noise).
+//   * every wait is an mbarrier wait with a watchdog (2 s): a lost signal aborts the launch instead of hanging the GPU.
 // Work per step per group: 30 x (16 + 8) K-steps of 128 x 256 x 16: ~3 070 tensor cycles per layer (the floor of this
-// design); algorithmic FLOPs 2 x 2 982 016 per sample per prompt.
+// design); algorithmic FLOPs 2 x 2 982 016 per sample per prompt.  MMK_TC_TRACE_T=<t> dumps an in-kernel timeline of step t.
 #include "common.cuh"
 #include "sampler.cuh"
 #include "wavenet_impl.h"
@@ -56,7 +63,7 @@ constexpr int TM_D1 = 0, TM_H = 256, TM_TEMP = 128, TM_LOGIT = 256;   // the ski
 // shared-memory map (bytes)
 constexpr int SM_XN = 0;                         // A tile: h_l(t) bf16 [128 x C]; head: hidden
 constexpr int SM_Y = 32768;                      // A tile: gated output y; head: skip sum
-constexpr int SM_ZX = 65536;                     // + 2 KB: with XN|Y the logits staging area (64 rows x 260 floats)
+// 65536 .. 67584: 2 KB that, with XN|Y, make the logits staging area (64 rows x 260 floats)
 constexpr int SM_XO = 67584;                     // A tile: h_l(t-d) from the ring
 constexpr int SM_W = 100352;                     // weight ring
 constexpr int SM_BAR = SM_W + NSLOT * SLOT_BYTES;
@@ -154,8 +161,6 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // generic-proxy st.shared -> async-proxy reads (tcgen05.mma operands): the cheap CTA-local form
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// generic-proxy st.global (ring slots) -> async-proxy bulk copies, once per step (the copies happen >= 1 step later)
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
@@ -275,7 +280,6 @@ __global__ void __launch_bounds__(NT, 1) wavenet_tc_kernel(const __grid_constant
     int* s_idx = reinterpret_cast<int*>(smem + SM_BAR + 8 * B_COUNT + 16);
     unsigned* abort_flag = P.abort_flag;
     const int L = P.L, C = P.C, S = P.S, Hh = P.Hh, Q = P.Q;
-    const int KA = C / 64;                                // 64-deep K atoms per conv tap = 64-channel chunks of y
     const unsigned tile_bytes = (unsigned)(MROWS * C * 2);
     const unsigned TM_SK = TM_H + C;
 
