@@ -112,3 +112,21 @@ def test_unsupported_configurations_fail_loudly():
     with pytest.raises(RuntimeError, match="unsupported configuration"):
         net.generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4)
     assert net.float().generate(torch.zeros(2, net.rf + 1, dtype=torch.int64), 4).shape == (2, net.rf + 5)
+
+
+@pytest.mark.parametrize("B,n,extra", [(1, 1, 0), (128, 3, 0), (257, 2, 1), (3, 70, 40)])
+def test_edge_geometries(B, n, extra):
+    """One prompt, exactly one full 128-row group, three groups with a ragged last one, a single step, prompts exactly
+    as long as the receptive field: logits within tolerance, replay exact, outputs of dead rows never written."""
+    net, orc = _bf16_net((2, 3), 64, 64, 64, seed=5)
+    g = torch.Generator().manual_seed(B * 7 + n)
+    P = net.rf + extra
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    seq, logits = net.generate(prompts, n, temperature=0.95, noise=noise, return_logits=True)
+    assert tuple(seq.shape) == (B, P + n) and torch.equal(seq[:, :P].cpu(), prompts)
+    assert int(seq.min()) >= 0 and int(seq.max()) <= 255
+    _, ref_logits = orc.generate(prompts.numpy(), n, None, None, forced=seq.cpu().numpy())
+    assert _rel_err(logits.cpu().numpy(), ref_logits) <= BF16_TOL
+    lg, dec = net.teacher_forced(seq, P, 0.95, noise)
+    assert torch.equal(dec, seq[:, P:]) and torch.equal(lg, logits)
