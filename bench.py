@@ -495,8 +495,13 @@ def run_features(args):
             "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"]},
             "kernels": {"mulaw_compress_table_kernel": {"ms": mu_ms, "GB/s": mu_gbs, "frac": mu_gbs / peak},
                         "stft2048_warp_kernel": {"ms": st_ms, "GB/s": st_gbs, "frac": st_gbs / peak}},
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of each kernel on 360 clips
+            # (profiles/r01_features_ncu_full_s6.txt), scaled to this launch's clip count: the kernels are streaming, traffic
+            # is linear in the clips.  STFT: 317.74 + 66.15 MB; mu-law: 317.81 + 585.84 MB (algorithmic: 3.97 / 9.53 GB for 10 h).
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s",
-                         "frac": dom[1] / peak, "traffic": None,
+                         "frac": dom[1] / peak,
+                         "traffic": ((317.74e6 + 66.15e6) if dom[0].startswith("stft") else (317.81e6 + 585.84e6)) * n_clips / 360.0,
+                         "traffic_source": "ncu --set full on a 360-clip launch, scaled by the clip count",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"},
         }
         print(json.dumps(line), flush=True)
