@@ -1,0 +1,54 @@
+"""CPU tests of checkpoint ingestion (mimikit_b200/checkpoint.py): networks built by the LIVE reference are exported with
+the duck-typed `export_network`, reloaded as this package's networks, and must carry the same weights, geometry and IO
+wiring.  (Skipped where /root/reference is absent, e.g. on the GPU box; generation parity from reference state dicts is
+what the golden GPU tests check.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="the reference tree is not present")
+
+
+def _roundtrip(ref_net, tmp_path):
+    from mimikit_b200 import export_network, load_exported, save_exported
+    path = save_exported(ref_net, str(tmp_path / "model.b200.pt"))
+    ours = load_exported(path)
+    sd_ref = {k: v for k, v in ref_net.state_dict().items()}
+    sd = ours.state_dict()
+    return ours, sd_ref, sd, export_network(ref_net)
+
+
+def test_wavenet_export_roundtrip(tmp_path):
+    ref_net = ref_loader.make_wavenet(blocks=(3, 2), dims=64, residuals_dim=64, skips_dim=48, mlp_dim=32, seed=3)
+    ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)
+    assert type(ours).__name__ == "WaveNet" and ours.rf == ref_net.rf and list(sd) == [k for k in sd_ref]
+    for k in sd_ref:
+        assert torch.equal(sd[k], sd_ref[k].float().cpu()), k
+    assert d["io"] == dict(sr=16000, q_levels=256, compression=1.0, input_module_type="embedding", mlp_dim=32,
+                           n_mlp_layers=0, min_temperature=1e-4)
+    assert ours.config.blocks == (3, 2) and ours.config.skips_dim == 48 and ours.config.act_g == "Sigmoid"
+    # an export of OUR network reloads too (same format)
+    from mimikit_b200 import export_network, load_exported
+    again = load_exported(export_network(ours))
+    assert all(torch.equal(again.state_dict()[k], sd[k]) for k in sd)
+
+
+def test_samplernn_export_roundtrip_and_errors(tmp_path):
+    ref_net = ref_loader.make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=64, mlp_dim=32, seed=5)
+    ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)
+    assert type(ours).__name__ == "SampleRNN" and tuple(ours.frame_sizes) == (8, 2, 1)
+    assert set(sd) == set(sd_ref)
+    for k in sd_ref:
+        assert torch.equal(sd[k], sd_ref[k].float().cpu()), k
+    assert d["io"]["input_module_type"] == "framed_linear" and d["config"]["rnn_class"] == "gru"
+    from mimikit_b200 import load_exported
+    with pytest.raises(ValueError):
+        load_exported({"format": "something else"})
+    bad = dict(d, config=dict(d["config"], no_such_field=1))
+    with pytest.raises(ValueError):
+        load_exported(bad)
+    lstm = dict(d, config=dict(d["config"], rnn_class="lstm"))
+    with pytest.raises(NotImplementedError):
+        load_exported(lstm)                      # unsupported configurations fail loudly, never silently
