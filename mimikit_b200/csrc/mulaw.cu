@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "../../include/mmk_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +31,8 @@
 
 namespace mmk {
 
+constexpr int MULAW_WIDE_DEFAULT = 1;     // int64 compressor: 32-byte stores (measured 1.69 ms for 10 h; 16-byte 1.91,
+                                          // 32-byte loads as well 1.87)
 constexpr int MULAW_TABLE_MAX_Q = 2048;   // 16 KB of shared memory for the (lower, upper) threshold pairs
 
 __device__ __forceinline__ float mulaw_level(float v, float mu, float C, float denom) {
@@ -162,7 +165,16 @@ __global__ void __launch_bounds__(256) mulaw_verify_kernel(const float* __restri
 }
 
 // ---- table kernels ---------------------------------------------------------------------------------------------
-template <typename OutT>
+__device__ __forceinline__ void st256(long long* p, long long a, long long b, long long c, long long d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+
+// WIDE: 0 = 16-byte accesses; 1 = one 32-byte store per 4 int64 results (STG.256, sm_100); 2 = 32-byte loads too
+template <typename OutT, int WIDE>
 __global__ void __launch_bounds__(256, 8) mulaw_compress_table_kernel(const float* __restrict__ x, OutT* __restrict__ q,
                                                                       size_t n, float mu, float C, MuLawFast f,
                                                                       const float* __restrict__ thr) {
@@ -178,17 +190,32 @@ __global__ void __launch_bounds__(256, 8) mulaw_compress_table_kernel(const floa
     auto store4 = [&](size_t i, const float4& v) {
         long long r0 = one(v.x), r1 = one(v.y), r2 = one(v.z), r3 = one(v.w);
         if constexpr (sizeof(OutT) == 8) {
-            longlong2* o = reinterpret_cast<longlong2*>(q) + 2 * i;
-            __stcs(o, make_longlong2(r0, r1));
-            __stcs(o + 1, make_longlong2(r2, r3));
+            if constexpr (WIDE >= 1) {
+                st256(reinterpret_cast<long long*>(q) + 4 * i, r0, r1, r2, r3);
+            } else {
+                longlong2* o = reinterpret_cast<longlong2*>(q) + 2 * i;
+                __stcs(o, make_longlong2(r0, r1));
+                __stcs(o + 1, make_longlong2(r2, r3));
+            }
         } else {
             reinterpret_cast<uchar4*>(q)[i] =
                 make_uchar4((unsigned char)r0, (unsigned char)r1, (unsigned char)r2, (unsigned char)r3);
         }
     };
-    // (two loads in flight per thread measured 7 % slower than one: 2.01 vs 1.88 ms for 10 h)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
-        store4(i, __ldcs(reinterpret_cast<const float4*>(x) + i));
+    if constexpr (WIDE == 2) {
+        const size_t n8 = n / 8;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+            float4 a, b;
+            ld256(x + 8 * i, a, b);
+            store4(2 * i, a);
+            store4(2 * i + 1, b);
+        }
+        if (n4 > 2 * n8 && blockIdx.x == 0 && threadIdx.x == 0) store4(2 * n8, __ldcs(reinterpret_cast<const float4*>(x) + 2 * n8));
+    } else {
+        // (two separate 16-byte loads in flight per thread measured 7 % slower than one: 2.01 vs 1.88 ms for 10 h)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+            store4(i, __ldcs(reinterpret_cast<const float4*>(x) + i));
+    }
     size_t t = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) q[t] = (OutT)one(x[t]);
 }
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
     long long* oq = reinterpret_cast<long long*>(out) + (size_t)blockIdx.y * row_len;
     const long long c0 = (long long)blockIdx.x * NORM_CHUNK4 * 4, c1 = min(row_len, c0 + (long long)NORM_CHUNK4 * 4);
     const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(MODE == 0 ? (void*)of : (void*)oq) & 15u) == 0);
+                     ((reinterpret_cast<uintptr_t>(MODE == 0 ? (void*)of : (void*)oq) & (MODE == 0 ? 15u : 31u)) == 0);
     long long done = c0;
     if (vec) {
         const long long n4 = (c1 - c0) / 4;
@@ -285,9 +312,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
             if (MODE == 0) {
                 __stcs(reinterpret_cast<float4*>(of + c0) + i, make_float4(a, b, c, e));
             } else {
-                longlong2* o = reinterpret_cast<longlong2*>(oq + c0) + 2 * i;
-                __stcs(o, make_longlong2(level(a), level(b)));
-                __stcs(o + 1, make_longlong2(level(c), level(e)));
+                st256(oq + c0 + 4 * i, level(a), level(b), level(c), level(e));      // one 32-byte store (STG.256)
             }
         }
         done = c0 + n4 * 4;
@@ -399,10 +424,17 @@ extern "C" int mmk_mulaw_compress(const float* d_x, int64_t* d_q, size_t n, int 
     const MuLawTable* t = nullptr;
     if (int rc = mulaw_table(q_levels, compression, (cudaStream_t)stream, &t)) return rc;
     const float mu = (float)q_levels - 1.0f;
-    if (t)
-        mulaw_compress_table_kernel<long long><<<feature_grid(n / 4 + 1), 256, q_levels * sizeof(float2), (cudaStream_t)stream>>>(
-            d_x, reinterpret_cast<long long*>(d_q), n, mu, compression, t->fast, t->thr);
-    else
+    if (t) {
+        int wide = (((uintptr_t)d_q % 32) == 0) ? MULAW_WIDE_DEFAULT : 0;
+        if (wide == 2 && ((uintptr_t)d_x % 32) != 0) wide = 1;
+        if (const char* e = getenv("MMK_MULAW_WIDE")) wide = std::min(wide, std::max(0, atoi(e)));
+        const int grid = feature_grid(n / 4 + 1);
+        const size_t sm = q_levels * sizeof(float2);
+        long long* q = reinterpret_cast<long long*>(d_q);
+        if (wide == 2) mulaw_compress_table_kernel<long long, 2><<<grid, 256, sm, (cudaStream_t)stream>>>(d_x, q, n, mu, compression, t->fast, t->thr);
+        else if (wide == 1) mulaw_compress_table_kernel<long long, 1><<<grid, 256, sm, (cudaStream_t)stream>>>(d_x, q, n, mu, compression, t->fast, t->thr);
+        else mulaw_compress_table_kernel<long long, 0><<<grid, 256, sm, (cudaStream_t)stream>>>(d_x, q, n, mu, compression, t->fast, t->thr);
+    } else
         mulaw_compress_kernel<long long><<<feature_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
             d_x, reinterpret_cast<long long*>(d_q), n, mu, compression);
     MMK_CUDA(cudaGetLastError());
@@ -419,7 +451,7 @@ extern "C" int mmk_mulaw_compress_u8(const float* d_x, uint8_t* d_q, size_t n, i
     if (int rc = mulaw_table(q_levels, compression, (cudaStream_t)stream, &t)) return rc;
     const float mu = (float)q_levels - 1.0f;
     if (t)
-        mulaw_compress_table_kernel<unsigned char><<<feature_grid(n / 4 + 1), 256, q_levels * sizeof(float2), (cudaStream_t)stream>>>(
+        mulaw_compress_table_kernel<unsigned char, 0><<<feature_grid(n / 4 + 1), 256, q_levels * sizeof(float2), (cudaStream_t)stream>>>(
             d_x, d_q, n, mu, compression, t->fast, t->thr);
     else
         mulaw_compress_kernel<unsigned char><<<feature_grid(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
