@@ -148,3 +148,19 @@ def test_remove_dc_oracle_vs_reference():
     assert np.array_equal(restate.remove_dc(restate.normalize_inf(d["dc_x"])).view(np.int32), d["dc_norm_y"].view(np.int32))
     y = restate.remove_dc(d["dc_x"])
     assert not y[3].any() and abs(float(y[4, -1])) < 1e-6 and abs(float(y[0, 2000:].mean())) < 1e-3   # silence, constant, DC gone
+
+
+def test_bf16_faithful_wavenet_oracle_tracks_the_fp32_oracle():
+    """WaveNetBf16Oracle (the tensor-core kernel's arithmetic on the CPU) stays within bf16 noise of the fp32 oracle on a
+    golden network, and its rounding helper is round-to-nearest-even."""
+    assert restate.bf16_round(np.float32(1.00390625)) == np.float32(1.0)            # tie -> even mantissa
+    assert restate.bf16_round(np.float32(1.01171875)) == np.float32(1.015625)       # tie -> even mantissa (up)
+    assert restate.bf16_round(np.float32(-3.1415927)) == np.float32(-3.140625)
+    d = load_golden("wavenet_res_skip_small")
+    sd = golden_state_dict(d)
+    blocks = tuple(int(b) for b in d["meta/blocks"])
+    P, seq = d["prompts"].shape[1], d["seq_argmax"]
+    _, lg32 = restate.WaveNetOracle(sd, blocks).generate(d["prompts"], seq.shape[1] - P, None, None, forced=seq)
+    lg16 = restate.WaveNetBf16Oracle(sd, blocks).logits_for(seq, P)
+    err = np.abs(lg16 - lg32).max() / np.abs(lg32).max()
+    assert 1e-5 < err < 2e-2, err
