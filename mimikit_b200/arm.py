@@ -70,6 +70,12 @@ class NativeARM:
     def parameters(self):
         return iter(self._sd.values())
 
+    @property
+    def q_levels(self) -> int:
+        """Size of the output alphabet (TargetSpec.out_dim, io_spec.py:136-149) — what the multi-GPU gather sizes its
+        wire dtype with."""
+        return int(self.config.io_spec.targets[0].out_dim)
+
     def state_dict(self):
         return OrderedDict((k, v.clone()) for k, v in self._sd.items())
 

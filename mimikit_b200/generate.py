@@ -18,7 +18,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["GenerateLoopV2", "fill", "prepare_prompt"]
+__all__ = ["GenerateLoopV2", "extend_with_blanks", "prepare_prompt"]
 
 
 def prepare_prompt(device, prompt, n_blanks, at_least_nd=2):
@@ -36,20 +36,13 @@ def prepare_prompt(device, prompt, n_blanks, at_least_nd=2):
     return prompt
 
 
-def fill(x, prior_t, n_steps):
-    """generate.py:50-73: `x` followed by blanks (zeros of x's dtype) or per-example constants."""
-    if isinstance(x, np.ndarray):
-        x = torch.from_numpy(x)
-    parts = [x] if x is not None else []
-    dt, dev = (x.dtype, x.device) if x is not None else (torch.float32, "cpu")
-    B, D = (x.size(0), tuple(x.shape[2:])) if x is not None else (1, (1,))
-    for kind, n in (prior_t, n_steps):
-        if isinstance(kind, torch.Tensor):
-            assert kind.shape == (B,)
-            parts.append(kind.expand(B, n, 1))
-        elif kind == "blank":
-            parts.append(torch.zeros(B, n, *D, dtype=dt, device=dev))
-    return torch.cat(parts, dim=1)
+def extend_with_blanks(x, n_steps):
+    """The working buffer of one network input: the prompt followed by `n_steps` zero positions of the same dtype
+    and trailing shape (what the reference's loop builds before stepping, loops/generate.py:197-200)."""
+    x = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+    out = x.new_zeros((x.shape[0], x.shape[1] + int(n_steps)) + tuple(x.shape[2:]))
+    out[:, :x.shape[1]] = x
+    return out
 
 
 class GenerateLoopV2:
@@ -125,38 +118,46 @@ class GenerateLoopV2:
             self.teardown()
 
     def _run_stepwise(self, batch, params):
-        """generate.py:195-219."""
-        rf, prior_t, n_steps = self.network.rf, batch[0].size(1), self.n_steps
-        tensors = tuple(fill(x, ("data", prior_t), ("blank", n_steps)) for x in batch)
-        until = 0
-        for t in range(prior_t, prior_t + n_steps):
-            if t < until:
-                continue
-            inputs = tuple(tensor[:, t - rf:t] for tensor in tensors)
-            outputs = self.network.generate_step(inputs, t=t, **params)
-            if not isinstance(outputs, tuple):
-                outputs = outputs,
-            for tensor, out in zip(tensors, outputs):
-                if out is not None:
-                    n_out = min(out.size(1), tensor.size(1) - t)
-                    tensor[:, t:t + n_out] = out[:, :n_out]
-                    until = t + n_out
-        return tuple(tensors)
+        """Foreign ARMs (no whole-sequence fast path): one `generate_step` per write position, the contract of
+        loops/generate.py:207-219 — the step sees the `rf` positions before the cursor of every buffer, may return a
+        single tensor or a tuple, `None` entries leave their buffer untouched, and an output of several positions
+        moves the cursor past all of them."""
+        rf, start = self.network.rf, batch[0].size(1)
+        stop = start + self.n_steps
+        buffers = tuple(extend_with_blanks(x, self.n_steps) for x in batch)
+        cursor = start
+        while cursor < stop:
+            produced = self.network.generate_step(tuple(buf[:, cursor - rf:cursor] for buf in buffers), t=cursor, **params)
+            produced = produced if isinstance(produced, tuple) else (produced,)
+            advance = 1
+            for buf, new in zip(buffers, produced):
+                if new is None:
+                    continue
+                width = min(new.size(1), stop - cursor)
+                buf[:, cursor:cursor + width] = new[:, :width]
+                advance = max(1, width)     # the reference resumes after the last buffer written
+            cursor += advance
+        return buffers
+
+    def _invert(self, sequences):
+        """`feature.inv` of every target (mu-law expand for the networks here; loops/generate.py:245, io_spec.py:77-79)."""
+        return tuple(spec.inv(seq) for spec, seq in zip(self.network.config.io_spec.targets, sequences))
 
     def process_outputs(self, final_outputs, prompt_idx, **template_vars):
-        """generate.py:231-252."""
+        """Same observable behaviour as loops/generate.py:231-252: the inverse transform runs only when somebody
+        consumes it (a logger that writes/displays, or the caller via `yield_inversed_outputs`); the logger sees every
+        example of every output with its prompt index; the yielded value is the waveform or the raw sequences."""
         cfg = self.config
-        if (self.logger is None or (not cfg.write_waveform and not cfg.display_waveform)) \
-                and not cfg.yield_inversed_outputs:
+        logging = self.logger is not None and (cfg.write_waveform or cfg.display_waveform)
+        if not logging and not cfg.yield_inversed_outputs:
             return final_outputs
-        features = self.network.config.io_spec.targets
-        outputs = tuple(feature.inv(out) for feature, out in zip(features, final_outputs))
+        waveforms = self._invert(final_outputs)
         if self.logger is not None:
-            for output in outputs:
-                for example, idx in zip(output, prompt_idx):
-                    idx = idx.item() if hasattr(idx, "item") else idx
+            ids = [i.item() if hasattr(i, "item") else i for i in prompt_idx]
+            for wave in waveforms:
+                for example, idx in zip(wave, ids):
                     if cfg.write_waveform:
                         self.logger.write(example, prompt_idx=idx, **template_vars)
                     if cfg.display_waveform:
                         self.logger.display(example, prompt_idx=idx, **template_vars)
-        return outputs if cfg.yield_inversed_outputs else final_outputs
+        return waveforms if cfg.yield_inversed_outputs else final_outputs

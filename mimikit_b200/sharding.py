@@ -45,7 +45,7 @@ def shard_of(x, world: int, rank: int, n_units: Optional[int] = None):
     return x[lo:hi]
 
 
-def gather_sequences(local: torch.Tensor, n_units: int, q_levels: int = 256, group=None) -> torch.Tensor:
+def gather_sequences(local: torch.Tensor, n_units: int, q_levels: Optional[int] = 256, group=None) -> torch.Tensor:
     """THE collective of the path: all-gather of every rank's (b_r, T) index block -> (n_units, T) int64 in prompt
     order on every rank.  Blocks travel as uint8 when the alphabet allows (8x less NVLink traffic than int64);
     ragged blocks are padded to the largest one."""
@@ -54,7 +54,14 @@ def gather_sequences(local: torch.Tensor, n_units: int, q_levels: int = 256, gro
         if local.shape[0] != n_units:
             raise ValueError("single process must hold every unit")
         return local
-    wire = torch.uint8 if q_levels <= 256 else (torch.int16 if q_levels <= 32768 else torch.int64)
+    if q_levels is None:
+        wire = torch.int64                      # alphabet unknown: do not narrow
+    else:
+        wire = torch.uint8 if q_levels <= 256 else (torch.int32 if q_levels <= 2 ** 31 else torch.int64)  # gloo and NCCL have no int16
+    if wire != torch.int64 and local.numel():
+        lo_v, hi_v = int(local.min()), int(local.max())
+        if lo_v < 0 or hi_v >= int(q_levels):
+            raise ValueError(f"sequence values [{lo_v}, {hi_v}] do not fit the declared alphabet of {q_levels} levels")
     b_max = shard_bounds(n_units, world, 0)[1]
     T = local.shape[1]
     send = torch.zeros((b_max, T), dtype=wire, device=local.device)
@@ -91,7 +98,12 @@ def generate_sharded(network, prompts: torch.Tensor, n_steps: int, temperature=N
         local = torch.empty((0, prompts.shape[1] + n_steps), dtype=torch.int64, device=prompts.device)
     if not gather:
         return local
-    q = getattr(network, "q_levels", 256)
+    q = getattr(network, "q_levels", None)
+    if q is None:
+        try:
+            q = int(network.config.io_spec.targets[0].out_dim)
+        except AttributeError:
+            q = None                             # unknown alphabet: the gather keeps int64 on the wire
     return gather_sequences(local, B, q, group)
 
 

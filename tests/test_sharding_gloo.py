@@ -35,6 +35,68 @@ class FakeARM:
         return seq
 
 
+class FakeARM512(FakeARM):
+    """A 512-level alphabet announced the way the real networks do it: through config.io_spec.targets[0].out_dim
+    (no `q_levels` attribute on the class) — values >= 256 must survive the gather (uint8 truncation)."""
+    q_levels = None
+
+    class _T:
+        out_dim = 512
+
+    class _IO:
+        pass
+
+    class _Cfg:
+        pass
+
+    def __init__(self):
+        super().__init__()
+        io = self._IO(); io.targets = (self._T(),)
+        self.config = self._Cfg(); self.config.io_spec = io
+
+    def generate(self, prompts, n_steps, temperature=None, noise=None):
+        seq = super().generate(prompts % 256, n_steps, temperature, noise)
+        seq[:, prompts.shape[1]:] += 256 * (seq[:, prompts.shape[1]:] % 2)     # half of the outputs land in [256, 512)
+        seq[:, :prompts.shape[1]] = prompts
+        return seq
+
+
+def _worker512(rank, world, port, B, P, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prompts, noise, _ = _inputs(B, P, n)
+        q.put((rank, sharding.generate_sharded(FakeARM512(), prompts + 200, n, temperature=0.9, noise=noise)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_keeps_wide_alphabets():
+    B, P, n, world = 5, 6, 7, 2
+    prompts, noise, _ = _inputs(B, P, n)
+    want = FakeARM512().generate(prompts + 200, n, temperature=0.9, noise=noise)
+    assert int(want.max()) >= 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker512, args=(r, world, port, B, P, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert torch.equal(got[r], want)
+    # a block that does not fit its declared alphabet is an error, never a silent truncation
+    with pytest.raises(ValueError):
+        class One:
+            pass
+        import unittest.mock as um
+        with um.patch.object(sharding, "_world", lambda group=None: (0, 2)):
+            sharding.gather_sequences(torch.full((3, 4), 300), 6, 256)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
