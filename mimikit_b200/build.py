@@ -36,14 +36,19 @@ def build(force=False, verbose=False):
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    objs, log = [], []
+    objs, log, jobs = [], [], []
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            jobs.append((src, [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]))
+    if jobs:   # one nvcc per translation unit, side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            results = list(pool.map(lambda j: subprocess.run(j[1], capture_output=True, text=True), jobs))
+        for (src, cmd), r in zip(jobs, results):
             log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+        for (src, cmd), r in zip(jobs, results):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
     if force or _stale(LIB, objs):

@@ -36,3 +36,14 @@ int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
             int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
             int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
             unsigned long long* d_step_ts, void* stream);
+
+// The layer-pipelined fp32 kernel (wavenet6.cu): one CTA pair per layer, critical weights in registers; same contract; tried first.
+struct wn6_handle;
+int wn6_create(const mmk_wavenet_desc* d, int max_batch, wn6_handle** out, int* unsupported);
+int wn6_destroy(wn6_handle* h);
+int wn6_launch_info(wn6_handle* h, mmk_launch_info* out);
+int wn6_sync_check(wn6_handle* h, void* stream);
+int wn6_run(wn6_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
+            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream);
