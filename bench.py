@@ -51,6 +51,7 @@ def parse():
                          "kernel (logits within 5e-2), one CTA per 128 prompts: use with --batch >= 128")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short side measurements of BASELINE configs 3, 4, 5")
     return ap.parse_args()
 
 
@@ -150,22 +151,28 @@ def cpu_sample_steps(workload):
     return 8 if workload == "wavenet" else 1024
 
 
-def time_cpu(workload, net, prompts, n_gen, budget_s=None, repeats=1):
-    """samples/s of the CPU port generating n_gen samples for every prompt (warm-up over the prompt included for
-    SampleRNN, as in the reference's before_generate)."""
+def time_cpu(workload, net, prompts, n_gen, n_full=None):
+    """(samples/s, seconds spent) of the CPU port.  WaveNet: every sample recomputes the receptive field, so the cost per
+    sample is constant and `n_gen` samples give the rate.  SampleRNN: the reference's before_generate walks the whole prompt
+    once (warm-up) before the first sample; charging that to a short sample of the horizon would bias the rate low, so the
+    warm-up (n_steps = 0) and the steady-state samples are timed separately and the rate is the one of the FULL workload:
+    B * n_full / (T_warm + n_full * t_step)."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     port = cpu_port(workload, net.state_dict(), net)
     B = prompts.shape[0]
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
+    t0 = time.perf_counter()
+    if workload == "samplernn":
+        port.generate(prompts, 0, None)
+        t_warm = time.perf_counter() - t0
         port.generate(prompts, n_gen, None)
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        if budget_s is not None and dt > budget_s:
-            break
-    return B * n_gen / best, best
+        t_step = max(dt - 2 * t_warm, 1e-9) / n_gen
+        n_full = n_full or n_gen
+        return B * n_full / (t_warm + n_full * t_step), dt, {"t_warm_s": t_warm, "t_step_us": t_step * 1e6}
+    port.generate(prompts, n_gen, None)
+    dt = time.perf_counter() - t0
+    return B * n_gen / dt, dt, {}
 
 
 def run_reference(args):
@@ -179,14 +186,14 @@ def run_reference(args):
     net = make_network(wl)
     prompts = synthetic_prompts(B, P)
     n_gen = cpu_sample_steps(wl)
-    _, probe_dt = time_cpu(wl, net, prompts, n_gen)   # CPU warm-up pass; also sizes each step to ~8 s of CPU work
+    _, probe_dt, _ = time_cpu(wl, net, prompts, n_gen, n_full)   # CPU warm-up pass; also sizes each step to ~8 s of CPU work
     n_gen = max(n_gen, min(n_full, int(n_gen * 8.0 / max(probe_dt, 1e-3))))
-    times = []
+    times, vals = [], []
     for _ in range(args.steps):
-        _, dt = time_cpu(wl, net, prompts, n_gen)
-        times.append(dt)
+        v, dt, _ = time_cpu(wl, net, prompts, n_gen, n_full)
+        times.append(dt); vals.append(v)
     dt = statistics.mean(times)
-    val = B * n_gen / dt
+    val = statistics.mean(vals)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "generated audio samples/sec", "value": val, "unit": "samples/s",
@@ -195,7 +202,8 @@ def run_reference(args):
         "config": workload_config(wl, B, P, n_full, args.gpus),
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"first {n_gen} autoregressive samples of the same {B}-prompt batch per step "
-                                   f"(step cost is constant in t; full workload is {n_full} samples per prompt)"},
+                                   f"(step cost is constant in t; full workload is {n_full} samples per prompt"
+                                   + ("; prompt warm-up timed separately and charged once per full horizon)" if wl == "samplernn" else ")")},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -214,10 +222,31 @@ def workload_config(wl, B, P, n, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# ncu `dram__bytes_read.sum + dram__bytes_write.sum` of ONE launch of the dominant kernel, from the `--set full` capture
+# under profiles/ (the persistent generation kernels keep weights on chip: traffic is ring spill + mailboxes + outputs)
+NCU_TRAFFIC = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = json.load(_f)
+except (OSError, ValueError):
+    pass
+
+
+def latency_floor_us(wl, sm_mhz):
+    """SURVEY §8(d) asks for the dependency-chain floor next to the throughput roofline: dependent stages x the latency
+    a stage cannot go below in this decomposition.  WaveNet (wavenet6.cu): 30 layers x (2 DSMEM hops of ~275 cycles
+    [215 transit + mbarrier wake, B300_MICROARCH.md] + the FFMA issue time of the two critical contractions of a 4-prompt
+    group on one SM: 2048 + 1024 warp-FMAs at 4 per cycle = 768 cycles) + ~5 000 cycles of head, sampler and the L2
+    feedback of the sampled index.  SampleRNN: see DESIGN.md §4.2."""
+    if wl == "wavenet":
+        return (30 * (2 * 275 + 768) + 5000) / sm_mhz
+    return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from mimikit_b200 import GenerateLoopV2
+    from mimikit_b200 import GenerateLoopV2, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -234,10 +263,12 @@ def run_b200(args):
         if wl != "wavenet":
             raise SystemExit("--dtype bf16 is implemented for the wavenet workload only")
         net.bfloat16()
-    prompts_host = synthetic_prompts(B, P, rank).pin_memory()
+    # the GLOBAL prompt batch (world x B prompts, rank r's block generated with r's seed); every rank holds it, as
+    # sharding.generate_sharded expects, and generates for its own block
+    prompts_host = torch.cat([synthetic_prompts(B, P, r) for r in range(world)], 0).pin_memory()
     prompts_dev = prompts_host.to(dev)
+    lo, hi = sharding.shard_bounds(world * B, world, rank)
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
-    gathered = torch.empty((world, B, P + n), dtype=torch.uint8, device=dev) if world > 1 else None
     temp = args.temperature
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
 
@@ -247,16 +278,15 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def step_device():
-        seq = net.generate(prompts_dev, n, temperature=temp, generator=gen)
-        if world > 1:   # the single collective of the path: gather every rank's output block
-            dist.all_gather_into_tensor(gathered, seq.to(torch.uint8))
-        return seq
+        # the package's multi-GPU entry point: this rank's block through ONE persistent kernel launch, then the single
+        # collective of the path (all-gather of the uint8 index blocks)
+        return sharding.generate_sharded(net, prompts_dev, n, temperature=temp, generator=gen)
 
     # ---- warm-up (also: per-step device timestamps for the p50 step latency) ----
     p50_us = None
     for w in range(max(args.warmup, 1)):
         if w == 0:
-            _, ts = net.generate(prompts_dev, n, temperature=temp, generator=gen, return_step_timestamps=True)
+            _, ts = net.generate(prompts_dev[lo:hi], n, temperature=temp, generator=gen, return_step_timestamps=True)
             d = (ts[1:] - ts[:-1]).double()
             d = d[-n + 1:] if d.numel() >= n else d     # generation steps only (the prefill steps come first)
             p50_us = float(d.median()) / 1e3
@@ -282,17 +312,20 @@ def run_b200(args):
     ms = float(t_ms)
     value = world * B * n * args.steps / (ms / 1e3)
 
-    # ---- e2e: public API, pinned host buffers in, host waveform out ----
+    # ---- e2e: public API (GenerateLoopV2), pinned host prompts in, host waveform out; at N > 1 the loop's real output
+    #      block goes through the package's gather (sharding.gather_sequences) ----
     cfg = GenerateLoopV2.Config(parameters=None if temp is None else {"temperature": temp}, display_waveform=False,
-                                yield_inversed_outputs=True)
+                                yield_inversed_outputs=False)
     out_host = torch.empty((B, P + n), dtype=torch.float32).pin_memory()
+    inv = net.config.io_spec.targets[0].inv
 
     def step_e2e():
-        loop = GenerateLoopV2(cfg, net, n, [[torch.arange(B), prompts_host]])
+        loop = GenerateLoopV2(cfg, net, n, [[torch.arange(lo, hi), prompts_host[lo:hi]]])
         for outs in loop.run():
-            out_host.copy_(outs[0], non_blocking=False)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.zeros((B, P + n), dtype=torch.uint8, device=dev))
+            seq = outs[0]
+            if world > 1:
+                sharding.gather_sequences(seq, world * B, net.q_levels)
+            out_host.copy_(inv(seq), non_blocking=False)
 
     step_e2e()
     barrier()
@@ -307,6 +340,8 @@ def run_b200(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_val = world * B * n * args.steps / float(t_e)
 
+    extras = None if args.no_extras else run_extras(args, dev, rank, world, barrier)
+
     if rank == 0:
         peaks = {}
         try:
@@ -315,13 +350,32 @@ def run_b200(args):
         except OSError:
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
         flop_launch = FLOP_PER_SAMPLE[wl] * B * n
         kernel_ms = ms / args.steps            # the persistent kernel IS the step (prefill included)
         ach = flop_launch / (kernel_ms / 1e3) / 1e12
         sm_mhz = ck["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         info = net.launch_info(B)
+        kname = {"wavenet": "wavenet_tc_kernel" if args.dtype == "bf16" else "wavenet6_kernel",
+                 "samplernn": "samplernn_cluster_kernel"}[wl]
+        tr = NCU_TRAFFIC.get(kname)
+        if args.dtype == "bf16":
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
+        else:
+            roof = {"bound": "fp32_fma", "kernel": kname, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak,
+                    "peak_source": "148 SMs x 128 FFMA lanes x 2 flop x the SM clock sampled during the run: the path computes in "
+                                   "fp32 FFMA (bit-exact argmax parity), so this, not the tensor peak, is its ceiling",
+                    "tensor_bf16": {"peak": peak_tf, "frac": ach / peak_tf},
+                    "latency_floor_us": latency_floor_us(wl, sm_mhz),
+                    "latency_floor_note": "dependency-chain floor of one generated sample in this decomposition (see "
+                                          "bench.py latency_floor_us); p50_step_latency_us is the measured counterpart"}
+        # dram bytes of one launch from the ncu --set full capture, scaled from the captured horizon to this one (the
+        # traffic is per generated sample: ring spill, mailboxes, logits/sequence writes); null when no capture is committed
+        roof["traffic"] = None if not tr else tr["dram_bytes"] * (B * n) / max(1, tr["prompts"] * tr["n_steps"])
+        if tr:
+            roof["traffic_source"] = tr.get("source")
         line = {
             "metric": "generated audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -334,25 +388,81 @@ def run_b200(args):
             "gpu_launches": 2 * args.steps,
             "launch": info,
             "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"]},
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
-                         "fp32_fma": {"peak": fp32_peak, "frac": ach / fp32_peak,
-                                      "note": "the f32 path computes in fp32 FFMA for bit-exact parity (this is its "
-                                              "ceiling); the bf16 path runs on tcgen05 (the tensor peak is its ceiling); "
-                                              "per-step time is bounded by the 31-stage dependency chain, see DESIGN.md"}},
+            "roofline": roof,
         }
+        if extras:
+            line["other_configs"] = extras
         if not args.no_cpu_baseline:
+            blk = prompts_host[lo:hi]
             n_gen = cpu_sample_steps(wl)
-            _, probe_dt = time_cpu(wl, net, prompts_host, n_gen)          # probe, then size the sample to ~15 s
+            _, probe_dt, _ = time_cpu(wl, net, blk, n_gen, n)             # probe, then size the sample to ~15 s
             n_gen = max(n_gen, min(n, int(n_gen * 15.0 / max(probe_dt, 1e-3))))
-            cpu_val, cpu_dt = time_cpu(wl, net, prompts_host, n_gen)
+            cpu_val, cpu_dt, cpu_parts = time_cpu(wl, net, blk, n_gen, n)
             line["cpu_baseline"] = {
                 "value": cpu_val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                 "sample": f"first {n_gen} autoregressive samples of the same {B}-prompt batch ({cpu_dt:.1f} s); the "
-                          f"port runs the reference's own per-sample algorithm (oracle/torch_port.py)"}
+                          f"port runs the reference's own per-sample algorithm (oracle/torch_port.py)"
+                          + ("; prompt warm-up and steady-state steps timed separately, rate extrapolated to the full "
+                             f"{n}-sample horizon" if wl == "samplernn" else ""), **cpu_parts}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, dev, rank, world, barrier):
+    """Short measurements of the other BASELINE.json configs on the same ranks, so that the driver's run sees them next to
+    the headline: cfg 3 (SampleRNN, 128 prompts sharded over the ranks), cfg 4 (WaveNet bf16 on tcgen05, 128 prompts per
+    GPU), cfg 5 (mu-law + STFT/mel, 1 h per GPU).  Device-timed, max over ranks, a fraction of a second each."""
+    import torch
+    import torch.distributed as dist
+    from mimikit_b200 import MagSpec, MelSpec, MuLawCompress, sharding
+    out = {}
+
+    def timed(fn, reps=1):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    try:
+        # cfg 3: strong scaling of a fixed 128-prompt batch
+        net = make_network("samplernn", dev)
+        Bg, P, n = 128, SR, SR // 4
+        pr = synthetic_prompts(Bg, P).to(dev)
+        ms = timed(lambda: sharding.generate_sharded(net, pr, n))
+        out["cfg3_samplernn_b128_sharded"] = {"value": Bg * n / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "strong",
+                                              "dtype": "f32", "workload": f"SampleRNN (8,2,1) GRU-512, 128 prompts over {world} GPU(s), "
+                                                                          f"1 s prompt -> {n} samples, one gather"}
+        del net
+        # cfg 4: tensor-core WaveNet, 128 prompts per GPU
+        net = make_network("wavenet", dev).bfloat16()
+        Bg, n = 128 * world, SR // 8
+        pr = torch.cat([synthetic_prompts(128, P, r) for r in range(world)], 0).to(dev)
+        ms = timed(lambda: sharding.generate_sharded(net, pr, n))
+        out["cfg4_wavenet_bf16_b128_per_gpu"] = {"value": Bg * n / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "weak",
+                                                 "dtype": "bf16", "workload": f"WaveNet W-30 on tcgen05, {Bg} prompts over {world} GPU(s), "
+                                                                              f"1 s prompt -> {n} samples, one gather"}
+        del net
+        # cfg 5: features, 1 h of 22.05 kHz audio per GPU
+        n_clips, L = 360, FEAT["clip"]
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        x = torch.rand((n_clips, L), generator=g, device=dev) * 2 - 1
+        mu, ms_, mel = MuLawCompress(256, 1.), MagSpec(FEAT["n_fft"], FEAT["hop"]), MelSpec(FEAT["n_mels"])
+        ms = timed(lambda: (mu(x), ms_.mel(x, mel)), reps=5)
+        out["cfg5_features_1h_per_gpu"] = {"value": world * n_clips * L / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "weak",
+                                           "dtype": "f32", "workload": f"mu-law (int64) + STFT(2048/512)->mel(128), {n_clips} clips x {L} "
+                                                                       f"samples per GPU, inputs resident in HBM"}
+    except Exception as e:   # the headline line must survive a failing side measurement
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -361,13 +471,12 @@ def run_b200(args):
 FEAT = dict(sr=22050, clip=220500, clips_10h=3600, n_fft=2048, hop=512, n_mels=128)
 
 
-def run_features_reference(args):
+def time_cpu_features(steps, n_clips=36):
+    """The reference's CPU feature chain (torch ops of MuLawCompress / MagSpec / MelSpec, oracle/torch_port.py) on a bounded
+    sample: 36 clips = 6 min of audio per step.  Returns (samples/s, seconds per step)."""
     import torch
     from oracle import restate, torch_port
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
     torch.set_num_threads(os.cpu_count() or 1)
-    n_clips = 36                                   # 6 min of audio per step: a bounded sample of the 10 h workload
     g = torch.Generator().manual_seed(1234)
     x = torch.rand(n_clips, FEAT["clip"], generator=g) * 2 - 1
     fb = torch.from_numpy(restate.mel_filterbank(FEAT["n_fft"], FEAT["n_mels"]))
@@ -377,10 +486,18 @@ def run_features_reference(args):
         torch_port.melspec(torch_port.magspec(x, FEAT["n_fft"], FEAT["hop"]), fb)
     one()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one()
-    dt = (time.perf_counter() - t0) / args.steps
-    val = n_clips * FEAT["clip"] / dt
+    dt = (time.perf_counter() - t0) / steps
+    return n_clips * FEAT["clip"] / dt, dt
+
+
+def run_features_reference(args):
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_clips = 36
+    val, dt = time_cpu_features(args.steps, n_clips)
     print(json.dumps({
         "impl": "reference", "metric": "feature-extracted audio samples/sec", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -504,6 +621,11 @@ def run_features(args):
                          "traffic_source": "ncu --set full on a 360-clip launch, scaled by the clip count",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"},
         }
+        if not args.no_cpu_baseline:
+            cpu_val, cpu_dt = time_cpu_features(2)
+            line["cpu_baseline"] = {"value": cpu_val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"36 clips x {L} samples per step ({cpu_dt:.1f} s; full workload: {n_clips} clips): the "
+                                              f"reference's torch ops on the host (oracle/torch_port.py)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -42,7 +42,7 @@ constexpr int GB = 4;             // prompts per pipeline group
 constexpr int KS = 16;            // k-slices (lanes that share one output row)
 constexpr int MAX_LAYERS = 96;
 constexpr int MAX_HC = 8;         // head CTAs
-constexpr int TRACE_EV = 16;
+constexpr int TRACE_EV = 24;
 
 struct Layer {
     int dilation, has_res;
@@ -55,7 +55,7 @@ struct Params {
     int nh1, nz, nzp;             // head: hidden rows / logit rows (padded to 4) per head CTA
     int skip_passes;              // ceil((S/2) / (C/2))
     int o_wold, o_wsk, o_bias, layer_block;      // float offsets inside a (layer, half) shared-memory weight block
-    int o_w1, o_w2, o_b1, o_b2, head_block;      // ... inside a head CTA's block
+    int o_w1, o_w2, o_b1, o_b2, o_wt, head_block;      // ... inside a head CTA's block (o_wt: temperature row + its bias)
     int s_in, inblk, s_y, yblk, s_sk, skblk, s_bar, smem_floats, zrow;
     float min_temp;
     Layer layers[MAX_LAYERS];
@@ -80,7 +80,8 @@ struct Params {
 
 // barrier roles (layer CTA | head CTA)
 enum { BAR_IN = 0 /* +buf: layer input | head input */, BAR_Y = 2 /* gated output | head hidden */,
-       BAR_SK = 4 /* incoming skip sum | logits */, BAR_FREE = 6 /* credits from the consumers */, BAR_COUNT = 8 };
+       BAR_SK = 4 /* incoming skip sum | logits */, BAR_FREE = 6 /* credits from the consumers */,
+       BAR_ZDONE = 8 /* head: the deciding warps are done with a logits buffer */, BAR_COUNT = 10 };
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -100,17 +101,27 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Credit return.  Relaxed on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU (0.6 stalled warps per issue in ncu) and
+// nothing needs publishing — the credit only says that this warp's shared-memory READS of the buffer are over, and they are
+// (their values were consumed by the arithmetic whose results were sent before this instruction issues).
 __device__ __forceinline__ void mbar_arrive_remote(unsigned raddr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void st_async_f32(unsigned raddr, float v, unsigned rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
                  ::"r"(raddr), "f"(v), "r"(rbar) : "memory");
+}
+// CTA barrier `id` over `nthreads` threads with an OR of a predicate
+__device__ __forceinline__ bool named_sync_or(int id, int nthreads, bool pred) {
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"((unsigned)(pred ? 1u : 0u)), "r"(id), "r"(nthreads) : "memory");
+    return r != 0u;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -183,12 +194,19 @@ __device__ __forceinline__ void fold(const float (&a)[N], float (&o)[N / 2], boo
         o[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
     }
 }
+// The same without the selects, for levels whose halves were swapped ahead of time: the weights are per-lane data, so a
+// lane whose bit is set simply holds its rows in the swapped order (row slot j = row j ^ lane bits, see the packing).
+template <int N>
+__device__ __forceinline__ void fold_swapped(const float (&a)[N], float (&o)[N / 2], int mask) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) o[i] = a[i] + __shfl_xor_sync(0xffffffffu, a[N / 2 + i], mask);
+}
 // 32 partial sums per lane over the 16 lanes of a k-slice group -> lane (b3 b2 b1 b0) keeps values 2 * lane16 + {0, 1}
 __device__ __forceinline__ float2 tree32x16(const float (&a)[32]) {
     const int lane = threadIdx.x & 31;
     float v16[16], v8[8], v4[4], v2[2];
-    fold<32>(a, v16, lane & 8, 8);
-    fold<16>(v16, v8, lane & 4, 4);
+    fold_swapped<32>(a, v16, 8);
+    fold_swapped<16>(v16, v8, 4);
     fold<8>(v8, v4, lane & 2, 2);
     fold<4>(v4, v2, lane & 1, 1);
     return make_float2(v2[0], v2[1]);
@@ -197,8 +215,8 @@ __device__ __forceinline__ float2 tree32x16(const float (&a)[32]) {
 __device__ __forceinline__ float tree16x16(const float (&a)[16]) {
     const int lane = threadIdx.x & 31;
     float v8[8], v4[4], v2[2], v1[1];
-    fold<16>(a, v8, lane & 8, 8);
-    fold<8>(v8, v4, lane & 4, 4);
+    fold_swapped<16>(a, v8, 8);
+    fold_swapped<8>(v8, v4, 4);
     fold<4>(v4, v2, lane & 2, 2);
     fold<2>(v2, v1, lane & 1, 1);
     return v1[0];
@@ -207,8 +225,8 @@ __device__ __forceinline__ float tree16x16(const float (&a)[16]) {
 __device__ __forceinline__ float tree16x32(const float (&a)[16]) {
     const int lane = threadIdx.x & 31;
     float v8[8], v4[4], v2[2], v1[1];
-    fold<16>(a, v8, lane & 16, 16);
-    fold<8>(v8, v4, lane & 8, 8);
+    fold_swapped<16>(a, v8, 16);
+    fold_swapped<8>(v8, v4, 8);
     fold<4>(v4, v2, lane & 4, 4);
     fold<2>(v2, v1, lane & 2, 2);
     return v1[0] + __shfl_xor_sync(0xffffffffu, v1[0], 1);
@@ -220,6 +238,13 @@ __device__ __forceinline__ float gate_act(float a, bool gate_half) {
     const float m = gate_half ? 1.0f : 2.0f;
     const float e = expf(-m * a);
     return __fdiv_rn(m, 1.0f + e) - (m - 1.0f);
+}
+
+// tanh(f) * sigmoid(g) with one division: t = exp(-2f), u = exp(-g): (1 - t) / ((1 + t) (1 + u)).  f is clamped at -30
+// (tanh is -1 to the last bit long before) so that t stays finite; u = inf gives 0, the limit of the sigmoid.
+__device__ __forceinline__ float gated(float f, float g) {
+    const float t = expf(-2.0f * fmaxf(f, -30.0f)), u = expf(-g);
+    return __fdiv_rn(1.0f - t, (1.0f + t) * (1.0f + u));
 }
 
 // acc[(i * 4 + p)] += w[i] * x[p] for 4 rows i, 4 prompts p
@@ -242,16 +267,45 @@ __device__ __forceinline__ void fma_gate(float (&acc)[32], const float4& wa, con
         }
 }
 
-// Head contraction: 4 output rows x 4 prompts, K split over the 32 lanes (k = lane + 32 j).  W4: [K/32][32] float4 = the
-// 4 rows at this lane's k; x4: [K] float4.  Lanes 2 i and 2 i + 1 return output (row = i >> 2, prompt = i & 3).
-__device__ __forceinline__ float head_rows(const float4* __restrict__ W4, const float4* __restrict__ x4, int K) {
+// Head contraction: NCH chunks of 4 output rows x 4 prompts at once (independent accumulators hide the latencies of a lone
+// warp), K split over the 32 lanes (k = lane + 32 j).  W4: chunk c at W4 + c * cstride, [K/32][32] float4 = the 4 rows at
+// this lane's k; x4: [K] float4.  out[c]: lanes 2 i and 2 i + 1 hold output (row = i >> 2, prompt = i & 3) of chunk c.
+template <int NCH>
+__device__ __forceinline__ void head_rows(const float4* __restrict__ W4, int cstride, const float4* __restrict__ x4, int K,
+                                          float (&out)[NCH]) {
     const int lane = threadIdx.x & 31;
-    float acc[16];
+    float acc[NCH][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
-#pragma unroll 4
-    for (int j = 0; j < K / 32; ++j) fma16(acc, W4[j * 32 + lane], x4[j * 32 + lane]);
-    return tree16x32(acc);
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c][i] = 0.0f;
+#pragma unroll 2
+    for (int j = 0; j < K / 32; ++j) {
+        const float4 x = x4[j * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) fma16(acc[c], W4[(size_t)c * cstride + j * 32 + lane], x);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) out[c] = tree16x32(acc[c]);
+}
+// One row x 4 prompts, K over the lanes: every lane returns output (prompt = (lane >> 1) & 3 ... see tree): used for the
+// learned-temperature row.  w: [K] floats of the row; returns in lanes 8 p .. 8 p + 7 the output of prompt p.
+__device__ __forceinline__ float head_row1(const float* __restrict__ w, const float4* __restrict__ x4, int K) {
+    const int lane = threadIdx.x & 31;
+    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int j = 0; j < K / 32; ++j) {
+        const float4 x = x4[j * 32 + lane];
+        const float wk = w[j * 32 + lane];
+        a[0] = fmaf(wk, x.x, a[0]); a[1] = fmaf(wk, x.y, a[1]); a[2] = fmaf(wk, x.z, a[2]); a[3] = fmaf(wk, x.w, a[3]);
+    }
+    float v2[2], v1[1];
+    fold<4>(a, v2, lane & 16, 16);
+    fold<2>(v2, v1, lane & 8, 8);
+    float v = v1[0];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -259,7 +313,7 @@ __device__ __forceinline__ float head_rows(const float4* __restrict__ W4, const 
 // thread = (k-slice s of 16, channel quad q): 4 channels (8 gate rows / 4 residual rows / 4 skip rows) x C/16 steps.
 // ------------------------------------------------------------------------------------------------------------
 template <int C, bool TRACE>
-__global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constant__ Params P) {
+__global__ void __maxnreg__(216) wavenet6_kernel(const __grid_constant__ Params P) {
     constexpr int NT = 2 * C, NW = NT / 32, KJ = C / KS, CH = C / 2, NQ = C / 8;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -297,7 +351,8 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(BAR_IN + b), 1); mbar_init(bar(BAR_Y + b), 1); mbar_init(bar(BAR_SK + b), 1);
             // credits: every warp of every consumer CTA arrives once per consumed delivery
-            mbar_init(bar(BAR_FREE + b), (unsigned)((last_layer ? P.NHC : 2) * NW));
+            mbar_init(bar(BAR_FREE + b), (unsigned)(last_layer ? P.NHC * (NW > GB ? NW - GB : NW) : 2 * NW));
+            mbar_init(bar(BAR_ZDONE + b), GB);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int b = 0; b < 2; ++b) {   // arm the first phase of every exchange barrier (tx bytes may land before or after)
@@ -384,6 +439,8 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
         float2 a0 = __ldcg(ring_ptr(P.t_begin, 0));     // parked older-tap pre-activations (f, g) of the unit about to start
         float pf_e[2] = {0.0f, 0.0f};                    // first layer: prefetched embedding values of the next unit
         bool pf_ok = false;
+        uint2 pf_x[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};   // mailbox-fed layer: the next unit's input words, fetched
+        bool pf_x_ok = false;                                        // a unit ahead (an L2 round trip per unit otherwise)
 
         for (long long t = P.t_begin; t < P.t_end && !dead; ++t) {
             const unsigned delivery = (unsigned)(t - P.t_begin);
@@ -413,11 +470,19 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                     } else if (flow) {
                         const unsigned dlv = last_layer ? (unsigned)(t - P.t_head) : delivery;   // same (group, parity) box two steps ago
                         if (dlv >= 2u) {
-                            if (lane == 0) dead |= !ack_wait(P.ack + (size_t)down_slot * G + g, (dlv - 1u) * (unsigned)(n_down * NW), abort_flag);
+                            const unsigned per_delivery = last_layer ? (unsigned)(P.NHC * (NW > GB ? NW - GB : NW)) : 2u * NW;   // consumer warps
+                            if (lane == 0) dead |= !ack_wait(P.ack + (size_t)down_slot * G + g, (dlv - 1u) * per_delivery, abort_flag);
                             dead = __any_sync(0xffffffffu, dead);
                         }
                     }
                 }
+
+                // ---- first layer, free-running generation: peek at the next unit's sampled index now (the word and then the
+                //      embedding row are two dependent L2 round trips; both fit under this unit's work when the sampler is ahead)
+                uint2 peek = make_uint2(0u, 0u);
+                const bool peeking = first && !P.teacher_forced && nt > P.t_head && nt < P.t_end;
+                if (peeking && ng * GB + (tid & 3) < P.B)
+                    peek = ld_poll_v2(reinterpret_cast<const uint2*>(P.samples + ng * GB + (tid & 3)));
 
                 // ---- layer input -> inb[nb]
                 float* xin = inb + nb * P.inblk;
@@ -453,11 +518,20 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int i = tid + u * NT;
-                        uint2 v = ld_poll_v2(mx + i);
+                        uint2 v = pf_x[u];
+                        if (!pf_x_ok) v = ld_poll_v2(mx + i);
                         if (v.y != tag) dead |= !poll_word(mx + i, tag, v, abort_flag);
                         xin[i] = __uint_as_float(v.x);
                     }
+                    pf_x_ok = false;
                     if (__syncthreads_or(dead ? 1 : 0)) { dead = true; break; }
+                    if (nt < P.t_end) {   // the next unit's words: valid already when this stage is the slower one
+                        const size_t boxn = ((size_t)slot * G + ng) * 2 + ((unsigned)(nt - P.t_begin) & 1u);
+                        const uint2* mxn = P.mail_x + boxn * (size_t)P.inblk;
+                        pf_x[0] = ld_poll_v2(mxn + tid);
+                        pf_x[1] = ld_poll_v2(mxn + tid + NT);
+                        pf_x_ok = true;
+                    }
                 } else {
                     dead |= !mbar_wait(bar(BAR_IN + nb), (n >> 1) & 1u, abort_flag);
                     if (tid == 0) mbar_expect_tx(bar(BAR_IN + nb), in_bytes_layer);   // arm the buffer's next use
@@ -473,8 +547,11 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                     for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
 #pragma unroll
                     for (int j = 0; j < KJ; ++j) fma_gate(acc, wga[j], wgb[j], X4[s + 16 * j]);
+                    stamp();
                     const float2 fg = tree32x16(acc);
-                    y = gate_act(fg.x + a0.x, false) * gate_act(fg.y + a0.y, true);      // tanh(f) * sigmoid(g)
+                    stamp();
+                    y = gated(fg.x + a0.x, fg.y + a0.y);      // tanh(f) * sigmoid(g)
+                    stamp();
                 }
                 {
                     if (need_y) {
@@ -498,6 +575,15 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
 
                 const float4* Y4 = reinterpret_cast<const float4*>(yb + nb * P.yblk);
                 bool y_waited = false;
+                // mailbox-fed layer: the incoming skip sums of this unit are asked for now and looked at in the skip phase
+                uint2 pf_s[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+                if (has_skip && !first && !up_local) {
+                    const size_t box = ((size_t)slot * G + g) * 2 + (delivery & 1u);
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass)
+                        if (pass < P.skip_passes && (pass * CH + 8 * warp) < SH)
+                            pf_s[pass] = ld_poll_v2(P.mail_s + box * (size_t)(S * GB) + (h * SH + pass * CH + cl) * GB + po);
+                }
                 // ---- residual 1x1 conv -> h_{l+1} = h_l + conv_res(y)   (wavenet_v2.py:172-175)
                 if (has_res) {
                     dead |= !mbar_wait(bar(BAR_Y + nb), (n >> 1) & 1u, abort_flag);
@@ -509,6 +595,7 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                     for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
 #pragma unroll
                     for (int j = 0; j < KJ; ++j) fma16(acc, wr[j], Y4[s + 16 * j]);
+                    stamp();
                     float v = tree16x16(acc) + b_res;
                     v = xin[ch * GB + po] + v;
                     if (down_local) {
@@ -553,7 +640,7 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                             } else {
                                 const size_t box = ((size_t)slot * G + g) * 2 + (delivery & 1u);
                                 const uint2* ms = P.mail_s + box * (size_t)(S * GB) + grow * GB + po;
-                                uint2 w = ld_poll_v2(ms);
+                                uint2 w = pf_s[pass];
                                 if (w.y != tag) dead |= !poll_word(ms, tag, w, abort_flag);
                                 v = v + __uint_as_float(w.x);
                             }
@@ -585,10 +672,29 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                     for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
 #pragma unroll
                     for (int j = 0; j < KJ; ++j) fma_gate(acc, Wold4[(2 * j + 0) * NT + tid], Wold4[(2 * j + 1) * NT + tid], X4[s + 16 * j]);
+                    stamp();
                     float2 park = tree32x16(acc);
+                    stamp();
                     park.x += b_gf; park.y += b_gg;
                     __stcg(ring_ptr(t, g), park);          // read back by this same thread at t + dilation
                     if (nt < P.t_end) a0 = __ldcg(ring_ptr(nt, ng));   // after the store: with one group and dilation 1 it is that word
+                }
+                if (peeking) {
+                    // every thread of a warp looks at the same 4 words: the warp agrees on whether the sampler was ahead
+                    const bool known = ng * GB + (tid & 3) >= P.B || peek.y == (unsigned)(nt - P.t_begin) + 1u;
+                    if (__all_sync(0xffffffffu, known)) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = tid + u * NT, p = i & 3, k = i >> 2, b = ng * GB + p;
+                            pf_e[u] = 0.0f;
+                            if (b < P.B) {
+                                long long qi = (long long)peek.x;
+                                qi = qi >= P.Q ? P.Q - 1 : qi;
+                                pf_e[u] = __ldg(P.E + (size_t)qi * C + k);
+                            }
+                        }
+                        pf_ok = true;
+                    }
                 }
                 if (first && nt < P.t_end && (P.teacher_forced || nt <= P.t_head)) {
                     // next unit's embedding values are known already (prompt / teacher forcing)
@@ -649,76 +755,125 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
         const int hrank0 = slot_rank0(P.head_slot);
         const int ro = (lane >> 3) & 3, po = (lane >> 1) & 3;   // after head_rows: row inside the chunk, prompt (lanes 2 i, 2 i + 1 agree)
         const int nc1 = P.nh1 / 4, nc2 = P.nzp / 4;
-        const int my_rows = min(P.nz, Q + 1 - hr * P.nz);       // logit rows of this head CTA (may be <= 0 for a trailing CTA)
-        unsigned nh = 0;
+        const int my_rows = min(P.nz, Q - hr * P.nz);           // logit rows of this head CTA (may be <= 0 for a trailing CTA)
+        // warps [0, GB) only decide (one prompt each, when it is this CTA's turn); the rows are shared by the other warps, so
+        // that a decision (~1 900 cycles) never delays the hidden rows the other head CTAs are waiting for.  (With 4 warps
+        // per CTA every warp does both.)
+        constexpr bool SPLIT = NW > GB;
+        constexpr int NRW = SPLIT ? NW - GB : NW;               // row warps
+        const bool row_warp = !SPLIT || warp >= GB;
+        const int rw = SPLIT ? warp - GB : warp, rtid = SPLIT ? tid - GB * 32 : tid;
+        const bool row_leader = row_warp && rw == NRW - 1 && lane == 0;   // re-arms the row warps' barriers
         const long long t0 = P.t_begin > P.t_head ? P.t_begin : P.t_head;
+        unsigned nh = 0;
         for (long long t = t0; t < P.t_end && !dead; ++t) {
             const unsigned delivery = (unsigned)(t - P.t_begin);
             const unsigned tag = delivery + 1u;
             for (int g = 0; g < P.n_groups; ++g, ++nh) {
                 if (TRACE) {
-                    trace_row = (P.trace && t == P.trace_t && tid == 0) ? P.trace + ((size_t)(P.head_slot + hr) * G + g) * TRACE_EV : nullptr;
+                    trace_row = (P.trace && t == P.trace_t && rtid == 0) ? P.trace + ((size_t)(P.head_slot + hr) * G + g) * TRACE_EV : nullptr;
                     trace_n = 0;
                     if (trace_row) trace_row[trace_n++] = (long long)globaltimer();
                 }
                 stamp();
                 const unsigned nb = nh & 1u;
-                float* hin = inb + nb * P.inblk;
-                if (up_local) {
-                    dead |= !mbar_wait(bar(BAR_IN + nb), (nh >> 1) & 1u, abort_flag);
-                    if (tid == 0) mbar_expect_tx(bar(BAR_IN + nb), hin_bytes);
-                } else {
-                    const size_t box = ((size_t)P.head_slot * G + g) * 2 + (delivery & 1u);
-                    const uint2* mx = P.mail_x + box * (size_t)P.inblk;
-                    for (int i = tid; i < Kh * GB; i += NT) {
-                        uint2 v = ld_poll_v2(mx + i);
-                        if (v.y != tag) dead |= !poll_word(mx + i, tag, v, abort_flag);
-                        hin[i] = __uint_as_float(v.x);
-                    }
-                    if (__syncthreads_or(dead ? 1 : 0)) { dead = true; break; }
-                }
-                stamp();
-                // hidden rows of this CTA, all-gathered over the head CTAs
-                for (int ck = warp; ck < nc1; ck += NW) {
-                    float v = head_rows(W1 + (size_t)ck * (Kh / 32) * 32, reinterpret_cast<const float4*>(hin), Kh);
-                    const int row = ck * 4 + ro;
-                    v = mish_acc(v + B1[row]);
-                    const unsigned dst = sbase + (unsigned)(P.s_y + nb * P.yblk + (hr * P.nh1 + row) * GB + po) * 4u;
-                    for (int dd = (lane & 1); dd < NHC; dd += 2) {
-                        const unsigned w = window(hrank0 + dd);
-                        st_async_f32(w + dst, v, w + bar(BAR_Y + nb));
-                    }
-                }
-                // the head input is consumed: return it to the last layer's CTAs
-                __syncwarp();
-                if (up_local) {
-                    if (lane == 0) mbar_arrive_remote(win_up0 + bar(BAR_FREE + nb));
-                    if (lane == 1) mbar_arrive_remote(win_up1 + bar(BAR_FREE + nb));
-                } else if (lane == 0) {
-                    red_add_u32(P.ack + (size_t)P.head_slot * G + g, 1u);
-                }
-                dead |= !mbar_wait(bar(BAR_Y + nb), (nh >> 1) & 1u, abort_flag);
-                if (tid == 0) mbar_expect_tx(bar(BAR_Y + nb), hid_bytes);
-                stamp();
-                // logit rows of this CTA (+ the learned-temperature row Q) -> the head CTA whose turn it is, [prompt][row]
                 const int decider = (int)(nh % (unsigned)NHC);
                 const unsigned zcnt = nh / (unsigned)NHC;             // units the decider has decided before this one
                 const unsigned zb = zcnt & 1u;
-                {
+                if (row_warp) {
+                    float* hin = inb + nb * P.inblk;
+                    if (up_local) {
+                        dead |= !mbar_wait(bar(BAR_IN + nb), (nh >> 1) & 1u, abort_flag);
+                        if (row_leader) mbar_expect_tx(bar(BAR_IN + nb), hin_bytes);
+                    } else {
+                        const size_t box = ((size_t)P.head_slot * G + g) * 2 + (delivery & 1u);
+                        const uint2* mx = P.mail_x + box * (size_t)P.inblk;
+                        for (int i = rtid; i < Kh * GB; i += NRW * 32) {
+                            uint2 v = ld_poll_v2(mx + i);
+                            if (v.y != tag) dead |= !poll_word(mx + i, tag, v, abort_flag);
+                            hin[i] = __uint_as_float(v.x);
+                        }
+                        if (named_sync_or(2, NRW * 32, dead)) { dead = true; break; }
+                    }
+                    stamp();
+                    // this CTA's logits buffer [zb] is refilled after this unit's hidden gather: the deciding warps must be done
+                    // with its previous contents before any of this CTA's hidden rows leaves
+                    if (hr == decider && zcnt >= 2u)
+                        dead |= !mbar_wait(bar(BAR_ZDONE + zb), ((zcnt >> 1) - 1u) & 1u, abort_flag);
+                    // hidden rows of this CTA, all-gathered over the head CTAs
+                    auto hidden_out = [&](int ck, float v) {
+                        const int row = ck * 4 + ro;
+                        v = mish_acc(v + B1[row]);
+                        const unsigned dst = sbase + (unsigned)(P.s_y + nb * P.yblk + (hr * P.nh1 + row) * GB + po) * 4u;
+                        for (int dd = (lane & 1); dd < NHC; dd += 2) {
+                            const unsigned w = window(hrank0 + dd);
+                            st_async_f32(w + dst, v, w + bar(BAR_Y + nb));
+                        }
+                    };
+                    {
+                        const int cs1 = (Kh / 32) * 32;
+                        int ck = rw;
+                        for (; ck + NRW < nc1; ck += 2 * NRW) {
+                            float v[2];
+                            head_rows<2>(W1 + (size_t)ck * cs1, NRW * cs1, reinterpret_cast<const float4*>(hin), Kh, v);
+                            hidden_out(ck, v[0]); hidden_out(ck + NRW, v[1]);
+                        }
+                        if (ck < nc1) {
+                            float v[1];
+                            head_rows<1>(W1 + (size_t)ck * cs1, 0, reinterpret_cast<const float4*>(hin), Kh, v);
+                            hidden_out(ck, v[0]);
+                        }
+                    }
+                    // the head input is consumed: return it to the last layer's CTAs
+                    __syncwarp();
+                    if (up_local) {
+                        if (lane == 0) mbar_arrive_remote(win_up0 + bar(BAR_FREE + nb));
+                        if (lane == 1) mbar_arrive_remote(win_up1 + bar(BAR_FREE + nb));
+                    } else if (lane == 0) {
+                        red_add_u32(P.ack + (size_t)P.head_slot * G + g, 1u);
+                    }
+                    dead |= !mbar_wait(bar(BAR_Y + nb), (nh >> 1) & 1u, abort_flag);
+                    if (row_leader) mbar_expect_tx(bar(BAR_Y + nb), hid_bytes);
+                    stamp();
+                    // logit rows of this CTA (+ the learned-temperature row Q) -> the head CTA whose turn it is, [prompt][row]
                     const unsigned w = window(hrank0 + decider);
-                    for (int ck = warp; ck < nc2; ck += NW) {
-                        const float v = head_rows(W2 + (size_t)ck * (Hh / 32) * 32, reinterpret_cast<const float4*>(yb + nb * P.yblk), Hh);
+                    const float4* hid4 = reinterpret_cast<const float4*>(yb + nb * P.yblk);
+                    auto logit_out = [&](int ck, float v) {
                         const int row = ck * 4 + ro;
                         if ((lane & 1) == 0 && row < my_rows)
                             st_async_f32(w + sbase + (unsigned)(P.s_sk + zb * P.skblk + po * P.zrow + hr * P.nz + row) * 4u, v + B2[row],
                                          w + bar(BAR_SK + zb));
+                    };
+                    {
+                        const int cs2 = (Hh / 32) * 32;
+                        int ck = rw;
+                        for (; ck + 3 * NRW < nc2; ck += 4 * NRW) {
+                            float v[4];
+                            head_rows<4>(W2 + (size_t)ck * cs2, NRW * cs2, hid4, Hh, v);
+                            logit_out(ck, v[0]); logit_out(ck + NRW, v[1]); logit_out(ck + 2 * NRW, v[2]); logit_out(ck + 3 * NRW, v[3]);
+                        }
+                        for (; ck + NRW < nc2; ck += 2 * NRW) {
+                            float v[2];
+                            head_rows<2>(W2 + (size_t)ck * cs2, NRW * cs2, hid4, Hh, v);
+                            logit_out(ck, v[0]); logit_out(ck + NRW, v[1]);
+                        }
+                        if (ck < nc2) {
+                            float v[1];
+                            head_rows<1>(W2 + (size_t)ck * cs2, 0, hid4, Hh, v);
+                            logit_out(ck, v[0]);
+                        }
                     }
+                    // the learned-temperature row (Q) is one more dot product per prompt: the decider's first row warp takes it
+                    if (hr == decider && rw == 0) {
+                        const float v = head_row1(smem + P.o_wt, hid4, Hh) + smem[P.o_wt + Hh];
+                        if ((lane & 7) == 0)
+                            st_async_f32(w + sbase + (unsigned)(P.s_sk + zb * P.skblk + (lane >> 3) * P.zrow + Q) * 4u, v, w + bar(BAR_SK + zb));
+                    }
+                    stamp();
                 }
-                stamp();
                 if (hr == decider && warp < GB) {
                     dead |= !mbar_wait(bar(BAR_SK + zb), (zcnt >> 1) & 1u, abort_flag);
                     if (tid == 0) mbar_expect_tx(bar(BAR_SK + zb), z_bytes);
-                    stamp();
                     const int p = warp, b = g * GB + p;
                     if (b < P.B && !dead) {
                         const long long hstep = t - P.t_head, n_head = P.t_end - P.t_head;
@@ -738,11 +893,9 @@ __global__ void __launch_bounds__(2 * C, 1) wavenet6_kernel(const __grid_constan
                             }
                         }
                     }
-                    stamp();
                     if (tid == 0 && g == P.n_groups - 1 && P.step_ts) P.step_ts[t - P.t_begin] = globaltimer();
-                    // warp 0 owns hidden rows in every unit: holding it here until the four deciding warps are done keeps the
-                    // next-but-one gather into this logits buffer behind the reads above
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(BAR_ZDONE + zb)) : "memory");
                 }
                 if (dead) break;
             }
@@ -798,12 +951,13 @@ static size_t wn6_plan(Params& p, int CS, int NHC) {
     p.layer_block = o;
     o = 0;
     p.nh1 = p.Hh / NHC;
-    p.nz = (p.Q + 1 + NHC - 1) / NHC;
+    p.nz = (p.Q + NHC - 1) / NHC;               // the learned-temperature row Q is handled apart
     p.nzp = pad4(p.nz);
     p.o_w1 = take(p.nh1 * p.Kh);
     p.o_w2 = take(p.nzp * p.Hh);
     p.o_b1 = take(p.nh1);
     p.o_b2 = take(p.nzp);
+    p.o_wt = take(p.Hh + 1);
     p.head_block = o;
     o = std::max(p.o_bias, p.head_block);       // biases of a layer block go straight from global memory to registers
     p.zrow = pad4(p.Q + 1) + 4;
@@ -925,8 +1079,9 @@ int wn6_create(const mmk_wavenet_desc* d, int max_batch, wn6_handle** out, int* 
                 const int s = tid & 15, q = tid >> 4;
                 for (int j = 0; j < KJ; ++j) {
                     const int k = s + 16 * j;
-                    for (int i = 0; i < 4; ++i) {          // channel 4 q + i of this half
-                        const int chn = hh * CH + 4 * q + i;
+                    for (int i = 0; i < 4; ++i) {          // slot i = channel 4 q + (i ^ (s >> 2)) of this half (pre-swapped for the folds)
+                        const int cq = i ^ (s >> 2);
+                        const int chn = hh * CH + 4 * q + cq;
                         for (int r = 0; r < 2; ++r) {      // filter row, gate row
                             const int o = (r ? C : 0) + chn;
                             const size_t unit = (size_t)(i / 2), el = (size_t)((i % 2) * 2 + r);
@@ -935,7 +1090,7 @@ int wn6_create(const mmk_wavenet_desc* d, int max_batch, wn6_handle** out, int* 
                         }
                         rg[(((size_t)(3 * j) + 2) * NT + tid) * 4 + i] = has_res ? d->conv_res_w[l][(size_t)chn * C + k] : 0.0f;
                         for (int pass = 0; pass < p.skip_passes; ++pass) {
-                            const int row = pass * CH + 4 * q + i;
+                            const int row = pass * CH + 4 * q + cq;
                             if (row < SH)
                                 sm[p.o_wsk + (((size_t)pass * KJ + j) * NT + tid) * 4 + i] = d->conv_skip_w[l][(size_t)(hh * SH + row) * C + k];
                         }
@@ -959,16 +1114,18 @@ int wn6_create(const mmk_wavenet_desc* d, int max_batch, wn6_handle** out, int* 
         // chunks of 4 rows: float4 (chunk, j, lane) = the 4 rows at contraction index lane + 32 j
         for (int row = 0; row < p.nh1; ++row) {
             for (int k = 0; k < p.Kh; ++k)
-                hb[p.o_w1 + ((((size_t)(row / 4) * (p.Kh / 32)) + k / 32) * 32 + k % 32) * 4 + row % 4] = d->head_w1[(size_t)(r * p.nh1 + row) * p.Kh + k];
+                hb[p.o_w1 + ((((size_t)(row / 4) * (p.Kh / 32)) + k / 32) * 32 + k % 32) * 4 + ((row % 4) ^ (((k % 32) >> 3) & 3))] = d->head_w1[(size_t)(r * p.nh1 + row) * p.Kh + k];
             hb[p.o_b1 + row] = d->head_b1[r * p.nh1 + row];
         }
         for (int row = 0; row < p.nz; ++row) {
             const int grow = r * p.nz + row;
-            if (grow > p.Q) break;
+            if (grow >= p.Q) break;
             for (int k = 0; k < p.Hh; ++k)
-                hb[p.o_w2 + ((((size_t)(row / 4) * (p.Hh / 32)) + k / 32) * 32 + k % 32) * 4 + row % 4] = d->head_w2[(size_t)grow * p.Hh + k];
+                hb[p.o_w2 + ((((size_t)(row / 4) * (p.Hh / 32)) + k / 32) * 32 + k % 32) * 4 + ((row % 4) ^ (((k % 32) >> 3) & 3))] = d->head_w2[(size_t)grow * p.Hh + k];
             hb[p.o_b2 + row] = d->head_b2[grow];
         }
+        for (int k = 0; k < p.Hh; ++k) hb[p.o_wt + k] = d->head_w2[(size_t)p.Q * p.Hh + k];
+        hb[p.o_wt + p.Hh] = d->head_b2[p.Q];
     }
     bool ok = true;
     auto dev_alloc = [&](size_t bytes, const void* src) -> void* {

@@ -164,3 +164,49 @@ def test_bf16_faithful_wavenet_oracle_tracks_the_fp32_oracle():
     lg16 = restate.WaveNetBf16Oracle(sd, blocks).logits_for(seq, P)
     err = np.abs(lg16 - lg32).max() / np.abs(lg32).max()
     assert 1e-5 < err < 2e-2, err
+
+
+@pytest.mark.parametrize("name", ["wavenet_default_small", "wavenet_res_skip_small"])
+def test_wavenet_torch_port_vs_reference(name):
+    """oracle/torch_port.py is what bench.py times as `cpu_baseline` / `--impl reference`: the window-recompute port must
+    produce the live reference's sequences (argmax and noise-sampled) bit for bit."""
+    import torch
+    from oracle import torch_port
+    d = load_golden(name)
+    sd = {k: torch.from_numpy(v) for k, v in golden_state_dict(d).items()}
+    blocks = tuple(int(b) for b in d["meta/blocks"])
+    _, dil = restate.wavenet_kernels_and_dilations((2,), blocks)
+    port = torch_port.WaveNetPort(sd, dil)
+    prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
+    n = noise.shape[1]
+    assert np.array_equal(port.generate(prompts, n).numpy(), d["seq_argmax"])
+    assert np.array_equal(port.generate(prompts, n, 1.0, noise).numpy(), d["seq_t1"])
+    P = prompts.shape[1]
+    lg = port.window_logits(torch.from_numpy(d["seq_argmax"]))[:, P - port.rf:P - port.rf + n].numpy()
+    np.testing.assert_allclose(lg, d["logits_argmax"], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["samplernn_821_small", "samplernn_821_small_ragged", "samplernn_41_small"])
+def test_samplernn_torch_port_vs_reference(name):
+    import torch
+    from oracle import torch_port
+    d = load_golden(name)
+    sd = {k: torch.from_numpy(v) for k, v in golden_state_dict(d).items()}
+    port = torch_port.SampleRNNPort(sd, tuple(int(b) for b in d["meta/frame_sizes"]))
+    prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
+    n = noise.shape[1]
+    assert np.array_equal(port.generate(prompts, n).numpy(), d["seq_argmax"])
+    assert np.array_equal(port.generate(prompts, n, 1.0, noise).numpy(), d["seq_t1"])
+
+
+def test_product_wavenet_structure_matches_the_reference_kats():
+    """The PRODUCT's WaveNet.get_kernels_and_dilation / rf (mimikit_b200/wavenet.py) against the KATs taken from the live
+    reference (wavenet_v2.py:295-342) — the same vectors the oracle's function is held to above."""
+    from mimikit_b200 import WaveNet
+    with open(os.path.join(GOLDEN, "wavenet_structure_kat.json")) as f:
+        kats = json.load(f)
+    for k in kats:
+        ks, ds = WaveNet.get_kernels_and_dilation(tuple(k["kernel_sizes"]), tuple(k["blocks"]))
+        assert [int(v) for v in ds] == k["dilations"], k
+        assert [int(v) for v in ks] == k["kernels"], k
+        assert sum((int(a) - 1) * int(b) for a, b in zip(ks, ds)) + 1 == k["rf"]

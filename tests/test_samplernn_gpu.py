@@ -1,5 +1,7 @@
 """GPU parity tests of the persistent SampleRNN kernel (through the C ABI) against the golden vectors produced by
 the live reference (tests/golden/samplernn_*.npz) and against the oracle on seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -77,6 +79,24 @@ def test_vs_oracle_partitions(monkeypatch, ctas, fs, H, B, P):
         assert _rel_err(logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
         assert np.array_equal(seq.cpu().numpy(), ref_seq), (ctas, temp)
         assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+
+
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 64, 19, 43), ((4, 4), 32, 3, 16), ((16, 4, 2), 48, 33, 64),
+                                      ((8, 4, 2, 1), 32, 6, 27), ((8, 2, 1), 512, 128, 40)])
+def test_default_geometry_hosts_every_net(fs, H, B, P):
+    """No environment overrides: the launcher's own choice of kernel and geometry must host every net of this file — a
+    geometry that should fit but regressed is a FAILURE here, not a skip."""
+    for var in ("MMK_SR_KERNEL", "MMK_SR_CLUSTER", "MMK_SR_CTAS"):
+        assert var not in os.environ
+    net = make_net(fs, H, mlp_dim=32, seed=5)
+    info = net.launch_info(B)
+    assert info["sm_used"] >= 1 and info["threads"] >= 32
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    g = torch.Generator().manual_seed(17)
+    prompts = torch.randint(0, 256, (min(B, 5), P), generator=g)
+    seq = net.generate(prompts, 9)
+    ref_seq, _ = orc.generate(prompts.numpy(), 9)
+    assert np.array_equal(seq.cpu().numpy(), ref_seq)
 
 
 @pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])

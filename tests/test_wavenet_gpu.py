@@ -128,6 +128,28 @@ def test_multi_stage_pipeline(monkeypatch, kernel, cluster, hazard, res, skips):
     assert np.array_equal(seq2.cpu().numpy(), ref_seq)
 
 
+@pytest.mark.parametrize("blocks,dims,res,skips,B", [((3, 3), 64, 64, 64, 11), ((4,), 128, None, None, 1),
+                                                     ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8),
+                                                     ((3, 2), 128, 128, 128, 40), ((8, 8, 7, 7), 128, 128, 128, 64)])
+def test_default_geometry_hosts_every_net(blocks, dims, res, skips, B):
+    """No environment overrides: the launcher's own choice of kernel and geometry must host every net of this file (a
+    geometry that should fit but regressed is a FAILURE here, not a skip), and the widths the layer-pipelined kernel
+    supports must actually land on it."""
+    for var in ("MMK_WN_KERNEL", "MMK_WN_CLUSTER", "MMK_WN_STAGES", "MMK_WN_HEAD_CTAS"):
+        assert var not in os.environ
+    net = make_net(blocks, dims, res, skips, mlp_dim=64, seed=7)
+    info = net.launch_info(B)
+    assert info["sm_used"] >= 1 and info["threads"] >= 32
+    if dims in (64, 128):
+        assert info["group_size"] == 4 and info["n_stages"] == sum(blocks) + 1 and info["threads"] == 2 * dims, info
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    g = torch.Generator().manual_seed(3)
+    prompts = torch.randint(0, 256, (min(B, 6), orc.rf + 2), generator=g)
+    seq = net.generate(prompts, 6)
+    ref_seq, _ = orc.generate(prompts.numpy(), 6)
+    assert np.array_equal(seq.cpu().numpy(), ref_seq)
+
+
 def test_stepwise_protocol_and_loop():
     """ARM protocol (before_generate / generate_step / after_generate) == whole-sequence path == oracle, and the
     GenerateLoopV2 mirror yields the expanded waveform (reference tests/test_wavenet.py:140-165 style)."""
