@@ -102,6 +102,13 @@ int mmk_stft_n_frames(int64_t clip_len, int n_fft, int hop, int center, int alig
  * fmax <= 0 means sr/2. */
 int mmk_mel_filterbank(int n_fft, int n_mels, float fmin, float fmax, int htk, float* h_out);
 
+/* MelSpec.np_func on PRECOMPUTED magnitudes — functionals.py:665-668: librosa.feature.melspectrogram(S=inputs.T, ...).T =
+ * inputs @ mel_basis^T.  d_mag fp32 (n_frames, n_bins) with row stride `mag_stride` elements (n_bins = n_fft/2+1),
+ * d_mel_fb fp32 (n_mels, n_bins) dense filterbank on the device (mmk_mel_filterbank builds the reference's on the host),
+ * d_mel_out fp32 (n_frames, n_mels) contiguous.  One warp per frame, sparse filter supports, HBM-bound. */
+int mmk_mel_apply(const float* d_mag, int64_t n_frames, int n_bins, int64_t mag_stride, const float* d_mel_fb, int n_mels,
+                  float* d_mel_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * WaveNet — WaveNet.generate_step / forward (mimikit/networks/wavenet_v2.py:447-452, 276-293), WNLayer.forward
  * (131-176), EmbeddingIO (modules/io.py:148-154), MLP head (networks/mlp.py:44-63), CategoricalSampler

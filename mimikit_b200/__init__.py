@@ -11,5 +11,7 @@ from .wavenet import WaveNet  # noqa: F401
 from .sample_rnn import SampleRNN  # noqa: F401
 from .generate import GenerateLoopV2  # noqa: F401
 from .checkpoint import export_network, load_exported, save_exported  # noqa: F401
+from .chunks import generate_chunks  # noqa: F401
+from .ensemble_generator import EnsembleGenerator, Event  # noqa: F401
 
 __version__ = "0.1.0"

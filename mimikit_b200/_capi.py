@@ -69,6 +69,7 @@ PROTOTYPES = {
                                  c_int, c_void_p, c_void_p]),
     "mmk_stft_n_frames": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "mmk_mel_filterbank": (c_int, [c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "mmk_mel_apply": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mmk_wavenet_create": (c_int, [POINTER(WaveNetDesc), c_int, POINTER(c_void_p)]),
     "mmk_wavenet_create_ex": (c_int, [POINTER(WaveNetDesc), c_int, c_int, POINTER(c_void_p)]),
     "mmk_tc_gemm_check": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -15,7 +15,7 @@ import torch
 from . import _capi
 
 __all__ = ["Continuous", "Discrete", "Sample", "Frame", "Functional", "Identity", "Compose", "Normalize", "RemoveDC",
-           "MuLawCompress", "MuLawExpand", "STFT", "MagSpec", "MelSpec", "mel_filterbank", "stft_n_frames"]
+           "MuLawCompress", "MuLawExpand", "STFT", "MagSpec", "MelSpec", "Resample", "mel_filterbank", "stft_n_frames"]
 
 N_FFT = 2048
 HOP_LENGTH = 512
@@ -213,6 +213,35 @@ class Compose(Functional):
 
 
 @dtc.dataclass
+class Resample(Functional):
+    """functionals.py:291-310 — torch_func = torchaudio.functional.resample.  Orchestration-side (EnsembleGenerator resamples
+    around every event): equal rates are the identity, anything else is handed to torchaudio on the tensor's device; it is
+    library code next to the hot path, not part of it."""
+    orig_sr: int = 22050
+    target_sr: int = 16000
+
+    @property
+    def unit(self):
+        return Sample(self.target_sr)
+
+    def torch_func(self, inputs):
+        if self.orig_sr == self.target_sr:
+            return inputs
+        as_np = isinstance(inputs, np.ndarray)
+        x = torch.from_numpy(inputs) if as_np else inputs
+        try:
+            import torchaudio.functional as AF
+        except ImportError as e:       # pragma: no cover
+            raise NotImplementedError("Resample between different rates needs torchaudio") from e
+        y = AF.resample(x, self.orig_sr, self.target_sr)
+        return y.numpy() if as_np else y
+
+    @property
+    def inv(self):
+        return Resample(self.target_sr, self.orig_sr)
+
+
+@dtc.dataclass
 class MuLawCompress(Functional):
     """functionals.py:313-342.  Bit-exact with the reference's torch_func on CPU (fp32)."""
     q_levels: int = Q_LEVELS
@@ -404,10 +433,9 @@ class MagSpec(Functional):
 
 @dtc.dataclass
 class MelSpec(Functional):
-    """functionals.py:649-676 ("expects a MagSpec as inputs").  The reference only implements np_func (librosa);
-    here torch tensors work too.  Standalone use runs the mel epilogue kernel-side from given magnitudes via a
-    1-frame pass is not needed: magnitudes @ filterbank is done by the fused kernel when called through
-    MagSpec.mel; called on magnitudes directly it launches the same sparse reduce."""
+    """functionals.py:649-676 ("expects a MagSpec as inputs").  The reference only implements np_func (librosa); here
+    numpy arrays and torch tensors both work: `MelSpec()(mag)` launches the stand-alone sparse mel kernel
+    (csrc/mel_apply.cu), `MagSpec.mel(x, MelSpec())` the fused STFT -> |.| -> mel kernel."""
     n_mels: int = 128
     fmin: float = 0.
     fmax: Optional[float] = None
@@ -431,9 +459,28 @@ class MelSpec(Functional):
         return cache[dkey]
 
     def torch_func(self, inputs):
-        raise NotImplementedError(
-            "MelSpec on precomputed magnitudes is not part of the B200 hot path; use MagSpec(...).mel(x, MelSpec(...)) "
-            "which fuses STFT -> |.| -> mel in one kernel (the reference's torch_func is `pass`, functionals.py:670-672)")
+        """(..., frames, n_fft/2+1) magnitudes -> (..., frames, n_mels): `inputs @ mel_basis.T`, what the reference's
+        np_func computes through librosa.feature.melspectrogram(S=inputs.T).T (functionals.py:665-668; its torch_func
+        is an unimplemented `pass`).  n_fft is read off the bin count, as librosa does (2 * (n_bins - 1))."""
+        x, restore = _to_device(inputs)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        if x.dim() < 1 or x.shape[-1] < 2:
+            raise ValueError(f"expected (..., frames, n_bins) magnitudes, got {tuple(x.shape)}")
+        n_bins = x.shape[-1]
+        fb = self.filterbank(2 * (n_bins - 1), x.device)
+        x2 = x.reshape(-1, n_bins)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        out = torch.empty((x2.shape[0], self.n_mels), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _capi.check(_capi.lib().mmk_mel_apply(x2.data_ptr(), x2.shape[0], n_bins, x2.stride(0), fb.data_ptr(),
+                                                  self.n_mels, out.data_ptr(), _capi.stream_ptr()))
+        return restore(out.reshape(*x.shape[:-1], self.n_mels))
+
+    @property
+    def inv(self):
+        return Identity()
 
 
 MelSpec._fb_cache = {}

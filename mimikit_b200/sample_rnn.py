@@ -208,12 +208,31 @@ class SampleRNN(NativeARM):
         U = prepare_noise(noise, T, B, n_steps, self.device, generator)
         logits, _, ts = self._run(seq, 0, self._warm_range(P), (P, P + n_steps), True, False, T, U, P,
                                   return_logits, False, return_step_timestamps)
+        self._cont = dict(handle=self._handle, B=B, t=P + n_steps, tail=seq[:, -self.rf:].clone())
         out = (seq,)
         if return_logits:
             out += (logits,)
         if return_step_timestamps:
             out += (ts,)
         return out[0] if len(out) == 1 else out
+
+    def generate_more(self, n_steps, temperature=None, noise=None, return_logits=False, generator=None):
+        """Continue the last `generate` / `generate_more` for the SAME batch with the GRU states as they are (no hidden
+        reset, no warm-up over a re-prompt): chunked long-form generation (loops/generate_chunks.py:39-56) as one
+        uninterrupted sequence.  Returns the (B, n_steps) new samples (and their logits)."""
+        c = getattr(self, "_cont", None)
+        if c is None or c["handle"] is not self._handle or self._handle is None:
+            raise RuntimeError("generate_more() continues a previous generate() on the same network: nothing to continue")
+        B, t, rf = c["B"], c["t"], self.rf
+        T = as_temperature(temperature, B, self.device)
+        U = prepare_noise(noise, T, B, n_steps, self.device, generator)
+        buf = torch.zeros((B, rf + n_steps), dtype=torch.int64, device=self.device)
+        buf[:, :rf] = c["tail"]
+        logits = None
+        if n_steps > 0:
+            logits, _, _ = self._run(buf, t - rf, (0, 0, 0), (t, t + n_steps), False, False, T, U, t, return_logits, False, False)
+            self._cont = dict(handle=self._handle, B=B, t=t + n_steps, tail=buf[:, -rf:].clone())
+        return (buf[:, rf:], logits) if return_logits else buf[:, rf:]
 
     def teacher_forced(self, sequence, prompt_len, temperature=None, noise=None):
         """Step-wise generate_step logits/decisions on forced inputs (this, not SampleRNN.forward,

@@ -108,6 +108,7 @@ class WaveNet(NativeARM):
         self.has_residuals = config.residuals_dim is not None
         self._sd = self._init_state_dict()
         self._gen = None  # state of the step-wise protocol
+        self._cont = None  # where the last generate() stopped (generate_more continues from the rings as they are)
         self._compute_dtype = torch.float32
 
     # ---- arithmetic ------------------------------------------------------------------------------
@@ -282,12 +283,34 @@ class WaveNet(NativeARM):
             # layers consume samples P-rf .. P+n-2; the head predicts sample t+1 for t >= P-1
             logits, _, ts = self._run(seq, 0, P - self.rf, P - 1, P + n_steps - 1, False, T, U, P, return_logits, False,
                                       return_step_timestamps)
+            self._cont = dict(handle=self._handle, B=B, t=P + n_steps - 1, last=seq[:, -1].clone())
         out = (seq,)
         if return_logits:
             out += (logits,)
         if return_step_timestamps:
             out += (ts,)
         return out[0] if len(out) == 1 else out
+
+    def generate_more(self, n_steps, temperature=None, noise=None, return_logits=False, generator=None):
+        """Continue the last `generate` / `generate_more` of this network for the SAME batch without re-prompting: the
+        dilation rings in the native handle still hold every layer's last `dilation` inputs, so the kernel is launched
+        with an empty prefill and its clock simply runs on (chunked long-form generation, loops/generate_chunks.py:39-56,
+        minus the window recompute of each re-prompt).  Returns the (B, n_steps) new samples (and their logits)."""
+        c = self._cont
+        if c is None or c["handle"] is not self._handle or self._handle is None:
+            raise RuntimeError("generate_more() continues a previous generate() on the same network: nothing to continue "
+                               "(the native handle was rebuilt or generate() was never called)")
+        B, t = c["B"], c["t"]
+        T = as_temperature(temperature, B, self.device)
+        U = prepare_noise(noise, T, B, n_steps, self.device, generator)
+        buf = torch.zeros((B, n_steps + 1), dtype=torch.int64, device=self.device)
+        buf[:, 0] = c["last"]
+        logits = None
+        if n_steps > 0:
+            # column 0 holds the newest known sample (time t): the layers consume t .. t+n-1, the head predicts t+1 .. t+n
+            logits, _, _ = self._run(buf, t, t, t, t + n_steps, False, T, U, t + 1, return_logits, False, False)
+            self._cont = dict(handle=self._handle, B=B, t=t + n_steps, last=buf[:, -1].clone())
+        return (buf[:, 1:], logits) if return_logits else buf[:, 1:]
 
     def teacher_forced(self, sequence, prompt_len, temperature=None, noise=None):
         """Logits and decisions for every position >= prompt_len of a GIVEN sequence (nothing is fed back).
