@@ -94,7 +94,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;

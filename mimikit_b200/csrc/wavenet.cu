@@ -544,6 +544,7 @@ using namespace mmk;
 struct mmk_wavenet_s {
     wn2_handle* v2 = nullptr;   // set when the latency-engineered kernel (wavenet2.cu) hosts this network
     wn3_handle* v3 = nullptr;   // set when the warp-autonomous kernel (wavenet3.cu) hosts this network
+    wn7_handle* v7 = nullptr;   // set when the layer-pipelined tensor-core kernel (wavenet7.cu) hosts this network (compute_mode 1)
     wn6_handle* v6 = nullptr;   // set when the layer-pipelined kernel (wavenet6.cu) hosts this network (the default)
     wn4_handle* v4 = nullptr;   // set when the bf16 tensor-core kernel (wavenet_tc.cu) hosts this network (compute_mode 1)
     WnParams p{};
@@ -662,6 +663,18 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
         int unsupported = 0;
         for (int l = 0; l < d->n_layers; ++l)
             if (!d->conv_dil_w[l] || !d->conv_dil_b[l]) { delete h; MMK_FAIL("missing conv_dil weights"); }
+        {
+            int unsup7 = 0;
+            if (wn7_create(d, max_batch, &h->v7, &unsup7) == 0) {
+                int rf7 = 1;
+                for (int l = 0; l < d->n_layers; ++l) rf7 += d->dilations[l];
+                h->rf = rf7; h->max_batch = max_batch;
+                *out = h;
+                return 0;
+            }
+            h->v7 = nullptr;
+            if (!unsup7) { delete h; return 1; }
+        }
         if (wn4_create(d, max_batch, &h->v4, &unsupported) != 0) { delete h; return 1; }
         int rf4 = 1;
         for (int l = 0; l < d->n_layers; ++l) rf4 += d->dilations[l];
@@ -865,6 +878,7 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
 extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
     if (!h) return 0;
     if (h->v4) wn4_destroy(h->v4);
+    if (h->v7) wn7_destroy(h->v7);
     if (h->v6) wn6_destroy(h->v6);
     if (h->v3) wn3_destroy(h->v3);
     if (h->v2) wn2_destroy(h->v2);
@@ -877,6 +891,7 @@ extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
 extern "C" int mmk_wavenet_sync_check(mmk_wavenet_t h, void* stream) {
     MMK_CHECK(h, "null handle");
     if (h->v4) return wn4_sync_check(h->v4, stream);
+    if (h->v7) return wn7_sync_check(h->v7, stream);
     if (h->v6) return wn6_sync_check(h->v6, stream);
     if (h->v3) return wn3_sync_check(h->v3, stream);
     if (h->v2) return wn2_sync_check(h->v2, stream);
@@ -892,6 +907,7 @@ extern "C" int mmk_wavenet_rf(mmk_wavenet_t h) { return h ? h->rf : -1; }
 extern "C" int mmk_wavenet_launch_info(mmk_wavenet_t h, mmk_launch_info* out) {
     MMK_CHECK(h && out, "null argument");
     if (h->v4) return wn4_launch_info(h->v4, out);
+    if (h->v7) return wn7_launch_info(h->v7, out);
     if (h->v6) return wn6_launch_info(h->v6, out);
     if (h->v3) return wn3_launch_info(h->v3, out);
     if (h->v2) return wn2_launch_info(h->v2, out);
@@ -921,6 +937,9 @@ extern "C" int mmk_wavenet_run(mmk_wavenet_t h, int64_t* d_seq, int B, int64_t s
     if (t_begin == t_end) return 0;
     if (h->v4)
         return wn4_run(h->v4, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
+                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
+    if (h->v7)
+        return wn7_run(h->v7, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
                        n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     if (h->v6)
         return wn6_run(h->v6, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,

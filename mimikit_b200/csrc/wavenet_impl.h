@@ -47,3 +47,15 @@ int wn6_run(wn6_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
             int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
             int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
             unsigned long long* d_step_ts, void* stream);
+
+// The layer-pipelined tensor-core kernel (wavenet7.cu: weights resident as the MMA M operand, 16-prompt groups as N): same
+// contract; tried first for compute_mode = MMK_COMPUTE_BF16_TC, W-30-shaped networks only (else wavenet_tc.cu).
+struct wn7_handle;
+int wn7_create(const mmk_wavenet_desc* d, int max_batch, wn7_handle** out, int* unsupported);
+int wn7_destroy(wn7_handle* h);
+int wn7_launch_info(wn7_handle* h, mmk_launch_info* out);
+int wn7_sync_check(wn7_handle* h, void* stream);
+int wn7_run(wn7_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
+            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
+            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
+            unsigned long long* d_step_ts, void* stream);

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for B in 128 16; do
+timeout 300 python bench.py --workload samplernn --batch $B --seconds 2 --steps 1 --warmup 2 --no-cpu-baseline --no-extras > gpurun_out/r2_sr_b$B.log 2>&1
+echo "sr b$B $(grep -o '"value": [0-9.]*' gpurun_out/r2_sr_b$B.log | head -1) $(grep -o '"p50_step_latency_us": [0-9.]*' gpurun_out/r2_sr_b$B.log) $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/r2_sr_b$B.log) $(tail -1 gpurun_out/r2_sr_b$B.log | cut -c1-200 | grep -v metric)"
+done

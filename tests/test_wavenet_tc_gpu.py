@@ -149,3 +149,69 @@ def test_logits_against_the_bf16_faithful_oracle(blocks, dims, skips, mlp, B, n)
     err = _rel_err(logits.cpu().numpy(), want)
     print(f"bf16 kernel vs bf16-faithful oracle, blocks={blocks}: rel err {err:.2e}")
     assert err <= 1e-2, err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the layer-pipelined tensor-core kernel (csrc/wavenet7.cu): weights resident as the MMA M operand, 16-prompt groups
+# ---------------------------------------------------------------------------------------------------------------------
+def _pipe_net(blocks, seed=0):
+    return _bf16_net(blocks, 128, 128, 128, seed=seed)
+
+
+@pytest.mark.parametrize("cluster", [None, "2", "4", "8", "16"])
+def test_pipeline_kernel_geometries(monkeypatch, cluster):
+    """Every cluster size (cluster boundaries are crossed through L2 mailboxes pulled in with bulk copies), ragged batch
+    (37 prompts = two full 16-prompt groups + 5): logits within the bf16 tolerance of the fp32 oracle and within 1e-2 of
+    the bf16-faithful oracle, replay exact, determinism, permutation equivariance, and the one-CTA kernel agrees."""
+    if cluster is not None:
+        monkeypatch.setenv("MMK_TC_CLUSTER", cluster)
+    blocks = (4, 3)
+    net, orc = _pipe_net(blocks, seed=4)
+    g = torch.Generator().manual_seed(21)
+    B, n, P = 37, 30, net.rf + 6
+    info = net.launch_info(B)
+    assert info["group_size"] == 16 and info["n_stages"] == sum(blocks) + 1 and info["sm_used"] == sum(blocks) + 1, info
+    if cluster is not None:
+        assert info["cluster_size"] == int(cluster)
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    tvec = torch.linspace(0.85, 0.999, B)
+    seq, logits = net.generate(prompts, n, temperature=tvec, noise=noise, return_logits=True)
+    assert torch.equal(seq, net.generate(prompts, n, temperature=tvec, noise=noise))
+    assert torch.equal(seq[:, :P].cpu(), prompts) and int(seq.min()) >= 0 and int(seq.max()) <= 255
+    lg, dec = net.teacher_forced(seq, P, tvec, noise)
+    assert torch.equal(dec, seq[:, P:]) and torch.equal(lg, logits)
+    _, ref_logits = orc.generate(prompts.numpy(), n, None, None, forced=seq.cpu().numpy())
+    assert _rel_err(logits.cpu().numpy(), ref_logits) <= BF16_TOL
+    faithful = restate.WaveNetBf16Oracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks)
+    err = _rel_err(logits.cpu().numpy(), faithful.logits_for(seq.cpu().numpy(), P))
+    print(f"pipeline kernel vs bf16-faithful oracle (cluster {cluster}): rel err {err:.2e}")
+    assert err <= 1e-2, err
+    perm = torch.randperm(B, generator=g)
+    seqp = net.generate(prompts[perm], n, temperature=tvec[perm], noise=noise[perm])
+    assert torch.equal(seqp.cpu(), seq.cpu()[perm])
+    # the first tensor-core kernel (one CTA per 128 prompts) on the same weights: same arithmetic up to summation order
+    monkeypatch.setenv("MMK_TC_KERNEL", "4")
+    net.float(); net.bfloat16()                       # drop the handle: the next call builds the other kernel
+    assert net.launch_info(B)["group_size"] == 128
+    lg4, _ = net.teacher_forced(seq, P, tvec, noise)
+    assert _rel_err(lg4.cpu().numpy(), logits.cpu().numpy()) <= 1e-2
+
+
+def test_pipeline_kernel_stepwise_and_continuation():
+    """ARM protocol one sample at a time == whole-sequence launch; generate_more continues from the rings."""
+    net, _ = _pipe_net((3, 3), seed=6)
+    g = torch.Generator().manual_seed(3)
+    B, n, P = 20, 14, net.rf + 3
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    want = net.generate(prompts, n)
+    seq = torch.cat([prompts, torch.zeros(B, n, dtype=torch.int64)], 1).cuda()
+    net.before_generate((prompts,), 0)
+    for t in range(P, P + n):
+        out, = net.generate_step((seq[:, t - net.rf:t],), t=t)
+        seq[:, t:t + 1] = out
+    net.after_generate((seq,), 0)
+    assert torch.equal(seq, want)
+    first = net.generate(prompts, 6)
+    more = net.generate_more(n - 6)
+    assert torch.equal(torch.cat([first, more], 1), want)
