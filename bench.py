@@ -435,12 +435,12 @@ def run_extras(args, dev, rank, world, barrier):
     try:
         # cfg 3: strong scaling of a fixed 128-prompt batch
         net = make_network("samplernn", dev)
-        Bg, P, n = 128, SR, SR // 4
+        Bg, P, n = 128, SR // 4, SR // 2
         pr = synthetic_prompts(Bg, P).to(dev)
         ms = timed(lambda: sharding.generate_sharded(net, pr, n))
         out["cfg3_samplernn_b128_sharded"] = {"value": Bg * n / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "strong",
                                               "dtype": "f32", "workload": f"SampleRNN (8,2,1) GRU-512, 128 prompts over {world} GPU(s), "
-                                                                          f"1 s prompt -> {n} samples, one gather"}
+                                                                          f"{P}-sample prompt -> {n} samples, one gather"}
         del net
         # cfg 4: tensor-core WaveNet, 128 prompts per GPU
         net = make_network("wavenet", dev).bfloat16()

@@ -228,6 +228,33 @@ typedef struct {
 } mmk_samplernn_desc;
 
 int mmk_samplernn_create(const mmk_samplernn_desc* desc, int max_batch, mmk_samplernn_t* out);
+
+/* The rest of SampleRNNTier's configuration surface (sample_rnn_v2.py:40-66, 101-119; networks/mlp.py:44-50):
+ * rnn_class "lstm" (the reference default) / "gru" / "rnn", n_rnn stacked layers, a non-zero initial state, and
+ * n_hidden_layers > 0 in the MLP head.  The GRU / one layer / zero state / plain head form runs in the cluster kernel
+ * (csrc/samplernn2.cu); everything else in the general kernel (csrc/samplernn.cu). */
+#define MMK_RNN_GRU 0
+#define MMK_RNN_LSTM 1
+#define MMK_RNN_TANH 2
+typedef struct {
+    mmk_samplernn_desc base;      /* geometry, input / up-sampler / bottom-tier weights, head fc.0 and the LAST head Linear
+                                     (head_w2 = fc.{2 + 2 n_hidden}.weight); base.w_ih .. base.b_hh are ignored */
+    int rnn_type;                 /* MMK_RNN_* : nn.GRU (gates r, z, n) | nn.LSTM (i, f, g, o) | nn.RNN (tanh) */
+    int n_rnn;                    /* stacked layers per frame tier, 1..4 */
+    /* HOST pointers, entry [tier * n_rnn + layer] = tiers.i.rnn.weight_ih_l{layer} (G*H, H), weight_hh_l{layer} (G*H, H),
+     * bias_ih_l{layer}, bias_hh_l{layer} (G*H), G = 3 | 4 | 1 */
+    const float* const* w_ih; const float* const* w_hh; const float* const* b_ih; const float* const* b_hh;
+    int head_hidden_layers;       /* MLP n_hidden_layers.  mlp.py:47-50 repeats a tuple holding ONE nn.Linear(Hh, Hh), so all the
+                                     hidden layers share the weights given here */
+    const float* head_wh;         /* output_modules.0.estimator.0.fc.2.weight (Hh, Hh) when head_hidden_layers > 0 */
+    const float* head_bh;         /* ...fc.2.bias (Hh) */
+    int need_set_hidden;          /* 1 = mmk_samplernn_set_hidden will be used (h0_init "ones" / "randn"): general kernel */
+} mmk_samplernn_desc_ex;
+int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* desc, int max_batch, mmk_samplernn_t* out);
+/* Installs an initial state — SampleRNNTier._reset_hidden / _init_h0 (sample_rnn_v2.py:101-119) with h0_init "ones" or
+ * "randn": d_values fp32 (B, H) on the device; which = 0 the hidden state, 1 the LSTM cell state.  Call after a run with
+ * reset_hidden = 1 and zero-length ranges (or on a fresh handle), then run with reset_hidden = 0. */
+int mmk_samplernn_set_hidden(mmk_samplernn_t h, int tier, int layer, int which, const float* d_values, int B, void* stream);
 int mmk_samplernn_destroy(mmk_samplernn_t h);
 int mmk_samplernn_launch_info(mmk_samplernn_t h, mmk_launch_info* out);
 /* As mmk_wavenet_sync_check: waits for the stream and fails if a grid barrier of the last launch timed out. */

@@ -50,6 +50,13 @@ class SampleRNNDesc(Structure):
                 ("head_w2", POINTER(c_float)), ("head_b2", POINTER(c_float))]
 
 
+class SampleRNNDescEx(Structure):
+    _fields_ = [("base", SampleRNNDesc), ("rnn_type", c_int), ("n_rnn", c_int),
+                ("w_ih", _fpp), ("w_hh", _fpp), ("b_ih", _fpp), ("b_hh", _fpp),
+                ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float)),
+                ("need_set_hidden", c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/mmk_b200.h declares
 PROTOTYPES = {
     "mmk_abi_version": (c_int, []),
@@ -82,6 +89,8 @@ PROTOTYPES = {
     "mmk_wavenet_generate": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "mmk_samplernn_create": (c_int, [POINTER(SampleRNNDesc), c_int, POINTER(c_void_p)]),
+    "mmk_samplernn_create_ex": (c_int, [POINTER(SampleRNNDescEx), c_int, POINTER(c_void_p)]),
+    "mmk_samplernn_set_hidden": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mmk_samplernn_destroy": (c_int, [c_void_p]),
     "mmk_samplernn_launch_info": (c_int, [c_void_p, POINTER(LaunchInfo)]),
     "mmk_samplernn_sync_check": (c_int, [c_void_p, c_void_p]),

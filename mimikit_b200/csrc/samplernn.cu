@@ -33,6 +33,7 @@ namespace mmk {
 constexpr int SR_NT = 256;       // threads per CTA
 constexpr int SR_PB = 16;        // prompts per staged chunk
 constexpr int SR_MAX_TIERS = 6;  // frame tiers (the sample-level tier is separate)
+constexpr int SR_MAX_RNN = 4;    // stacked recurrent layers per tier (n_rnn)
 constexpr unsigned SR_SPIN_LIMIT = 1u << 26;
 
 using Tile = TileGemm<SR_PB, SR_NT>;
@@ -40,21 +41,23 @@ using Tile = TileGemm<SR_PB, SR_NT>;
 struct SrTier {
     int fs, up, kdiv;             // frame size, up-sampling factor, fs_{i-1}/fs_i (1 for the top tier)
     int NU, up_rows;              // padded up-sampler columns per CTA, total up-sampler rows (up * H)
-    int off_wih, off_whh, off_wup;  // float offsets in the CTA's weight block: W[H][N] followed by bias[N]
+    int off_wih[SR_MAX_RNN], off_whh[SR_MAX_RNN], off_wup;  // float offsets in the CTA's weight block: W[H][N] followed by bias[N]
     const float* in_w;            // (H, fs) row-major, global
     const float* in_b;            // (H)
-    float* hbuf;                  // [2][H][Bp] ping-pong hidden state
+    float* hbuf[SR_MAX_RNN];      // per layer: [2][H][Bp] ping-pong hidden state
+    float* cbuf[SR_MAX_RNN];      // LSTM: per layer [2][H][Bp] ping-pong cell state
     float* obuf;                  // [up*H][Bp] up-sampled block
 };
 
 struct SrParams {
     int n_ft, H, Hh, Q, NC, JP, NG, NH1, NZ, fs_last;
-    int off_w1, off_w2, cta_block;             // float offsets / size of the per-CTA weight block
+    int rnn_type, G, n_rnn, n_hh;              // cell (MMK_RNN_*), gates per cell (3 | 4 | 1), layers per tier, head hidden layers
+    int off_w1, off_w2, off_wh, cta_block;     // float offsets / size of the per-CTA weight block
     int off_x, off_part, off_gi, off_lin, smem_floats;
     const float* wpack;
     const float* conv_w;          // (H, fs_last)
     const float* conv_b;          // (H)
-    float* hid;                   // [Hh][Bp]
+    float* hid;                   // [2][Hh][Bp] (ping-pong over the head's hidden layers)
     float* z;                     // [Q+1][Bp]
     unsigned long long* bar;      // grid barrier counter
     unsigned* abort_flag;
@@ -181,52 +184,75 @@ __global__ void __launch_bounds__(SR_NT, 1) samplernn_kernel(const __grid_consta
                 if (t % T.fs != 0) continue;
                 const float* cond = nullptr;
                 if (i > 0) cond = P.tiers[i - 1].obuf + (size_t)((t / T.fs) % T.kdiv) * H * Bp;
-                const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
-                float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
-                const float* Wih = w_s + T.off_wih; const float* bih = Wih + (size_t)H * P.NG;
-                const float* Whh = w_s + T.off_whh; const float* bhh = Whh + (size_t)H * P.NG;
-                // ---- GRU cell on this CTA's hidden indices ----
-                if (nj > 0) {
-                    for (int pc = 0; pc < n_chunks; ++pc) {
-                        const int b0 = pc * SR_PB;
-                        stage_frame_input(P, xs, lin_s, T.in_w, T.in_b, T.fs, tw, cond, b0);
-                        const Tile tl(P.NG);
-                        {
-                            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                            tl.accum(acc, Wih, P.NG, xs, H);
-                            tl.store(acc, part);
+                // ---- n_rnn stacked cells (nn.GRU / nn.LSTM / nn.RNN, sample_rnn_v2.py:62-66, 92-96) on this CTA's hidden indices:
+                //      layer 0 reads the tier input, layer k the new state of layer k - 1 (all rows: a grid barrier apart)
+                float* hnext = nullptr;
+                for (int k = 0; k < P.n_rnn; ++k) {
+                    const float* hcur = T.hbuf[k] + (size_t)hsel[i] * H * Bp;
+                    const float* below = hnext;                    // new hidden state of the layer below (k > 0)
+                    hnext = T.hbuf[k] + (size_t)(hsel[i] ^ 1) * H * Bp;
+                    const float* ccur = P.rnn_type == MMK_RNN_LSTM ? T.cbuf[k] + (size_t)hsel[i] * H * Bp : nullptr;
+                    float* cnext = P.rnn_type == MMK_RNN_LSTM ? T.cbuf[k] + (size_t)(hsel[i] ^ 1) * H * Bp : nullptr;
+                    const float* Wih = w_s + T.off_wih[k]; const float* bih = Wih + (size_t)H * P.NG;
+                    const float* Whh = w_s + T.off_whh[k]; const float* bhh = Whh + (size_t)H * P.NG;
+                    if (nj > 0) {
+                        for (int pc = 0; pc < n_chunks; ++pc) {
+                            const int b0 = pc * SR_PB;
+                            if (k == 0) stage_frame_input(P, xs, lin_s, T.in_w, T.in_b, T.fs, tw, cond, b0);
+                            else stage_rows(xs, below, H, Bp, b0);
+                            const Tile tl(P.NG);
+                            {
+                                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                                tl.accum(acc, Wih, P.NG, xs, H);
+                                tl.store(acc, part);
+                            }
+                            __syncthreads();
+                            for (int o = tid; o < P.G * P.JP * SR_PB; o += SR_NT) {
+                                const int col = o / SR_PB, p = o - col * SR_PB;
+                                gi_s[o] = Tile::reduce(part, P.NG, col, p) + bih[col];
+                            }
+                            __syncthreads();
+                            stage_rows(xs, hcur, H, Bp, b0);
+                            {
+                                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                                tl.accum(acc, Whh, P.NG, xs, H);
+                                tl.store(acc, part);
+                            }
+                            __syncthreads();
+                            for (int o = tid; o < nj * SR_PB; o += SR_NT) {
+                                const int jj = o / SR_PB, p = o - jj * SR_PB;
+                                float hnew;
+                                if (P.rnn_type == MMK_RNN_GRU) {            // gates r, z, n
+                                    const int cr = jj, cz = P.JP + jj, cn = 2 * P.JP + jj;
+                                    const float hr = Tile::reduce(part, P.NG, cr, p) + bhh[cr];
+                                    const float hz = Tile::reduce(part, P.NG, cz, p) + bhh[cz];
+                                    const float hn = Tile::reduce(part, P.NG, cn, p) + bhh[cn];
+                                    const float r = sigmoid_acc(gi_s[cr * SR_PB + p] + hr);
+                                    const float zg = sigmoid_acc(gi_s[cz * SR_PB + p] + hz);
+                                    const float n = tanhf(gi_s[cn * SR_PB + p] + r * hn);
+                                    const float hold = xs[(j_lo + jj) * SR_PB + p];
+                                    hnew = (1.0f - zg) * n + zg * hold;
+                                } else if (P.rnn_type == MMK_RNN_LSTM) {    // gates i, f, g, o; c' = f c + i g; h' = o tanh(c')
+                                    const int ci = jj, cf = P.JP + jj, cg = 2 * P.JP + jj, co = 3 * P.JP + jj;
+                                    const float ai = gi_s[ci * SR_PB + p] + (Tile::reduce(part, P.NG, ci, p) + bhh[ci]);
+                                    const float af = gi_s[cf * SR_PB + p] + (Tile::reduce(part, P.NG, cf, p) + bhh[cf]);
+                                    const float ag = gi_s[cg * SR_PB + p] + (Tile::reduce(part, P.NG, cg, p) + bhh[cg]);
+                                    const float ao = gi_s[co * SR_PB + p] + (Tile::reduce(part, P.NG, co, p) + bhh[co]);
+                                    const float cold = (b0 + p < P.B) ? __ldcg(ccur + (size_t)(j_lo + jj) * Bp + b0 + p) : 0.0f;
+                                    const float cnew = sigmoid_acc(af) * cold + sigmoid_acc(ai) * tanhf(ag);
+                                    hnew = sigmoid_acc(ao) * tanhf(cnew);
+                                    if (b0 + p < P.B) __stcg(cnext + (size_t)(j_lo + jj) * Bp + b0 + p, cnew);
+                                } else {                                     // nn.RNN (tanh)
+                                    hnew = tanhf(gi_s[jj * SR_PB + p] + (Tile::reduce(part, P.NG, jj, p) + bhh[jj]));
+                                }
+                                if (b0 + p < P.B) __stcg(hnext + (size_t)(j_lo + jj) * Bp + b0 + p, hnew);
+                            }
+                            __syncthreads();
                         }
-                        __syncthreads();
-                        for (int o = tid; o < 3 * P.JP * SR_PB; o += SR_NT) {
-                            const int col = o / SR_PB, p = o - col * SR_PB;
-                            gi_s[o] = Tile::reduce(part, P.NG, col, p) + bih[col];
-                        }
-                        __syncthreads();
-                        stage_rows(xs, hcur, H, Bp, b0);
-                        {
-                            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                            tl.accum(acc, Whh, P.NG, xs, H);
-                            tl.store(acc, part);
-                        }
-                        __syncthreads();
-                        for (int o = tid; o < nj * SR_PB; o += SR_NT) {
-                            const int jj = o / SR_PB, p = o - jj * SR_PB;
-                            const int cr = jj, cz = P.JP + jj, cn = 2 * P.JP + jj;
-                            const float hr = Tile::reduce(part, P.NG, cr, p) + bhh[cr];
-                            const float hz = Tile::reduce(part, P.NG, cz, p) + bhh[cz];
-                            const float hn = Tile::reduce(part, P.NG, cn, p) + bhh[cn];
-                            const float r = sigmoid_acc(gi_s[cr * SR_PB + p] + hr);
-                            const float zg = sigmoid_acc(gi_s[cz * SR_PB + p] + hz);
-                            const float n = tanhf(gi_s[cn * SR_PB + p] + r * hn);
-                            const float hold = xs[(j_lo + jj) * SR_PB + p];
-                            const float hnew = (1.0f - zg) * n + zg * hold;
-                            if (b0 + p < P.B) __stcg(hnext + (size_t)(j_lo + jj) * Bp + b0 + p, hnew);
-                        }
-                        __syncthreads();
                     }
+                    grid_barrier(P, epoch);
                 }
                 hsel[i] ^= 1;
-                grid_barrier(P, epoch);
                 // ---- LinearResampler rows of this CTA ----
                 const int u_lo = part_lo(c, T.up_rows, NC), nu = part_lo(c + 1, T.up_rows, NC) - u_lo;
                 if (nu > 0) {
@@ -273,11 +299,38 @@ __global__ void __launch_bounds__(SR_NT, 1) samplernn_kernel(const __grid_consta
                 }
             }
             grid_barrier(P, epoch);
+            // MLP hidden layers (networks/mlp.py:47-50): the tuple repetition there makes it ONE Linear(Hh, Hh) + Mish applied
+            // n_hidden_layers times; the buffers ping-pong
+            const float* hid_in = P.hid;
+            for (int r = 0; r < P.n_hh; ++r) {
+                float* hid_out = P.hid + (size_t)((r + 1) & 1) * P.Hh * Bp;
+                if (nh1 > 0) {
+                    const float* Wh = w_s + P.off_wh; const float* bh = Wh + (size_t)P.Hh * P.NH1;
+                    for (int pc = 0; pc < n_chunks; ++pc) {
+                        const int b0 = pc * SR_PB;
+                        stage_rows(xs, hid_in, P.Hh, Bp, b0);
+                        const Tile tl(P.NH1);
+                        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        tl.accum(acc, Wh, P.NH1, xs, P.Hh);
+                        tl.store(acc, part);
+                        __syncthreads();
+                        for (int o = tid; o < nh1 * SR_PB; o += SR_NT) {
+                            const int col = o / SR_PB, p = o - col * SR_PB;
+                            if (b0 + p < P.B)
+                                __stcg(hid_out + (size_t)(h1_lo + col) * Bp + b0 + p,
+                                       mish_acc(Tile::reduce(part, P.NH1, col, p) + bh[col]));
+                        }
+                        __syncthreads();
+                    }
+                }
+                hid_in = hid_out;
+                grid_barrier(P, epoch);
+            }
             if (nz > 0) {
                 const float* W2 = w_s + P.off_w2; const float* b2 = W2 + (size_t)P.Hh * P.NZ;
                 for (int pc = 0; pc < n_chunks; ++pc) {
                     const int b0 = pc * SR_PB;
-                    stage_rows(xs, P.hid, P.Hh, Bp, b0);
+                    stage_rows(xs, hid_in, P.Hh, Bp, b0);
                     const Tile tl(P.NZ);
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     tl.accum(acc, W2, P.NZ, xs, P.Hh);
@@ -334,7 +387,7 @@ struct mmk_samplernn_s {
     size_t smem_bytes = 0;
     std::vector<int> fs;
     std::vector<void*> allocs;
-    size_t hbuf_floats[SR_MAX_TIERS] = {0};
+    size_t hbuf_floats = 0;       // floats of one [2][H][Bp] state buffer
 };
 
 static int sr_free(mmk_samplernn_s* h) {
@@ -347,12 +400,28 @@ static int sr_free(mmk_samplernn_s* h) {
 
 extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, mmk_samplernn_t* out) {
     MMK_CHECK(d && out, "mmk_samplernn_create: null argument");
+    mmk_samplernn_desc_ex ex{};
+    ex.base = *d;
+    ex.rnn_type = MMK_RNN_GRU; ex.n_rnn = 1;
+    ex.w_ih = d->w_ih; ex.w_hh = d->w_hh; ex.b_ih = d->b_ih; ex.b_hh = d->b_hh;
+    return mmk_samplernn_create_ex(&ex, max_batch, out);
+}
+
+extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_batch, mmk_samplernn_t* out) {
+    MMK_CHECK(dx && out, "mmk_samplernn_create_ex: null argument");
+    const mmk_samplernn_desc* d = &dx->base;
+    MMK_CHECK(dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM || dx->rnn_type == MMK_RNN_TANH, "rnn_type must be MMK_RNN_GRU, _LSTM or _TANH");
+    MMK_CHECK(dx->n_rnn >= 1 && dx->n_rnn <= SR_MAX_RNN, "n_rnn must be in [1, 4]");
+    MMK_CHECK(dx->head_hidden_layers >= 0 && dx->head_hidden_layers <= 8, "head_hidden_layers must be in [0, 8]");
+    MMK_CHECK(dx->head_hidden_layers == 0 || (dx->head_wh && dx->head_bh), "missing head hidden-layer weights");
+    const int G = dx->rnn_type == MMK_RNN_GRU ? 3 : (dx->rnn_type == MMK_RNN_LSTM ? 4 : 1);
+    const bool plain = dx->rnn_type == MMK_RNN_GRU && dx->n_rnn == 1 && dx->head_hidden_layers == 0 && !dx->need_set_hidden;
     MMK_CHECK(d->n_tiers >= 2 && d->n_tiers - 1 <= SR_MAX_TIERS, "n_tiers must be in [2, 7]");
     MMK_CHECK(d->hidden_dim >= 4 && d->hidden_dim % 4 == 0, "hidden_dim must be a positive multiple of 4");
     MMK_CHECK(d->head_hidden >= 4 && d->head_hidden % 4 == 0, "head_hidden must be a positive multiple of 4");
     MMK_CHECK(d->q_levels >= 2 && d->q_levels <= 1024, "q_levels must be in [2, 1024]");
     MMK_CHECK(max_batch >= 1, "max_batch must be >= 1");
-    MMK_CHECK(d->frame_sizes && d->in_w && d->in_b && d->w_ih && d->w_hh && d->b_ih && d->b_hh && d->up_w && d->up_b &&
+    MMK_CHECK(d->frame_sizes && d->in_w && d->in_b && dx->w_ih && dx->w_hh && dx->b_ih && dx->b_hh && d->up_w && d->up_b &&
               d->conv_w && d->conv_b && d->head_w1 && d->head_b1 && d->head_w2 && d->head_b2, "missing weight pointers");
     int ndev = 0;
     MMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: mmk_b200 has no CPU fallback");
@@ -366,9 +435,11 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
     MMK_CUDA(cudaGetDevice(&h->device));
     {   // MMK_SR_KERNEL: "1" = general kernel only, "2" = cluster kernel only, unset = cluster kernel when it fits
         const char* force = getenv("MMK_SR_KERNEL");
-        if (!force || atoi(force) != 1) {
+        if (plain && (!force || atoi(force) != 1)) {
             int unsupported = 0;
-            if (sr2_create(d, max_batch, &h->v2, &unsupported) == 0) {
+            mmk_samplernn_desc d2 = *d;      // the cluster kernel hosts the GRU / one layer / plain head form only
+            d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;
+            if (sr2_create(&d2, max_batch, &h->v2, &unsupported) == 0) {
                 h->max_batch = max_batch; h->rf = d->frame_sizes[0];
                 *out = h;
                 return 0;
@@ -388,7 +459,8 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
     NC = std::min(NC, H / ceil_div(H, NC));
     if (const char* e = getenv("MMK_SR_CTAS")) NC = std::max(1, std::min(std::min(sms, H), atoi(e)));
     p.n_ft = n_ft; p.H = H; p.Hh = Hh; p.Q = Q; p.NC = NC;
-    p.JP = ceil_div(H, NC); p.NG = pad4(3 * p.JP);
+    p.rnn_type = dx->rnn_type; p.G = G; p.n_rnn = dx->n_rnn; p.n_hh = dx->head_hidden_layers;
+    p.JP = ceil_div(H, NC); p.NG = pad4(G * p.JP);
     p.NH1 = pad4(ceil_div(Hh, NC)); p.NZ = pad4(ceil_div(Q + 1, NC));
     p.fs_last = d->frame_sizes[n_ft];
     p.min_temp = d->min_temperature;
@@ -405,14 +477,17 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
         T.kdiv = i > 0 ? d->frame_sizes[i - 1] / T.fs : 1;
         T.up_rows = T.up * H;
         T.NU = pad4(ceil_div(T.up_rows, NC));
-        T.off_wih = take(H * p.NG + p.NG);
-        T.off_whh = take(H * p.NG + p.NG);
+        for (int k = 0; k < p.n_rnn; ++k) {
+            T.off_wih[k] = take(H * p.NG + p.NG);
+            T.off_whh[k] = take(H * p.NG + p.NG);
+        }
         T.off_wup = take(H * T.NU + T.NU);
         fs_max = std::max(fs_max, T.fs);
         widest = std::max(widest, T.NU);
     }
     p.off_w1 = take(H * p.NH1 + p.NH1);
     p.off_w2 = take(Hh * p.NZ + p.NZ);
+    p.off_wh = p.n_hh > 0 ? take(Hh * p.NH1 + p.NH1) : 0;
     p.cta_block = o;
     const int zrow = pad4(Q + 1) + 4;
     p.off_x = take(std::max(std::max(H, Hh) * SR_PB, (SR_NT / 32) * zrow));
@@ -435,18 +510,20 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
         const int j_lo = part_lo(c, H, NC), nj = part_lo(c + 1, H, NC) - j_lo;
         for (int i = 0; i < n_ft; ++i) {
             const SrTier& T = p.tiers[i];
-            for (int m = 0; m < 2; ++m) {
-                const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
-                const float* b = m == 0 ? d->b_ih[i] : d->b_hh[i];
-                float* Ws = blk + (m == 0 ? T.off_wih : T.off_whh);
-                float* bs = Ws + (size_t)H * p.NG;
-                for (int g = 0; g < 3; ++g)
-                    for (int jj = 0; jj < nj; ++jj) {
-                        const int col = g * p.JP + jj, row = g * H + j_lo + jj;
-                        for (int k = 0; k < H; ++k) Ws[(size_t)k * p.NG + col] = W[(size_t)row * H + k];
-                        bs[col] = b[row];
-                    }
-            }
+            for (int lay = 0; lay < p.n_rnn; ++lay)
+                for (int m = 0; m < 2; ++m) {
+                    const int e = i * p.n_rnn + lay;
+                    const float* W = m == 0 ? dx->w_ih[e] : dx->w_hh[e];
+                    const float* b = m == 0 ? dx->b_ih[e] : dx->b_hh[e];
+                    float* Ws = blk + (m == 0 ? T.off_wih[lay] : T.off_whh[lay]);
+                    float* bs = Ws + (size_t)H * p.NG;
+                    for (int g = 0; g < G; ++g)
+                        for (int jj = 0; jj < nj; ++jj) {
+                            const int col = g * p.JP + jj, row = g * H + j_lo + jj;
+                            for (int k = 0; k < H; ++k) Ws[(size_t)k * p.NG + col] = W[(size_t)row * H + k];
+                            bs[col] = b[row];
+                        }
+                }
             const int u_lo = part_lo(c, T.up_rows, NC), nu = part_lo(c + 1, T.up_rows, NC) - u_lo;
             float* Wu = blk + T.off_wup; float* bu = Wu + (size_t)H * T.NU;
             for (int col = 0; col < nu; ++col) {
@@ -466,6 +543,13 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
             for (int k = 0; k < Hh; ++k) W2[(size_t)k * p.NZ + col] = d->head_w2[(size_t)(z_lo + col) * Hh + k];
             b2[col] = d->head_b2[z_lo + col];
         }
+        if (p.n_hh > 0) {
+            float* Wh = blk + p.off_wh; float* bh = Wh + (size_t)Hh * p.NH1;
+            for (int col = 0; col < nh1; ++col) {
+                for (int k = 0; k < Hh; ++k) Wh[(size_t)k * p.NH1 + col] = dx->head_wh[(size_t)(h1_lo + col) * Hh + k];
+                bh[col] = dx->head_bh[h1_lo + col];
+            }
+        }
     }
     auto dev_alloc = [&](size_t bytes, const void* src) -> void* {
         void* ptr = nullptr;
@@ -481,13 +565,16 @@ extern "C" int mmk_samplernn_create(const mmk_samplernn_desc* d, int max_batch, 
         SrTier& T = p.tiers[i];
         T.in_w = up(d->in_w[i], (size_t)H * T.fs);
         T.in_b = up(d->in_b[i], H);
-        h->hbuf_floats[i] = (size_t)2 * H * p.Bp;
-        T.hbuf = up(nullptr, h->hbuf_floats[i]);
+        h->hbuf_floats = (size_t)2 * H * p.Bp;
+        for (int k = 0; k < p.n_rnn; ++k) {
+            T.hbuf[k] = up(nullptr, h->hbuf_floats);
+            T.cbuf[k] = p.rnn_type == MMK_RNN_LSTM ? up(nullptr, h->hbuf_floats) : nullptr;
+        }
         T.obuf = up(nullptr, (size_t)T.up_rows * p.Bp);
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
     p.conv_b = up(d->conv_b, H);
-    p.hid = up(nullptr, (size_t)Hh * p.Bp);
+    p.hid = up(nullptr, (size_t)2 * Hh * p.Bp);
     p.z = up(nullptr, (size_t)(Q + 1) * p.Bp);
     p.bar = (unsigned long long*)dev_alloc(64, nullptr);
     ok = ok && p.bar;
@@ -533,7 +620,10 @@ extern "C" int mmk_samplernn_run(mmk_samplernn_t h, int64_t* d_seq, int B, int64
     SrParams p = h->p;
     if (reset_hidden) {
         for (int i = 0; i < p.n_ft; ++i) {
-            MMK_CUDA(cudaMemsetAsync(p.tiers[i].hbuf, 0, h->hbuf_floats[i] * sizeof(float), st));
+            for (int k = 0; k < p.n_rnn; ++k) {
+                MMK_CUDA(cudaMemsetAsync(p.tiers[i].hbuf[k], 0, h->hbuf_floats * sizeof(float), st));
+                if (p.tiers[i].cbuf[k]) MMK_CUDA(cudaMemsetAsync(p.tiers[i].cbuf[k], 0, h->hbuf_floats * sizeof(float), st));
+            }
             h->p.hsel[i] = 0;
         }
         p = h->p;
@@ -559,6 +649,28 @@ extern "C" int mmk_samplernn_run(mmk_samplernn_t h, int64_t* d_seq, int B, int64
         const long long n = firings(warm_begin, warm_end) + firings(gen_begin, gen_end);
         h->p.hsel[i] ^= (int)(n & 1);
     }
+    return 0;
+}
+
+namespace mmk {
+__global__ void sr_set_hidden_kernel(float* dst, const float* src, int B, int H, int Bp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // dst [H][Bp] <- src (B, H)
+    if (i < B * H) { const int b = i / H, j = i - b * H; dst[(size_t)j * Bp + b] = src[i]; }
+}
+}  // namespace mmk
+
+extern "C" int mmk_samplernn_set_hidden(mmk_samplernn_t h, int tier, int layer, int which, const float* d_values, int B,
+                                        void* stream) {
+    MMK_CHECK(h && d_values, "mmk_samplernn_set_hidden: null argument");
+    MMK_CHECK(!h->v2, "this handle runs the cluster kernel (zero initial state only): create it with need_set_hidden = 1");
+    const SrParams& p = h->p;
+    MMK_CHECK(tier >= 0 && tier < p.n_ft && layer >= 0 && layer < p.n_rnn, "tier / layer out of range");
+    MMK_CHECK(which == 0 || (which == 1 && p.rnn_type == MMK_RNN_LSTM), "which: 0 = hidden state, 1 = LSTM cell state");
+    MMK_CHECK(B >= 1 && B <= h->max_batch, "batch exceeds the max_batch the handle was created for");
+    float* base = which == 0 ? p.tiers[tier].hbuf[layer] : p.tiers[tier].cbuf[layer];
+    float* dst = base + (size_t)p.hsel[tier] * p.H * p.Bp;
+    sr_set_hidden_kernel<<<(B * p.H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dst, d_values, B, p.H, p.Bp);
+    MMK_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -43,12 +43,13 @@ class SampleRNN(NativeARM):
         need(c.io_spec is not None and len(c.io_spec.inputs) == 1 and len(c.io_spec.targets) == 1,
              "more than one input/target")
         need(c.io_spec.inputs[0].module_type == "framed_linear", "input_module_type other than 'framed_linear'")
-        need(str(c.rnn_class) == "gru", "rnn_class other than 'gru'")
-        need(c.n_rnn == 1 and c.rnn_bias, "n_rnn > 1 or rnn_bias=False")
-        need(str(c.h0_init) == "zeros", "h0_init other than 'zeros'")
+        need(str(c.rnn_class) in ("gru", "lstm", "rnn"), "rnn_class other than 'lstm', 'gru' or 'rnn'")
+        need(1 <= c.n_rnn <= 4 and c.rnn_bias, "n_rnn outside [1, 4] or rnn_bias=False")
+        need(str(c.h0_init) in ("zeros", "ones", "randn"), "h0_init other than 'zeros', 'ones' or 'randn'")
         need(str(c.inputs_mode) == "sum", "inputs_mode other than 'sum'")
         need(len(c.frame_sizes) >= 2, "fewer than two tiers")
-        need(c.io_spec.targets[0].module.n_hidden_layers == 0, "n_mlp_layers > 0")
+        need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
+        need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
         fs = c.frame_sizes
         for i in range(len(fs) - 2):
             need(fs[i] % fs[i + 1] == 0, "frame sizes that do not divide each other")
@@ -84,6 +85,15 @@ class SampleRNN(NativeARM):
         head = c.io_spec.targets[0].module
         return c.hidden_dim, head.hidden_dim, c.io_spec.targets[0].out_dim
 
+    @property
+    def _gates(self):
+        """Rows of weight_ih / weight_hh per hidden unit: nn.GRU 3 (r, z, n), nn.LSTM 4 (i, f, g, o), nn.RNN 1."""
+        return {"gru": 3, "lstm": 4, "rnn": 1}[str(self._config.rnn_class)]
+
+    @property
+    def _n_mlp_hidden(self):
+        return int(self._config.io_spec.targets[0].module.n_hidden_layers)
+
     def _up(self, i):
         """sample_rnn_v2.py:155-158: the last frame tier up-samples to the sample rate."""
         fs = self.frame_sizes
@@ -97,10 +107,11 @@ class SampleRNN(NativeARM):
             p = f"tiers.{i}."
             e[p + "input_module.heads.0.2.weight"] = (H, fs[i])
             e[p + "input_module.heads.0.2.bias"] = (H,)
-            e[p + "rnn.weight_ih_l0"] = (3 * H, H)
-            e[p + "rnn.weight_hh_l0"] = (3 * H, H)
-            e[p + "rnn.bias_ih_l0"] = (3 * H,)
-            e[p + "rnn.bias_hh_l0"] = (3 * H,)
+            for k in range(self._config.n_rnn):       # nn.GRU / nn.LSTM / nn.RNN parameter names, layer by layer
+                e[p + f"rnn.weight_ih_l{k}"] = (self._gates * H, H)
+                e[p + f"rnn.weight_hh_l{k}"] = (self._gates * H, H)
+                e[p + f"rnn.bias_ih_l{k}"] = (self._gates * H,)
+                e[p + f"rnn.bias_hh_l{k}"] = (self._gates * H,)
             e[p + "up_sampler.fc.weight"] = (H * self._up(i), H)
             e[p + "up_sampler.fc.bias"] = (H * self._up(i),)
         p = f"tiers.{len(fs) - 1}.input_module.heads.0.2.2.cv."
@@ -110,8 +121,14 @@ class SampleRNN(NativeARM):
         e[p + "min_temp"] = ()
         e[p + "fc.0.weight"] = (Hh, H)
         e[p + "fc.0.bias"] = (Hh,)
-        e[p + "fc.2.weight"] = (Q + 1, Hh)
-        e[p + "fc.2.bias"] = (Q + 1,)
+        # networks/mlp.py:47-50 builds the hidden layers by repeating a TUPLE that holds one nn.Linear: fc.2, fc.4, ... are
+        # the same module (the reference's state_dict lists it under every index); the last Linear follows them
+        nh = self._n_mlp_hidden
+        for r in range(nh):
+            e[p + f"fc.{2 + 2 * r}.weight"] = (Hh, Hh)
+            e[p + f"fc.{2 + 2 * r}.bias"] = (Hh,)
+        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + 1, Hh)
+        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + 1,)
         return e
 
     def _init_state_dict(self):
@@ -130,6 +147,10 @@ class SampleRNN(NativeARM):
                 wshape = shape if k.endswith("weight") else shapes[k[:-4] + "weight"]
                 bound = 1.0 / math.sqrt(max(1, int(torch.tensor(wshape[1:]).prod())))
             sd[k] = (torch.rand(shape) * 2 - 1) * bound
+        p = "output_modules.0.estimator.0."
+        for r in range(1, self._n_mlp_hidden):            # one shared Linear under several names
+            sd[p + f"fc.{2 + 2 * r}.weight"] = sd[p + "fc.2.weight"]
+            sd[p + f"fc.{2 + 2 * r}.bias"] = sd[p + "fc.2.bias"]
         return sd
 
     # ---- native handle --------------------------------------------------------------------------
@@ -137,7 +158,9 @@ class SampleRNN(NativeARM):
         H, Hh, Q = self._dims()
         fs = self.frame_sizes
         n = len(fs)
-        d = _capi.SampleRNNDesc()
+        c = self._config
+        dx = _capi.SampleRNNDescEx()
+        d = dx.base
         d.n_tiers, d.hidden_dim, d.head_hidden, d.q_levels = n, H, Hh, Q
         fsa = (ctypes.c_int * n)(*fs)
         d.frame_sizes = fsa
@@ -147,17 +170,33 @@ class SampleRNN(NativeARM):
             a = self._warray([fmt.format(i) for i in range(n - 1)])
             keep.append(a)
             return a
+        def rnn_arr(name):
+            a = self._warray([f"tiers.{i}.rnn.{name}_l{k}" for i in range(n - 1) for k in range(c.n_rnn)])
+            keep.append(a)
+            return a
         d.in_w, d.in_b = arr("tiers.{}.input_module.heads.0.2.weight"), arr("tiers.{}.input_module.heads.0.2.bias")
-        d.w_ih, d.w_hh = arr("tiers.{}.rnn.weight_ih_l0"), arr("tiers.{}.rnn.weight_hh_l0")
-        d.b_ih, d.b_hh = arr("tiers.{}.rnn.bias_ih_l0"), arr("tiers.{}.rnn.bias_hh_l0")
+        dx.rnn_type = {"gru": 0, "lstm": 1, "rnn": 2}[str(c.rnn_class)]
+        dx.n_rnn = int(c.n_rnn)
+        dx.w_ih, dx.w_hh = rnn_arr("weight_ih"), rnn_arr("weight_hh")
+        dx.b_ih, dx.b_hh = rnn_arr("bias_ih"), rnn_arr("bias_hh")
         d.up_w, d.up_b = arr("tiers.{}.up_sampler.fc.weight"), arr("tiers.{}.up_sampler.fc.bias")
         p = f"tiers.{n - 1}.input_module.heads.0.2.2.cv."
         d.conv_w, d.conv_b = self._w(p + "weight"), self._w(p + "bias")
         p = "output_modules.0.estimator.0."
+        nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
-        d.head_w2, d.head_b2 = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
+        d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        dx.head_hidden_layers = nh
+        if nh > 0:
+            for r in range(1, nh):
+                if not (torch.equal(self._sd[p + f"fc.{2 + 2 * r}.weight"], self._sd[p + "fc.2.weight"])
+                        and torch.equal(self._sd[p + f"fc.{2 + 2 * r}.bias"], self._sd[p + "fc.2.bias"])):
+                    raise RuntimeError("the hidden layers of the reference MLP share one Linear (networks/mlp.py:47-50): "
+                                       "fc.2, fc.4, ... must hold the same tensors")
+            dx.head_wh, dx.head_bh = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
+        dx.need_set_hidden = int(str(c.h0_init) != "zeros")
         h = ctypes.c_void_p()
-        _capi.check(_capi.lib().mmk_samplernn_create(ctypes.byref(d), int(max_batch), ctypes.byref(h)))
+        _capi.check(_capi.lib().mmk_samplernn_create_ex(ctypes.byref(dx), int(max_batch), ctypes.byref(h)))
         return h
 
     def _destroy_handle(self, h):
@@ -188,6 +227,41 @@ class SampleRNN(NativeARM):
             _capi.check(_capi.lib().mmk_samplernn_sync_check(h, _capi.stream_ptr()))
         return logits, decisions, ts
 
+    def _initial_state(self, B, generator=None, h0=None):
+        """SampleRNNTier._init_h0 (sample_rnn_v2.py:113-119): zeros (None here: the kernel's reset does it), ones, or randn.
+        Returns {(tier, layer, which): (B, H) cuda tensor}; which = 1 is the LSTM cell state, drawn like the hidden state.
+        `h0` overrides the draw with explicit tensors under the same keys (the reference draws randn from torch's global
+        generator at its first forward; pass what it drew to reproduce it)."""
+        c = self._config
+        if h0 is not None:
+            return {k: torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous() for k, v in h0.items()}
+        if str(c.h0_init) == "zeros":
+            return None
+        H = c.hidden_dim
+        out = {}
+        for i in range(len(self.frame_sizes) - 1):
+            for which in ((0, 1) if str(c.rnn_class) == "lstm" else (0,)):
+                if str(c.h0_init) == "ones":
+                    block = torch.ones((c.n_rnn, B, H), device=self.device)
+                else:
+                    block = torch.randn((c.n_rnn, B, H), generator=generator,
+                                        device=generator.device if generator is not None else "cpu").to(self.device)
+                for k in range(c.n_rnn):
+                    out[(i, k, which)] = block[k].contiguous()
+        return out
+
+    def _install_state(self, state, B):
+        """Zero every state (a run with reset_hidden = 1 over empty ranges), then write the non-zero initial values."""
+        h = self._get_handle(B)
+        dummy = torch.zeros((B, self.rf), dtype=torch.int64, device=self.device)
+        self._run(dummy, 0, (0, 0, 0), (self.rf, self.rf), True, True, None, None, 0, False, False, False)
+        with torch.cuda.device(self.device):
+            for (tier, layer, which), v in state.items():
+                if tuple(v.shape) != (B, self._config.hidden_dim):
+                    raise ValueError(f"initial state {(tier, layer, which)} must be ({B}, {self._config.hidden_dim})")
+                _capi.check(_capi.lib().mmk_samplernn_set_hidden(h, int(tier), int(layer), int(which), v.data_ptr(), B,
+                                                                 _capi.stream_ptr()))
+
     def _warm_range(self, P):
         """before_generate (sample_rnn_v2.py:229-234): logical t in [rf, P - P % rf), data shifted by P % rf."""
         offset = P % self.rf
@@ -195,10 +269,10 @@ class SampleRNN(NativeARM):
 
     # ---- whole-sequence fast path ---------------------------------------------------------------
     def generate(self, prompts, n_steps, temperature=None, noise=None, return_logits=False,
-                 return_step_timestamps=False, generator=None):
+                 return_step_timestamps=False, generator=None, h0=None):
         """before_generate (hidden reset + warm-up over the prompt) followed by n_steps of generate_step as
         GenerateLoopV2.run drives them (loops/generate.py:193-219), in ONE kernel launch.  Arguments and returns as
-        `WaveNet.generate`."""
+        `WaveNet.generate`; `h0` (optional) = explicit initial states, see `_initial_state`."""
         seq = prepare_sequence(prompts, n_steps, self.device)
         B, total = seq.shape
         P = total - n_steps
@@ -206,7 +280,10 @@ class SampleRNN(NativeARM):
             raise RuntimeError(f"prompt length {P} is shorter than the top frame size {self.rf}")
         T = as_temperature(temperature, B, self.device)
         U = prepare_noise(noise, T, B, n_steps, self.device, generator)
-        logits, _, ts = self._run(seq, 0, self._warm_range(P), (P, P + n_steps), True, False, T, U, P,
+        state = self._initial_state(B, generator, h0)
+        if state is not None:
+            self._install_state(state, B)
+        logits, _, ts = self._run(seq, 0, self._warm_range(P), (P, P + n_steps), state is None, False, T, U, P,
                                   return_logits, False, return_step_timestamps)
         self._cont = dict(handle=self._handle, B=B, t=P + n_steps, tail=seq[:, -self.rf:].clone())
         out = (seq,)
@@ -234,7 +311,7 @@ class SampleRNN(NativeARM):
             self._cont = dict(handle=self._handle, B=B, t=t + n_steps, tail=buf[:, -rf:].clone())
         return (buf[:, rf:], logits) if return_logits else buf[:, rf:]
 
-    def teacher_forced(self, sequence, prompt_len, temperature=None, noise=None):
+    def teacher_forced(self, sequence, prompt_len, temperature=None, noise=None, h0=None):
         """Step-wise generate_step logits/decisions on forced inputs (this, not SampleRNN.forward,
         is the teacher-forced definition for SampleRNN)."""
         seq = prepare_sequence(sequence, 0, self.device)
@@ -245,7 +322,10 @@ class SampleRNN(NativeARM):
         n = total - P
         T = as_temperature(temperature, B, self.device)
         U = prepare_noise(noise, T, B, n, self.device)
-        logits, dec, _ = self._run(seq, 0, self._warm_range(P), (P, total), True, True, T, U, P, True, True, False)
+        state = self._initial_state(B, None, h0)
+        if state is not None:
+            self._install_state(state, B)
+        logits, dec, _ = self._run(seq, 0, self._warm_range(P), (P, total), state is None, True, T, U, P, True, True, False)
         return logits, dec
 
     # ---- step-wise ARM protocol -------------------------------------------------------------------
@@ -258,7 +338,10 @@ class SampleRNN(NativeARM):
         P = p.shape[1]
         if P < self.rf:
             raise RuntimeError(f"prompt length {P} is shorter than the top frame size {self.rf}")
-        self._run(p, 0, self._warm_range(P), (P, P), True, True, None, None, 0, False, False, False)
+        state = self._initial_state(p.shape[0])
+        if state is not None:
+            self._install_state(state, p.shape[0])
+        self._run(p, 0, self._warm_range(P), (P, P), state is None, True, None, None, 0, False, False, False)
         self._prompt_len = P
 
     def generate_step(self, inputs, *, t: int = 0, temperature=None, noise=None):

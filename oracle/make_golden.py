@@ -22,6 +22,42 @@ def sd_arrays(sd):
     return {"sd/" + k: v.detach().cpu().numpy() for k, v in sd.items()}
 
 
+def gen_samplernn_variant(name, prompts, n_steps, h0_seed=None, **kw):
+    """A SampleRNN of the live reference outside the GRU / one layer / zero state / plain head form: LSTM (the reference
+    default), stacked layers, h0_init ones / randn, hidden MLP layers.  For randn the reference draws its initial states
+    from torch's global generator at the first forward of every tier (sample_rnn_v2.py:101-119): the generator is seeded
+    right before each run and the same draws, in the same order, are stored as `h0/<tier>_<layer>_<which>`."""
+    net = ref_loader.make_samplernn(**kw)
+    B = prompts.shape[0]
+    noise = torch.rand(B, n_steps, generator=torch.Generator().manual_seed(4321))
+    meta = dict(frame_sizes=kw["frame_sizes"], hidden_dim=kw["hidden_dim"], mlp_dim=kw["mlp_dim"],
+                rnn_class=kw.get("rnn_class", "gru"), n_rnn=kw.get("n_rnn", 1), h0_init=kw.get("h0_init", "zeros"),
+                n_mlp_layers=kw.get("n_mlp_layers", 0))
+    out = dict(sd_arrays(net.state_dict()), prompts=prompts.numpy(), noise=noise.numpy(),
+               **{"meta/" + k: np.asarray(v) for k, v in meta.items()})
+    H, n_rnn, lstm = kw["hidden_dim"], meta["n_rnn"], meta["rnn_class"] == "lstm"
+
+    def run(temperature):
+        for tier in net.tiers:
+            tier.hidden = None                      # a fresh draw per run, as after_generate / reset_hidden leave it
+        if h0_seed is not None:
+            torch.manual_seed(h0_seed)
+        return ref_loader.run_generate_loop(net, prompts, n_steps, temperature, noise)
+    if meta["h0_init"] == "randn":
+        torch.manual_seed(h0_seed)
+        for i in range(len(kw["frame_sizes"]) - 1):           # every tier fires at the first warm-up step, top tier first
+            for which in ((0, 1) if lstm else (0,)):
+                block = torch.randn(n_rnn, B, H)
+                for k in range(n_rnn):
+                    out[f"h0/{i}_{k}_{which}"] = block[k].numpy()
+    seq, lg = run(None)
+    out["seq_argmax"], out["logits_argmax"] = seq.numpy(), lg.numpy()
+    seq, lg = run(1.0)
+    out["seq_t1"], out["logits_t1"] = seq.numpy(), lg.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
+
+
 def gen_network(name, net, prompts, n_steps, meta):
     B = prompts.shape[0]
     noise = torch.rand(B, n_steps, generator=torch.Generator().manual_seed(4321))
@@ -75,6 +111,18 @@ def main():
     ref = ref_loader.load()
     if len(sys.argv) > 1 and sys.argv[1] == "normalize":   # only this fixture (the others are unchanged)
         return gen_normalize(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
+        g = torch.Generator().manual_seed(77)
+        gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,
+                              frame_sizes=(8, 2, 1), hidden_dim=32, mlp_dim=32, rnn_class="lstm", seed=5)
+        gen_samplernn_variant("samplernn_lstm_2layers_ones", torch.randint(0, 256, (2, 35), generator=g), 30,
+                              frame_sizes=(4, 2), hidden_dim=32, mlp_dim=32, rnn_class="lstm", n_rnn=2, h0_init="ones", seed=6)
+        gen_samplernn_variant("samplernn_gru_3layers_randn_mlp2", torch.randint(0, 256, (3, 32), generator=g), 30,
+                              h0_seed=99, frame_sizes=(8, 2, 1), hidden_dim=32, mlp_dim=32, rnn_class="gru", n_rnn=3,
+                              h0_init="randn", n_mlp_layers=2, seed=7)
+        gen_samplernn_variant("samplernn_rnn_tanh_mlp1", torch.randint(0, 256, (2, 24), generator=g), 24,
+                              frame_sizes=(4, 1), hidden_dim=32, mlp_dim=32, rnn_class="rnn", n_mlp_layers=1, seed=8)
+        return
     gen_normalize(ref)
     g = torch.Generator().manual_seed(1234)
 

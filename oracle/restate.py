@@ -268,9 +268,13 @@ def _mish(x):
     return (x * np.tanh(sp)).astype(f32)
 
 
-def mlp_head(x, W1, b1, W2, b2, min_temp, Q):
-    """networks/mlp.py:44-63 with n_hidden_layers=0: Linear, Mish, Linear(+1), learned-temperature divide."""
-    z = _mish(x @ W1.T + b1) @ W2.T + b2
+def mlp_head(x, W1, b1, W2, b2, min_temp, Q, Wh=None, bh=None, n_hidden=0):
+    """networks/mlp.py:44-63: Linear, Mish, n_hidden x (the SAME Linear(Hh, Hh), Mish — the tuple repetition of :47-50 shares
+    one module), Linear(+1), learned-temperature divide."""
+    hid = _mish(x @ W1.T + b1)
+    for _ in range(n_hidden):
+        hid = _mish((hid @ Wh.T + bh).astype(f32))
+    z = hid @ W2.T + b2
     temp = np.maximum(_sigmoid(z[..., Q:Q + 1]), f32(min_temp))
     return (z[..., :Q] / temp).astype(f32)
 
@@ -506,9 +510,11 @@ class SampleRNNOracle:
     """Restatement of SampleRNN.before_generate / generate_step
     (networks/sample_rnn_v2.py:226-260) with SampleRNNTier.forward (83-99), FramedLinearIO / FramedConv1dIO
     (modules/io.py:106-133,185-198), LinearResampler (modules/resamplers.py:13-23) and GRU cells (PyTorch gate
-    order r,z,n).  n_rnn=1, h0 zeros, inputs_mode='sum', single mu-law input."""
+    order r,z,n), LSTM cells (i,f,g,o) or tanh RNN cells, n_rnn stacked layers (sample_rnn_v2.py:62-66), the initial state of
+    _init_h0 (:113-119; `h0` = {(tier, layer, which): (B, H)}, which 1 = LSTM cell state; default zeros) and the MLP head
+    with n_hidden_layers shared hidden layers (networks/mlp.py:47-50).  inputs_mode='sum', single mu-law input."""
 
-    def __init__(self, state_dict, frame_sizes, q_levels=256):
+    def __init__(self, state_dict, frame_sizes, q_levels=256, rnn_class="gru", n_rnn=1, n_mlp_hidden=0):
         sd = fold_weight_norm(state_dict) if any(k.endswith("_g") for k in state_dict) else state_dict
         self.fs = tuple(int(f) for f in frame_sizes)
         self.n_tiers = len(self.fs)
@@ -518,16 +524,22 @@ class SampleRNNOracle:
             p = f"tiers.{i}."
             self.tiers.append(dict(
                 Win=_np(sd, p + "input_module.heads.0.2.weight"), bin=_np(sd, p + "input_module.heads.0.2.bias"),
-                Wih=_np(sd, p + "rnn.weight_ih_l0"), Whh=_np(sd, p + "rnn.weight_hh_l0"),
-                bih=_np(sd, p + "rnn.bias_ih_l0"), bhh=_np(sd, p + "rnn.bias_hh_l0"),
+                Wih=[_np(sd, p + f"rnn.weight_ih_l{k}") for k in range(n_rnn)],
+                Whh=[_np(sd, p + f"rnn.weight_hh_l{k}") for k in range(n_rnn)],
+                bih=[_np(sd, p + f"rnn.bias_ih_l{k}") for k in range(n_rnn)],
+                bhh=[_np(sd, p + f"rnn.bias_hh_l{k}") for k in range(n_rnn)],
                 Wup=_np(sd, p + "up_sampler.fc.weight"), bup=_np(sd, p + "up_sampler.fc.bias")))
         p = f"tiers.{self.n_tiers - 1}.input_module.heads.0.2.2.cv."
         self.Wc = _np(sd, p + "weight")[:, 0, :]  # (H, fs_last)
         self.bc = _np(sd, p + "bias")
         self.H = self.Wc.shape[0]
         p = "output_modules.0.estimator.0."
+        self.rnn_class, self.n_rnn, self.n_mlp_hidden = str(rnn_class), int(n_rnn), int(n_mlp_hidden)
         self.W1, self.b1 = _np(sd, p + "fc.0.weight"), _np(sd, p + "fc.0.bias")
-        self.W2, self.b2 = _np(sd, p + "fc.2.weight"), _np(sd, p + "fc.2.bias")
+        last = 2 + 2 * self.n_mlp_hidden
+        self.Wh = _np(sd, p + "fc.2.weight") if self.n_mlp_hidden else None      # ONE shared Linear (mlp.py:47-50)
+        self.bh = _np(sd, p + "fc.2.bias") if self.n_mlp_hidden else None
+        self.W2, self.b2 = _np(sd, p + f"fc.{last}.weight"), _np(sd, p + f"fc.{last}.bias")
         self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
         self.rf = self.fs[0]
         # sample_rnn_v2.py:155-158
@@ -537,14 +549,31 @@ class SampleRNNOracle:
         """Linearizer (modules/io.py:111-112)."""
         return ((q.astype(f32) / f32(self.Q)) - f32(0.5)) * f32(2.0)
 
-    def _gru(self, tier, x, h):
+    def _cell(self, tier, k, x, state):
+        """One step of layer k: state = h (GRU, RNN) or (h, c) (LSTM).  Returns the new state."""
         H = self.H
-        gi = x @ tier["Wih"].T + tier["bih"]
-        gh = h @ tier["Whh"].T + tier["bhh"]
-        r = _sigmoid(gi[:, :H] + gh[:, :H])
-        z = _sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
-        n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:]).astype(f32)
-        return ((1.0 - z) * n + z * h).astype(f32)
+        h = state[0] if self.rnn_class == "lstm" else state
+        gi = x @ tier["Wih"][k].T + tier["bih"][k]
+        gh = h @ tier["Whh"][k].T + tier["bhh"][k]
+        if self.rnn_class == "gru":
+            r = _sigmoid(gi[:, :H] + gh[:, :H])
+            z = _sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:]).astype(f32)
+            return ((1.0 - z) * n + z * h).astype(f32)
+        if self.rnn_class == "lstm":
+            a = (gi + gh).astype(f32)
+            i, f = _sigmoid(a[:, :H]), _sigmoid(a[:, H:2 * H])
+            g, o = np.tanh(a[:, 2 * H:3 * H]).astype(f32), _sigmoid(a[:, 3 * H:])
+            c = (f * state[1] + i * g).astype(f32)
+            return (o * np.tanh(c).astype(f32)).astype(f32), c
+        return np.tanh((gi + gh).astype(f32)).astype(f32)
+
+    def _rnn(self, tier, x, states):
+        """n_rnn stacked layers: layer k reads the new hidden state of layer k - 1.  `states` is updated in place."""
+        for k in range(self.n_rnn):
+            states[k] = self._cell(tier, k, x, states[k])
+            x = states[k][0] if self.rnn_class == "lstm" else states[k]
+        return x
 
     def _frame_tiers(self, window, t, hid, O):
         """the `for i in range(len(tiers) - 1)` part of generate_step (sample_rnn_v2.py:245-253);
@@ -555,17 +584,25 @@ class SampleRNNOracle:
                 x = self.lin(window[:, -fs[i]:]) @ tier["Win"].T + tier["bin"]
                 if i > 0:
                     x = x + O[i - 1][:, (t // fs[i]) % (fs[i - 1] // fs[i])]
-                hid[i] = self._gru(tier, x.astype(f32), hid[i])
-                O[i] = (hid[i] @ tier["Wup"].T + tier["bup"]).reshape(-1, self.up[i], self.H)
+                top = self._rnn(tier, x.astype(f32), hid[i])
+                O[i] = (top @ tier["Wup"].T + tier["bup"]).reshape(-1, self.up[i], self.H)
 
-    def generate(self, prompts, n_steps, temperature=None, noise=None, forced=None):
+    def _initial_states(self, B, h0):
+        def get(i, k, which):
+            v = None if h0 is None else h0.get((i, k, which))
+            return np.zeros((B, self.H), dtype=f32) if v is None else np.asarray(v, dtype=f32).copy()
+        if self.rnn_class == "lstm":
+            return [[(get(i, k, 0), get(i, k, 1)) for k in range(self.n_rnn)] for i in range(len(self.tiers))]
+        return [[get(i, k, 0) for k in range(self.n_rnn)] for i in range(len(self.tiers))]
+
+    def generate(self, prompts, n_steps, temperature=None, noise=None, forced=None, h0=None):
         prompts = np.asarray(prompts, dtype=np.int64)
         B, P = prompts.shape
         fs, rf = self.fs, self.rf
         if P < rf:
             raise ValueError(f"prompt length {P} < frame size {rf}")
         T = normalize_temperature(temperature, B)
-        hid = [np.zeros((B, self.H), dtype=f32) for _ in self.tiers]
+        hid = self._initial_states(B, h0)
         O = [None] * len(self.tiers)
         offset = P % rf                      # sample_rnn_v2.py:229-231
         plen = P - offset
@@ -580,7 +617,7 @@ class SampleRNNOracle:
             self._frame_tiers(window, t, hid, O)
             x = self.lin(window[:, -fs[-1]:]) @ self.Wc.T + self.bc          # Conv1d(1,H,k=fs_last), one frame
             x = (x + O[-1][:, (t % fs[-2]) - fs[-2]]).astype(f32)            # :256-257
-            lg = mlp_head(x, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+            lg = mlp_head(x, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q, self.Wh, self.bh, self.n_mlp_hidden)
             logits_out[:, i] = lg
             seq[:, t] = argmax_first(lg) if T is None else sample_inverse_cdf(lg, T, noise[:, i])
         return seq, logits_out

@@ -49,6 +49,24 @@ def test_samplernn_export_roundtrip_and_errors(tmp_path):
     bad = dict(d, config=dict(d["config"], no_such_field=1))
     with pytest.raises(ValueError):
         load_exported(bad)
-    lstm = dict(d, config=dict(d["config"], rnn_class="lstm"))
+    none = dict(d, config=dict(d["config"], rnn_class="none"))
     with pytest.raises(NotImplementedError):
-        load_exported(lstm)                      # unsupported configurations fail loudly, never silently
+        load_exported(none)                      # unsupported configurations fail loudly, never silently
+    lstm = dict(d, config=dict(d["config"], rnn_class="lstm"))
+    with pytest.raises(RuntimeError):
+        load_exported(lstm)                      # ... and a GRU state dict does not fit an LSTM network
+
+
+def test_samplernn_reference_defaults_export_roundtrip(tmp_path):
+    """The reference's DEFAULT tier (rnn_class 'lstm', sample_rnn_v2.py:127), two stacked layers and two hidden MLP layers —
+    whose shared Linear the reference's state_dict lists under fc.2 AND fc.4 (mlp.py:47-50) — survive the hand-over."""
+    ref_net = ref_loader.make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=32, mlp_dim=32, seed=5, rnn_class="lstm", n_rnn=2,
+                                        n_mlp_layers=2, h0_init="ones")
+    ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)
+    assert set(sd) == set(sd_ref) and d["config"]["rnn_class"] == "lstm" and d["config"]["n_rnn"] == 2
+    assert d["io"]["n_mlp_layers"] == 2 and d["config"]["h0_init"] == "ones"
+    for k in sd_ref:
+        assert torch.equal(sd[k], sd_ref[k].float().cpu()), k
+    p = "output_modules.0.estimator.0."
+    assert torch.equal(sd[p + "fc.2.weight"], sd[p + "fc.4.weight"]) and tuple(sd[p + "fc.6.weight"].shape) == (257, 32)
+    assert tuple(sd["tiers.0.rnn.weight_ih_l1"].shape) == (128, 32)

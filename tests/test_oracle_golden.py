@@ -210,3 +210,35 @@ def test_product_wavenet_structure_matches_the_reference_kats():
         assert [int(v) for v in ds] == k["dilations"], k
         assert [int(v) for v in ks] == k["kernels"], k
         assert sum((int(a) - 1) * int(b) for a, b in zip(ks, ds)) + 1 == k["rf"]
+
+
+VARIANTS = ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2", "samplernn_rnn_tanh_mlp1"]
+
+
+def variant_setup(d):
+    """(oracle kwargs, h0 dict) of a samplernn_* variant golden (oracle/make_golden.py: gen_samplernn_variant)."""
+    m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
+    kw = dict(rnn_class=str(m["rnn_class"]), n_rnn=int(m["n_rnn"]), n_mlp_hidden=int(m["n_mlp_layers"]))
+    B, H = d["prompts"].shape[0], int(m["hidden_dim"])
+    h0 = None
+    if str(m["h0_init"]) == "ones":
+        n_ft = len(m["frame_sizes"]) - 1
+        h0 = {(i, k, w): np.ones((B, H), np.float32) for i in range(n_ft) for k in range(kw["n_rnn"])
+              for w in ((0, 1) if kw["rnn_class"] == "lstm" else (0,))}
+    elif str(m["h0_init"]) == "randn":
+        h0 = {tuple(int(v) for v in k[3:].split("_")): d[k] for k in d if k.startswith("h0/")}
+    return m, kw, h0
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_samplernn_variant_oracle_vs_reference(name):
+    """LSTM (the reference default), stacked layers, h0_init ones / randn, tanh RNN, hidden MLP layers (sample_rnn_v2.py:
+    62-66, 101-119; mlp.py:47-50): the oracle against sequences and logits of the live reference."""
+    d = load_golden(name)
+    m, kw, h0 = variant_setup(d)
+    orc = restate.SampleRNNOracle(golden_state_dict(d), tuple(int(b) for b in m["frame_sizes"]), **kw)
+    n = d["noise"].shape[1]
+    for tag, T in [("argmax", None), ("t1", 1.0)]:
+        seq, lg = orc.generate(d["prompts"], n, T, d["noise"], h0=h0)
+        assert np.array_equal(seq, d["seq_" + tag]), (name, tag)
+        np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)

@@ -187,10 +187,11 @@ def test_weight_norm_checkpoint_and_errors():
     with pytest.raises(RuntimeError):
         net.generate(torch.zeros(2, 3, dtype=torch.int64), 4)      # prompt shorter than the top frame
     with pytest.raises(NotImplementedError):
-        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), rnn_class="lstm"))
+        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), rnn_class="none"))
     with pytest.raises(NotImplementedError):
-        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), rnn_class="gru",
-                                               h0_init="randn"))
+        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), rnn_class="gru", n_rnn=5))
+    with pytest.raises(NotImplementedError):
+        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), inputs_mode="mean"))
 
 
 def test_s3_full_width_properties():
@@ -215,3 +216,84 @@ def test_s3_full_width_properties():
     assert _rel_err(got_logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
     assert np.array_equal(got_seq.cpu().numpy(), ref_seq)
     assert np.array_equal(seq.cpu().numpy()[sub][:, :P + 32], ref_seq)
+
+
+@pytest.mark.parametrize("name", ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2",
+                                  "samplernn_rnn_tanh_mlp1"])
+def test_variant_goldens(name):
+    """The rest of SampleRNNTier's configuration surface against the live reference (tests/golden, generated by
+    oracle/make_golden.py samplernn_variants): rnn_class "lstm" (the reference DEFAULT) / "rnn", n_rnn 2 and 3, h0_init
+    "ones" and "randn" (the reference's own draws, replayed), 1 and 2 hidden MLP layers (one shared Linear, mlp.py:47-50)."""
+    from mimikit_b200 import IOSpec, SampleRNN
+    from test_oracle_golden import variant_setup
+    d = load_golden(name)
+    m, kw, h0 = variant_setup(d)
+    fs = tuple(int(f) for f in m["frame_sizes"])
+    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]), n_mlp_layers=kw["n_mlp_hidden"])),
+                           frame_sizes=fs, hidden_dim=int(m["hidden_dim"]), rnn_class=kw["rnn_class"], n_rnn=kw["n_rnn"],
+                           h0_init=str(m["h0_init"]))
+    net = SampleRNN.from_config(cfg).to("cuda")
+    net.load_state_dict(golden_state_dict(d))
+    prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
+    P, n = prompts.shape[1], noise.shape[1]
+    explicit = None if str(m["h0_init"]) != "randn" else {k: torch.from_numpy(v) for k, v in h0.items()}
+    for tag, T in (("argmax", None), ("t1", 1.0)):
+        seq, logits = net.generate(prompts, n, temperature=T, noise=noise, return_logits=True, h0=explicit)
+        assert _rel_err(logits.cpu().numpy()[:, 0], d["logits_" + tag][:, 0]) <= REL_TOL, (name, tag)
+        assert np.array_equal(seq.cpu().numpy(), d["seq_" + tag]), (name, tag)
+        assert _rel_err(logits.cpu().numpy(), d["logits_" + tag]) <= REL_TOL
+    lg, dec = net.teacher_forced(torch.from_numpy(d["seq_t1"]), P, 1.0, noise, h0=explicit)
+    assert np.array_equal(dec.cpu().numpy(), d["seq_t1"][:, P:])
+    # the state survives between launches: generate_more continues, the step-wise protocol == the whole-sequence launch
+    if str(m["h0_init"]) != "randn":
+        first = net.generate(prompts, n // 2)
+        more = net.generate_more(n - n // 2)
+        assert np.array_equal(torch.cat([first, more], 1).cpu().numpy(), d["seq_argmax"])
+        x = torch.cat([prompts, torch.zeros(prompts.shape[0], n, dtype=torch.int64)], 1).cuda()
+        net.before_generate((x[:, :P],), 0)
+        for t in range(P, P + n):
+            x[:, t:t + 1] = net.generate_step((x[:, t - net.rf:t],), t=t)[0]
+        assert np.array_equal(x.cpu().numpy(), d["seq_argmax"])
+
+
+def test_lstm_is_the_default_and_randn_draws():
+    """SampleRNN.Config() defaults (rnn_class 'lstm', sample_rnn_v2.py:127) build and generate; h0_init 'randn' draws its
+    own states from a generator (reproducibly) when none are passed; bad explicit states are rejected."""
+    from mimikit_b200 import IOSpec, SampleRNN
+    torch.manual_seed(3)
+    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=32)), frame_sizes=(8, 2, 1), hidden_dim=48)
+    assert cfg.rnn_class == "lstm"
+    net = SampleRNN.from_config(cfg).to("cuda")
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, (8, 2, 1), rnn_class="lstm")
+    g = torch.Generator().manual_seed(2)
+    prompts = torch.randint(0, 256, (21, 50), generator=g)
+    noise = torch.rand(21, 20, generator=g)
+    seq, lg = net.generate(prompts, 20, temperature=0.9, noise=noise, return_logits=True)
+    ref_seq, ref_lg = orc.generate(prompts.numpy(), 20, 0.9, noise.numpy())
+    assert np.array_equal(seq.cpu().numpy(), ref_seq) and _rel_err(lg.cpu().numpy(), ref_lg) <= REL_TOL
+    cfg2 = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=32)), frame_sizes=(4, 2), hidden_dim=32,
+                            rnn_class="gru", h0_init="randn")
+    net2 = SampleRNN.from_config(cfg2).to("cuda")
+    gen = lambda seed: net2.generate(prompts[:4], 16, return_logits=True, generator=torch.Generator(device="cuda").manual_seed(seed))
+    (a, la), (b, lb), (c, lc) = gen(5), gen(5), gen(6)
+    assert torch.equal(a, b) and torch.equal(la, lb) and not torch.equal(la, lc)
+    with pytest.raises(ValueError):
+        net2.generate(prompts[:4], 4, h0={(0, 0, 0): torch.zeros(3, 32)})
+
+
+def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
+    """export_network -> file -> load_exported (mimikit_b200/checkpoint.py) of an LSTM network built from the
+    live reference's state dict: the reloaded network generates the reference's sequence."""
+    from mimikit_b200 import IOSpec, SampleRNN, load_exported, save_exported
+    from test_oracle_golden import variant_setup
+    d = load_golden("samplernn_lstm_2layers_ones")
+    m, kw, _ = variant_setup(d)
+    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]))),
+                           frame_sizes=tuple(int(f) for f in m["frame_sizes"]), hidden_dim=int(m["hidden_dim"]),
+                           rnn_class="lstm", n_rnn=2, h0_init="ones")
+    net = SampleRNN.from_config(cfg)
+    net.load_state_dict(golden_state_dict(d))
+    again = load_exported(save_exported(net, str(tmp_path / "m.b200.pt")), device="cuda")
+    assert again.config.rnn_class == "lstm" and again.config.n_rnn == 2 and again.config.h0_init == "ones"
+    seq = again.generate(torch.from_numpy(d["prompts"]), d["noise"].shape[1])
+    assert np.array_equal(seq.cpu().numpy(), d["seq_argmax"])

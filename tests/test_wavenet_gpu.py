@@ -225,3 +225,15 @@ def test_w30_full_width_properties():
     assert _rel_err(got_logits.cpu().numpy()[:, 0], ref_logits[:, 0]) <= REL_TOL
     assert np.array_equal(got_seq.cpu().numpy(), ref_seq)
     assert np.array_equal(seq.cpu().numpy()[sub][:, :P + 24], ref_seq)
+
+
+def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
+    """export_network -> file -> load_exported of a network carrying the live reference's weights: the reloaded network
+    generates the reference's argmax sequence."""
+    from mimikit_b200 import load_exported, save_exported
+    d = load_golden("wavenet_res_skip_mid")
+    net = net_from_golden(d)
+    again = load_exported(save_exported(net, str(tmp_path / "m.b200.pt")), device="cuda")
+    assert again.rf == net.rf and again.config.skips_dim == net.config.skips_dim
+    seq = again.generate(torch.from_numpy(d["prompts"]), d["noise"].shape[1])
+    assert np.array_equal(seq.cpu().numpy(), d["seq_argmax"])
