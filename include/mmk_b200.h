@@ -154,6 +154,21 @@ int mmk_wavenet_create(const mmk_wavenet_desc* desc, int max_batch, mmk_wavenet_
 #define MMK_COMPUTE_FP32 0
 #define MMK_COMPUTE_BF16_TC 1
 int mmk_wavenet_create_ex(const mmk_wavenet_desc* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
+/* The rest of the WaveNet configuration surface that changes only ring depth, tap count and one add:
+ * per-layer kernel sizes (wavenet_v2.py:295-327; conv_dil_w[l] is then (2C, C, k_l)), layerwise_inputs (:283-284) and
+ * n_hidden_layers > 0 in the MLP head (networks/mlp.py:47-50: one shared Linear).  These run in the general fp32 kernel;
+ * a desc with kernel sizes all 2, no layerwise inputs and a plain head takes the same route as mmk_wavenet_create_ex.
+ * (pad_side = 1 needs nothing here: the generation loop evaluates the last position of an rf-long window, where the
+ * padded and the unpadded network agree.) */
+typedef struct {
+    mmk_wavenet_desc base;
+    const int* kernel_sizes;      /* [n_layers], each 2..4; NULL = all 2 */
+    int layerwise_inputs;         /* 0 / 1 */
+    int head_hidden_layers;       /* MLP n_hidden_layers; base.head_w2 is then the LAST Linear (fc.{2 + 2 n}) */
+    const float* head_wh;         /* output_modules.0.estimator.0.fc.2.weight (Hh, Hh) when head_hidden_layers > 0 */
+    const float* head_bh;         /* ...fc.2.bias (Hh) */
+} mmk_wavenet_desc_ex;
+int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
 /* Diagnostic for the tensor-core path: d_D (128, N) fp32 = d_A (128, K) . d_B (N, K)^T with operands rounded to bf16,
  * through the same shared-memory descriptors (K-major SWIZZLE_128B), tcgen05.mma and TMEM loads as the bf16 kernel.
  * N a multiple of 16 <= 256, K a multiple of 64 <= 256.  h_cycles: nullable HOST pointer; receives the clock cycles of 8

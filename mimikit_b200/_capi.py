@@ -40,6 +40,11 @@ class WaveNetDesc(Structure):
                 ("head_w2", POINTER(c_float)), ("head_b2", POINTER(c_float))]
 
 
+class WaveNetDescEx(Structure):
+    _fields_ = [("base", WaveNetDesc), ("kernel_sizes", POINTER(c_int)), ("layerwise_inputs", c_int),
+                ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float))]
+
+
 class SampleRNNDesc(Structure):
     _fields_ = [("n_tiers", c_int), ("frame_sizes", POINTER(c_int)), ("hidden_dim", c_int), ("head_hidden", c_int),
                 ("q_levels", c_int), ("min_temperature", c_float),
@@ -79,6 +84,7 @@ PROTOTYPES = {
     "mmk_mel_apply": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mmk_wavenet_create": (c_int, [POINTER(WaveNetDesc), c_int, POINTER(c_void_p)]),
     "mmk_wavenet_create_ex": (c_int, [POINTER(WaveNetDesc), c_int, c_int, POINTER(c_void_p)]),
+    "mmk_wavenet_create_cfg": (c_int, [POINTER(WaveNetDescEx), c_int, c_int, POINTER(c_void_p)]),
     "mmk_tc_gemm_check": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mmk_wavenet_destroy": (c_int, [c_void_p]),
     "mmk_wavenet_rf": (c_int, [c_void_p]),

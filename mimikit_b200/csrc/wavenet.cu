@@ -39,10 +39,13 @@ constexpr int WN_MAX_LAYERS = 96;
 constexpr int WN_MAX_STAGES = 32;
 constexpr unsigned WN_SPIN_LIMIT = 1u << 24;
 
+constexpr int WN_MAX_K = 4;  // conv kernel sizes 2..4
+
 struct WnLayer {
     int dilation;
     int nres;             // residual output columns per CTA (nf or 0)
-    long long ring_off;   // float offset of this layer's ring in the ring buffer
+    int ksize;            // taps of the dilated conv (tap j reads the layer input (ksize - 1 - j) dilations back)
+    long long ring_off;   // float offset of this layer's ring in the ring buffer: (ksize - 1) * dilation slots
 };
 
 struct WnParams {
@@ -53,6 +56,9 @@ struct WnParams {
     int NA, NB, NH, NZ;        // the same, padded to multiples of 4 (NA covers f and g: 2*nf)
     int layer_block;           // floats per (layer, rank) weight block
     int head_block;            // floats per rank head block
+    int kmax;                  // largest conv kernel size of the network
+    int layerwise;             // layerwise_inputs (wavenet_v2.py:283-284): the embedded input is added to every layer's output
+    int n_hh;                  // hidden layers of the MLP head (one shared Linear, mlp.py:47-50)
     int G;                     // groups the rings are laid out for
     float min_temp;
     WnLayer layers[WN_MAX_LAYERS];
@@ -79,7 +85,7 @@ struct WnParams {
     long long* decisions;
     unsigned long long* step_ts;
     // shared-memory carve-up (float offsets)
-    int off_w, off_head, off_x1, off_x0, off_y, off_sacc, off_hin, off_hid, off_z, off_part, off_slice, smem_floats;
+    int off_w, off_head, off_x1, off_x0, off_y, off_sacc, off_hin, off_hid, off_z, off_part, off_slice, off_e, smem_floats;
     int zrow;                  // padded row length of the logits buffer
 };
 
@@ -237,7 +243,8 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
     float* w_s = smem + P.off_w;
     float* head_s = smem + P.off_head;
     float* x1 = smem + P.off_x1;      // [C][GB]   current layer input h_l(t)
-    float* x0 = smem + P.off_x0;      // [2][C][GB] ring reads h_l(t-d), double buffered
+    float* x0 = smem + P.off_x0;      // [2][kmax-1][C][GB] ring reads h_l(t - a d), a = k-1 .. 1, double buffered
+    float* eown = smem + P.off_e;     // [nf][GB] this CTA's channels of the embedded network input (layerwise_inputs)
     float* ybuf = smem + P.off_y;     // [2][C][GB] gated outputs, double buffered
     float* sacc = smem + P.off_sacc;  // [ns][GB]   this CTA's slice of the running skip sum
     float* hin = smem + P.off_hin;    // [Kh][GB]   head input
@@ -265,20 +272,27 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
     cluster_sync_all<CS>();
 
     const size_t blk = (size_t)C * GB;   // floats of one (group) activation block
+    const size_t x0set = (size_t)(P.kmax - 1) * blk;   // one parity of the tap buffers
     unsigned par = 0;                    // parity of the double-buffered x0 / ybuf, advances once per layer
+    // the older taps of layer ly at time t: tap j (j < k - 1) is the input (k - 1 - j) dilations back; the ring has
+    // (k - 1) d slots, the slot of time t' is t' mod that
+    auto prefetch_taps = [&](const WnLayer& ly, long long t, int g, float* dst) {
+        const long long R = (long long)(ly.ksize - 1) * ly.dilation;
+        for (int j = 0; j < ly.ksize - 1; ++j) {
+            long long sl = (t - (long long)(ly.ksize - 1 - j) * ly.dilation) % R;
+            if (sl < 0) sl += R;
+            const float* src = P.rings + ly.ring_off + ((size_t)sl * P.G + g) * blk;
+            for (int i = tid; i < (int)(blk / 4); i += WN_NT) cp_async16(dst + (size_t)j * blk + i * 4, src + i * 4);
+        }
+    };
 
     for (long long t = P.t_begin; t < P.t_end; ++t) {
         const unsigned delivery = (unsigned)(t - P.t_begin);
         const bool head_on = t >= P.t_head;
         for (int g = 0; g < P.n_groups; ++g) {
             // ---------------- stage input ----------------
-            {   // prefetch the ring read of the first owned layer
-                const WnLayer& ly = P.layers[l_lo];
-                const float* src = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk;
-                float* dst = x0 + par * blk;
-                for (int i = tid; i < (int)(blk / 4); i += WN_NT) cp_async16(dst + i * 4, src + i * 4);
-                cp_async_commit();
-            }
+            prefetch_taps(P.layers[l_lo], t, g, x0 + par * x0set);   // ring reads of the first owned layer
+            cp_async_commit();
             if (first_stage) {
                 wait_s64(P.avail + g, t + 1, P.abort_flag);
                 // embedding gather: x1[k][p] = E[q_{b,t}][k]   (EmbeddingIO, modules/io.py:148-154)
@@ -302,16 +316,26 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                 __syncthreads();
                 if (tid == 0) red_release_add(P.ack + stage * P.G + g, 1u);
             }
+            if (P.layerwise) {   // this CTA's channels of E[q_{b,t}] (the sample is in seq: it was published before the group
+                                 // was handed to this stage)
+                for (int o = tid; o < nf * GB; o += WN_NT) {
+                    const int i = o / GB, pp = o - i * GB, b = g * GB + pp;
+                    long long q = 0;
+                    if (b < P.B) q = __ldcg(P.seq + (size_t)b * P.seq_stride + t);
+                    q = q < 0 ? 0 : (q >= P.Q ? P.Q - 1 : q);
+                    eown[o] = (b < P.B) ? __ldg(P.E + (size_t)q * C + rank * nf + i) : 0.0f;
+                }
+            }
             __syncthreads();
 
             // ---------------- owned layers ----------------
             for (int l = l_lo; l < l_hi; ++l) {
                 const WnLayer& ly = P.layers[l];
-                const float* W1 = w_s + (size_t)(l - l_lo) * P.layer_block;   // [2C][NA]
-                const float* b1 = W1 + (size_t)2 * C * P.NA;                  // [NA]
+                const float* W1 = w_s + (size_t)(l - l_lo) * P.layer_block;   // [kmax C][NA], tap j at rows [j C, (j+1) C)
+                const float* b1 = W1 + (size_t)P.kmax * C * P.NA;             // [NA]
                 const float* W2 = b1 + P.NA;                                  // [C][NB]
                 const float* b2 = W2 + (size_t)C * P.NB;                      // [NB]
-                float* x0c = x0 + par * blk;
+                float* x0c = x0 + par * x0set;
                 float* yc = ybuf + par * blk;
                 const bool last_owned = (l == l_hi - 1);
                 const bool last_layer = (l == P.L - 1);
@@ -324,8 +348,9 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                 {
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     const Tile tl = make_tile(P.NA);
-                    gemm_accum(acc, tl, W1, P.NA, x0c, C);
-                    gemm_accum(acc, tl, W1 + (size_t)C * P.NA, P.NA, x1, C);
+                    for (int j = 0; j < ly.ksize - 1; ++j)
+                        gemm_accum(acc, tl, W1 + (size_t)j * C * P.NA, P.NA, x0c + (size_t)j * blk, C);
+                    gemm_accum(acc, tl, W1 + (size_t)(ly.ksize - 1) * C * P.NA, P.NA, x1, C);
                     gemm_store_partials(acc, tl, part);
                     __syncthreads();
                     for (int o = tid; o < nf * GB; o += WN_NT) {
@@ -341,16 +366,12 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
 
                 // (d) ring write of this layer's input (own channel slice), then prefetch the next ring read
                 {
-                    float* dst = P.rings + ly.ring_off + ((size_t)(t % ly.dilation) * P.G + g) * blk + (size_t)rank * nf * GB;
+                    const long long Rl = (long long)(ly.ksize - 1) * ly.dilation;
+                    float* dst = P.rings + ly.ring_off + ((size_t)(t % Rl) * P.G + g) * blk + (size_t)rank * nf * GB;
                     const float* src = x1 + (size_t)rank * nf * GB;
                     for (int i = tid; i < nf * GB / 4; i += WN_NT)
                         __stcg(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(src)[i]);
-                    if (!last_owned) {
-                        const WnLayer& nx = P.layers[l + 1];
-                        const float* s2 = P.rings + nx.ring_off + ((size_t)(t % nx.dilation) * P.G + g) * blk;
-                        float* d2 = x0 + (par ^ 1u) * blk;
-                        for (int i = tid; i < (int)(blk / 4); i += WN_NT) cp_async16(d2 + i * 4, s2 + i * 4);
-                    }
+                    if (!last_owned) prefetch_taps(P.layers[l + 1], t, g, x0 + (par ^ 1u) * x0set);
                     cp_async_commit();
                 }
 
@@ -366,7 +387,9 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                         const int i = o / GB, p = o - i * GB;
                         const float v = gemm_reduce(part, P.NB, i, p) + b2[i];
                         if (i < ly.nres) {
-                            slice[o] = x1[((size_t)rank * nf + i) * GB + p] + v;   // h_{l+1} = h_l + conv_res(y)
+                            float hn = x1[((size_t)rank * nf + i) * GB + p] + v;   // h_{l+1} = h_l + conv_res(y)
+                            if (P.layerwise) hn += eown[i * GB + p];               // + inputs[0] (wavenet_v2.py:283-284)
+                            slice[o] = hn;
                         } else {
                             const int j = i - ly.nres;
                             sacc[j * GB + p] = (l == 0) ? v : (v + sacc[j * GB + p]);  // skips = conv_skip(y) + skips
@@ -374,11 +397,21 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                     }
                     __syncthreads();
                 }
-                // next-layer input h_{l+1}: own slice is in `slice` (residual) or is y itself
-                const float* hnext_slice = (ly.nres > 0) ? slice : (yc + (size_t)rank * nf * GB);
+                // next-layer input h_{l+1}: own slice is in `slice` (residual and / or layerwise input) or is y itself
+                const bool own_slice = ly.nres > 0 || P.layerwise;
+                if (P.layerwise && ly.nres == 0) {
+                    for (int o = tid; o < nf * GB; o += WN_NT) slice[o] = yc[(size_t)rank * nf * GB + o] + eown[o];
+                    __syncthreads();
+                }
+                const float* hnext_slice = own_slice ? slice : (yc + (size_t)rank * nf * GB);
+                if (last_layer && ns == 0 && P.layerwise && head_on) {
+                    // no skips: the head reads h_L = y + inputs[0]: gather it where the skip sum would have gone
+                    scatter_slice<CS>(cluster, hin + (size_t)rank * nf * GB, slice, nf * GB / 4);
+                    cluster_sync_all<CS>();
+                }
                 if (!last_layer) {
                     if (!last_owned) {
-                        if (ly.nres > 0) {
+                        if (own_slice) {
                             scatter_slice<CS>(cluster, x1 + (size_t)rank * nf * GB, hnext_slice, nf * GB / 4);
                             cluster_sync_all<CS>();   // #2
                         } else {
@@ -413,13 +446,15 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                 const float* hb1 = hW1 + (size_t)P.Kh * P.NH;       // [NH]
                 const float* hW2 = hb1 + P.NH;                      // [Hh][NZ]
                 const float* hb2 = hW2 + (size_t)P.Hh * P.NZ;       // [NZ]
+                const float* hWh = hb2 + P.NZ;                      // [Hh][NH] the shared hidden Linear (n_hh > 0)
+                const float* hbh = hWh + (size_t)P.Hh * P.NH;       // [NH]
                 const float* head_in;
                 if (ns > 0) {
                     scatter_slice<CS>(cluster, hin + (size_t)rank * ns * GB, sacc, ns * GB / 4);
                     cluster_sync_all<CS>();
                     head_in = hin;
                 } else {
-                    head_in = ylast;                             // no skips: the head reads h_L = y of the last layer
+                    head_in = P.layerwise ? hin : ylast;         // no skips: the head reads h_L = y (+ inputs[0]) of the last layer
                 }
                 {   // hidden = mish(W1 x + b1)
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -435,10 +470,27 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                     scatter_slice<CS>(cluster, hid + (size_t)rank * P.nh * GB, slice, P.nh * GB / 4);
                 }
                 cluster_sync_all<CS>();
+                const float* hid_in = hid;
+                for (int r = 0; r < P.n_hh; ++r) {   // hidden layers: ONE Linear(Hh, Hh) + Mish applied n_hh times (mlp.py:47-50)
+                    float* hid_out = hid + (size_t)((r + 1) & 1) * P.Hh * GB;
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    const Tile tl = make_tile(P.NH);
+                    gemm_accum(acc, tl, hWh, P.NH, hid_in, P.Hh);
+                    gemm_store_partials(acc, tl, part);
+                    __syncthreads();
+                    for (int o = tid; o < P.nh * GB; o += WN_NT) {
+                        const int i = o / GB, p = o - i * GB;
+                        slice[o] = mish_acc(gemm_reduce(part, P.NH, i, p) + hbh[i]);
+                    }
+                    __syncthreads();
+                    scatter_slice<CS>(cluster, hid_out + (size_t)rank * P.nh * GB, slice, P.nh * GB / 4);
+                    cluster_sync_all<CS>();
+                    hid_in = hid_out;
+                }
                 {   // z = W2 hidden + b2 : Q+1 values, this CTA's columns [rank*nz, ...)
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     const Tile tl = make_tile(P.NZ);
-                    gemm_accum(acc, tl, hW2, P.NZ, hid, P.Hh);
+                    gemm_accum(acc, tl, hW2, P.NZ, hid_in, P.Hh);
                     gemm_store_partials(acc, tl, part);
                     __syncthreads();
                     float* z0 = (CS == 1) ? zbuf : cluster.map_shared_rank(zbuf, 0);
@@ -612,8 +664,9 @@ static size_t wn_plan(WnParams& p, int CS, int max_layers_per_stage, bool has_he
     p.CS = CS;
     p.nf = p.C / CS; p.ns = p.S / CS; p.nh = p.Hh / CS; p.nz = (p.Q + 1 + CS - 1) / CS;
     p.NA = pad4(2 * p.nf); p.NB = std::max(4, pad4(p.nf + p.ns)); p.NH = pad4(p.nh); p.NZ = pad4(p.nz);
-    p.layer_block = pad4(2 * p.C * p.NA + p.NA + p.C * p.NB + p.NB);
-    p.head_block = pad4(p.Kh * p.NH + p.NH + p.Hh * p.NZ + p.NZ);
+    if (p.kmax < 2) p.kmax = 2;
+    p.layer_block = pad4(p.kmax * p.C * p.NA + p.NA + p.C * p.NB + p.NB);
+    p.head_block = pad4(p.Kh * p.NH + p.NH + p.Hh * p.NZ + p.NZ + (p.n_hh > 0 ? p.Hh * p.NH + p.NH : 0));
     const int n = (p.Q + 31) / 32;
     p.zrow = pad4(p.Q + 1 + 4);
     (void)n;
@@ -622,26 +675,45 @@ static size_t wn_plan(WnParams& p, int CS, int max_layers_per_stage, bool has_he
     p.off_w = take(max_layers_per_stage * p.layer_block);
     p.off_head = take(has_head ? p.head_block : 4);
     p.off_x1 = take(p.C * WN_GB);
-    p.off_x0 = take(2 * p.C * WN_GB);
+    p.off_x0 = take(2 * (p.kmax - 1) * p.C * WN_GB);
     p.off_y = take(2 * p.C * WN_GB);
     p.off_sacc = take(std::max(4, p.ns * WN_GB));
     p.off_hin = take(std::max(4, p.Kh * WN_GB));
-    p.off_hid = take(p.Hh * WN_GB);
+    p.off_hid = take(2 * p.Hh * WN_GB);
     p.off_z = take(WN_GB * p.zrow);
     p.off_part = take(WN_NT * 8);
     p.off_slice = take(std::max(std::max(p.nf, p.nh), p.nf + p.ns) * WN_GB + 8);
+    p.off_e = take(std::max(4, p.nf * WN_GB));
     p.smem_floats = o;
     return (size_t)o * sizeof(float);
 }
-
-extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, int compute_mode, mmk_wavenet_t* out);
 
 extern "C" int mmk_wavenet_create(const mmk_wavenet_desc* d, int max_batch, mmk_wavenet_t* out) {
     return mmk_wavenet_create_ex(d, max_batch, MMK_COMPUTE_FP32, out);
 }
 
 extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, int compute_mode, mmk_wavenet_t* out) {
-    MMK_CHECK(d && out, "mmk_wavenet_create: null argument");
+    MMK_CHECK(d, "mmk_wavenet_create: null argument");
+    mmk_wavenet_desc_ex dx{};
+    dx.base = *d;
+    return mmk_wavenet_create_cfg(&dx, max_batch, compute_mode, out);
+}
+
+extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_batch, int compute_mode, mmk_wavenet_t* out) {
+    MMK_CHECK(dx && out, "mmk_wavenet_create: null argument");
+    const mmk_wavenet_desc* d = &dx->base;
+    MMK_CHECK(dx->head_hidden_layers >= 0 && dx->head_hidden_layers <= 8, "head_hidden_layers must be in [0, 8]");
+    MMK_CHECK(dx->head_hidden_layers == 0 || (dx->head_wh && dx->head_bh), "missing head hidden-layer weights");
+    int kmax = 2;
+    bool plain = dx->layerwise_inputs == 0 && dx->head_hidden_layers == 0;
+    if (dx->kernel_sizes)
+        for (int l = 0; l < d->n_layers; ++l) {
+            MMK_CHECK(dx->kernel_sizes[l] >= 2 && dx->kernel_sizes[l] <= WN_MAX_K, "kernel sizes must be in [2, 4]");
+            kmax = std::max(kmax, dx->kernel_sizes[l]);
+            plain = plain && dx->kernel_sizes[l] == 2;
+        }
+    MMK_CHECK(plain || compute_mode == MMK_COMPUTE_FP32,
+              "kernel sizes > 2, layerwise_inputs and hidden MLP layers run in the fp32 general kernel only");
     MMK_CHECK(compute_mode == MMK_COMPUTE_FP32 || compute_mode == MMK_COMPUTE_BF16_TC, "unknown compute_mode");
     MMK_CHECK(d->n_layers >= 1 && d->n_layers <= WN_MAX_LAYERS, "n_layers out of range [1, 96]");
     MMK_CHECK(d->dilated_dim >= 4 && d->dilated_dim % 4 == 0, "dilated_dim must be a positive multiple of 4");
@@ -683,7 +755,7 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
         return 0;
     }
     {
-        const char* force = getenv("MMK_WN_KERNEL");   // "1" = general kernel, "2" = chain kernel, "3" = warp kernel only
+        const char* force = plain ? getenv("MMK_WN_KERNEL") : "1";   // "1" = general kernel, "2" = chain kernel, "3" = warp kernel only
         if (!force || atoi(force) == 6) {
             int unsupported = 0;
             if (wn6_create(d, max_batch, &h->v6, &unsupported) == 0) {
@@ -726,13 +798,14 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
     }
     p.L = d->n_layers; p.C = d->dilated_dim; p.S = d->skips_dim; p.Hh = d->head_hidden; p.Q = d->q_levels;
     p.Kh = p.S > 0 ? p.S : p.C;
+    p.kmax = kmax; p.layerwise = dx->layerwise_inputs ? 1 : 0; p.n_hh = dx->head_hidden_layers;
     p.min_temp = d->min_temperature;
     h->max_batch = max_batch;
     p.G = (max_batch + WN_GB - 1) / WN_GB;
     int rf = 1;
     for (int l = 0; l < p.L; ++l) {
         MMK_CHECK(d->dilations[l] >= 1, "dilation must be >= 1");
-        rf += d->dilations[l];
+        rf += d->dilations[l] * ((dx->kernel_sizes ? dx->kernel_sizes[l] : 2) - 1);
         MMK_CHECK(d->conv_dil_w[l] && d->conv_dil_b[l], "missing conv_dil weights");
         MMK_CHECK(!(l == p.L - 1 && d->conv_res_w[l]), "the last layer never has a residual conv (wavenet_v2.py:216)");
     }
@@ -794,27 +867,28 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
     MMK_CUDA(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     if (CS > 8) MMK_CUDA(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
-    // ---- pack weights: per (layer, rank) block = W1[2C][NA] | b1[NA] | W2[C][NB] | b2[NB]
+    // ---- pack weights: per (layer, rank) block = W1[kmax C][NA] (tap j at rows [j C, (j+1) C)) | b1[NA] | W2[C][NB] | b2[NB]
     const int C = p.C, S = p.S, nf = p.nf, ns = p.ns;
     std::vector<float> wpack((size_t)p.L * CS * p.layer_block, 0.0f);
     long long ring_off = 0;
     for (int l = 0; l < p.L; ++l) {
         const bool has_res = d->conv_res_w[l] != nullptr;
+        const int ks = dx->kernel_sizes ? dx->kernel_sizes[l] : 2;
         p.layers[l].dilation = d->dilations[l];
         p.layers[l].nres = has_res ? nf : 0;
+        p.layers[l].ksize = ks;
         p.layers[l].ring_off = ring_off;
-        ring_off += (long long)d->dilations[l] * p.G * C * WN_GB;
-        const float* wd = d->conv_dil_w[l];   // (2C, C, 2): [o][c][tap], tap 0 = older sample
+        ring_off += (long long)(ks - 1) * d->dilations[l] * p.G * C * WN_GB;
+        const float* wd = d->conv_dil_w[l];   // (2C, C, ks): [o][c][tap], tap 0 = oldest sample
         const float* bd = d->conv_dil_b[l];
         for (int r = 0; r < CS; ++r) {
             float* blk = wpack.data() + ((size_t)l * CS + r) * p.layer_block;
-            float* W1 = blk; float* b1 = W1 + (size_t)2 * C * p.NA; float* W2 = b1 + p.NA; float* b2 = W2 + (size_t)C * p.NB;
+            float* W1 = blk; float* b1 = W1 + (size_t)p.kmax * C * p.NA; float* W2 = b1 + p.NA; float* b2 = W2 + (size_t)C * p.NB;
             for (int j = 0; j < 2 * nf; ++j) {
                 const int o = (j < nf) ? (r * nf + j) : (C + r * nf + (j - nf));   // f channels first, then g
-                for (int c = 0; c < C; ++c) {
-                    W1[(size_t)c * p.NA + j] = wd[((size_t)o * C + c) * 2 + 0];
-                    W1[(size_t)(C + c) * p.NA + j] = wd[((size_t)o * C + c) * 2 + 1];
-                }
+                for (int c = 0; c < C; ++c)
+                    for (int tap = 0; tap < ks; ++tap)
+                        W1[(size_t)(tap * C + c) * p.NA + j] = wd[((size_t)o * C + c) * ks + tap];
                 b1[j] = bd[o];
             }
             int col = 0;
@@ -840,6 +914,14 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
             const int o = r * p.nh + j;
             for (int c = 0; c < p.Kh; ++c) W1[(size_t)c * p.NH + j] = d->head_w1[(size_t)o * p.Kh + c];
             b1[j] = d->head_b1[o];
+        }
+        if (p.n_hh > 0) {
+            float* Wh = b2 + p.NZ; float* bh = Wh + (size_t)p.Hh * p.NH;
+            for (int j = 0; j < p.nh; ++j) {
+                const int o = r * p.nh + j;
+                for (int c = 0; c < p.Hh; ++c) Wh[(size_t)c * p.NH + j] = dx->head_wh[(size_t)o * p.Hh + c];
+                bh[j] = dx->head_bh[o];
+            }
         }
         for (int j = 0; j < p.nz; ++j) {
             const int o = r * p.nz + j;

@@ -86,12 +86,13 @@ class WaveNet(NativeARM):
         need(not c.apply_residuals and not c.with_affine_residuals, "apply_residuals / with_affine_residuals")
         need(c.groups == 1, "groups > 1")
         need(str(c.act_f) == "Tanh" and str(c.act_g) == "Sigmoid", "activations other than Tanh/Sigmoid gating")
-        need(c.pad_side == 0 and c.stride == 1 and c.bias, "pad_side != 0, stride != 1 or bias=False")
-        need(not (c.tie_io_weights or c.layerwise_inputs or c.reverse_layer_order),
-             "tie_io_weights / layerwise_inputs / reverse_layer_order")
-        need(c.io_spec.targets[0].module.n_hidden_layers == 0, "n_mlp_layers > 0")
+        need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
+        need(not (c.tie_io_weights or c.reverse_layer_order), "tie_io_weights / reverse_layer_order")
+        need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
+        need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
+        need(len(c.blocks) > 0, "blocks=() (the reference then keeps conv_res on the last layer)")
         ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
-        need(all(k == 2 for k in ks), "kernel sizes other than 2")
+        need(all(2 <= k <= 4 for k in ks), "kernel sizes outside [2, 4]")
 
     @classmethod
     def from_config(cls, config: "WaveNet.Config") -> "WaveNet":
@@ -102,8 +103,9 @@ class WaveNet(NativeARM):
         super().__init__()
         self._check_supported(config)
         self._config = config
-        _, dil = self.get_kernels_and_dilation(config.kernel_sizes, config.blocks)
-        self.dilations = [int(d) for d in dil]
+        ks, dil = self.get_kernels_and_dilation(config.kernel_sizes, config.blocks)
+        self.kernels = [int(k) for k, _ in zip(ks, dil)]
+        self.dilations = [int(d) for _, d in zip(ks, dil)]
         self.has_skips = config.skips_dim is not None
         self.has_residuals = config.residuals_dim is not None
         self._sd = self._init_state_dict()
@@ -142,15 +144,26 @@ class WaveNet(NativeARM):
 
     @property
     def rf(self) -> int:
-        """wavenet_v2.py:337-339."""
-        return sum(self.dilations) + 1
+        """wavenet_v2.py:337-339: sum of the layers' causes (kernel_size - 1) * dilation, + 1."""
+        return sum((k - 1) * d for k, d in zip(self.kernels, self.dilations)) + 1
 
     @property
     def shift(self) -> int:
-        return self.rf  # pad_side == 0
+        """wavenet_v2.py:333-335."""
+        return 1 if self._config.pad_side == 1 else self.rf
 
     def output_length(self, n_input_steps: int) -> int:
-        return n_input_steps - self.shift + 1
+        """wavenet_v2.py:341-342."""
+        return n_input_steps if self._config.pad_side != 0 else n_input_steps - self.shift + 1
+
+    @property
+    def _n_mlp_hidden(self):
+        return int(self._config.io_spec.targets[0].module.n_hidden_layers)
+
+    @property
+    def _plain(self):
+        """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
+        return all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
 
     @property
     def generate_params(self):
@@ -172,7 +185,7 @@ class WaveNet(NativeARM):
         e = OrderedDict()
         e["input_modules.0.0.weight"] = (self._config.io_spec.inputs[0].class_size, C)
         for l in range(L):
-            e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, 2)
+            e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, self.kernels[l])
             e[f"layers.{l}.conv_dil.0.0.bias"] = (2 * C,)
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
@@ -184,8 +197,12 @@ class WaveNet(NativeARM):
         e[p + "min_temp"] = ()
         e[p + "fc.0.weight"] = (Hh, S if self.has_skips else C)
         e[p + "fc.0.bias"] = (Hh,)
-        e[p + "fc.2.weight"] = (Q + 1, Hh)
-        e[p + "fc.2.bias"] = (Q + 1,)
+        nh = self._n_mlp_hidden                           # mlp.py:47-50: fc.2, fc.4, ... are ONE shared Linear(Hh, Hh)
+        for r in range(nh):
+            e[p + f"fc.{2 + 2 * r}.weight"] = (Hh, Hh)
+            e[p + f"fc.{2 + 2 * r}.bias"] = (Hh,)
+        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + 1, Hh)
+        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + 1,)
         return e
 
     def _init_state_dict(self):
@@ -201,13 +218,18 @@ class WaveNet(NativeARM):
                 wshape = shape if k.endswith("weight") else self._expected_shapes()[k[:-4] + "weight"]
                 bound = 1.0 / math.sqrt(max(1, int(torch.tensor(wshape[1:]).prod())))
                 sd[k] = (torch.rand(shape) * 2 - 1) * bound
+        p = "output_modules.0.estimator.0."
+        for r in range(1, self._n_mlp_hidden):
+            sd[p + f"fc.{2 + 2 * r}.weight"] = sd[p + "fc.2.weight"]
+            sd[p + f"fc.{2 + 2 * r}.bias"] = sd[p + "fc.2.bias"]
         return sd
 
     # ---- native handle --------------------------------------------------------------------------
     def _create_handle(self, max_batch):
         C, S, Hh, Q = self._dims()
         L = len(self.dilations)
-        d = _capi.WaveNetDesc()
+        dx = _capi.WaveNetDescEx()
+        d = dx.base
         d.n_layers, d.dilated_dim, d.skips_dim, d.head_hidden, d.q_levels = L, C, S, Hh, Q
         d.min_temperature = float(self._sd["output_modules.0.estimator.0.min_temp"])
         dil = (ctypes.c_int * L)(*self.dilations)
@@ -227,11 +249,24 @@ class WaveNet(NativeARM):
         d.conv_res_w = arr("layers.{}.conv_res.weight", has_res)
         d.conv_res_b = arr("layers.{}.conv_res.bias", has_res)
         p = "output_modules.0.estimator.0."
+        nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
-        d.head_w2, d.head_b2 = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
+        d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        ks = (ctypes.c_int * L)(*self.kernels)
+        keep.append(ks)
+        dx.kernel_sizes = ks
+        dx.layerwise_inputs = int(bool(self._config.layerwise_inputs))
+        dx.head_hidden_layers = nh
+        if nh > 0:
+            for r in range(1, nh):
+                if not (torch.equal(self._sd[p + f"fc.{2 + 2 * r}.weight"], self._sd[p + "fc.2.weight"])
+                        and torch.equal(self._sd[p + f"fc.{2 + 2 * r}.bias"], self._sd[p + "fc.2.bias"])):
+                    raise RuntimeError("the hidden layers of the reference MLP share one Linear (networks/mlp.py:47-50): "
+                                       "fc.2, fc.4, ... must hold the same tensors")
+            dx.head_wh, dx.head_bh = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
         h = ctypes.c_void_p()
         mode = 1 if self._compute_dtype == torch.bfloat16 else 0      # MMK_COMPUTE_BF16_TC / MMK_COMPUTE_FP32
-        _capi.check(_capi.lib().mmk_wavenet_create_ex(ctypes.byref(d), int(max_batch), mode, ctypes.byref(h)))
+        _capi.check(_capi.lib().mmk_wavenet_create_cfg(ctypes.byref(dx), int(max_batch), mode, ctypes.byref(h)))
         return h
 
     def _destroy_handle(self, h):

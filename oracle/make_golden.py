@@ -111,6 +111,22 @@ def main():
     ref = ref_loader.load()
     if len(sys.argv) > 1 and sys.argv[1] == "normalize":   # only this fixture (the others are unchanged)
         return gen_normalize(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_variants":
+        g = torch.Generator().manual_seed(88)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=11, pad_side=1, **kw)
+        gen_network("wavenet_pad_side1", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, pad_side=1))
+        net = ref_loader.make_wavenet(seed=12, layerwise_inputs=True, **kw)
+        gen_network("wavenet_layerwise_inputs", net, torch.randint(0, 256, (3, 24), generator=g), 32,
+                    dict(kw, layerwise_inputs=1))
+        kw2 = dict(blocks=(4,), dims=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=13, layerwise_inputs=True, n_mlp_layers=2, **kw2)
+        gen_network("wavenet_layerwise_noskip_mlp2", net, torch.randint(0, 256, (2, 30), generator=g), 28,
+                    dict(kw2, layerwise_inputs=1, n_mlp_layers=2))
+        kw3 = dict(blocks=(2, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=14, kernel_sizes=(3,), **kw3)
+        gen_network("wavenet_kernel3", net, torch.randint(0, 256, (3, 30), generator=g), 28, dict(kw3, kernel_size=3))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

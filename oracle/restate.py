@@ -347,24 +347,29 @@ def wavenet_rf(kernel_sizes, blocks):
 
 class WaveNetOracle:
     """Cached-step restatement of WaveNet.generate_step == forward on the last rf samples
-    (networks/wavenet_v2.py:447-452, 276-293; WNLayer.forward 131-176), for the mu-law embedding-input, gated,
-    pad_side=0, kernel_size=2 configuration."""
+    (networks/wavenet_v2.py:447-452, 276-293; WNLayer.forward 131-176), for the mu-law embedding-input, gated configuration:
+    any kernel sizes (tap j of a size-k layer reads the sample (k - 1 - j) dilations back), `layerwise_inputs` (:283-284:
+    the embedded network input is added to every layer's output) and hidden MLP layers (mlp.py:47-50: one shared Linear).
+    `pad_side` does not enter: the generation loop evaluates the LAST position of an rf-long window (eval_slice, :273), whose
+    dependency cone never touches the left padding, so pad_side=1 and pad_side=0 give the same value there."""
 
-    def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256):
+    def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256, layerwise_inputs=False, n_mlp_hidden=0):
         sd = state_dict
         ks, ds = wavenet_kernels_and_dilations(kernel_sizes, blocks)
+        self.kernels = [int(k) for k, _ in zip(ks, ds)]
         self.dilations = [int(d) for _, d in zip(ks, ds)]
-        assert all(k == 2 for k in ks), "oracle restates kernel_size=2 only"
         self.L = len(self.dilations)
         self.Q = q_levels
+        self.layerwise_inputs = bool(layerwise_inputs)
+        self.n_mlp_hidden = int(n_mlp_hidden)
         self.E = _np(sd, "input_modules.0.0.weight")
         self.C = self.E.shape[1]
-        self.Wd0, self.Wd1, self.bd, self.Ws, self.bs, self.Wr, self.br = [], [], [], [], [], [], []
+        self.Wd, self.bd, self.Ws, self.bs, self.Wr, self.br = [], [], [], [], [], []
         self.has_skips = "layers.0.conv_skip.weight" in sd
         for l in range(self.L):
-            w = _np(sd, f"layers.{l}.conv_dil.0.0.weight")  # (2C, C, 2): tap 0 = older sample (cross-correlation)
-            self.Wd0.append(np.ascontiguousarray(w[:, :, 0]))
-            self.Wd1.append(np.ascontiguousarray(w[:, :, 1]))
+            w = _np(sd, f"layers.{l}.conv_dil.0.0.weight")  # (2C, C, k): tap 0 = oldest sample (cross-correlation)
+            assert w.shape[2] == self.kernels[l]
+            self.Wd.append([np.ascontiguousarray(w[:, :, j]) for j in range(w.shape[2])])
             self.bd.append(_np(sd, f"layers.{l}.conv_dil.0.0.bias"))
             if self.has_skips:
                 self.Ws.append(_np(sd, f"layers.{l}.conv_skip.weight")[:, :, 0])
@@ -375,32 +380,54 @@ class WaveNetOracle:
             else:
                 self.Wr.append(None)
                 self.br.append(None)
+        self.Wd0 = [w[0] for w in self.Wd]           # the two taps of a size-2 layer, as the bf16 oracle names them
+        self.Wd1 = [w[-1] for w in self.Wd]
         p = "output_modules.0.estimator.0."
+        last = 2 + 2 * self.n_mlp_hidden
         self.W1, self.b1 = _np(sd, p + "fc.0.weight"), _np(sd, p + "fc.0.bias")
-        self.W2, self.b2 = _np(sd, p + "fc.2.weight"), _np(sd, p + "fc.2.bias")
+        self.Wh = _np(sd, p + "fc.2.weight") if self.n_mlp_hidden else None
+        self.bh = _np(sd, p + "fc.2.bias") if self.n_mlp_hidden else None
+        self.W2, self.b2 = _np(sd, p + f"fc.{last}.weight"), _np(sd, p + f"fc.{last}.bias")
         self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
-        self.rf = sum(self.dilations) + 1
+        self.rf = sum((k - 1) * d for k, d in zip(self.kernels, self.dilations)) + 1
 
-    def _layer(self, l, x0, x1, skips):
+    def _head(self, out):
+        return mlp_head(out, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q, self.Wh, self.bh, self.n_mlp_hidden)
+
+    def _layer(self, l, taps, skips, e=None):
+        """taps: the k inputs of the layer, oldest first (the last one is the current sample); e: the embedded network input
+        aligned with the output (layerwise_inputs)."""
         C = self.C
-        a = x0 @ self.Wd0[l].T + x1 @ self.Wd1[l].T + self.bd[l]          # wavenet_v2.py:101,150
+        a = self.bd[l]
+        for w, x in zip(self.Wd[l], taps):                               # wavenet_v2.py:101,150
+            a = x @ w.T + a if a.ndim == 1 else a + x @ w.T
+        a = a.astype(f32)
         y = (np.tanh(a[..., :C]) * _sigmoid(a[..., C:])).astype(f32)     # :102,151
         if self.has_skips:
             s = y @ self.Ws[l].T + self.bs[l]                            # :165-171
             skips = s if skips is None else (s + skips).astype(f32)
-        h = (x1 + (y @ self.Wr[l].T + self.br[l])).astype(f32) if self.Wr[l] is not None else y  # :172-175
+        h = (taps[-1] + (y @ self.Wr[l].T + self.br[l])).astype(f32) if self.Wr[l] is not None else y  # :172-175
+        if e is not None:
+            h = (h + e).astype(f32)                                      # :283-284
         return h, skips
+
+    def _dense_taps(self, l, h):
+        k, d = self.kernels[l], self.dilations[l]
+        n = h.shape[1] - (k - 1) * d
+        return [h[:, j * d:j * d + n] for j in range(k)]
 
     def logits_teacher_forced(self, x):
         """x (B,T>=rf) int64 -> (B, T-rf+1, Q): entry i uses x[:, i:i+rf] and predicts sample i+rf
         (== train-mode forward of the reference)."""
-        h = self.E[np.asarray(x)]
+        h0 = h = self.E[np.asarray(x)]
         skips = None
-        for l, d in enumerate(self.dilations):
-            sk = None if skips is None else skips[:, d:]
-            h, skips = self._layer(l, h[:, :-d], h[:, d:], sk)
+        for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
+            taps = self._dense_taps(l, h)
+            sk = None if skips is None else skips[:, (k - 1) * d:]
+            e = h0[:, -taps[-1].shape[1]:] if self.layerwise_inputs else None
+            h, skips = self._layer(l, taps, sk, e)
         out = skips if self.has_skips else h
-        return mlp_head(out, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+        return self._head(out)
 
     def generate(self, prompts, n_steps, temperature=None, noise=None, forced=None):
         """GenerateLoopV2.run semantics (loops/generate.py:184-229) with cached per-layer histories.
@@ -415,24 +442,26 @@ class WaveNetOracle:
         seq = np.concatenate([prompts, np.zeros((B, n_steps), dtype=np.int64)], 1)
         # hist[l][:, j] = h_l(P - W + j): inputs of layer l; prefill densely over the last rf prompt samples
         hist = [np.zeros((B, W + n_steps, self.C), dtype=f32) for _ in range(self.L)]
-        h = self.E[prompts[:, P - W:]]
+        h0 = h = self.E[prompts[:, P - W:]]
         off = 0
-        for l, d in enumerate(self.dilations):
+        for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
             hist[l][:, off:W] = h
-            h, _ = self._layer(l, h[:, :-d], h[:, d:], None)
-            off += d
+            taps = self._dense_taps(l, h)
+            h, _ = self._layer(l, taps, None, h0[:, -taps[-1].shape[1]:] if self.layerwise_inputs else None)
+            off += (k - 1) * d
         logits_out = np.zeros((B, n_steps, self.Q), dtype=f32)
         for i in range(n_steps):
             t = P + i
             j = W + i - 1                      # column of time t-1
             src = seq if forced is None else np.asarray(forced)
-            x1 = self.E[src[:, t - 1]]
+            e = x1 = self.E[src[:, t - 1]]
             skips = None
-            for l, d in enumerate(self.dilations):
+            for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
                 hist[l][:, j] = x1
-                x1, skips = self._layer(l, hist[l][:, j - d], x1, skips)
+                taps = [hist[l][:, j - (k - 1 - a) * d] for a in range(k)]
+                x1, skips = self._layer(l, taps, skips, e if self.layerwise_inputs else None)
             out = skips if self.has_skips else x1
-            lg = mlp_head(out, self.W1, self.b1, self.W2, self.b2, self.min_temp, self.Q)
+            lg = self._head(out)
             logits_out[:, i] = lg
             seq[:, t] = argmax_first(lg) if T is None else sample_inverse_cdf(lg, T, noise[:, i])
         return seq, logits_out

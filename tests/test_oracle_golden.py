@@ -242,3 +242,30 @@ def test_samplernn_variant_oracle_vs_reference(name):
         seq, lg = orc.generate(d["prompts"], n, T, d["noise"], h0=h0)
         assert np.array_equal(seq, d["seq_" + tag]), (name, tag)
         np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
+
+
+WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3"]
+
+
+def wavenet_variant_kwargs(d):
+    m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
+    return m, dict(kernel_sizes=(int(m.get("kernel_size", 2)),), layerwise_inputs=bool(int(m.get("layerwise_inputs", 0))),
+                   n_mlp_hidden=int(m.get("n_mlp_layers", 0)))
+
+
+@pytest.mark.parametrize("name", WN_VARIANTS)
+def test_wavenet_variant_oracle_vs_reference(name):
+    """pad_side=1 (same value at the evaluated position), layerwise_inputs, hidden MLP layers and kernel_size 3
+    (wavenet_v2.py:137-138, 273, 283-284, 295-327; mlp.py:47-50): the oracle against the live reference, incl. its real loop."""
+    d = load_golden(name)
+    m, kw = wavenet_variant_kwargs(d)
+    orc = restate.WaveNetOracle(golden_state_dict(d), tuple(int(b) for b in m["blocks"]), **kw)
+    n = d["noise"].shape[1]
+    for tag, T in [("argmax", None), ("t1", 1.0), ("tvec", d["tvec"])]:
+        seq, lg = orc.generate(d["prompts"], n, T, d["noise"])
+        assert np.array_equal(seq, d["seq_" + tag]), (name, tag)
+        np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
+    assert np.array_equal(d["seq_argmax"], d["seq_argmax_real_loop"])
+    tf = orc.logits_teacher_forced(d["seq_argmax"])
+    P = d["prompts"].shape[1]
+    np.testing.assert_allclose(tf[:, P - orc.rf:P - orc.rf + n], d["logits_argmax"], rtol=1e-3, atol=1e-5)

@@ -194,9 +194,14 @@ def test_errors():
         net.generate(torch.zeros(2, 16, dtype=torch.int64), 4, temperature=(1., 2., 3.))
     io = IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding"))
     with pytest.raises(NotImplementedError):
-        WaveNet.from_config(WaveNet.Config(io_spec=io, pad_side=1))
+        WaveNet.from_config(WaveNet.Config(io_spec=io, pad_side=-1))
     with pytest.raises(NotImplementedError):
-        WaveNet.from_config(WaveNet.Config(io_spec=io, kernel_sizes=(3,)))
+        WaveNet.from_config(WaveNet.Config(io_spec=io, kernel_sizes=(5,)))
+    with pytest.raises(NotImplementedError):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, dims_1x1=(16,)))
+    with pytest.raises(NotImplementedError):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, blocks=()))
+    assert WaveNet.from_config(WaveNet.Config(io_spec=io, pad_side=1, blocks=(3,))).shift == 1
     with pytest.raises(RuntimeError):
         net.load_state_dict({"bogus": torch.zeros(1)})
 
@@ -237,3 +242,63 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
     assert again.rf == net.rf and again.config.skips_dim == net.config.skips_dim
     seq = again.generate(torch.from_numpy(d["prompts"]), d["noise"].shape[1])
     assert np.array_equal(seq.cpu().numpy(), d["seq_argmax"])
+
+
+@pytest.mark.parametrize("name", ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3"])
+def test_variant_goldens(name):
+    """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
+    pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
+    logits within 1e-3; the step-wise protocol and the carried-state continuation agree with the one-launch path."""
+    from mimikit_b200 import IOSpec, WaveNet
+    from test_oracle_golden import wavenet_variant_kwargs
+    d = load_golden(name)
+    m, kw = wavenet_variant_kwargs(d)
+    cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=int(m["mlp_dim"]),
+                                                                      n_mlp_layers=kw["n_mlp_hidden"])),
+                         blocks=tuple(int(b) for b in m["blocks"]), dims_dilated=(int(m["dims"]),),
+                         residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
+                         skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
+                         layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)))
+    net = WaveNet.from_config(cfg).to("cuda")
+    net.load_state_dict(golden_state_dict(d))
+    prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
+    P, n = prompts.shape[1], noise.shape[1]
+    for tag, T in (("argmax", None), ("t1", 1.0), ("tvec", torch.from_numpy(d["tvec"]))):
+        seq, logits = net.generate(prompts, n, temperature=T, noise=noise, return_logits=True)
+        assert np.array_equal(seq.cpu().numpy(), d["seq_" + tag]), (name, tag)
+        assert _rel_err(logits.cpu().numpy(), d["logits_" + tag]) <= REL_TOL
+    assert np.array_equal(d["seq_argmax"], d["seq_argmax_real_loop"])
+    first = net.generate(prompts, n // 2)
+    assert np.array_equal(torch.cat([first, net.generate_more(n - n // 2)], 1).cpu().numpy(), d["seq_argmax"])
+    x = torch.cat([prompts, torch.zeros(prompts.shape[0], n, dtype=torch.int64)], 1).cuda()
+    net.before_generate((x[:, :P],), 0)
+    for t in range(P, P + n):
+        x[:, t:t + 1] = net.generate_step((x[:, t - net.rf:t],), t=t)[0]
+    assert np.array_equal(x.cpu().numpy(), d["seq_argmax"])
+
+
+@pytest.mark.parametrize("cluster", ["2", "4"])
+def test_variants_vs_oracle_bigger(monkeypatch, cluster):
+    """Mixed kernel sizes per layer, layerwise inputs and a hidden MLP layer together, several prompt groups and pipeline
+    stages of the general kernel, against the oracle."""
+    from mimikit_b200 import IOSpec, WaveNet
+    monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
+    monkeypatch.setenv("MMK_WN_STAGES", "3")
+    torch.manual_seed(21)
+    blocks, ks = (2, 3), (2, 3, 2, 4, 2)
+    cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=64, n_mlp_layers=1)),
+                         blocks=blocks, kernel_sizes=ks, dims_dilated=(64,), residuals_dim=64, skips_dim=32,
+                         layerwise_inputs=True)
+    net = WaveNet.from_config(cfg).to("cuda")
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks, kernel_sizes=ks,
+                                layerwise_inputs=True, n_mlp_hidden=1)
+    assert net.rf == orc.rf
+    g = torch.Generator().manual_seed(4)
+    B, P, n = 21, orc.rf + 4, 30
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    for temp in (None, 0.9):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert np.array_equal(seq.cpu().numpy(), ref_seq), temp
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
