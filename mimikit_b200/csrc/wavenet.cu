@@ -594,8 +594,6 @@ static int pad4(int v) { return (v + 3) / 4 * 4; }
 using namespace mmk;
 
 struct mmk_wavenet_s {
-    wn2_handle* v2 = nullptr;   // set when the latency-engineered kernel (wavenet2.cu) hosts this network
-    wn3_handle* v3 = nullptr;   // set when the warp-autonomous kernel (wavenet3.cu) hosts this network
     wn7_handle* v7 = nullptr;   // set when the layer-pipelined tensor-core kernel (wavenet7.cu) hosts this network (compute_mode 1)
     wn6_handle* v6 = nullptr;   // set when the layer-pipelined kernel (wavenet6.cu) hosts this network (the default)
     wn4_handle* v4 = nullptr;   // set when the bf16 tensor-core kernel (wavenet_tc.cu) hosts this network (compute_mode 1)
@@ -755,7 +753,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         return 0;
     }
     {
-        const char* force = plain ? getenv("MMK_WN_KERNEL") : "1";   // "1" = general kernel, "2" = chain kernel, "3" = warp kernel only
+        const char* force = plain ? getenv("MMK_WN_KERNEL") : "1";   // "1" = general kernel only, "6" = layer-pipelined kernel only
         if (!force || atoi(force) == 6) {
             int unsupported = 0;
             if (wn6_create(d, max_batch, &h->v6, &unsupported) == 0) {
@@ -768,32 +766,6 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
             h->v6 = nullptr;
             if (!unsupported) { delete h; return 1; }
             if (force) { delete h; MMK_FAIL("configuration not supported by the layer-pipelined fp32 kernel (MMK_WN_KERNEL=6)"); }
-        }
-        if (!force || atoi(force) == 3) {
-            int unsupported = 0;
-            if (wn3_create(d, max_batch, &h->v3, &unsupported) == 0) {
-                int rf3 = 1;
-                for (int l = 0; l < d->n_layers; ++l) rf3 += d->dilations[l];
-                h->rf = rf3; h->max_batch = max_batch;
-                *out = h;
-                return 0;
-            }
-            h->v3 = nullptr;
-            if (!unsupported) { delete h; return 1; }
-            if (force) { delete h; MMK_FAIL("configuration not supported by the warp kernel (MMK_WN_KERNEL=3)"); }
-        }
-        if (!(force && atoi(force) == 1)) {
-            int unsupported = 0;
-            if (wn2_create(d, max_batch, &h->v2, &unsupported) == 0) {
-                int rf2 = 1;
-                for (int l = 0; l < d->n_layers; ++l) rf2 += d->dilations[l];
-                h->rf = rf2; h->max_batch = max_batch;
-                *out = h;
-                return 0;
-            }
-            h->v2 = nullptr;
-            if (!unsupported) { delete h; return 1; }
-            if (force && atoi(force) == 2) { delete h; MMK_FAIL("configuration not supported by the chain kernel (MMK_WN_KERNEL=2)"); }
         }
     }
     p.L = d->n_layers; p.C = d->dilated_dim; p.S = d->skips_dim; p.Hh = d->head_hidden; p.Q = d->q_levels;
@@ -962,8 +934,6 @@ extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h) {
     if (h->v4) wn4_destroy(h->v4);
     if (h->v7) wn7_destroy(h->v7);
     if (h->v6) wn6_destroy(h->v6);
-    if (h->v3) wn3_destroy(h->v3);
-    if (h->v2) wn2_destroy(h->v2);
     cudaFree(h->d_wpack); cudaFree(h->d_hpack); cudaFree(h->d_E); cudaFree(h->d_rings);
     cudaFree(h->d_mail_h); cudaFree(h->d_mail_s); cudaFree(h->d_flags);
     delete h;
@@ -975,8 +945,6 @@ extern "C" int mmk_wavenet_sync_check(mmk_wavenet_t h, void* stream) {
     if (h->v4) return wn4_sync_check(h->v4, stream);
     if (h->v7) return wn7_sync_check(h->v7, stream);
     if (h->v6) return wn6_sync_check(h->v6, stream);
-    if (h->v3) return wn3_sync_check(h->v3, stream);
-    if (h->v2) return wn2_sync_check(h->v2, stream);
     unsigned aborted = 0;
     MMK_CUDA(cudaMemcpyAsync(&aborted, h->p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -991,8 +959,6 @@ extern "C" int mmk_wavenet_launch_info(mmk_wavenet_t h, mmk_launch_info* out) {
     if (h->v4) return wn4_launch_info(h->v4, out);
     if (h->v7) return wn7_launch_info(h->v7, out);
     if (h->v6) return wn6_launch_info(h->v6, out);
-    if (h->v3) return wn3_launch_info(h->v3, out);
-    if (h->v2) return wn2_launch_info(h->v2, out);
     out->cluster_size = h->p.CS; out->n_stages = h->p.NST; out->group_size = WN_GB; out->threads = WN_NT;
     out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.CS * h->p.NST;
     return 0;
@@ -1025,12 +991,6 @@ extern "C" int mmk_wavenet_run(mmk_wavenet_t h, int64_t* d_seq, int B, int64_t s
                        n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     if (h->v6)
         return wn6_run(h->v6, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
-                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
-    if (h->v3)
-        return wn3_run(h->v3, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
-                       n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
-    if (h->v2)
-        return wn2_run(h->v2, d_seq, B, seq_stride, seq_t0, t_begin, t_head, t_end, teacher_forced, d_temperature,
                        n_temperature, d_noise, noise_stride, noise_t0, d_logits_out, d_decisions, d_step_ts, stream);
     cudaStream_t st = (cudaStream_t)stream;
     WnParams p = h->p;

@@ -1,30 +1,8 @@
-// Internal interface between the WaveNet C ABI (wavenet.cu) and the latency-engineered kernel (wavenet2.cu).
+// Internal interface between the WaveNet C ABI (wavenet.cu, which also holds the general fp32 kernel) and the specialised
+// kernels.  Every create returns 0 and a handle when the configuration fits; 1 with *unsupported = 1 when the caller should
+// fall back to the general kernel; 1 with *unsupported = 0 on a real error (message set).
 #pragma once
 #include "../../include/mmk_b200.h"
-
-struct wn2_handle;
-
-// Returns 0 and a handle when the configuration fits the v2 kernel; returns 1 with *unsupported = 1 when the caller
-// should fall back to the general kernel, or 1 with *unsupported = 0 on a real error (message set).
-int wn2_create(const mmk_wavenet_desc* d, int max_batch, wn2_handle** out, int* unsupported);
-int wn2_destroy(wn2_handle* h);
-int wn2_launch_info(wn2_handle* h, mmk_launch_info* out);
-int wn2_sync_check(wn2_handle* h, void* stream);
-int wn2_run(wn2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
-            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
-            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
-            unsigned long long* d_step_ts, void* stream);
-
-// The warp-autonomous kernel (wavenet3.cu): same contract as the wn2_* functions; tried first.
-struct wn3_handle;
-int wn3_create(const mmk_wavenet_desc* d, int max_batch, wn3_handle** out, int* unsupported);
-int wn3_destroy(wn3_handle* h);
-int wn3_launch_info(wn3_handle* h, mmk_launch_info* out);
-int wn3_sync_check(wn3_handle* h, void* stream);
-int wn3_run(wn3_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t seq_t0, int64_t t_begin, int64_t t_head,
-            int64_t t_end, int teacher_forced, const float* d_temperature, int n_temperature, const float* d_noise,
-            int64_t noise_stride, int64_t noise_t0, float* d_logits_out, int64_t* d_decisions,
-            unsigned long long* d_step_ts, void* stream);
 
 // The bf16 tensor-core kernel (wavenet_tc.cu, tcgen05 + TMEM): same contract; used when compute_mode = MMK_COMPUTE_BF16_TC.
 struct wn4_handle;

@@ -59,15 +59,14 @@ def test_golden_sequences_and_logits(name):
     assert _rel_err(lg.cpu().numpy(), d["logits_t1"]) <= REL_TOL
 
 
-@pytest.mark.parametrize("kernel", ["1", "2", "3", "6"])
+@pytest.mark.parametrize("kernel", ["1", "6"])
 @pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
 @pytest.mark.parametrize("blocks,dims,res,skips,B", [((3, 3), 64, 64, 64, 11), ((4,), 128, None, None, 1),
                                                      ((2, 3), 64, None, 32, 17), ((5,), 32, 32, None, 8),
                                                      ((3, 2), 128, 128, 128, 40)])
 def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims, res, skips, B):
-    """Seeded weights/prompts, all kernels (1 = general, 2 = chain kernel, 3 = warp-autonomous kernel), every cluster
-    geometry the launcher can pick, ragged batches (B not a multiple of the 8-prompt pipeline group), with/without
-    residual and skip convs."""
+    """Seeded weights/prompts, both fp32 kernels (1 = general, 6 = layer-pipelined), every cluster geometry the launcher can
+    pick, ragged batches (B not a multiple of the pipeline group), with/without residual and skip convs."""
     if kernel != "6" and (dims % int(cluster) or (skips or dims) % int(cluster)):
         pytest.skip("dims not divisible by the cluster size")
     monkeypatch.setenv("MMK_WN_KERNEL", kernel)
@@ -91,18 +90,13 @@ def test_vs_oracle_all_cluster_sizes(monkeypatch, kernel, cluster, blocks, dims,
         assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
 
 
-@pytest.mark.parametrize("kernel,cluster,hazard,res,skips", [("1", "2", None, 64, 64), ("2", "2", "0", 64, 64),
-                                                             ("2", "4", "1", 64, 64), ("2", "2", "0", None, 64),
-                                                             ("2", "4", None, None, None), ("2", "2", "0", 64, None),
-                                                             ("3", "4", None, 64, 64), ("3", "4", None, None, 64),
-                                                             ("3", "16", None, 64, None), ("3", "8", None, None, None),
-                                                             ("3", "8", None, 64, 64),
+@pytest.mark.parametrize("kernel,cluster,hazard,res,skips", [("1", "2", None, 64, 64), ("1", "4", None, None, 64),
                                                              ("6", "2", None, 64, 64), ("6", "4", None, None, 64),
                                                              ("6", "16", None, 64, None), ("6", "8", None, None, None),
                                                              ("6", "8", None, 64, 64), ("6", "4", None, 64, None)])
 def test_multi_stage_pipeline(monkeypatch, kernel, cluster, hazard, res, skips):
-    """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups; the chain
-    kernel in both ring modes (prefetched TMA ring reads / barrier-ordered) and every residual/skip combination."""
+    """Force several pipeline stages (inter-cluster mailboxes) on a small net and many prompt groups, every residual / skip
+    combination."""
     monkeypatch.setenv("MMK_WN_KERNEL", kernel)
     monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
     monkeypatch.setenv("MMK_WN_STAGES", "4")
