@@ -49,6 +49,11 @@ struct Tier {
     int so_inw;
     const float* in_w; const float* in_b;
     float* hbuf; float* obuf;
+    // lane-major engine (Params::fast): weights packed per lane, see pack_fast() — GRU [NC][24][H/4] float4, up-sampler
+    // [NC][NV][H/4] float4, frame Linear [fs][H/4] float4 + bias [H/4] float4, gate biases [NC][24], up-sampler biases [NC][NV]
+    const float4* wg4; const float4* wu4; const float4* iw4; const float4* ib4;
+    const float* gb; const float* ub;
+    int NV;                          // up-sampler rows of a CTA (4 * up)
 };
 
 struct Params {
@@ -74,6 +79,9 @@ struct Params {
     float* logits_out; long long* decisions; unsigned long long* step_ts;
     unsigned long long* dbg;         // MMK_SR_DEBUG: time (ns) spent by CTA 0 per section
     int exp;                         // MMK_SR_EXP: timing experiments (results invalid)
+    // lane-major frame-tier engine
+    int fast, NKQ, CHP;              // K quarters (H / 128), prompts per block of the walk (2 per warp)
+    int s_part, s_hold, s_lin;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -362,10 +370,282 @@ __device__ __forceinline__ void reduce_partials(float (&acc)[16], const Map& m, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Lane-major frame-tier engine (Params::fast; H = 4 * NC, H in {128, 256, 512}, frame sizes and up-sampling factors
+// in {1, 2, 4, 8} / {1, 2, 4}).  The column split over the CTAs stays (CTA c owns hidden indices 4c .. 4c + 3 and the
+// up-sampler rows NV c .. NV c + NV - 1), but a contraction is laid out the other way round:
+//   * activations live in HBM as [prompt][H]; lane l of K-quarter warp q owns k = 128 q + 4 l .. + 3, so a warp reads
+//     its 512 bytes of a prompt's x and h rows with one coalesced 16-byte load per lane straight from L2 into
+//     REGISTERS, one iteration (two prompts) ahead of their use — no shared-memory staging, no barrier per chunk.
+//     (Measured, scripts/ubench/bulk_stream.cu: a cp.async.bulk costs its issuing thread ~600 cycles whatever its size,
+//     so one elected thread feeding 8 KB chunks tops out at 14 B/clk per SM — the first version of this engine; cluster
+//     multicast of 4 saves no L2 traffic; LDS.128 costs 4 cycles per warp instruction whatever the broadcast, which
+//     bound the tile engine.)
+//   * the lane's weights (24 float4 for the GRU, NV for the up-sampler) sit in REGISTERS for the whole firing, loaded
+//     from L2 before the grid barrier that precedes the firing — no shared-memory weight traffic at all;
+//   * the sums over k meet in a transposing shuffle tree: 16 values per lane -> 1 (a different one per lane pair) in
+//     16 SHFL + 16 FADD.  The tree levels that fold hidden indices need no selects because the weights are packed
+//     per lane with the indices pre-swapped (slot a on lane l is hidden index a ^ jm(l)); the two levels that fold
+//     gates (r, z, n_i, n_h) use selects so that the zero blocks (W_ih has no n_h column) cost no FMA;
+//   * K-quarter partials meet in shared memory; gates / biases run once per (prompt, hidden index).
+// Every CTA reads the same rows: each starts at a different prompt block (rotation), so that the grid does not ask the
+// same L2 lines in the same cycle — prompts are independent, any order gives the same bits.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NTF = 256;         // 8 warps: NKQ K-quarters x 8 / NKQ prompt groups (9 warps would cap the registers at 168)
+
+struct Fast {                    // shared-memory map of the lane-major engine
+    float* part; float4* hold; float* lin;
+    long long tl, ta[12];        // MMK_SR_DEBUG: SM cycles spent by CTA 0 per section of a firing
+    bool timing;
+};
+__device__ __forceinline__ void fast_lap(Fast& F, int slot) {
+    if (F.timing) { const long long n = clock64(); F.ta[slot] += n - F.tl; F.tl = n; }
+}
+
+// Row fast_col<NV>(l) is what lane l holds after the transposing tree over NV homogeneous values (up-sampler rows): the
+// fold level that uses lane bit (16 >> j) pairs slot i with slot i + (NV >> (j + 1)); the lane with the bit set holds
+// its slots pre-swapped (pack_up), so every lane keeps its lower half.
+template <int NV>
+__device__ __host__ __forceinline__ int fast_col(int lane) {
+    int m = 0, j = 0;
+    for (int half = NV / 2; half >= 1; half >>= 1, ++j) m |= ((lane >> (4 - j)) & 1) * half;
+    return m;
+}
+template <int NV>
+__device__ __forceinline__ bool fast_writer(int lane) {   // one lane per row writes: the lanes whose unused bits are 0
+    int used = 0, j = 0;
+    for (int half = NV / 2; half >= 1; half >>= 1, ++j) used |= 16 >> j;
+    return (lane & ~used & 31) == 0;
+}
+
+// GRU cell of frame tier T at window end tw on this CTA's 4 hidden indices (sample_rnn_v2.py:226-260, modules/io.py:106-133).
+template <int FS>
+__device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const float* cond, const float* hcur, float* hnext,
+                                         long long tw, bool pre_barrier, unsigned long long& epoch, Fast& F) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
+    const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
+    const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
+    float4 wg[24], iw[FS], ib;
+    {                                                          // issued before the barrier wait: the latency hides behind it
+        const float4* w = T.wg4 + (size_t)c * 24 * TW + kq * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) wg[i] = __ldg(w + i * TW);
+#pragma unroll
+        for (int f = 0; f < FS; ++f) iw[f] = __ldg(T.iw4 + f * TW + kq * 32 + lane);
+        ib = __ldg(T.ib4 + kq * 32 + lane);
+    }
+    fast_lap(F, 0);
+    if (pre_barrier && !grid_barrier(P, epoch)) return false;
+    fast_lap(F, 1);
+    const int Bl = (P.B + CHP - 1) / CHP * CHP, nchunk = Bl / CHP;
+    const int rot = (int)(((long long)c * nchunk) / P.NC);
+    auto rotated = [&](int ch) { const int x = ch + rot; return x >= nchunk ? x - nchunk : x; };
+    const int koff = kq * 128 + 4 * lane;
+    // the first two prompts' rows are on their way while the frame is linearised
+    float4 hn[2], cn[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const size_t row = (size_t)(rotated(0) * CHP + pg + q * NPG) * H + koff;
+        hn[q] = __ldcg(reinterpret_cast<const float4*>(hcur + row));
+        cn[q] = cond != nullptr ? __ldcg(reinterpret_cast<const float4*>(cond + row)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    const float Qf = (float)P.Q;
+    for (int idx = tid; idx < Bl * FS; idx += NTF) {           // Linearizer of the frame (modules/io.py:111-112)
+        const int p = idx / FS, f = idx - p * FS;
+        long long q = 0;
+        if (p < P.B) q = __ldcg(P.seq + (size_t)p * P.seq_stride + (tw - FS + f));
+        F.lin[idx] = linearize(q, Qf);
+    }
+    __syncthreads();
+    fast_lap(F, 2);
+    {
+        const int j_lo = c * 4, hold_kq = j_lo / 128, hold_lane = (j_lo % 128) / 4;
+        const bool b4 = (lane & 4) != 0, b2 = (lane & 2) != 0;
+        const int out_slot = (b4 ? 8 : 0) + (b2 ? 4 : 0) + (((lane >> 4) & 1) << 1 | ((lane >> 3) & 1));   // gate * 4 + hidden index
+        const bool nofma = (P.exp & 2) != 0;
+        for (int ch = 0; ch < nchunk; ++ch) {                   // the warp's two prompts of the block, interleaved for ILP
+            const int pr[2] = {rotated(ch) * CHP + pg, rotated(ch) * CHP + pg + NPG};
+            float4 h4[2], c4[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { h4[q] = hn[q]; c4[q] = cn[q]; }
+            if (ch + 1 < nchunk && !(P.exp & 1)) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const size_t row = (size_t)(rotated(ch + 1) * CHP + pg + q * NPG) * H + koff;
+                    hn[q] = __ldcg(reinterpret_cast<const float4*>(hcur + row));
+                    if (cond != nullptr) cn[q] = __ldcg(reinterpret_cast<const float4*>(cond + row));
+                }
+            }
+            if (nofma) continue;
+            float x[2][4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float* lp = F.lin + pr[q] * FS;
+                x[q][0] = x[q][1] = x[q][2] = x[q][3] = 0.0f;
+#pragma unroll
+                for (int f = 0; f < FS; ++f) {                 // FramedLinearIO: Linear(frame) + bias (+ conditioning)
+                    const float l = lp[f];
+                    x[q][0] = fmaf(l, iw[f].x, x[q][0]); x[q][1] = fmaf(l, iw[f].y, x[q][1]);
+                    x[q][2] = fmaf(l, iw[f].z, x[q][2]); x[q][3] = fmaf(l, iw[f].w, x[q][3]);
+                }
+                x[q][0] += ib.x; x[q][1] += ib.y; x[q][2] += ib.z; x[q][3] += ib.w;
+                if (cond != nullptr) { x[q][0] += c4[q].x; x[q][1] += c4[q].y; x[q][2] += c4[q].z; x[q][3] += c4[q].w; }
+            }
+            float acc[2][16];                                   // slot a * 4 + gate (r, z, n_i, n_h); a = hidden index ^ jm(lane)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 wir = wg[a], wiz = wg[4 + a], win = wg[8 + a], whr = wg[12 + a], whz = wg[16 + a], whn = wg[20 + a];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float hv[4] = {h4[q].x, h4[q].y, h4[q].z, h4[q].w};
+                    float r = wir.x * x[q][0], z = wiz.x * x[q][0], ni = win.x * x[q][0], nh = whn.x * hv[0];
+                    r = fmaf(wir.y, x[q][1], r); z = fmaf(wiz.y, x[q][1], z); ni = fmaf(win.y, x[q][1], ni); nh = fmaf(whn.y, hv[1], nh);
+                    r = fmaf(wir.z, x[q][2], r); z = fmaf(wiz.z, x[q][2], z); ni = fmaf(win.z, x[q][2], ni); nh = fmaf(whn.z, hv[2], nh);
+                    r = fmaf(wir.w, x[q][3], r); z = fmaf(wiz.w, x[q][3], z); ni = fmaf(win.w, x[q][3], ni); nh = fmaf(whn.w, hv[3], nh);
+                    r = fmaf(whr.x, hv[0], r); z = fmaf(whz.x, hv[0], z);
+                    r = fmaf(whr.y, hv[1], r); z = fmaf(whz.y, hv[1], z);
+                    r = fmaf(whr.z, hv[2], r); z = fmaf(whz.z, hv[2], z);
+                    r = fmaf(whr.w, hv[3], r); z = fmaf(whz.w, hv[3], z);
+                    acc[q][a * 4] = r; acc[q][a * 4 + 1] = z; acc[q][a * 4 + 2] = ni; acc[q][a * 4 + 3] = nh;
+                }
+            }
+            // hidden-index folds (pre-swapped slots), then gate folds (selects), then the last lane bit
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][8 + i], 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][4 + i], 8);
+            float k0[2], k1[2], kk[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float s0 = b4 ? acc[q][0] : acc[q][2], s1 = b4 ? acc[q][1] : acc[q][3];
+                k0[q] = b4 ? acc[q][2] : acc[q][0]; k1[q] = b4 ? acc[q][3] : acc[q][1];
+                k0[q] += __shfl_xor_sync(0xffffffffu, s0, 4);
+                k1[q] += __shfl_xor_sync(0xffffffffu, s1, 4);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float s2 = b2 ? k0[q] : k1[q];
+                kk[q] = b2 ? k1[q] : k0[q];
+                kk[q] += __shfl_xor_sync(0xffffffffu, s2, 2);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                kk[q] += __shfl_xor_sync(0xffffffffu, kk[q], 1);
+                if ((lane & 1) == 0) F.part[((size_t)kq * Bp + pr[q]) * 16 + out_slot] = kk[q];
+                if (kq == hold_kq && lane == hold_lane) F.hold[pr[q]] = h4[q];
+            }
+        }
+    }
+    __syncthreads();
+    fast_lap(F, 3);
+    const float* gb = T.gb + (size_t)c * 24;
+    for (int o = tid; o < Bl * 4; o += NTF) {                  // PyTorch GRU cell, gates r, z, n
+        const int p = o >> 2, jj = o & 3;
+        float sg[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sg[g] = F.part[(size_t)p * 16 + g * 4 + jj];
+        for (int q = 1; q < NKQ; ++q)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) sg[g] += F.part[((size_t)q * Bp + p) * 16 + g * 4 + jj];
+        const float r = sigmoid_acc((sg[0] + __ldg(gb + jj)) + __ldg(gb + 12 + jj));
+        const float zg = sigmoid_acc((sg[1] + __ldg(gb + 4 + jj)) + __ldg(gb + 16 + jj));
+        const float n = tanhf((sg[2] + __ldg(gb + 8 + jj)) + r * (sg[3] + __ldg(gb + 20 + jj)));
+        const float hold = reinterpret_cast<const float*>(F.hold + p)[jj];
+        const float hnew = (1.0f - zg) * n + zg * hold;
+        if (p < P.B) __stcg(hnext + (size_t)p * H + c * 4 + jj, hnew);
+    }
+    fast_lap(F, 4);
+    return true;
+}
+
+// LinearResampler rows of this CTA (modules/resamplers.py:13-23) on the freshly written hidden state: always behind a
+// grid barrier.  Row u = NV c + col of the (up * H) rows goes to obuf[u / H][prompt][u % H].
+template <int NV>
+__device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const float* hsrc, unsigned long long& epoch, Fast& F) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
+    const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
+    const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
+    float4 wu[NV];
+    {
+        const float4* w = T.wu4 + (size_t)c * NV * TW + kq * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) wu[i] = __ldg(w + i * TW);
+    }
+    fast_lap(F, 5);
+    if (!grid_barrier(P, epoch)) return false;
+    fast_lap(F, 6);
+    const int Bl = (P.B + CHP - 1) / CHP * CHP, nchunk = Bl / CHP;
+    const int rot = (int)(((long long)c * nchunk) / P.NC);
+    auto rotated = [&](int ch) { const int x = ch + rot; return x >= nchunk ? x - nchunk : x; };
+    const int koff = kq * 128 + 4 * lane;
+    {
+        const int col = fast_col<NV>(lane);
+        const bool writer = fast_writer<NV>(lane);
+        const bool nofma = (P.exp & 2) != 0;
+        float4 hn[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) hn[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)(rotated(0) * CHP + pg + q * NPG) * H + koff));
+        for (int ch = 0; ch < nchunk; ++ch) {
+            float4 h4[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) h4[q] = hn[q];
+            if (ch + 1 < nchunk && !(P.exp & 1)) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) hn[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)(rotated(ch + 1) * CHP + pg + q * NPG) * H + koff));
+            }
+            if (nofma) continue;
+            float acc[2][NV];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    float a = wu[i].x * h4[q].x;
+                    a = fmaf(wu[i].y, h4[q].y, a); a = fmaf(wu[i].z, h4[q].z, a); a = fmaf(wu[i].w, h4[q].w, a);
+                    acc[q][i] = a;
+                }
+            }
+            int bit = 16;
+#pragma unroll
+            for (int half = NV / 2; half >= 1; half >>= 1, bit >>= 1)
+#pragma unroll
+                for (int i = 0; i < half; ++i)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][half + i], bit);
+#pragma unroll
+            for (; bit >= 1; bit >>= 1)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) acc[q][0] += __shfl_xor_sync(0xffffffffu, acc[q][0], bit);
+            if (writer)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) F.part[((size_t)kq * Bp + rotated(ch) * CHP + pg + q * NPG) * 16 + col] = acc[q][0];
+        }
+    }
+    __syncthreads();
+    fast_lap(F, 7);
+    const float* ub = T.ub + (size_t)c * NV;
+    for (int o = tid; o < Bl * NV; o += NTF) {
+        const int p = o / NV, col = o - p * NV;
+        float sv = F.part[(size_t)p * 16 + col];
+        for (int q = 1; q < NKQ; ++q) sv += F.part[((size_t)q * Bp + p) * 16 + col];
+        sv += __ldg(ub + col);
+        const int urow = c * NV + col, slot = urow / H, kk = urow - slot * H;
+        if (p < P.B) __stcg(T.obuf + ((size_t)slot * Bp + p) * H + kk, sv);
+    }
+    fast_lap(F, 8);
+    return true;
+}
+
 enum { BAR_HID = 0, BAR_Z, BAR_Q, BAR_COUNT };
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_constant__ Params P) {
+template <bool FAST>
+__global__ void __launch_bounds__(FAST ? NTF : NT, 1) samplernn_cluster_kernel(const __grid_constant__ Params P) {
+    constexpr int NTK = FAST ? NTF : NT;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, NC = P.NC, H = P.H, Bp = P.Bp, CS = P.CS;
@@ -383,7 +663,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
     for (int r = 0; r < P.n_res; ++r) {   // resident pieces (what does not fit is streamed from L2 when used)
         const float4* src = reinterpret_cast<const float4*>(gblock + P.res_goff[r]);
         float4* dst = reinterpret_cast<float4*>(smem + P.res_soff[r]);
-        for (int i = tid; i < P.res_len[r] / 4; i += NT) dst[i] = __ldg(src + i);
+        for (int i = tid; i < P.res_len[r] / 4; i += NTK) dst[i] = __ldg(src + i);
     }
     const int GP = P.GP, npq_h = GP >> 2;
     const unsigned hid_bytes = (unsigned)(CS * P.RS * GP) * 4u;
@@ -399,6 +679,12 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
     __syncthreads();
     cluster_sync_all();
 
+    Fast F{};
+    if (FAST) {
+        F.part = smem + P.s_part; F.hold = reinterpret_cast<float4*>(smem + P.s_hold); F.lin = smem + P.s_lin;
+        F.timing = P.dbg && c == 0 && tid == 0; F.tl = clock64();
+        for (int i = 0; i < 12; ++i) F.ta[i] = 0;
+    }
     const int j_lo = c * P.JP;
     const int rot = (int)(((unsigned)c * 11u) % (unsigned)(H / KC));   // reduced modulo the chunk count where used
     int hsel[MAX_TIERS];
@@ -406,7 +692,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
     for (int i = 0; i < MAX_TIERS; ++i) hsel[i] = P.hsel[i];
     unsigned long long epoch = 0;
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = globaltimer();
-    auto lap = [&](int slot) { if (P.dbg && c == 0 && tid == 0) { const unsigned long long n = globaltimer(); tacc[slot] += n - tlast; tlast = n; } };
+    auto lap = [&](int slot) { if (!FAST && P.dbg && c == 0 && tid == 0) { const unsigned long long n = globaltimer(); tacc[slot] += n - tlast; tlast = n; } };
     unsigned head_phase = 0;              // completed head exchanges (parity of the three mbarriers)
     bool dead = false;
     bool heads_pending = false;           // head steps ran since the last grid barrier
@@ -422,6 +708,41 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
             const long long tw = t + off;   // the window ends at data index tw (exclusive)
             // ---------------- frame tiers (weight-stationary over the whole grid) ----------------
             bool fired = false;
+            if constexpr (FAST) {
+                bool pending_up = false;
+                for (int i = 0; i < P.n_ft && !dead; ++i) {
+                    const Tier& T = P.tiers[i];
+                    if (t % T.fs != 0) continue;
+                    fast_lap(F, 11);
+                    const bool pre = pending_up || heads_pending;     // last head samples / last up-sampler rows must be visible
+                    heads_pending = false;
+                    fired = true;
+                    const float* cond = nullptr;
+                    if (i > 0) cond = P.tiers[i - 1].obuf + (size_t)((t / T.fs) % T.kdiv) * H * Bp;
+                    const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
+                    float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
+                    bool ok = false;
+                    switch (T.fs) {
+                        case 1: ok = fast_gru<1>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                        case 2: ok = fast_gru<2>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                        case 4: ok = fast_gru<4>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                        default: ok = fast_gru<8>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                    }
+                    hsel[i] ^= 1;
+                    if (ok) switch (T.NV) {
+                        case 4: ok = fast_up<4>(P, T, hnext, epoch, F); break;
+                        case 8: ok = fast_up<8>(P, T, hnext, epoch, F); break;
+                        default: ok = fast_up<16>(P, T, hnext, epoch, F); break;
+                    }
+                    if (!ok) { dead = true; break; }
+                    pending_up = true;
+                }
+                if (pending_up && !dead) {
+                    if (gen || t == t_hi - 1) { if (!grid_barrier(P, epoch)) dead = true; }   // the head reads the bottom tier's rows
+                    else heads_pending = true;                               // warm-up: the next firing's barrier covers it
+                    fast_lap(F, 9);
+                }
+            } else {
             for (int i = 0; i < P.n_ft && !dead; ++i) {
                 const Tier& T = P.tiers[i];
                 if (t % T.fs != 0) continue;
@@ -445,12 +766,12 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 const float* inw_s = w_s + T.so_inw;
                 const int fs = T.fs;
                 // ---- GRU cell on this CTA's hidden indices ----
-                const int cap_g = min(PBW, (NT / (P.NG >> 2)) << 2);
+                const int cap_g = min(PBW, (NTK / (P.NG >> 2)) << 2);
                 float* gh_s = region + P.region - P.NG * PBW;          // [NG][pbw] hidden-side gate pre-activations
                 for (int pb0 = 0; pb0 < Bl; pb0 += cap_g) {
                     const int pbw = min(cap_g, Bl - pb0);
                     float* lin_s = gi_s;
-                    for (int idx = tid; idx < fs * pbw; idx += NT) {
+                    for (int idx = tid; idx < fs * pbw; idx += NTK) {
                         const int f = idx / pbw, p = idx - f * pbw, b = pb0 + p;
                         long long q = 0;
                         if (b < P.B) q = __ldcg(P.seq + (size_t)b * P.seq_stride + (tw - fs + f));
@@ -495,7 +816,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                         }
                     }
                     __syncthreads();
-                    for (int o = tid; o < P.JP * pbw; o += NT) {      // PyTorch GRU cell, gates r, z, n
+                    for (int o = tid; o < P.JP * pbw; o += NTK) {      // PyTorch GRU cell, gates r, z, n
                         const int jj = o / pbw, p = o - jj * pbw;
                         const int cr = jj, cz = P.JP + jj, cn = 2 * P.JP + jj;
                         const float r = sigmoid_acc(gi_s[cr * pbw + p] + gh_s[cr * pbw + p]);
@@ -517,7 +838,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                     const float* Wup_g = gblock + T.off_wup;
                     const float* Wup = T.so_wup >= 0 ? w_s + T.so_wup : nullptr;
                     const float* bup = T.so_wup >= 0 ? Wup + (size_t)H * T.NU : Wup_g + (size_t)H * T.NU;
-                    const int cap_u = min(PBW, (NT / (T.NU >> 2)) << 2);
+                    const int cap_u = min(PBW, (NTK / (T.NU >> 2)) << 2);
                     for (int pb0 = 0; pb0 < Bl; pb0 += cap_u) {
                         const int pbw = min(cap_u, Bl - pb0);
                         const Map m = make_map(T.NU >> 2, pbw, P.region, H, Wup == nullptr, P.xstage, P.wstage);
@@ -546,6 +867,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 if (!grid_barrier(P, epoch)) { dead = true; break; }
                 lap(6);
             }
+            }
             if (!gen || dead) continue;
 
             // ---------------- sample-level tier + head + sampler: cluster-local, 8 prompts per group ----------------
@@ -568,8 +890,8 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 const int b0 = g * GP;
                 const unsigned par = head_phase & 1u;
                 // -- 1. this CTA's rows of x = Conv1d(lin(q[t-fs:t])) + conditioning (modules/io.py:185-198)
-                for (int idx = tid; idx < KS * GP; idx += NT) {
-                    const int kl = idx / GP, p = idx - kl * GP, k = rank * KS + kl, b = b0 + p;
+                for (int idx = tid; idx < KS * GP; idx += NTK) {
+                    const int kl = FAST ? idx % KS : idx / GP, p = FAST ? idx / KS : idx - kl * GP, k = rank * KS + kl, b = b0 + p;
                     float a = 0.0f;
                     for (int f = 0; f < fsl; ++f) {
                         long long q = 0;
@@ -580,8 +902,8 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                         a = fmaf(linearize(q, Qf), __ldg(P.conv_w + (size_t)k * fsl + f), a);
                     }
                     a += __ldg(P.conv_b + k);
-                    a += (b < P.B) ? __ldcg(condL + (size_t)k * Bp + b) : 0.0f;
-                    xh[idx] = a;
+                    a += (b < P.B) ? __ldcg(FAST ? condL + (size_t)b * H + k : condL + (size_t)k * Bp + b) : 0.0f;
+                    xh[kl * GP + p] = a;
                 }
                 __syncthreads();
                 // -- 2. partial hidden over this CTA's K slice, reduce-scattered by hidden row
@@ -590,7 +912,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                     int nq = HT / tiles, p2 = 1;
                     while (p2 * 2 <= nq && p2 * 2 <= KS) p2 *= 2;
                     nq = p2;
-                    for (int tb = 0; tb < tiles * nq; tb += NT) {   // one pass unless the head is very wide
+                    for (int tb = 0; tb < tiles * nq; tb += NTK) {   // one pass unless the head is very wide
                         const int id = tb + tid;
                         if (id < tiles * nq) {
                             const int tile = id % tiles, s = id / tiles, rq = tile / npq_h, pq = tile - rq * npq_h;
@@ -612,7 +934,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                         }
                     }
                     __syncthreads();
-                    for (int i = tid; i < Hh * npq_h; i += NT) {
+                    for (int i = tid; i < Hh * npq_h; i += NTK) {
                         const int row = i / npq_h, half = i - row * npq_h, tile = (row >> 2) * npq_h + half;
                         float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         for (int s = 0; s < nq; ++s) {
@@ -628,7 +950,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 dead |= !mbar_wait(bar(BAR_HID), par, abort_flag);
                 if (tid == 0) mbar_expect_tx(bar(BAR_HID), hid_bytes);
                 // -- 3. hidden rows of this CTA: sum the partials in rank order, bias, Mish (mlp.py:44-53)
-                for (int i = tid; i < RS * GP; i += NT) {
+                for (int i = tid; i < RS * GP; i += NTK) {
                     float s = 0.0f;
                     for (int src = 0; src < CS; ++src) s += inbox_h[src * RS * GP + i];
                     hid_s[i] = mish_acc(s + b1s[i / GP]);
@@ -637,7 +959,7 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
                 // -- 4. partial logits over this CTA's hidden rows, reduce-scattered by prompt
                 {
                     const int tiles = (ZR >> 2) * npq_h;
-                    for (int tile = tid; tile < tiles; tile += NT) {
+                    for (int tile = tid; tile < tiles; tile += NTK) {
                         const int rq = tile / npq_h, pq = tile - rq * npq_h;
                         float acc[16];
 #pragma unroll
@@ -703,11 +1025,14 @@ __global__ void __launch_bounds__(NT, 1) samplernn_cluster_kernel(const __grid_c
             }
             heads_pending = true;
             lap(7);
+            if (FAST) fast_lap(F, 10);
             if (c == 0 && tid == 0 && P.step_ts) P.step_ts[hstep] = globaltimer();
         }
     }
     if (P.dbg && c == 0 && tid == 0)
         for (int i = 0; i < 8; ++i) P.dbg[i] += tacc[i];
+    if (FAST && F.timing)
+        for (int i = 0; i < 12; ++i) P.dbg[8 + i] += (unsigned long long)F.ta[i];
     // no CTA may exit while peers can still store into its shared memory
     __syncthreads();
     cluster_sync_all();
@@ -734,17 +1059,18 @@ int sr2_destroy(sr2_handle* h) {
     return 0;
 }
 
-static int sr2_max_clusters(int CS, size_t smem, int sms) {
-    const void* k = (const void*)samplernn_cluster_kernel;
+static int sr2_max_clusters(int CS, size_t smem, int sms, bool fast) {
+    const void* k = fast ? (const void*)samplernn_cluster_kernel<true> : (const void*)samplernn_cluster_kernel<false>;
+    const int NTH = fast ? NTF : NT;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (CS == 1) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NTH, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
         return per_sm * sms;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CS * 4);
-    cfg.blockDim = dim3(NT);
+    cfg.blockDim = dim3(NTH);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -753,6 +1079,111 @@ static int sr2_max_clusters(int CS, size_t smem, int sms) {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+
+// ---- lane-major engine: plan (shared-memory map, cluster size) and per-lane weight packing
+static bool fast_supported(const mmk_samplernn_desc* d, int sms) {
+    const int n_ft = d->n_tiers - 1, H = d->hidden_dim;
+    if (getenv("MMK_SR_ENGINE") && atoi(getenv("MMK_SR_ENGINE")) == 2) return false;     // 2: the tile engine
+    if (H % 128 != 0 || (H != 128 && H != 256 && H != 512) || H / 4 > sms || d->head_hidden % 4 != 0 || n_ft > MAX_TIERS) return false;
+    for (int i = 0; i < n_ft; ++i) {
+        const int fs = d->frame_sizes[i], nxt = i < n_ft - 1 ? d->frame_sizes[i + 1] : 1;
+        if (fs != 1 && fs != 2 && fs != 4 && fs != 8) return false;
+        if (fs % nxt != 0) return false;
+        const int up = fs / nxt;
+        if (up != 1 && up != 2 && up != 4) return false;
+    }
+    return true;
+}
+
+static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sms, int max_optin, Params* out, size_t* out_smem) {
+    const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels, NC = H / 4;
+    if (NC % CS || H % CS || Hh % CS) return false;
+    Params p{};
+    const int GP = CS == 8 ? 8 : 4;
+    p.fast = 1; p.NKQ = H / 128; p.CHP = 16 / p.NKQ;
+    p.n_ft = n_ft; p.H = H; p.Hh = Hh; p.Q = Q; p.NC = NC; p.CS = CS; p.GP = GP;
+    p.JP = 4; p.NG = 12;
+    p.fs_last = d->frame_sizes[n_ft]; p.fs_lt = d->frame_sizes[n_ft - 1];
+    p.KS = H / CS; p.RS = Hh / CS; p.ZR = pad4(Q + 1);
+    p.min_temp = d->min_temperature;
+    p.Bp = (max_batch + p.CHP - 1) / p.CHP * p.CHP;
+    int o = 0, fs_max = 1;
+    auto take = [&](int floats) { int r = o; o += pad4(floats); return r; };
+    for (int i = 0; i < n_ft; ++i) {
+        Tier& T = p.tiers[i];
+        T.fs = d->frame_sizes[i];
+        T.up = T.fs / (i < n_ft - 1 ? d->frame_sizes[i + 1] : 1);
+        T.kdiv = i > 0 ? d->frame_sizes[i - 1] / T.fs : 1;
+        T.up_rows = T.up * H;
+        T.NV = 4 * T.up; T.NU = T.NV;
+        T.so_wih = T.so_whh = T.so_wup = T.so_inw = -1;
+        fs_max = std::max(fs_max, T.fs);
+    }
+    p.off_w1 = take(p.KS * Hh);
+    p.off_b1 = take(p.RS);
+    p.off_w2 = take(p.RS * p.ZR);
+    p.cta_block = o;
+    // head buffers
+    int ho = 0;
+    auto htake = [&](int floats) { int r = ho; ho += pad4(floats); return r; };
+    p.h_x = htake(p.KS * GP);
+    p.h_inh = htake(Hh * GP);
+    p.h_hid = htake(p.RS * GP);
+    p.h_un = ho;
+    const int tiles_h = (Hh / 4) * (GP / 4);
+    int nq = std::max(1, HT / tiles_h), p2 = 1;
+    while (p2 * 2 <= nq && p2 * 2 <= p.KS) p2 *= 2;
+    const int part_floats = tiles_h * p2 * 16;
+    const int inz_floats = GP * p.ZR;
+    p.h_zs = p.h_un + pad4(inz_floats);
+    const int head_floats = ho + std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
+    const int budget = max_optin / (int)sizeof(float) - 256;
+    o = 0;
+    p.region = head_floats;
+    p.xregion = p.wregion = p.xstage = p.wstage = 0;
+    p.s_region = take(p.region);
+    p.s_gi = o;
+    p.s_bar = take(2 * BAR_COUNT + 16 * GP);
+    p.s_part = take(p.NKQ * p.Bp * 16);
+    p.s_hold = take(p.Bp * 4);
+    p.s_lin = take(p.Bp * fs_max);
+    p.n_res = 0;
+    bool ok = true;
+    auto resident = [&](int goff, int len, int* soff) {
+        len = pad4(len);
+        if (o + len > budget) { ok = false; return; }
+        *soff = o;
+        p.res_goff[p.n_res] = goff; p.res_soff[p.n_res] = o; p.res_len[p.n_res] = len; ++p.n_res;
+        o += len;
+    };
+    resident(p.off_w1, p.KS * Hh, &p.so_w1);
+    resident(p.off_b1, p.RS, &p.so_b1);
+    resident(p.off_w2, p.RS * p.ZR, &p.so_w2);
+    if (!ok) return false;
+    p.smem_floats = o;
+    const size_t smem = (size_t)o * sizeof(float);
+    const int max_clusters = sr2_max_clusters(CS, smem, sms, true);
+    if (getenv("MMK_SR_DEBUG"))
+        fprintf(stderr, "[sr2] lane-major engine: CS=%d NC=%d GP=%d smem=%zu max_clusters=%d\n", CS, NC, GP, smem, max_clusters);
+    if (max_clusters * CS < NC) return false;
+    *out = p; *out_smem = smem;
+    return true;
+}
+
+// Per-lane packing.  Thread t = 32 q + l of a weight row owns k = 4 t .. 4 t + 3 (q = K quarter, l = lane).
+//   GRU, CTA c, entry w = m * 12 + gate * 4 + a (m: 0 W_ih, 1 W_hh; gate r, z, n; slot a): row gate * H + 4 c + (a ^ jm(l)),
+//   jm(l) = (lane bit 16) * 2 + (lane bit 8) — the two hidden-index folds of the shuffle tree keep the lower half on every lane.
+//   up-sampler, CTA c, slot i: row NV c + (i ^ fast_col<NV>(l)).
+template <int NV>
+static void pack_up(float* dst, const float* up_w, int c, int H) {
+    const int TW = H / 4;
+    for (int i = 0; i < NV; ++i)
+        for (int t = 0; t < TW; ++t) {
+            const int row = c * NV + (i ^ fast_col<NV>(t & 31));
+            for (int kk = 0; kk < 4; ++kk) dst[((size_t)i * TW + t) * 4 + kk] = up_w[(size_t)row * H + 4 * t + kk];
+        }
 }
 
 int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int* unsupported) {
@@ -772,7 +1203,13 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     size_t best_smem = 0;
     bool found = false;
     const int groups_per_cluster_max = 16;
+    if (fast_supported(d, sms))
+        for (int CS : {4, 8, 2, 1}) {
+            if (force_cs && atoi(force_cs) != CS) continue;
+            if (plan_fast(d, max_batch, CS, sms, max_optin, &best, &best_smem)) { found = true; break; }
+        }
     for (int CS : {8, 4, 2, 1}) {
+        if (found) break;
         if (force_cs && atoi(force_cs) != CS) continue;
         if (H % CS || Hh % CS) continue;
         // NC: the largest multiple of CS that divides H (GRU rows split evenly by hidden index) and fits the device
@@ -868,7 +1305,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         const int un_floats = std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
         if (ho + un_floats > REGION || p.NG * PBW * 2 > REGION) continue;
         const size_t smem = (size_t)o * sizeof(float);
-        const int max_clusters = sr2_max_clusters(CS, smem, sms);
+        const int max_clusters = sr2_max_clusters(CS, smem, sms, false);
         if (getenv("MMK_SR_DEBUG")) {
             fprintf(stderr, "[sr2] CS=%d NC=%d GP=%d smem=%zu max_clusters=%d resident:", CS, NC, GP, smem, max_clusters);
             for (int i = 0; i < n_ft; ++i) fprintf(stderr, " t%d(ih=%d hh=%d up=%d)", i, p.tiers[i].so_wih >= 0, p.tiers[i].so_whh >= 0, p.tiers[i].so_wup >= 0);
@@ -884,9 +1321,10 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     p = best;
     h->smem_bytes = best_smem;
     h->max_batch = max_batch; h->rf = d->frame_sizes[0];
-    p.Bp = (max_batch + 3) / 4 * 4;
+    if (!p.fast) p.Bp = (max_batch + 3) / 4 * 4;
     const int NC = p.NC, CS = p.CS, GP = p.GP;
-    MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    if (p.fast) MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    else MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     {
         const int n_groups = (max_batch + GP - 1) / GP, n_clusters = NC / CS;
         if ((n_groups + n_clusters - 1) / n_clusters > groups_per_cluster_max) { sr2_destroy(h); *unsupported = 1; return 1; }
@@ -897,7 +1335,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     for (int c = 0; c < NC; ++c) {
         float* blk = wpack.data() + (size_t)c * p.cta_block;
         const int j_lo = c * p.JP, rank = c % CS;
-        for (int i = 0; i < n_ft; ++i) {
+        for (int i = 0; i < n_ft && !p.fast; ++i) {
             const Tier& T = p.tiers[i];
             for (int m = 0; m < 2; ++m) {
                 const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
@@ -945,6 +1383,38 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         h->hbuf_floats[i] = (size_t)2 * H * p.Bp;
         T.hbuf = up(nullptr, h->hbuf_floats[i]);
         T.obuf = up(nullptr, (size_t)T.up_rows * p.Bp);
+        if (!p.fast) continue;
+        const int TW = H / 4;
+        std::vector<float> wg((size_t)NC * 24 * TW * 4), wu((size_t)NC * T.NV * TW * 4), iw((size_t)T.fs * TW * 4), gb((size_t)NC * 24),
+            ub((size_t)NC * T.NV);
+        for (int c = 0; c < NC; ++c) {
+            for (int m = 0; m < 2; ++m) {
+                const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
+                const float* b = m == 0 ? d->b_ih[i] : d->b_hh[i];
+                for (int g = 0; g < 3; ++g)
+                    for (int a = 0; a < 4; ++a) {
+                        for (int t = 0; t < TW; ++t) {
+                            const int l = t & 31, jm = ((l >> 4) & 1) << 1 | ((l >> 3) & 1), row = g * H + 4 * c + (a ^ jm);
+                            for (int kk = 0; kk < 4; ++kk)
+                                wg[(((size_t)c * 24 + m * 12 + g * 4 + a) * TW + t) * 4 + kk] = W[(size_t)row * H + 4 * t + kk];
+                        }
+                        gb[(size_t)c * 24 + m * 12 + g * 4 + a] = b[g * H + 4 * c + a];
+                    }
+            }
+            float* wuc = wu.data() + (size_t)c * T.NV * TW * 4;
+            if (T.NV == 4) pack_up<4>(wuc, d->up_w[i], c, H);
+            else if (T.NV == 8) pack_up<8>(wuc, d->up_w[i], c, H);
+            else pack_up<16>(wuc, d->up_w[i], c, H);
+            for (int col = 0; col < T.NV; ++col) ub[(size_t)c * T.NV + col] = d->up_b[i][c * T.NV + col];
+        }
+        for (int f = 0; f < T.fs; ++f)
+            for (int k = 0; k < H; ++k) iw[(size_t)f * H + k] = d->in_w[i][(size_t)k * T.fs + f];
+        T.wg4 = reinterpret_cast<const float4*>(up(wg.data(), wg.size()));
+        T.wu4 = reinterpret_cast<const float4*>(up(wu.data(), wu.size()));
+        T.iw4 = reinterpret_cast<const float4*>(up(iw.data(), iw.size()));
+        T.ib4 = reinterpret_cast<const float4*>(T.in_b);
+        T.gb = up(gb.data(), gb.size());
+        T.ub = up(ub.data(), ub.size());
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
     p.conv_b = up(d->conv_b, H);
@@ -953,7 +1423,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     ok = ok && p.bar;
     if (!ok) { sr2_destroy(h); MMK_FAIL("cudaMalloc failed while creating the SampleRNN handle"); }
     p.abort_flag = (unsigned*)(p.bar + 1);
-    if (getenv("MMK_SR_DEBUG")) p.dbg = (unsigned long long*)dev_alloc(64, nullptr);
+    if (getenv("MMK_SR_DEBUG")) p.dbg = (unsigned long long*)dev_alloc(256, nullptr);
     if (const char* e = getenv("MMK_SR_EXP")) p.exp = atoi(e);
     MMK_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -961,7 +1431,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
 }
 
 int sr2_launch_info(sr2_handle* h, mmk_launch_info* out) {
-    out->cluster_size = h->p.CS; out->n_stages = h->p.NC / h->p.CS; out->group_size = h->p.GP; out->threads = NT;
+    out->cluster_size = h->p.CS; out->n_stages = h->p.NC / h->p.CS; out->group_size = h->p.GP; out->threads = h->p.fast ? NTF : NT;
     out->smem_bytes = (int)h->smem_bytes; out->sm_used = h->p.NC;
     return 0;
 }
@@ -972,9 +1442,17 @@ int sr2_sync_check(sr2_handle* h, void* stream) {
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MMK_CHECK(aborted == 0, "SampleRNN kernel watchdog fired: a barrier wait timed out (results invalid)");
     if (h->p.dbg) {
-        unsigned long long t[8];
+        unsigned long long t[20];
         MMK_CUDA(cudaMemcpy(t, h->p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
         MMK_CUDA(cudaMemset(h->p.dbg, 0, sizeof(t)));
+        if (h->p.fast) {
+            static const char* names[12] = {"weights", "pre-barrier", "frame", "gru stream", "gates", "up weights", "barrier", "up stream", "up rows",
+                                            "last barrier", "head", "other"};
+            fprintf(stderr, "[sr2] CTA0 Mcycles:");
+            for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.1f", names[i], t[8 + i] / 1e6);
+            fprintf(stderr, "\n");
+            return 0;
+        }
         fprintf(stderr, "[sr2] CTA0 ms: other %.2f pre-barrier %.2f gemm_ih %.2f gemm_hh+gate %.2f barrier %.2f up %.2f barrier %.2f head %.2f\n",
                 t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6, t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6);
     }
@@ -1006,7 +1484,7 @@ int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.NC);
-    cfg.blockDim = dim3(NT);
+    cfg.blockDim = dim3(p.fast ? NTF : NT);
     cfg.dynamicSmemBytes = h->smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1014,7 +1492,7 @@ int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     at[0].val.clusterDim.x = p.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     void* args[] = {&p};
-    MMK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)samplernn_cluster_kernel, args));
+    MMK_CUDA(cudaLaunchKernelExC(&cfg, p.fast ? (const void*)samplernn_cluster_kernel<true> : (const void*)samplernn_cluster_kernel<false>, args));
     // the hidden ping-pong advances once per tier firing: keep the handle's view in step with the device
     for (int i = 0; i < p.n_ft; ++i) {
         const long long fs = p.tiers[i].fs;

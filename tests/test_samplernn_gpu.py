@@ -134,6 +134,38 @@ def test_cluster_kernel_vs_oracle(monkeypatch, cluster, ctas, fs, H, B, P):
     assert _rel_err(lg.cpu().numpy(), ref_logits) <= REL_TOL
 
 
+@pytest.mark.parametrize("cluster", [None, "1", "2", "8"])
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 43), ((8, 2, 1), 512, 128, 24), ((4, 4), 256, 3, 16), ((8, 4, 2, 1), 128, 22, 27),
+                                      ((4, 2), 128, 9, 10), ((8, 4, 2), 256, 70, 40), ((2, 2, 1), 128, 5, 9), ((2, 1, 1), 128, 4, 8)])
+def test_lane_major_engine_vs_oracle(monkeypatch, cluster, fs, H, B, P):
+    """The lane-major frame-tier engine of samplernn2.cu (H in {128, 256, 512}: weights in registers, [prompt][H] rows
+    prefetched into registers, transposing shuffle trees): every supported K-quarter count, up-sampling factor and frame
+    size, ragged batches, all cluster sizes of the head; sequences bit-exact, logits in tolerance."""
+    if cluster is not None:
+        monkeypatch.setenv("MMK_SR_CLUSTER", cluster)
+    net = make_net(fs, H, mlp_dim=32, seed=5)
+    try:
+        info = net.launch_info(B)
+    except _capi.MmkError as e:   # this cluster size cannot host the net
+        pytest.skip(str(e))
+    assert info["threads"] == 256 and info["sm_used"] == H // 4, info     # the lane-major engine, one CTA per 4 hidden units
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    g = torch.Generator().manual_seed(17)
+    n = 21
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    sub = list(range(B)) if B <= 40 else [0, 1, B // 2, B - 2, B - 1]
+    for temp in (None, 0.95):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), n, temp, noise[sub].numpy())
+        assert _rel_err(logits.cpu().numpy()[sub][:, 0], ref_logits[:, 0]) <= REL_TOL
+        assert np.array_equal(seq.cpu().numpy()[sub], ref_seq), (cluster, temp)
+        assert _rel_err(logits.cpu().numpy()[sub], ref_logits) <= REL_TOL
+    lg, dec = net.teacher_forced(torch.from_numpy(ref_seq), P, 0.95, noise[sub])
+    assert np.array_equal(dec.cpu().numpy(), ref_seq[:, P:])
+    assert _rel_err(lg.cpu().numpy(), ref_logits) <= REL_TOL
+
+
 def test_stepwise_protocol_and_loop():
     """before_generate / generate_step / after_generate == whole-sequence path == oracle; GenerateLoopV2 integration as
     the reference's tests/test_sample_rnn.py:90-112 (batch 2, 512-sample prompt + 512 steps, temperature=(1.,))."""
