@@ -356,7 +356,9 @@ def run_b200(args):
         sm_mhz = ck["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         info = net.launch_info(B)
-        kname = {"wavenet": "wavenet_tc_kernel" if args.dtype == "bf16" else "wavenet6_kernel",
+        # bf16: the layer-pipelined tcgen05 kernel hosts 16-prompt groups on one CTA per layer; anything else is the fall-back
+        tc_name = "wavenet7_kernel" if (info.get("group_size") == 16 and info.get("n_stages", 0) > 1) else "wavenet_tc_kernel"
+        kname = {"wavenet": tc_name if args.dtype == "bf16" else "wavenet6_kernel",
                  "samplernn": "samplernn_cluster_kernel"}[wl]
         tr = NCU_TRAFFIC.get(kname)
         if args.dtype == "bf16":
@@ -371,9 +373,10 @@ def run_b200(args):
                     "latency_floor_us": latency_floor_us(wl, sm_mhz),
                     "latency_floor_note": "dependency-chain floor of one generated sample in this decomposition (see "
                                           "bench.py latency_floor_us); p50_step_latency_us is the measured counterpart"}
-        # dram bytes of one launch from the ncu --set full capture, scaled from the captured horizon to this one (the
-        # traffic is per generated sample: ring spill, mailboxes, logits/sequence writes); null when no capture is committed
-        roof["traffic"] = None if not tr else tr["dram_bytes"] * (B * n) / max(1, tr["prompts"] * tr["n_steps"])
+        # dram bytes of one launch from the committed ncu capture (profiles/ncu_traffic.json), scaled from the captured launch to
+        # this one by the samples a launch pushes through the net (prompt prefill + generated, per prompt: sequence reads, ring
+        # spill, mailboxes, sequence writes all go with them); null when no capture is committed
+        roof["traffic"] = None if not tr else tr["dram_bytes"] * (B * (P + n)) / max(1, tr["prompts"] * (tr["prompt_len"] + tr["n_steps"]))
         if tr:
             roof["traffic_source"] = tr.get("source")
         line = {
