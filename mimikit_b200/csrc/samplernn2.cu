@@ -394,6 +394,15 @@ __device__ __forceinline__ void reduce_partials(float (&acc)[16], const Map& m, 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NTF = 256;         // 8 warps: NKQ K-quarters x 8 / NKQ prompt groups (9 warps would cap the registers at 168)
 
+// Packed fp32 pairs (FFMA2 / FADD2, sm_100): one issue slot for two IEEE fp32 operations (the FMA pipe still spends two cycles —
+// scripts/ubench/ffma2_bench.cu — so this buys issue slots for the shuffles, not FMA throughput)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 shfl2(u64 v, int bit) { return __shfl_xor_sync(0xffffffffu, v, bit); }
+
 struct Fast {                    // shared-memory map of the lane-major engine
     float* part; float4* hold; float* lin;
     long long tl, ta[12];        // MMK_SR_DEBUG: SM cycles spent by CTA 0 per section of a firing
@@ -426,15 +435,17 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
     const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
     const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
-    float4 wg[24], iw[FS], ib;
+    // 48 weight pairs per lane (pack_fast): [0,16) (W_ir, W_iz)[slot a][k], [16,24) (W_in[2a'], W_in[2a'+1])[k], [24,48) the same of W_hh
+    ulonglong2 wq[24], iw[FS], ib;
     {                                                          // issued before the barrier wait: the latency hides behind it
-        const float4* w = T.wg4 + (size_t)c * 24 * TW + kq * 32 + lane;
+        const ulonglong2* w = reinterpret_cast<const ulonglong2*>(T.wg4) + (size_t)c * 24 * TW + kq * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) wg[i] = __ldg(w + i * TW);
+        for (int i = 0; i < 24; ++i) wq[i] = __ldg(w + i * TW);
 #pragma unroll
-        for (int f = 0; f < FS; ++f) iw[f] = __ldg(T.iw4 + f * TW + kq * 32 + lane);
-        ib = __ldg(T.ib4 + kq * 32 + lane);
+        for (int f = 0; f < FS; ++f) iw[f] = __ldg(reinterpret_cast<const ulonglong2*>(T.iw4) + f * TW + kq * 32 + lane);
+        ib = __ldg(reinterpret_cast<const ulonglong2*>(T.ib4) + kq * 32 + lane);
     }
+#define WQ(e) (((e) & 1) ? wq[(e) >> 1].y : wq[(e) >> 1].x)
     fast_lap(F, 0);
     if (pre_barrier && !grid_barrier(P, epoch)) return false;
     fast_lap(F, 1);
@@ -478,52 +489,73 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
                 }
             }
             if (nofma) continue;
-            float x[2][4];
+            float kk[2];
+            u64 rz[2][4], ni[2][2], nh[2][2];                   // (r, z) of slot a; (n_i, n_h) of slots 2a', 2a'+1; slot a = hidden index ^ jm(lane)
+            u64 xd[2][4], hd[2][4];                             // (x_k, x_k), (h_k, h_k)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const float* lp = F.lin + pr[q] * FS;
-                x[q][0] = x[q][1] = x[q][2] = x[q][3] = 0.0f;
+                u64 x01 = 0ull, x23 = 0ull;
 #pragma unroll
                 for (int f = 0; f < FS; ++f) {                 // FramedLinearIO: Linear(frame) + bias (+ conditioning)
                     const float l = lp[f];
-                    x[q][0] = fmaf(l, iw[f].x, x[q][0]); x[q][1] = fmaf(l, iw[f].y, x[q][1]);
-                    x[q][2] = fmaf(l, iw[f].z, x[q][2]); x[q][3] = fmaf(l, iw[f].w, x[q][3]);
+                    const u64 ll = pack2(l, l);
+                    x01 = fma2(ll, iw[f].x, x01); x23 = fma2(ll, iw[f].y, x23);
                 }
-                x[q][0] += ib.x; x[q][1] += ib.y; x[q][2] += ib.z; x[q][3] += ib.w;
-                if (cond != nullptr) { x[q][0] += c4[q].x; x[q][1] += c4[q].y; x[q][2] += c4[q].z; x[q][3] += c4[q].w; }
+                x01 = add2(x01, ib.x); x23 = add2(x23, ib.y);
+                if (cond != nullptr) { x01 = add2(x01, pack2(c4[q].x, c4[q].y)); x23 = add2(x23, pack2(c4[q].z, c4[q].w)); }
+                float x0, x1, x2, x3;
+                unpack2(x01, x0, x1); unpack2(x23, x2, x3);
+                xd[q][0] = pack2(x0, x0); xd[q][1] = pack2(x1, x1); xd[q][2] = pack2(x2, x2); xd[q][3] = pack2(x3, x3);
+                hd[q][0] = pack2(h4[q].x, h4[q].x); hd[q][1] = pack2(h4[q].y, h4[q].y);
+                hd[q][2] = pack2(h4[q].z, h4[q].z); hd[q][3] = pack2(h4[q].w, h4[q].w);
             }
-            float acc[2][16];                                   // slot a * 4 + gate (r, z, n_i, n_h); a = hidden index ^ jm(lane)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const float4 wir = wg[a], wiz = wg[4 + a], win = wg[8 + a], whr = wg[12 + a], whz = wg[16 + a], whn = wg[20 + a];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float hv[4] = {h4[q].x, h4[q].y, h4[q].z, h4[q].w};
-                    float r = wir.x * x[q][0], z = wiz.x * x[q][0], ni = win.x * x[q][0], nh = whn.x * hv[0];
-                    r = fmaf(wir.y, x[q][1], r); z = fmaf(wiz.y, x[q][1], z); ni = fmaf(win.y, x[q][1], ni); nh = fmaf(whn.y, hv[1], nh);
-                    r = fmaf(wir.z, x[q][2], r); z = fmaf(wiz.z, x[q][2], z); ni = fmaf(win.z, x[q][2], ni); nh = fmaf(whn.z, hv[2], nh);
-                    r = fmaf(wir.w, x[q][3], r); z = fmaf(wiz.w, x[q][3], z); ni = fmaf(win.w, x[q][3], ni); nh = fmaf(whn.w, hv[3], nh);
-                    r = fmaf(whr.x, hv[0], r); z = fmaf(whz.x, hv[0], z);
-                    r = fmaf(whr.y, hv[1], r); z = fmaf(whz.y, hv[1], z);
-                    r = fmaf(whr.z, hv[2], r); z = fmaf(whz.z, hv[2], z);
-                    r = fmaf(whr.w, hv[3], r); z = fmaf(whz.w, hv[3], z);
-                    acc[q][a * 4] = r; acc[q][a * 4 + 1] = z; acc[q][a * 4 + 2] = ni; acc[q][a * 4 + 3] = nh;
-                }
-            }
-            // hidden-index folds (pre-swapped slots), then gate folds (selects), then the last lane bit
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][8 + i], 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][4 + i], 8);
-            float k0[2], k1[2], kk[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const float s0 = b4 ? acc[q][0] : acc[q][2], s1 = b4 ? acc[q][1] : acc[q][3];
-                k0[q] = b4 ? acc[q][2] : acc[q][0]; k1[q] = b4 ? acc[q][3] : acc[q][1];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) rz[q][a] = 0ull;
+                ni[q][0] = ni[q][1] = nh[q][0] = nh[q][1] = 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                         // input side, k ascending per accumulator ...
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) rz[q][a] = fma2(WQ(a * 4 + k), xd[q][k], rz[q][a]);
+                    ni[q][0] = fma2(WQ(16 + k), xd[q][k], ni[q][0]);
+                    ni[q][1] = fma2(WQ(20 + k), xd[q][k], ni[q][1]);
+                }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                         // ... then the hidden side
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) rz[q][a] = fma2(WQ(24 + a * 4 + k), hd[q][k], rz[q][a]);
+                    nh[q][0] = fma2(WQ(40 + k), hd[q][k], nh[q][0]);
+                    nh[q][1] = fma2(WQ(44 + k), hd[q][k], nh[q][1]);
+                }
+            // hidden-index folds (pre-swapped slots), then gate folds (selects), then the last lane bit
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                rz[q][0] = add2(rz[q][0], shfl2(rz[q][2], 16)); rz[q][1] = add2(rz[q][1], shfl2(rz[q][3], 16));
+                ni[q][0] = add2(ni[q][0], shfl2(ni[q][1], 16)); nh[q][0] = add2(nh[q][0], shfl2(nh[q][1], 16));
+            }
+            float g4[2][4];                                     // r, z, n_i, n_h of hidden index jm(lane)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                rz[q][0] = add2(rz[q][0], shfl2(rz[q][1], 8));
+                float n0, n1, m0, m1;
+                unpack2(ni[q][0], n0, n1); unpack2(nh[q][0], m0, m1);
+                n0 += __shfl_xor_sync(0xffffffffu, n1, 8);
+                m0 += __shfl_xor_sync(0xffffffffu, m1, 8);
+                unpack2(rz[q][0], g4[q][0], g4[q][1]);
+                g4[q][2] = n0; g4[q][3] = m0;
+            }
+            float k0[2], k1[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float s0 = b4 ? g4[q][0] : g4[q][2], s1 = b4 ? g4[q][1] : g4[q][3];
+                k0[q] = b4 ? g4[q][2] : g4[q][0]; k1[q] = b4 ? g4[q][3] : g4[q][1];
                 k0[q] += __shfl_xor_sync(0xffffffffu, s0, 4);
                 k1[q] += __shfl_xor_sync(0xffffffffu, s1, 4);
             }
@@ -541,6 +573,7 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
             }
         }
     }
+#undef WQ
     __syncthreads();
     fast_lap(F, 3);
     const float* gb = T.gb + (size_t)c * 24;
@@ -570,12 +603,13 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
     const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
     const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
-    float4 wu[NV];
+    ulonglong2 wu[NV];           // 2 NV weight pairs per lane (pack_up): entry i2 * 4 + k = (W[slot 2 i2][k], W[slot 2 i2 + 1][k])
     {
-        const float4* w = T.wu4 + (size_t)c * NV * TW + kq * 32 + lane;
+        const ulonglong2* w = reinterpret_cast<const ulonglong2*>(T.wu4) + (size_t)c * NV * TW + kq * 32 + lane;
 #pragma unroll
         for (int i = 0; i < NV; ++i) wu[i] = __ldg(w + i * TW);
     }
+#define WU(e) (((e) & 1) ? wu[(e) >> 1].y : wu[(e) >> 1].x)
     fast_lap(F, 5);
     if (!grid_barrier(P, epoch)) return false;
     fast_lap(F, 6);
@@ -599,23 +633,33 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
                 for (int q = 0; q < 2; ++q) hn[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)(rotated(ch + 1) * CHP + pg + q * NPG) * H + koff));
             }
             if (nofma) continue;
-            float acc[2][NV];
+            u64 a2[2][NV / 2];                                  // (slot 2 i2, slot 2 i2 + 1)
+            float acc[2][1];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+                const u64 hd[4] = {pack2(h4[q].x, h4[q].x), pack2(h4[q].y, h4[q].y), pack2(h4[q].z, h4[q].z), pack2(h4[q].w, h4[q].w)};
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    float a = wu[i].x * h4[q].x;
-                    a = fmaf(wu[i].y, h4[q].y, a); a = fmaf(wu[i].z, h4[q].z, a); a = fmaf(wu[i].w, h4[q].w, a);
-                    acc[q][i] = a;
+                for (int i2 = 0; i2 < NV / 2; ++i2) {
+                    u64 a = 0ull;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a = fma2(WU(i2 * 4 + k), hd[k], a);
+                    a2[q][i2] = a;
                 }
             }
             int bit = 16;
 #pragma unroll
-            for (int half = NV / 2; half >= 1; half >>= 1, bit >>= 1)
+            for (int half = NV / 4; half >= 1; half >>= 1, bit >>= 1)      // folds of whole pairs
 #pragma unroll
                 for (int i = 0; i < half; ++i)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][half + i], bit);
+                    for (int q = 0; q < 2; ++q) a2[q][i] = add2(a2[q][i], shfl2(a2[q][half + i], bit));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                       // the last fold: slot 1 into slot 0
+                float lo, hi;
+                unpack2(a2[q][0], lo, hi);
+                acc[q][0] = lo + __shfl_xor_sync(0xffffffffu, hi, bit);
+            }
+            bit >>= 1;
 #pragma unroll
             for (; bit >= 1; bit >>= 1)
 #pragma unroll
@@ -625,6 +669,7 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
                 for (int q = 0; q < 2; ++q) F.part[((size_t)kq * Bp + rotated(ch) * CHP + pg + q * NPG) * 16 + col] = acc[q][0];
         }
     }
+#undef WU
     __syncthreads();
     fast_lap(F, 7);
     const float* ub = T.ub + (size_t)c * NV;
@@ -1173,16 +1218,18 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
 }
 
 // Per-lane packing.  Thread t = 32 q + l of a weight row owns k = 4 t .. 4 t + 3 (q = K quarter, l = lane).
-//   GRU, CTA c, entry w = m * 12 + gate * 4 + a (m: 0 W_ih, 1 W_hh; gate r, z, n; slot a): row gate * H + 4 c + (a ^ jm(l)),
-//   jm(l) = (lane bit 16) * 2 + (lane bit 8) — the two hidden-index folds of the shuffle tree keep the lower half on every lane.
-//   up-sampler, CTA c, slot i: row NV c + (i ^ fast_col<NV>(l)).
+//   GRU, CTA c, slot a of lane l: hidden index 4 c + (a ^ jm(l)), jm(l) = (lane bit 16) * 2 + (lane bit 8) — the two
+//   hidden-index folds of the shuffle tree keep the lower half on every lane; weights stored as the FFMA2 operand pairs.
+//   up-sampler, CTA c, slot i: row NV c + (i ^ fast_col<NV>(l)); pairs of adjacent slots.
 template <int NV>
 static void pack_up(float* dst, const float* up_w, int c, int H) {
     const int TW = H / 4;
-    for (int i = 0; i < NV; ++i)
-        for (int t = 0; t < TW; ++t) {
-            const int row = c * NV + (i ^ fast_col<NV>(t & 31));
-            for (int kk = 0; kk < 4; ++kk) dst[((size_t)i * TW + t) * 4 + kk] = up_w[(size_t)row * H + 4 * t + kk];
+    for (int t = 0; t < TW; ++t)
+        for (int e = 0; e < 2 * NV; ++e) {                      // pair e = i2 * 4 + k: (W[slot 2 i2][k], W[slot 2 i2 + 1][k]); float4 e / 2 of the lane
+            const int i2 = e / 4, k = e % 4, m = fast_col<NV>(t & 31);
+            float* o = dst + ((size_t)(e / 2) * TW + t) * 4 + (e & 1) * 2;
+            o[0] = up_w[(size_t)(c * NV + ((2 * i2) ^ m)) * H + 4 * t + k];
+            o[1] = up_w[(size_t)(c * NV + ((2 * i2 + 1) ^ m)) * H + 4 * t + k];
         }
 }
 
@@ -1388,18 +1435,25 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         std::vector<float> wg((size_t)NC * 24 * TW * 4), wu((size_t)NC * T.NV * TW * 4), iw((size_t)T.fs * TW * 4), gb((size_t)NC * 24),
             ub((size_t)NC * T.NV);
         for (int c = 0; c < NC; ++c) {
+            // 48 pairs per lane, e = 0..47: [0,16) (W_ir, W_iz)[slot e / 4][k = e % 4], [16,24) (W_in[slot 2a'], W_in[slot 2a'+1])[k],
+            // [24,48) the same of W_hh; slot a of lane l is hidden index 4c + (a ^ jm(l)).  Pair e lives in float4 e / 2 of the lane.
+            for (int t = 0; t < TW; ++t) {
+                const int l = t & 31, jm = ((l >> 4) & 1) << 1 | ((l >> 3) & 1);
+                for (int e = 0; e < 48; ++e) {
+                    const int m = e / 24, r = e % 24, k = r % 4;
+                    const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
+                    int row_lo, row_hi;
+                    if (r < 16) { const int a = r / 4; row_lo = 0 * H + 4 * c + (a ^ jm); row_hi = 1 * H + 4 * c + (a ^ jm); }
+                    else { const int a2 = (r - 16) / 4; row_lo = 2 * H + 4 * c + ((2 * a2) ^ jm); row_hi = 2 * H + 4 * c + ((2 * a2 + 1) ^ jm); }
+                    float* dst = wg.data() + (((size_t)c * 24 + e / 2) * TW + t) * 4 + (e & 1) * 2;
+                    dst[0] = W[(size_t)row_lo * H + 4 * t + k];
+                    dst[1] = W[(size_t)row_hi * H + 4 * t + k];
+                }
+            }
             for (int m = 0; m < 2; ++m) {
-                const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
                 const float* b = m == 0 ? d->b_ih[i] : d->b_hh[i];
                 for (int g = 0; g < 3; ++g)
-                    for (int a = 0; a < 4; ++a) {
-                        for (int t = 0; t < TW; ++t) {
-                            const int l = t & 31, jm = ((l >> 4) & 1) << 1 | ((l >> 3) & 1), row = g * H + 4 * c + (a ^ jm);
-                            for (int kk = 0; kk < 4; ++kk)
-                                wg[(((size_t)c * 24 + m * 12 + g * 4 + a) * TW + t) * 4 + kk] = W[(size_t)row * H + 4 * t + kk];
-                        }
-                        gb[(size_t)c * 24 + m * 12 + g * 4 + a] = b[g * H + 4 * c + a];
-                    }
+                    for (int a = 0; a < 4; ++a) gb[(size_t)c * 24 + m * 12 + g * 4 + a] = b[g * H + 4 * c + a];
             }
             float* wuc = wu.data() + (size_t)c * T.NV * TW * 4;
             if (T.NV == 4) pack_up<4>(wuc, d->up_w[i], c, H);

@@ -6,8 +6,5 @@ tail -4 gpurun_out/pytest_sr3.log
 run() { echo "$* : $(env "$@" timeout 200 python bench.py --workload samplernn --batch $B --seconds 1 --steps 1 --warmup 1 --no-cpu-baseline --no-extras 2>&1 | grep 'Mcycles\|"ms_per_step"' | sed 's/.*"ms_per_step": \([0-9.]*\).*/ms \1/' | tail -2 | tr '\n' ' ')"; }
 for B in 128 64 16; do
 echo "== B=$B"
-run MMK_SR_ENGINE=1
 run MMK_SR_DEBUG=1
-run MMK_SR_DEBUG=1 MMK_SR_EXP=1
-run MMK_SR_DEBUG=1 MMK_SR_EXP=2
 done
