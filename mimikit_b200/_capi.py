@@ -59,7 +59,7 @@ class SampleRNNDescEx(Structure):
     _fields_ = [("base", SampleRNNDesc), ("rnn_type", c_int), ("n_rnn", c_int),
                 ("w_ih", _fpp), ("w_hh", _fpp), ("b_ih", _fpp), ("b_hh", _fpp),
                 ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float)),
-                ("need_set_hidden", c_int)]
+                ("need_set_hidden", c_int), ("compute_mode", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/mmk_b200.h declares

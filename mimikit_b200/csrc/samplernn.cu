@@ -435,17 +435,20 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
     MMK_CUDA(cudaGetDevice(&h->device));
     {   // MMK_SR_KERNEL: "1" = general kernel only, "2" = cluster kernel only, unset = cluster kernel when it fits
         const char* force = getenv("MMK_SR_KERNEL");
-        if (plain && (!force || atoi(force) != 1)) {
+        const int tc = dx->compute_mode == MMK_COMPUTE_BF16_TC ? 1 : 0;
+        if (tc && !plain) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU tiers with one layer, a zero initial state and a plain head"); }
+        if (plain && (tc || !force || atoi(force) != 1)) {
             int unsupported = 0;
             mmk_samplernn_desc d2 = *d;      // the cluster kernel hosts the GRU / one layer / plain head form only
             d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;
-            if (sr2_create(&d2, max_batch, &h->v2, &unsupported) == 0) {
+            if (sr2_create(&d2, max_batch, tc, &h->v2, &unsupported) == 0) {
                 h->max_batch = max_batch; h->rf = d->frame_sizes[0];
                 *out = h;
                 return 0;
             }
             h->v2 = nullptr;
             if (!unsupported) { sr_free(h); return 1; }
+            if (tc) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode needs hidden_dim in {128, 256, 512}, frame sizes / up-sampling factors in {1,2,4,8} / {1,2,4} and max_batch <= 128"); }
             if (force && atoi(force) == 2) { sr_free(h); MMK_FAIL("configuration not supported by the cluster kernel (MMK_SR_KERNEL=2)"); }
         }
     }

@@ -18,8 +18,11 @@
 #include "sampler.cuh"
 #include "samplernn_impl.h"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 
@@ -54,6 +57,14 @@ struct Tier {
     const float4* wg4; const float4* wu4; const float4* iw4; const float4* ib4;
     const float* gb; const float* ub;
     int NV;                          // up-sampler rows of a CTA (4 * up)
+    // tensor-core engine (Params::tc): bf16 images in the UMMA K-major SWIZZLE_128B layout — [128 prompts x H] activations
+    // (16 KB atoms of 64 k), [16 columns x K] weight tiles per CTA
+    unsigned char* himg;             // hidden state, two images (ping-pong like hbuf)
+    unsigned char* oimg;             // up-sampler output (the next tier's conditioning), one image per slot; null for the bottom frame tier
+    const unsigned char* wgimg;      // [NC][fills][4 KB]: r | z | n_i | n_h columns over K = [conditioning | hidden]
+    const unsigned char* wuimg;      // [NC][H / 128][4 KB]
+    const float* wf;                 // [NC][16][fs]: W_ih . in_w rows of the columns (frame Linear folded into the gate)
+    const float* bfold;              // [NC][16]: b_ih + b_hh + W_ih . in_b (n_i: without b_hh; n_h: b_hh alone)
 };
 
 struct Params {
@@ -82,6 +93,7 @@ struct Params {
     // lane-major frame-tier engine
     int fast, NKQ, CHP;              // K quarters (H / 128), prompts per block of the walk (2 per warp)
     int s_part, s_hold, s_lin;
+    int tc, s_tcbar;                 // tensor-core frame tiers (bf16 operands, fp32 accumulation): compute mode MMK_COMPUTE_BF16_TC
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -394,6 +406,12 @@ __device__ __forceinline__ void reduce_partials(float (&acc)[16], const Map& m, 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NTF = 256;         // 8 warps: NKQ K-quarters x 8 / NKQ prompt groups (9 warps would cap the registers at 168)
 
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // Packed fp32 pairs (FFMA2 / FADD2, sm_100): one issue slot for two IEEE fp32 operations (the FMA pipe still spends two cycles —
 // scripts/ubench/ffma2_bench.cu — so this buys issue slots for the shuffles, not FMA throughput)
 typedef unsigned long long u64;
@@ -685,11 +703,234 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
     return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core frame-tier engine (Params::tc; compute mode bf16): the same column split (CTA c owns hidden indices
+// 4c .. 4c + 3 and NV up-sampler rows), but a contraction is ONE tcgen05 accumulation: D[128 prompts x 16 columns] (TMEM,
+// fp32) += A[128 x K] (activations, bf16) . B[16 x K]^T (this CTA's weight rows, bf16), K = [conditioning | hidden].
+//   * the producers keep the activations in HBM as ready-made UMMA tiles (bf16, K-major, SWIZZLE_128B: 16 KB atoms of
+//     128 prompts x 64 k): a CTA writes the 8 bytes of a prompt row it owns, every CTA pulls whole atoms with
+//     cp.async.bulk — three issuing threads, one per stage, because a bulk copy costs its issuer ~600 cycles;
+//   * the frame Linear is folded into the gate algebraically (W_ih (in_w lin + in_b) = (W_ih in_w) lin + W_ih in_b,
+//     precomputed in fp32), so the A operand needs no per-CTA rebuild: it is the conditioning image and the hidden image;
+//   * the epilogue thread of a prompt reads its 16 accumulator columns (r, z, n_i, n_h of 4 hidden indices) with one
+//     tcgen05.ld, adds the folded terms, applies the GRU cell in fp32 and writes h' twice: fp32 (state, carry) and bf16
+//     (the next operand).  The head stays the fp32 cluster head.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TC_STAGES = 3;
+constexpr unsigned TC_A_BYTES = 32768u, TC_B_BYTES = 4096u, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;   // 128 k per fill
+enum { TCB_FULL = 0, TCB_EMPTY = TC_STAGES, TCB_ACC = 2 * TC_STAGES, TCB_COUNT };
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (as csrc/wavenet7.cu): a tile of R rows x K bf16 = K / 64 atoms of R x 128-byte
+// lines, 8 rows = 1024 bytes (SBO), chunk c of line r at position c ^ (r & 7); atoms R * 128 bytes apart.
+__host__ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr & 0x3ffffu) >> 4);
+    d |= (unsigned long long)1u << 16;
+    d |= (unsigned long long)(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+__host__ __device__ __forceinline__ unsigned kstep16(int kk, int R) { return (unsigned)((kk >> 2) * (R * 8) + (kk & 3) * 2); }
+__host__ __device__ __forceinline__ unsigned umma_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+}
+__host__ __device__ __forceinline__ unsigned tile_off(int m, int kc, int R) {   // byte offset of row m, 16-byte chunk kc
+    return (unsigned)((kc >> 3) * (R * 128) + (m >> 3) * 1024 + (m & 7) * 128 + (((kc & 7) ^ (m & 7)) << 4));
+}
+__device__ __forceinline__ unsigned bf16x2_bits(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&v);
+}
+
+struct Tc {
+    unsigned stage0, bar0, tmem;     // shared-memory address of stage 0 (1024-byte aligned), of the mbarriers; TMEM base
+    unsigned gf, na;                 // fills streamed / accumulations finished so far (same in every thread)
+    float* lin;
+};
+__device__ __forceinline__ unsigned tc_bar(const Tc& X, int i) { return X.bar0 + 8u * (unsigned)i; }
+
+// Warps 5..7 (one issuing lane each, stage = warp - 5) stream the fills, warp 4 issues the MMAs: D (TMEM columns 0..15)
+// = sum over the fills of A_fill[128 x 128] . B_fill[16 x 128]^T.  Fill j < n0 comes from img0, the rest from img1.
+__device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsigned char* img0, int n0, const unsigned char* img1, int n1,
+                                            const unsigned char* wimg, int warp, int lane) {
+    const int nfill = n0 + n1;
+    bool ok = true;
+    if (warp >= 5) {
+        if (lane == 0) {
+            const unsigned s = (unsigned)(warp - 5);
+            fence_proxy_async();     // rows written with st.global by other CTAs before the grid barrier -> async-proxy reads
+            for (int j = 0; j < nfill && ok; ++j) {
+                const unsigned g = X.gf + (unsigned)j;
+                if (g % TC_STAGES != s) continue;
+                const unsigned u = g / TC_STAGES;
+                if (u > 0) ok = mbar_wait(tc_bar(X, TCB_EMPTY + s), (u - 1u) & 1u, P.abort_flag);
+                mbar_expect_tx(tc_bar(X, TCB_FULL + s), TC_STAGE_BYTES);
+                const unsigned char* src = j < n0 ? img0 + (size_t)j * TC_A_BYTES : img1 + (size_t)(j - n0) * TC_A_BYTES;
+                bulk_g2s(X.stage0 + s * TC_STAGE_BYTES, src, TC_A_BYTES, tc_bar(X, TCB_FULL + s));
+                bulk_g2s(X.stage0 + s * TC_STAGE_BYTES + TC_A_BYTES, wimg + (size_t)j * TC_B_BYTES, TC_B_BYTES, tc_bar(X, TCB_FULL + s));
+            }
+        }
+    } else if (warp == 4) {
+        const unsigned idesc = umma_idesc(16);
+        for (int j = 0; j < nfill; ++j) {
+            const unsigned g = X.gf + (unsigned)j, s = g % TC_STAGES, u = g / TC_STAGES;
+            ok = __all_sync(0xffffffffu, (mbar_wait(tc_bar(X, TCB_FULL + s), u & 1u, P.abort_flag) && ok) ? 1 : 0) != 0;
+            if (!ok) break;
+            tc_fence_after();
+            unsigned pred;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+            if (pred) {
+                const unsigned long long dA = umma_desc(X.stage0 + s * TC_STAGE_BYTES), dB = umma_desc(X.stage0 + s * TC_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) umma_bf16(X.tmem, dA + kstep16(kk, 128), dB + kstep16(kk, 16), idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(tc_bar(X, TCB_EMPTY + s));
+                if (j == nfill - 1) umma_commit(tc_bar(X, TCB_ACC));
+            }
+            __syncwarp();
+        }
+    }
+    return ok;
+}
+
+// GRU cell of frame tier T on this CTA's 4 hidden indices (sample_rnn_v2.py:226-260, modules/io.py:106-133), bf16 tensor-core form.
+template <int FS>
+__device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const unsigned char* cimg, const unsigned char* himg, unsigned char* himg_next,
+                                       const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
+    if (pre_barrier && !grid_barrier(P, epoch)) return false;
+    const float Qf = (float)P.Q;
+    for (int idx = tid; idx < 128 * FS; idx += NTF) {          // Linearizer of the frame (modules/io.py:111-112)
+        const int p = idx / FS, f = idx - p * FS;
+        long long q = 0;
+        if (p < P.B) q = __ldcg(P.seq + (size_t)p * P.seq_stride + (tw - FS + f));
+        X.lin[idx] = linearize(q, Qf);
+    }
+    __syncthreads();
+    const int nimg = H / 128;                                   // fills per image
+    bool ok = tc_contract(P, X, cimg ? cimg : himg, nimg, himg, cimg ? nimg : 0,
+                          T.wgimg + (size_t)c * (2 * nimg) * TC_B_BYTES, warp, lane);
+    if (warp < 4) {
+        const int p = tid;
+        const float4 hold = __ldcg(reinterpret_cast<const float4*>(hcur + (size_t)p * H + 4 * c));
+        const float* wf = T.wf + (size_t)c * 16 * FS;
+        const float* bfo = T.bfold + (size_t)c * 16;
+        float pre[16];
+#pragma unroll
+        for (int col = 0; col < 16; ++col) {
+            float a = __ldg(bfo + col);
+            if (col < 12) {
+#pragma unroll
+                for (int f = 0; f < FS; ++f) a = fmaf(__ldg(wf + col * FS + f), X.lin[p * FS + f], a);
+            }
+            pre[col] = a;
+        }
+        ok = mbar_wait(tc_bar(X, TCB_ACC), X.na & 1u, P.abort_flag) && ok;
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(X.tmem + ((unsigned)(32 * warp) << 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
+        float hn[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {                        // PyTorch GRU cell, gates r, z, n
+            const float r = sigmoid_acc(v[jj] + pre[jj]);
+            const float zg = sigmoid_acc(v[4 + jj] + pre[4 + jj]);
+            const float n = tanhf((v[8 + jj] + pre[8 + jj]) + r * (v[12 + jj] + pre[12 + jj]));
+            hn[jj] = (1.0f - zg) * n + zg * ho[jj];
+        }
+        if (p < P.B) {
+            __stcg(reinterpret_cast<float4*>(hnext + (size_t)p * H + 4 * c), make_float4(hn[0], hn[1], hn[2], hn[3]));
+            const int k0 = 4 * c;
+            __stcg(reinterpret_cast<uint2*>(himg_next + tile_off(p, k0 >> 3, 128) + (k0 & 7) * 2),
+                   make_uint2(bf16x2_bits(hn[0], hn[1]), bf16x2_bits(hn[2], hn[3])));
+        }
+    }
+    X.gf += (unsigned)(cimg ? 2 * nimg : nimg);
+    X.na += 1u;
+    return __syncthreads_or(ok ? 0 : 1) == 0;
+}
+
+// LinearResampler rows of this CTA (modules/resamplers.py:13-23) on the new hidden image: always behind a grid barrier.
+__device__ __forceinline__ bool tc_up(const Params& P, const Tier& T, const unsigned char* himg, unsigned long long& epoch, Tc& X) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H, NV = T.NV;
+    if (!grid_barrier(P, epoch)) return false;
+    const int nimg = H / 128;
+    bool ok = tc_contract(P, X, himg, nimg, himg, 0, T.wuimg + (size_t)c * nimg * TC_B_BYTES, warp, lane);
+    if (warp < 4) {
+        const int p = tid;
+        ok = mbar_wait(tc_bar(X, TCB_ACC), X.na & 1u, P.abort_flag) && ok;
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(X.tmem + ((unsigned)(32 * warp) << 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float* ub = T.ub + (size_t)c * NV;
+        const int urow = c * NV, slot = urow / H, k0 = urow - slot * H;     // NV divides H: the CTA's rows share a slot
+#pragma unroll
+        for (int col = 0; col < 16; ++col) v[col] += col < NV ? __ldg(ub + col) : 0.0f;
+        if (p < P.B) {
+            if (T.oimg != nullptr) {                            // conditioning of the next frame tier: bf16 image of the slot
+                unsigned char* img = T.oimg + (size_t)slot * ((size_t)H * 256);
+                if (NV == 4) {
+                    __stcg(reinterpret_cast<uint2*>(img + tile_off(p, k0 >> 3, 128) + (k0 & 7) * 2), make_uint2(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3])));
+                } else {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8)
+                        if (h8 * 8 < NV)
+                            __stcg(reinterpret_cast<uint4*>(img + tile_off(p, (k0 >> 3) + h8, 128)),
+                                   make_uint4(bf16x2_bits(v[h8 * 8], v[h8 * 8 + 1]), bf16x2_bits(v[h8 * 8 + 2], v[h8 * 8 + 3]),
+                                              bf16x2_bits(v[h8 * 8 + 4], v[h8 * 8 + 5]), bf16x2_bits(v[h8 * 8 + 6], v[h8 * 8 + 7])));
+                }
+            } else {                                            // the head reads fp32 [slot][prompt][H]
+                float* dst = T.obuf + ((size_t)slot * P.Bp + p) * H + k0;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    if (q4 * 4 < NV) __stcg(reinterpret_cast<float4*>(dst + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));
+            }
+        }
+    }
+    X.gf += (unsigned)nimg;
+    X.na += 1u;
+    return __syncthreads_or(ok ? 0 : 1) == 0;
+}
+
 enum { BAR_HID = 0, BAR_Z, BAR_Q, BAR_COUNT };
 
 // ------------------------------------------------------------------------------------------------------------
-template <bool FAST>
-__global__ void __launch_bounds__(FAST ? NTF : NT, 1) samplernn_cluster_kernel(const __grid_constant__ Params P) {
+template <int ENGINE>   // 0: tile engine, 1: lane-major fp32 engine, 2: tensor-core bf16 engine (frame tiers; the head is the same)
+__global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel(const __grid_constant__ Params P) {
+    constexpr bool FAST = ENGINE != 0;
     constexpr int NTK = FAST ? NTF : NT;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -724,8 +965,24 @@ __global__ void __launch_bounds__(FAST ? NTF : NT, 1) samplernn_cluster_kernel(c
     __syncthreads();
     cluster_sync_all();
 
+    Tc X{};
+    if (ENGINE == 2) {
+        X.stage0 = (sbase + (unsigned)P.s_region * 4u + 1023u) & ~1023u;      // the region carries 1 KB of slack for this
+        X.bar0 = sbase + (unsigned)P.s_tcbar * 4u;
+        X.lin = smem + P.s_lin;
+        unsigned* s_tmem = reinterpret_cast<unsigned*>(smem + P.s_tcbar) + 2 * TCB_COUNT;
+        if (tid == 0) {
+            for (int i = 0; i < TCB_COUNT; ++i) mbar_init(tc_bar(X, i), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 4) { tmem_alloc(smem_u32(s_tmem), 32); tmem_relinquish(); }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        X.tmem = *reinterpret_cast<volatile unsigned*>(s_tmem);
+    }
     Fast F{};
-    if (FAST) {
+    if (ENGINE == 1) {
         F.part = smem + P.s_part; F.hold = reinterpret_cast<float4*>(smem + P.s_hold); F.lin = smem + P.s_lin;
         F.timing = P.dbg && c == 0 && tid == 0; F.tl = clock64();
         for (int i = 0; i < 12; ++i) F.ta[i] = 0;
@@ -753,7 +1010,37 @@ __global__ void __launch_bounds__(FAST ? NTF : NT, 1) samplernn_cluster_kernel(c
             const long long tw = t + off;   // the window ends at data index tw (exclusive)
             // ---------------- frame tiers (weight-stationary over the whole grid) ----------------
             bool fired = false;
-            if constexpr (FAST) {
+            if constexpr (ENGINE == 2) {
+                bool pending_up = false;
+                for (int i = 0; i < P.n_ft && !dead; ++i) {
+                    const Tier& T = P.tiers[i];
+                    if (t % T.fs != 0) continue;
+                    const bool pre = pending_up || heads_pending;
+                    heads_pending = false;
+                    fired = true;
+                    const size_t img = (size_t)H * 256;           // bytes of a [128 x H] bf16 image
+                    const unsigned char* cimg = i > 0 ? P.tiers[i - 1].oimg + (size_t)((t / T.fs) % T.kdiv) * img : nullptr;
+                    const unsigned char* himg = T.himg + (size_t)hsel[i] * img;
+                    unsigned char* himg_next = T.himg + (size_t)(hsel[i] ^ 1) * img;
+                    const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
+                    float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
+                    bool ok = false;
+                    switch (T.fs) {
+                        case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
+                        case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
+                        case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
+                        default: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
+                    }
+                    hsel[i] ^= 1;
+                    if (ok) ok = tc_up(P, T, himg_next, epoch, X);
+                    if (!ok) { dead = true; break; }
+                    pending_up = true;
+                }
+                if (pending_up && !dead) {
+                    if (gen || t == t_hi - 1) { if (!grid_barrier(P, epoch)) dead = true; }
+                    else heads_pending = true;
+                }
+            } else if constexpr (ENGINE == 1) {
                 bool pending_up = false;
                 for (int i = 0; i < P.n_ft && !dead; ++i) {
                     const Tier& T = P.tiers[i];
@@ -1070,16 +1357,18 @@ __global__ void __launch_bounds__(FAST ? NTF : NT, 1) samplernn_cluster_kernel(c
             }
             heads_pending = true;
             lap(7);
-            if (FAST) fast_lap(F, 10);
+            if (ENGINE == 1) fast_lap(F, 10);
             if (c == 0 && tid == 0 && P.step_ts) P.step_ts[hstep] = globaltimer();
         }
     }
     if (P.dbg && c == 0 && tid == 0)
         for (int i = 0; i < 8; ++i) P.dbg[i] += tacc[i];
-    if (FAST && F.timing)
+    if (ENGINE == 1 && F.timing)
         for (int i = 0; i < 12; ++i) P.dbg[8 + i] += (unsigned long long)F.ta[i];
     // no CTA may exit while peers can still store into its shared memory
+    if (ENGINE == 2) tc_fence_before();
     __syncthreads();
+    if (ENGINE == 2 && warp == 4) { tc_fence_after(); tmem_dealloc(X.tmem, 32); }
     cluster_sync_all();
 }
 
@@ -1104,9 +1393,12 @@ int sr2_destroy(sr2_handle* h) {
     return 0;
 }
 
-static int sr2_max_clusters(int CS, size_t smem, int sms, bool fast) {
-    const void* k = fast ? (const void*)samplernn_cluster_kernel<true> : (const void*)samplernn_cluster_kernel<false>;
-    const int NTH = fast ? NTF : NT;
+static const void* sr2_kernel(int engine) {
+    return engine == 2 ? (const void*)samplernn_cluster_kernel<2> : engine == 1 ? (const void*)samplernn_cluster_kernel<1> : (const void*)samplernn_cluster_kernel<0>;
+}
+static int sr2_max_clusters(int CS, size_t smem, int sms, int engine) {
+    const void* k = sr2_kernel(engine);
+    const int NTH = engine ? NTF : NT;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (CS == 1) {
         int per_sm = 0;
@@ -1142,18 +1434,20 @@ static bool fast_supported(const mmk_samplernn_desc* d, int sms) {
     return true;
 }
 
-static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sms, int max_optin, Params* out, size_t* out_smem) {
+static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sms, int max_optin, bool tc, Params* out, size_t* out_smem) {
     const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels, NC = H / 4;
     if (NC % CS || H % CS || Hh % CS) return false;
     Params p{};
     const int GP = CS == 8 ? 8 : 4;
     p.fast = 1; p.NKQ = H / 128; p.CHP = 16 / p.NKQ;
+    p.tc = tc ? 1 : 0;
+    if (tc && max_batch > 128) return false;                 // one M = 128 tile of prompts
     p.n_ft = n_ft; p.H = H; p.Hh = Hh; p.Q = Q; p.NC = NC; p.CS = CS; p.GP = GP;
     p.JP = 4; p.NG = 12;
     p.fs_last = d->frame_sizes[n_ft]; p.fs_lt = d->frame_sizes[n_ft - 1];
     p.KS = H / CS; p.RS = Hh / CS; p.ZR = pad4(Q + 1);
     p.min_temp = d->min_temperature;
-    p.Bp = (max_batch + p.CHP - 1) / p.CHP * p.CHP;
+    p.Bp = tc ? 128 : (max_batch + p.CHP - 1) / p.CHP * p.CHP;
     int o = 0, fs_max = 1;
     auto take = [&](int floats) { int r = o; o += pad4(floats); return r; };
     for (int i = 0; i < n_ft; ++i) {
@@ -1186,14 +1480,16 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
     const int head_floats = ho + std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
     const int budget = max_optin / (int)sizeof(float) - 256;
     o = 0;
-    p.region = head_floats;
+    // tensor-core engine: the stages (1024-byte aligned inside the region: 1 KB of slack) share the region with the head buffers
+    p.region = tc ? std::max(head_floats, (int)(TC_STAGES * TC_STAGE_BYTES + 1024) / 4) : head_floats;
     p.xregion = p.wregion = p.xstage = p.wstage = 0;
     p.s_region = take(p.region);
     p.s_gi = o;
     p.s_bar = take(2 * BAR_COUNT + 16 * GP);
-    p.s_part = take(p.NKQ * p.Bp * 16);
-    p.s_hold = take(p.Bp * 4);
+    p.s_part = take(tc ? 4 : p.NKQ * p.Bp * 16);
+    p.s_hold = take(tc ? 4 : p.Bp * 4);
     p.s_lin = take(p.Bp * fs_max);
+    p.s_tcbar = take(2 * TCB_COUNT + 4);
     p.n_res = 0;
     bool ok = true;
     auto resident = [&](int goff, int len, int* soff) {
@@ -1209,7 +1505,7 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
     if (!ok) return false;
     p.smem_floats = o;
     const size_t smem = (size_t)o * sizeof(float);
-    const int max_clusters = sr2_max_clusters(CS, smem, sms, true);
+    const int max_clusters = sr2_max_clusters(CS, smem, sms, tc ? 2 : 1);
     if (getenv("MMK_SR_DEBUG"))
         fprintf(stderr, "[sr2] lane-major engine: CS=%d NC=%d GP=%d smem=%zu max_clusters=%d\n", CS, NC, GP, smem, max_clusters);
     if (max_clusters * CS < NC) return false;
@@ -1233,7 +1529,7 @@ static void pack_up(float* dst, const float* up_w, int c, int H) {
         }
 }
 
-int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int* unsupported) {
+int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** out, int* unsupported) {
     *unsupported = 1;
     const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels;
     if (H % KC != 0 || Hh % 4 != 0 || n_ft > MAX_TIERS) return 1;
@@ -1253,8 +1549,9 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     if (fast_supported(d, sms))
         for (int CS : {4, 8, 2, 1}) {
             if (force_cs && atoi(force_cs) != CS) continue;
-            if (plan_fast(d, max_batch, CS, sms, max_optin, &best, &best_smem)) { found = true; break; }
+            if (plan_fast(d, max_batch, CS, sms, max_optin, tc != 0, &best, &best_smem)) { found = true; break; }
         }
+    if (tc && !found) { sr2_destroy(h); return 1; }            // the tensor-core engine hosts H in {128, 256, 512}, <= 128 prompts
     for (int CS : {8, 4, 2, 1}) {
         if (found) break;
         if (force_cs && atoi(force_cs) != CS) continue;
@@ -1352,7 +1649,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         const int un_floats = std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
         if (ho + un_floats > REGION || p.NG * PBW * 2 > REGION) continue;
         const size_t smem = (size_t)o * sizeof(float);
-        const int max_clusters = sr2_max_clusters(CS, smem, sms, false);
+        const int max_clusters = sr2_max_clusters(CS, smem, sms, 0);
         if (getenv("MMK_SR_DEBUG")) {
             fprintf(stderr, "[sr2] CS=%d NC=%d GP=%d smem=%zu max_clusters=%d resident:", CS, NC, GP, smem, max_clusters);
             for (int i = 0; i < n_ft; ++i) fprintf(stderr, " t%d(ih=%d hh=%d up=%d)", i, p.tiers[i].so_wih >= 0, p.tiers[i].so_whh >= 0, p.tiers[i].so_wup >= 0);
@@ -1370,8 +1667,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
     h->max_batch = max_batch; h->rf = d->frame_sizes[0];
     if (!p.fast) p.Bp = (max_batch + 3) / 4 * 4;
     const int NC = p.NC, CS = p.CS, GP = p.GP;
-    if (p.fast) MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    else MMK_CUDA(cudaFuncSetAttribute(samplernn_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    MMK_CUDA(cudaFuncSetAttribute(sr2_kernel(p.tc ? 2 : p.fast), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     {
         const int n_groups = (max_batch + GP - 1) / GP, n_clusters = NC / CS;
         if ((n_groups + n_clusters - 1) / n_clusters > groups_per_cluster_max) { sr2_destroy(h); *unsupported = 1; return 1; }
@@ -1469,6 +1765,61 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, sr2_handle** out, int
         T.ib4 = reinterpret_cast<const float4*>(T.in_b);
         T.gb = up(gb.data(), gb.size());
         T.ub = up(ub.data(), ub.size());
+        if (!p.tc) continue;
+        // ---- tensor-core engine: bf16 weight tiles [16 columns x 128 k] per fill (K = [conditioning | hidden], the top tier: hidden only),
+        //      columns gate * 4 + jj with gates r, z, n_i, n_h; the frame Linear and all biases folded into wf / bfold (fp64 -> fp32)
+        const int nimg = H / 128, nfill = 2 * nimg;
+        auto bf = [](float v) { __nv_bfloat16 b = __float2bfloat16_rn(v); unsigned short u; memcpy(&u, &b, 2); return u; };
+        std::vector<unsigned char> wgi((size_t)NC * nfill * TC_B_BYTES, 0), wui((size_t)NC * nimg * TC_B_BYTES, 0);
+        std::vector<float> wfv((size_t)NC * 16 * T.fs, 0.0f), bfv((size_t)NC * 16, 0.0f);
+        const float* Wih = d->w_ih[i]; const float* Whh = d->w_hh[i];
+        for (int c = 0; c < NC; ++c) {
+            for (int col = 0; col < 16; ++col) {
+                const int g4 = col / 4, jj = col % 4, j = 4 * c + jj;
+                const int grow = (g4 == 0 ? 0 : g4 == 1 ? 1 : 2) * H + j;          // row of W_ih / W_hh (r, z, n)
+                for (int part = 0; part < 2; ++part) {            // 0: conditioning (W_ih), 1: hidden (W_hh)
+                    if (part == 0 && i == 0) continue;            // the top tier has no conditioning
+                    const bool zero = (part == 0 && g4 == 3) || (part == 1 && g4 == 2);
+                    const float* W = part == 0 ? Wih : Whh;
+                    const int fill0 = (i == 0) ? 0 : part * nimg;
+                    for (int k = 0; k < H; ++k) {
+                        const unsigned short v = zero ? 0 : bf(W[(size_t)grow * H + k]);
+                        unsigned char* tile = wgi.data() + ((size_t)c * nfill + fill0 + k / 128) * TC_B_BYTES;
+                        memcpy(tile + tile_off(col, (k % 128) / 8, 16) + (k % 8) * 2, &v, 2);
+                    }
+                }
+                // folded terms (the input x = in_w lin + in_b + conditioning enters W_ih only: columns r, z, n_i)
+                double b = 0.0;
+                if (g4 < 3) {
+                    b = d->b_ih[i][grow];
+                    for (int k = 0; k < H; ++k) b += (double)Wih[(size_t)grow * H + k] * (double)d->in_b[i][k];
+                    for (int f = 0; f < T.fs; ++f) {
+                        double a = 0.0;
+                        for (int k = 0; k < H; ++k) a += (double)Wih[(size_t)grow * H + k] * (double)d->in_w[i][(size_t)k * T.fs + f];
+                        wfv[((size_t)c * 16 + col) * T.fs + f] = (float)a;
+                    }
+                }
+                if (g4 < 2 || g4 == 3) b += d->b_hh[i][grow];
+                bfv[(size_t)c * 16 + col] = (float)b;
+            }
+            for (int col = 0; col < T.NV; ++col)
+                for (int k = 0; k < H; ++k) {
+                    const unsigned short v = bf(d->up_w[i][(size_t)(c * T.NV + col) * H + k]);
+                    unsigned char* tile = wui.data() + ((size_t)c * nimg + k / 128) * TC_B_BYTES;
+                    memcpy(tile + tile_off(col, (k % 128) / 8, 16) + (k % 8) * 2, &v, 2);
+                }
+        }
+        auto upb = [&](const void* src, size_t bytes) { void* q = dev_alloc(bytes, src); ok = ok && q; return (unsigned char*)q; };
+        T.wgimg = upb(wgi.data(), wgi.size());
+        T.wuimg = upb(wui.data(), wui.size());
+        T.wf = up(wfv.data(), wfv.size());
+        T.bfold = up(bfv.data(), bfv.size());
+        T.himg = upb(nullptr, (size_t)2 * H * 256);
+        T.oimg = i < n_ft - 1 ? upb(nullptr, (size_t)T.up * H * 256) : nullptr;
+        // ub of the plain order (the tensor-core up-sampler columns are the rows NV c .. in order)
+        std::vector<float> ubp((size_t)NC * T.NV);
+        for (int c = 0; c < NC; ++c) for (int col = 0; col < T.NV; ++col) ubp[(size_t)c * T.NV + col] = d->up_b[i][c * T.NV + col];
+        T.ub = up(ubp.data(), ubp.size());
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
     p.conv_b = up(d->conv_b, H);
@@ -1522,6 +1873,7 @@ int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     if (reset_hidden) {
         for (int i = 0; i < h->p.n_ft; ++i) {
             MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].hbuf, 0, h->hbuf_floats[i] * sizeof(float), st));
+            if (h->p.tc) MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].himg, 0, (size_t)2 * h->p.H * 256, st));
             h->p.hsel[i] = 0;
         }
     }
@@ -1546,7 +1898,7 @@ int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     at[0].val.clusterDim.x = p.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     void* args[] = {&p};
-    MMK_CUDA(cudaLaunchKernelExC(&cfg, p.fast ? (const void*)samplernn_cluster_kernel<true> : (const void*)samplernn_cluster_kernel<false>, args));
+    MMK_CUDA(cudaLaunchKernelExC(&cfg, sr2_kernel(p.tc ? 2 : p.fast), args));
     // the hidden ping-pong advances once per tier firing: keep the handle's view in step with the device
     for (int i = 0; i < p.n_ft; ++i) {
         const long long fs = p.tiers[i].fs;

@@ -65,10 +65,36 @@ class SampleRNN(NativeARM):
         self.frame_sizes = tuple(int(f) for f in config.frame_sizes)
         self._sd = self._init_state_dict()
         self._prompt_len = None
+        self._compute_dtype = torch.float32
 
     @property
     def config(self):
         return self._config
+
+    # ---- arithmetic ------------------------------------------------------------------------------
+    @property
+    def compute_dtype(self):
+        """torch.float32 (default): fp32 FFMA kernels, sequences bit-exact with the oracle.
+        torch.bfloat16: the frame tiers' GRU and up-sampler contractions run on the tensor cores (tcgen05.mma, accumulators in
+        TMEM; csrc/samplernn2.cu) with bf16 operands and fp32 accumulation; the cell, the head and the sampler stay fp32.
+        Logits within 5e-2 relative.  GRU tiers, one layer, zero initial state, hidden_dim in {128, 256, 512}, <= 128 prompts."""
+        return self._compute_dtype
+
+    @compute_dtype.setter
+    def compute_dtype(self, dtype):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("compute_dtype must be torch.float32 or torch.bfloat16")
+        if dtype != self._compute_dtype:
+            self._release()
+            self._compute_dtype = dtype
+
+    def bfloat16(self):
+        self.compute_dtype = torch.bfloat16
+        return self
+
+    def float(self):
+        self.compute_dtype = torch.float32
+        return self
 
     @property
     def rf(self):
@@ -195,6 +221,7 @@ class SampleRNN(NativeARM):
                                        "fc.2, fc.4, ... must hold the same tensors")
             dx.head_wh, dx.head_bh = self._w(p + "fc.2.weight"), self._w(p + "fc.2.bias")
         dx.need_set_hidden = int(str(c.h0_init) != "zeros")
+        dx.compute_mode = 1 if self._compute_dtype == torch.bfloat16 else 0      # MMK_COMPUTE_BF16_TC / MMK_COMPUTE_FP32
         h = ctypes.c_void_p()
         _capi.check(_capi.lib().mmk_samplernn_create_ex(ctypes.byref(dx), int(max_batch), ctypes.byref(h)))
         return h

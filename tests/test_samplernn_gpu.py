@@ -166,6 +166,39 @@ def test_lane_major_engine_vs_oracle(monkeypatch, cluster, fs, H, B, P):
     assert _rel_err(lg.cpu().numpy(), ref_logits) <= REL_TOL
 
 
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 48), ((8, 2, 1), 512, 128, 24), ((4, 4), 256, 3, 16), ((8, 4, 2, 1), 128, 22, 32),
+                                      ((2, 2, 1), 128, 5, 10), ((8, 4, 2), 256, 70, 40)])
+def test_tensor_core_mode_vs_oracle(fs, H, B, P):
+    """compute_dtype bfloat16: the frame tiers' GRU and up-sampler contractions on tcgen05 (bf16 operands, fp32 accumulation in
+    TMEM, frame Linear folded into the gate), cell / head / sampler in fp32.  Teacher-forced logits within the north star's 5e-2
+    of the fp32 oracle, decisions = argmax of the kernel's own logits, free-running generation deterministic and consistent with
+    its own logits."""
+    net = make_net(fs, H, mlp_dim=32, seed=5).bfloat16()
+    info = net.launch_info(B)
+    assert info["threads"] == 256 and info["sm_used"] == H // 4, info
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    g = torch.Generator().manual_seed(17)
+    n = 24
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    sub = list(range(B)) if B <= 24 else [0, 1, B // 2, B - 2, B - 1]
+    ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), n, None, None)
+    full = torch.cat([prompts, torch.zeros(B, n, dtype=torch.long)], 1)
+    full[sub] = torch.from_numpy(ref_seq)
+    lg, dec = net.teacher_forced(full, P)
+    rel = _rel_err(lg.cpu().numpy()[sub], ref_logits)
+    print(f"bf16 SampleRNN {fs} H={H} B={B}: teacher-forced logits rel err {rel:.2e}")
+    assert rel <= 5e-2
+    assert np.array_equal(dec.cpu().numpy(), restate.argmax_first(lg.cpu().numpy()))
+    seq, logits = net.generate(prompts, n, return_logits=True)
+    seq2 = net.generate(prompts, n)
+    assert torch.equal(seq, seq2)
+    assert np.array_equal(seq.cpu().numpy()[:, P:], restate.argmax_first(logits.cpu().numpy()))
+    # and back: the fp32 engine of the same object still reproduces the oracle bit for bit
+    net.float()
+    seq32 = net.generate(prompts[sub], n)
+    assert np.array_equal(seq32.cpu().numpy(), ref_seq)
+
+
 def test_stepwise_protocol_and_loop():
     """before_generate / generate_step / after_generate == whole-sequence path == oracle; GenerateLoopV2 integration as
     the reference's tests/test_sample_rnn.py:90-112 (batch 2, 512-sample prompt + 512 steps, temperature=(1.,))."""
