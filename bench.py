@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--prompt-seconds", type=float, default=1.0)
     ap.add_argument("--temperature", type=float, default=None, help="default: argmax (what GenerateLoopV2 does)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
-                    help="wavenet only: f32 = FFMA kernels (bit-exact sequences, the default); bf16 = tcgen05 tensor-core "
-                         "kernel (logits within 5e-2), one CTA per 128 prompts: use with --batch >= 128")
+                    help="f32 = FFMA kernels (bit-exact sequences, the default); bf16 = tcgen05 tensor-core kernels (logits "
+                         "within 5e-2): WaveNet layer pipeline, SampleRNN frame tiers (<= 128 prompts per GPU)")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short side measurements of BASELINE configs 3, 4, 5")
@@ -260,8 +260,6 @@ def run_b200(args):
     P, n = int(SR * args.prompt_seconds), int(SR * args.seconds)
     net = make_network(wl, dev)
     if args.dtype == "bf16":
-        if wl != "wavenet":
-            raise SystemExit("--dtype bf16 is implemented for the wavenet workload only")
         net.bfloat16()
     # the GLOBAL prompt batch (world x B prompts, rank r's block generated with r's seed); every rank holds it, as
     # sharding.generate_sharded expects, and generates for its own block
@@ -362,7 +360,7 @@ def run_b200(args):
                  "samplernn": "samplernn_cluster_kernel"}[wl]
         tr = NCU_TRAFFIC.get(kname)
         if args.dtype == "bf16":
-            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            roof = {"bound": "tensor", "kernel": kname + ("<2>" if wl == "samplernn" else ""), "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
         else:
             roof = {"bound": "fp32_fma", "kernel": kname, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -444,6 +442,12 @@ def run_extras(args, dev, rank, world, barrier):
         out["cfg3_samplernn_b128_sharded"] = {"value": Bg * n / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "strong",
                                               "dtype": "f32", "workload": f"SampleRNN (8,2,1) GRU-512, 128 prompts over {world} GPU(s), "
                                                                           f"{P}-sample prompt -> {n} samples, one gather"}
+        if world == 1:          # the same config with the frame tiers on tcgen05 (bf16 operands; one M = 128 tile of prompts)
+            net.bfloat16()
+            ms = timed(lambda: sharding.generate_sharded(net, pr, n))
+            out["cfg3_samplernn_b128_bf16"] = {"value": Bg * n / (ms / 1e3), "unit": "samples/s", "ms": ms, "scaling": "strong",
+                                               "dtype": "bf16", "workload": f"SampleRNN (8,2,1) GRU-512 frame tiers on tcgen05, 128 prompts, "
+                                                                            f"{P}-sample prompt -> {n} samples"}
         del net
         # cfg 4: tensor-core WaveNet, 128 prompts per GPU
         net = make_network("wavenet", dev).bfloat16()

@@ -258,6 +258,8 @@ class MuLawCompress(Functional):
         if x.dtype != torch.float32:
             raise TypeError("MuLawCompress: the B200 path computes in fp32 (the reference's dtype for audio)")
         x = x.contiguous()
+        if x.data_ptr() % 16:                # a contiguous slice such as x[1:]: the kernels load 16-byte vectors
+            x = x.clone()
         lib = _capi.lib()
         if out_dtype == torch.int64:
             out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
@@ -309,6 +311,8 @@ class MuLawExpand(Functional):
         if q.dtype != torch.int64:
             q = q.to(torch.int64)
         q = q.contiguous()
+        if q.data_ptr() % 16:
+            q = q.clone()
         out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
             _capi.check(_capi.lib().mmk_mulaw_expand(q.data_ptr(), out.data_ptr(), q.numel(), int(self.q_levels),
@@ -365,10 +369,12 @@ def _stft_mag_mel(x, n_fft, hop, center, alignment, want_mag, fb):
 
 @dtc.dataclass
 class STFT(Functional):
-    """functionals.py:450-528 — only coordinate='mag' is on the hot path (MagSpec); other coordinates raise."""
+    """functionals.py:450-528 — only coordinate='mag' is on the hot path (MagSpec); the reference's default 'pol' and 'car'
+    raise NotImplementedError, as does any window other than 'hann' (the reference's torch path always uses hann; its numpy
+    path with window=None is rectangular — not built)."""
     n_fft: int = N_FFT
     hop_length: int = HOP_LENGTH
-    coordinate: str = 'mag'
+    coordinate: str = 'pol'
     center: bool = True
     window: Optional[str] = "hann"
     pad_mode: str = "constant"
@@ -385,6 +391,8 @@ class STFT(Functional):
     def torch_func(self, inputs):
         if self.coordinate != "mag":
             raise NotImplementedError("the B200 path implements coordinate='mag' (MagSpec) only")
+        if self.window != "hann":
+            raise NotImplementedError("the B200 path implements window='hann' only")
         if self.pad_mode != "constant":
             raise NotImplementedError("the B200 path implements pad_mode='constant' (the reference default) only")
         x, restore = _to_device(inputs)

@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — loader for the UNMODIFIED reference (ktonal/mimikit 0.4.3).
 
 Nothing in the product package (`mimikit_b200/`) may import this module.  It is used by
-`oracle/make_golden.py` (to produce the committed fixtures under `tests/golden/`) and by the
-container-only cross-check tests (`tests/test_oracle_vs_reference.py`), which skip when
+`oracle/make_golden.py` (to produce the committed fixtures under `tests/golden/`) and by
+`tests/test_checkpoint_export.py` (networks of the live reference exported and reloaded), which skips when
 `/root/reference` is absent (it does not exist on the GPU box).
 
 The reference cannot be imported with a plain `import mimikit` in this image:

@@ -297,3 +297,20 @@ def test_remove_dc_time_split_is_always_exact(monkeypatch, chunk, warmup, expect
     y = f(x)
     assert np.array_equal(y.cpu().numpy().view(np.int32), restate.remove_dc(x.cpu().numpy()).view(np.int32))
     assert (f.recomputed_rows > 0) == expect_recompute, f.recomputed_rows
+
+
+def test_misaligned_inputs_and_stft_defaults():
+    """A contiguous CUDA slice that is not 16-byte aligned is cloned, not refused; STFT keeps the reference's default coordinate
+    ('pol', functionals.py:455) and says what the B200 path does not build."""
+    from mimikit_b200 import MuLawCompress, MuLawExpand, STFT
+    x = torch.from_numpy(restate.synthetic_waveform(1, 4099, sr=22050)[0]).cuda()
+    q = MuLawCompress()(x[1:])
+    assert np.array_equal(q.cpu().numpy(), restate.mulaw_compress(x[1:].cpu().numpy()))
+    w = MuLawExpand()(q[3:])
+    assert np.array_equal(w.cpu().numpy(), restate.mulaw_expand(q[3:].cpu().numpy()))
+    assert STFT().coordinate == "pol"
+    with pytest.raises(NotImplementedError):
+        STFT()(x)
+    with pytest.raises(NotImplementedError):
+        STFT(coordinate="mag", window=None)(x)
+    assert STFT(coordinate="mag")(x).shape[-1] == 1025
