@@ -40,9 +40,13 @@ namespace mmk7 {
 
 constexpr int NP = 16;             // prompts per group = MMA N
 constexpr int CC = 128;            // channels = MMA M (dilated = skips = head hidden)
-constexpr int NT = 256;            // warps 0-3 epilogue (thread = channel), 4 MMA issuer, 5 copy thread, 6-7 decide only (head)
-constexpr int NEPI = 128;
-constexpr int W_MMA = 4, W_CP = 5;
+constexpr int NT = 320;            // layers: warps 0-7 epilogue (thread = channel x half of the group's prompts), 8 MMA issuer, 9 copy thread
+                                   // head: warps 0-3 epilogue (thread = channel), 8 MMA issuer, 9 mailbox pull, every warp decides
+constexpr int NEPI_H = 128;        // epilogue threads of the head
+constexpr int NEPI_L = 256;        // ... of a layer
+constexpr int EW_H = 4, EW_L = 8;  // epilogue warps (arrivals per credit / ack / mailbox flag)
+constexpr int NPH = NP / 2;        // prompts per layer epilogue thread
+constexpr int W_MMA = 8, W_CP = 9;
 constexpr int MAXL = 96;
 constexpr int TILE_A = CC * CC * 2;        // 32 KB: a weight tile
 constexpr int TILE_B = NP * CC * 2;        // 4 KB: an activation tile (16 prompts x 128 channels, bf16)
@@ -254,6 +258,14 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     unsigned r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -309,6 +321,13 @@ __device__ __forceinline__ void store_column_bf16(unsigned char* tile, int c, co
         *reinterpret_cast<unsigned short*>(tile + tile_off(n, c >> 3, NP) + (c & 7) * 2) = bf16_bits(v[n]);
 }
 
+// thread (c, half) writes its 8 values (prompts p0 .. p0 + 7) of channel c
+__device__ __forceinline__ void store_half_column_bf16(unsigned char* tile, int c, int p0, const float (&v)[8]) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+        *reinterpret_cast<unsigned short*>(tile + tile_off(p0 + n, c >> 3, NP) + (c & 7) * 2) = bf16_bits(v[n]);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // The kernel: CTA (cluster, rank) = pipeline slot cluster * CS + rank: layers 0 .. L-1, then the head.
 // ------------------------------------------------------------------------------------------------------------
@@ -335,14 +354,16 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
         if (sb & 1023u) atomicExch(abort_flag, 2u);       // the swizzled tiles need a 1024-byte aligned window
         mbar_init(bar(B_XF), 1); mbar_init(bar(B_SK), 1);
         const bool built_here = !is_layer || first || mail_fed;           // else the layer above writes the tile remotely
-        mbar_init(bar(B_XB_FULL), built_here ? NEPI : 1);
+        mbar_init(bar(B_XB_FULL), built_here ? (is_layer ? NEPI_L : NEPI_H) : 1);
         mbar_init(bar(B_XB_FREE), 1);
-        mbar_init(bar(B_CR_XB), 5);
+        mbar_init(bar(B_CR_XB), EW_L + 1);                                // the layer below: its epilogue warps + its copy thread
         mbar_init(bar(B_XO_FULL), 1); mbar_init(bar(B_XO_FREE), 1);
         mbar_init(bar(B_GATE0), 1); mbar_init(bar(B_GATE1), 1);
-        mbar_init(bar(B_Y_FULL), NEPI);
+        mbar_init(bar(B_Y_FULL), is_layer ? NEPI_L : NEPI_H);
         mbar_init(bar(B_RS0), 1); mbar_init(bar(B_RS1), 1);
-        mbar_init(bar(B_CR_XF), 4); mbar_init(bar(B_CR_SK), 4); mbar_init(bar(B_IN_FREE), 4);
+        mbar_init(bar(B_CR_XF), EW_L);
+        mbar_init(bar(B_CR_SK), slot + 1 == L ? EW_H : EW_L);             // the consumer of my skip sum: the head or a layer
+        mbar_init(bar(B_IN_FREE), EW_L);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (up_local) {   // arm the first phase of the DSMEM-fed inputs (tx bytes may land before or after)
             if (is_layer) {
@@ -391,12 +412,13 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
             if (s < 0) s += d + 1;
             return ring + ((size_t)s * G + g) * TILE_B;
         };
-        if (warp < 4) {
+        if (warp < EW_L) {
             // =================================================================================================
-            // epilogue warps: thread c = channel c = TMEM lane c
+            // epilogue warps: thread = (channel c = TMEM lane c, half ph of the group's 16 prompts): warps w and w + 4 share the
+            // TMEM lane quarter w and split the columns, so an epilogue is 8 values per thread instead of 16
             // =================================================================================================
-            const int c = tid;
-            const unsigned tm_lane = tmem + ((unsigned)(32 * warp) << 16);
+            const int c = tid & 127, ph = tid >> 7, p0 = ph * NPH;
+            const unsigned tm_lane = tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)p0;
             const float b_f = __ldg(P.b1 + (size_t)l * 256 + c), b_g = __ldg(P.b1 + (size_t)l * 256 + 128 + c);
             const bool built_here = first || mail_fed;
             unsigned n = 0, nh = 0;
@@ -412,47 +434,47 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                     stamp();
                     const unsigned nb = n & 1u;
                     unsigned char* xb = smem + SM_XB;
-                    float xf[16];
+                    float xf[NPH];
                     // ---- E0 (first layer / cluster-boundary layer only): build the bf16 B tile of the layer input here.  Every
                     //      other layer receives that tile ready-made from the layer above (st.async, straight into xb).
                     if (built_here) {
                         if (first) {
                             // embedding gather (EmbeddingIO, modules/io.py:148-154): x[c][p] = E[q_{b,t}][c]
-                            long long q[16];
+                            long long q[NPH];
                             if (!P.teacher_forced && t > P.t_head) {
-                                uint2 w[16];
+                                uint2 w[NPH];
 #pragma unroll
-                                for (int p = 0; p < NP; ++p) w[p] = ld_poll_v2(reinterpret_cast<const uint2*>(P.samples + g * NP + p));
+                                for (int p = 0; p < NPH; ++p) w[p] = ld_poll_v2(reinterpret_cast<const uint2*>(P.samples + g * NP + p0 + p));
 #pragma unroll
-                                for (int p = 0; p < NP; ++p) {
-                                    if (g * NP + p < P.B && w[p].y != tag)
-                                        dead |= !poll_word(reinterpret_cast<const uint2*>(P.samples + g * NP + p), tag, w[p], abort_flag);
+                                for (int p = 0; p < NPH; ++p) {
+                                    if (g * NP + p0 + p < P.B && w[p].y != tag)
+                                        dead |= !poll_word(reinterpret_cast<const uint2*>(P.samples + g * NP + p0 + p), tag, w[p], abort_flag);
                                     q[p] = (long long)w[p].x;
                                 }
                             } else {
 #pragma unroll
-                                for (int p = 0; p < NP; ++p) {
-                                    const int b = g * NP + p;
+                                for (int p = 0; p < NPH; ++p) {
+                                    const int b = g * NP + p0 + p;
                                     q[p] = b < P.B ? __ldcg(P.seq + (size_t)b * P.seq_stride + t) : 0;
                                 }
                             }
 #pragma unroll
-                            for (int p = 0; p < NP; ++p) {
+                            for (int p = 0; p < NPH; ++p) {
                                 const long long qi = q[p] < 0 ? 0 : (q[p] >= P.Q ? P.Q - 1 : q[p]);
-                                xf[p] = (g * NP + p < P.B) ? __ldg(P.E + (size_t)qi * CC + c) : 0.0f;
+                                xf[p] = (g * NP + p0 + p < P.B) ? __ldg(P.E + (size_t)qi * CC + c) : 0.0f;
                             }
                         } else {
                             dead |= !mbar_wait(bar(B_XF), n & 1u, abort_flag);
-                            const float4* s4 = reinterpret_cast<const float4*>(smem + SM_XF) + c * 4;
+                            const float4* s4 = reinterpret_cast<const float4*>(smem + SM_XF) + c * 4 + 2 * ph;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
+                            for (int i = 0; i < 2; ++i) {
                                 const float4 v = s4[i];
                                 xf[4 * i] = v.x; xf[4 * i + 1] = v.y; xf[4 * i + 2] = v.z; xf[4 * i + 3] = v.w;
                             }
                         }
                         stamp();
                         if (n >= 1u) dead |= !mbar_wait(bar(B_XB_FREE), (n - 1u) & 1u, abort_flag);   // ring store has read the old tile
-                        store_column_bf16(xb, c, xf);
+                        store_half_column_bf16(xb, c, p0, xf);
                         fence_proxy_async_smem();
                         mbar_arrive(bar(B_XB_FULL));
                     }
@@ -462,18 +484,19 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                     tc_fence_after();
                     if (!built_here && tid == 0) mbar_expect_tx(bar(B_XB_FULL), TILE_B);   // the newer-tap MMAs have read the tile: re-arm
                     stamp();
-                    float y[16];
+                    float y[NPH];
                     {
-                        float fg[32];
-                        tmem_ld32(tm_lane + 64u * nb, fg);
+                        float f8[NPH], g8[NPH];
+                        tmem_ld8(tm_lane + 64u * nb, f8);
+                        tmem_ld8(tm_lane + 64u * nb + 16u, g8);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int p = 0; p < NP; ++p) y[p] = gate_fast(fg[p] + b_f, fg[16 + p] + b_g);
+                        for (int p = 0; p < NPH; ++p) y[p] = gate_fast(f8[p] + b_f, g8[p] + b_g);
                     }
                     // the y tile doubled as the staging area of the bf16 tile sent downstream in the previous unit: that bulk copy is
                     // certainly over once the layer below has returned the tile (its credit also frees its x tile for this unit's)
                     if (!last_layer && down_local && n >= 1u) dead |= !mbar_wait(bar(B_CR_XB), (n - 1u) & 1u, abort_flag);
-                    store_column_bf16(smem + SM_YB, c, y);
+                    store_half_column_bf16(smem + SM_YB, c, p0, y);
                     fence_proxy_async_smem();
                     tc_fence_before();
                     mbar_arrive(bar(B_Y_FULL));
@@ -482,9 +505,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                     if (!built_here) {   // the fp32 stream of the group arrived right behind its bf16 tile
                         dead |= !mbar_wait(bar(B_XF), n & 1u, abort_flag);
                         if (tid == 0) mbar_expect_tx(bar(B_XF), TILE_F);
-                        const float4* s4 = reinterpret_cast<const float4*>(smem + SM_XF) + c * 4;
+                        const float4* s4 = reinterpret_cast<const float4*>(smem + SM_XF) + c * 4 + 2 * ph;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             const float4 v = s4[i];
                             xf[4 * i] = v.x; xf[4 * i + 1] = v.y; xf[4 * i + 2] = v.z; xf[4 * i + 3] = v.w;
                         }
@@ -501,45 +524,45 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                     const unsigned cnt_dn = last_layer ? nh : n;             // deliveries made downstream so far
                     const bool sends = !last_layer || head_on;
                     const size_t box_dn = (((size_t)(slot + 1) * G + g) * 2 + (delivery & 1u));
-                    float rs[32];
-                    tmem_ld32(tm_lane + 64u * nb + 32u, rs);
+                    float rs[NPH], sk[NPH];
+                    tmem_ld8(tm_lane + 64u * nb + 32u, rs);
+                    tmem_ld8(tm_lane + 64u * nb + 48u, sk);
                     tmem_ld_wait();
                     if (!last_layer) {
 #pragma unroll
-                        for (int p = 0; p < NP; ++p) xf[p] += rs[p];         // h_{l+1} = h_l + conv_res(y); biases folded (see b1)
+                        for (int p = 0; p < NPH; ++p) xf[p] += rs[p];        // h_{l+1} = h_l + conv_res(y); biases folded (see b1)
                         if (down_local) {
                             // the bf16 tile first (the next layer's MMAs wait for nothing else).  It must reach the other CTA through
                             // the ASYNC proxy: a tile written with st.async (generic proxy) was not reliably seen by the tensor core
                             // there, whatever proxy fence the consumer used.  So it is staged here — in the y tile, idle since the
                             // res / skip MMAs finished — and one thread sends it with a shared::cta -> shared::cluster bulk copy.
-                            store_column_bf16(smem + SM_YB, c, xf);
+                            store_half_column_bf16(smem + SM_YB, c, p0, xf);
                             fence_proxy_async_smem();
-                            asm volatile("bar.sync 3, 128;" ::: "memory");
+                            asm volatile("bar.sync 3, 256;" ::: "memory");
                             if (tid == 0) bulk_s2s(win_dn + sb + (unsigned)SM_XB, sb + SM_YB, TILE_B, win_dn + bar(B_XB_FULL));
                             if (cnt_dn >= 1u) dead |= !mbar_wait(bar(B_CR_XF), (cnt_dn - 1u) & 1u, abort_flag);
-                            const unsigned dst = win_dn + sb + (unsigned)SM_XF + (unsigned)c * 64u, rb = win_dn + bar(B_XF);
+                            const unsigned dst = win_dn + sb + (unsigned)SM_XF + (unsigned)c * 64u + 32u * (unsigned)ph, rb = win_dn + bar(B_XF);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
+                            for (int i = 0; i < 2; ++i)
                                 st_async_v4(dst + 16u * i, make_float4(xf[4 * i], xf[4 * i + 1], xf[4 * i + 2], xf[4 * i + 3]), rb);
                         } else {
                             if (flow && delivery >= 2u) {
-                                if (lane == 0) dead |= !count_wait(P.ack + (size_t)(slot + 1) * G + g, 4u * (delivery - 1u), abort_flag);
+                                if (lane == 0) dead |= !count_wait(P.ack + (size_t)(slot + 1) * G + g, (unsigned)EW_L * (delivery - 1u), abort_flag);
                                 dead = __any_sync(0xffffffffu, dead);
                             }
-                            float4* mx = reinterpret_cast<float4*>(P.mail + box_dn * (size_t)(2 * CC * NP)) + c * 4;
+                            float4* mx = reinterpret_cast<float4*>(P.mail + box_dn * (size_t)(2 * CC * NP)) + c * 4 + 2 * ph;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) __stcg(mx + i, make_float4(xf[4 * i], xf[4 * i + 1], xf[4 * i + 2], xf[4 * i + 3]));
+                            for (int i = 0; i < 2; ++i) __stcg(mx + i, make_float4(xf[4 * i], xf[4 * i + 1], xf[4 * i + 2], xf[4 * i + 3]));
                         }
                     }
                     stamp();
                     {
-                        float* sk = rs + 16;
                         if (!first) {
                             dead |= !mbar_wait(bar(B_SK), n & 1u, abort_flag);
                             if (up_local && tid == 0) mbar_expect_tx(bar(B_SK), TILE_F);
-                            const float4* s4 = reinterpret_cast<const float4*>(smem + SM_SK) + c * 4;
+                            const float4* s4 = reinterpret_cast<const float4*>(smem + SM_SK) + c * 4 + 2 * ph;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
+                            for (int i = 0; i < 2; ++i) {
                                 const float4 v = s4[i];
                                 sk[4 * i] += v.x; sk[4 * i + 1] += v.y; sk[4 * i + 2] += v.z; sk[4 * i + 3] += v.w;
                             }
@@ -550,18 +573,18 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                         if (sends) {
                             if (down_local) {
                                 if (cnt_dn >= 1u) dead |= !mbar_wait(bar(B_CR_SK), (cnt_dn - 1u) & 1u, abort_flag);
-                                const unsigned dst = win_dn + sb + (unsigned)SM_SK + (unsigned)c * 64u, rb = win_dn + bar(B_SK);
+                                const unsigned dst = win_dn + sb + (unsigned)SM_SK + (unsigned)c * 64u + 32u * (unsigned)ph, rb = win_dn + bar(B_SK);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i)
+                                for (int i = 0; i < 2; ++i)
                                     st_async_v4(dst + 16u * i, make_float4(sk[4 * i], sk[4 * i + 1], sk[4 * i + 2], sk[4 * i + 3]), rb);
                             } else {
                                 if (last_layer && flow && (unsigned)(t - t0_head) >= 2u) {
-                                    if (lane == 0) dead |= !count_wait(P.ack + (size_t)(slot + 1) * G + g, 4u * ((unsigned)(t - t0_head) - 1u), abort_flag);
+                                    if (lane == 0) dead |= !count_wait(P.ack + (size_t)(slot + 1) * G + g, (unsigned)EW_H * ((unsigned)(t - t0_head) - 1u), abort_flag);
                                     dead = __any_sync(0xffffffffu, dead);
                                 }
-                                float4* ms = reinterpret_cast<float4*>(P.mail + box_dn * (size_t)(2 * CC * NP) + CC * NP) + c * 4;
+                                float4* ms = reinterpret_cast<float4*>(P.mail + box_dn * (size_t)(2 * CC * NP) + CC * NP) + c * 4 + 2 * ph;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) __stcg(ms + i, make_float4(sk[4 * i], sk[4 * i + 1], sk[4 * i + 2], sk[4 * i + 3]));
+                                for (int i = 0; i < 2; ++i) __stcg(ms + i, make_float4(sk[4 * i], sk[4 * i + 1], sk[4 * i + 2], sk[4 * i + 3]));
                                 __syncwarp();
                                 if (lane == 0) red_release_add_u32(P.mail_flag + box_dn, 1u);   // publishes the x block as well
                             }
@@ -646,7 +669,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                 auto pull_mail = [&](long long t, int g) -> bool {
                     const unsigned delivery = (unsigned)(t - P.t_begin);
                     const size_t box = ((size_t)slot * G + g) * 2 + (delivery & 1u);
-                    if (!count_wait(P.mail_flag + box, 4u * (delivery / 2u + 1u), abort_flag)) return false;
+                    if (!count_wait(P.mail_flag + box, (unsigned)EW_L * (delivery / 2u + 1u), abort_flag)) return false;
                     const float* m = P.mail + box * (size_t)(2 * CC * NP);
                     mbar_expect_tx(bar(B_XF), TILE_F);
                     bulk_g2s(sb + SM_XF, m, TILE_F, bar(B_XF));
@@ -718,7 +741,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                 stamp();
                 if (warp == W_CP && mail_fed && lane == 0) {
                     const size_t box = ((size_t)slot * G + g) * 2 + (delivery & 1u);
-                    if (count_wait(P.mail_flag + box, 4u * ((unsigned)(t - t0_head) / 2u + 1u), abort_flag)) {
+                    if (count_wait(P.mail_flag + box, (unsigned)EW_L * ((unsigned)(t - t0_head) / 2u + 1u), abort_flag)) {
                         mbar_expect_tx(bar(B_SK), TILE_F);
                         bulk_g2s(sb + SM_SK, P.mail + box * (size_t)(2 * CC * NP) + CC * NP, TILE_F, bar(B_SK));
                     }
