@@ -357,10 +357,10 @@ def run_b200(args):
         # bf16: the layer-pipelined tcgen05 kernel hosts 16-prompt groups on one CTA per layer; anything else is the fall-back
         tc_name = "wavenet7_kernel" if (info.get("group_size") == 16 and info.get("n_stages", 0) > 1) else "wavenet_tc_kernel"
         kname = {"wavenet": tc_name if args.dtype == "bf16" else "wavenet6_kernel",
-                 "samplernn": "samplernn_cluster_kernel"}[wl]
+                 "samplernn": "samplernn_cluster_kernel" + ("<2>" if args.dtype == "bf16" else "")}[wl]
         tr = NCU_TRAFFIC.get(kname)
         if args.dtype == "bf16":
-            roof = {"bound": "tensor", "kernel": kname + ("<2>" if wl == "samplernn" else ""), "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
         else:
             roof = {"bound": "fp32_fma", "kernel": kname, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",

@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet7_kernel(const __grid_constant__
                             store_half_column_bf16(smem + SM_YB, c, p0, xf);
                             fence_proxy_async_smem();
                             asm volatile("bar.sync 3, 256;" ::: "memory");
+                            stamp();
                             if (tid == 0) bulk_s2s(win_dn + sb + (unsigned)SM_XB, sb + SM_YB, TILE_B, win_dn + bar(B_XB_FULL));
+                            stamp();
                             if (cnt_dn >= 1u) dead |= !mbar_wait(bar(B_CR_XF), (cnt_dn - 1u) & 1u, abort_flag);
                             const unsigned dst = win_dn + sb + (unsigned)SM_XF + (unsigned)c * 64u + 32u * (unsigned)ph, rb = win_dn + bar(B_XF);
 #pragma unroll

@@ -13,7 +13,8 @@ OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 KERNELS = {"wn6": ("wavenet6_kernel", "fp32 layer-pipelined WaveNet (csrc/wavenet6.cu)"),
            "wn7": ("wavenet7_kernel", "bf16 tcgen05 layer-pipelined WaveNet (csrc/wavenet7.cu)"),
-           "sr": ("samplernn_cluster_kernel", "SampleRNN cluster kernel, lane-major frame-tier engine (csrc/samplernn2.cu)")}
+           "sr": ("samplernn_cluster_kernel", "SampleRNN cluster kernel, lane-major fp32 frame-tier engine (csrc/samplernn2.cu, ENGINE 1)"),
+           "srtc": ("samplernn_cluster_kernel", "SampleRNN cluster kernel, tcgen05 bf16 frame-tier engine (csrc/samplernn2.cu, ENGINE 2)")}
 
 
 def rows(path, kname):
@@ -50,7 +51,7 @@ for tag, (kname, what) in KERNELS.items():
                 kinfo = (kn, grid, block)
         f.write(f"\n# kernel {kinfo[0][:80]} grid {kinfo[1]} block {kinfo[2]}\n")
     if "dram__bytes_read.sum" in vals and cfg:
-        traffic[kname] = {"dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+        traffic[kname + ("<2>" if tag == "srtc" else "")] = {"dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
                           "l2_bytes": vals.get("lts__t_bytes.sum"), "duration_ns": vals.get("gpu__time_duration.sum"),
                           "prompts": cfg["batch_per_gpu"], "prompt_len": cfg["prompt_len"], "n_steps": cfg["n_steps"],
                           "source": f"profiles/r02_{tag}_ncu_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch: "
