@@ -87,7 +87,8 @@ class WaveNet(NativeARM):
         need(c.groups == 1, "groups > 1")
         need(str(c.act_f) == "Tanh" and str(c.act_g) == "Sigmoid", "activations other than Tanh/Sigmoid gating")
         need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
-        need(not (c.tie_io_weights or c.reverse_layer_order), "tie_io_weights / reverse_layer_order")
+        # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
+        # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
         need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
         need(len(c.blocks) > 0, "blocks=() (the reference then keeps conv_res on the last layer)")
@@ -104,8 +105,11 @@ class WaveNet(NativeARM):
         self._check_supported(config)
         self._config = config
         ks, dil = self.get_kernels_and_dilation(config.kernel_sizes, config.blocks)
-        self.kernels = [int(k) for k, _ in zip(ks, dil)]
-        self.dilations = [int(d) for _, d in zip(ks, dil)]
+        kd = [(int(k), int(d)) for k, d in zip(ks, dil)]
+        if config.reverse_layer_order:       # wavenet_v2.py:270: the ModuleList is reversed, so layers.0 is the widest dilation
+            kd.reverse()                     # and the layer built WITHOUT conv_res (wavenet_v2.py:216) runs first
+        self.kernels = [k for k, _ in kd]
+        self.dilations = [d for _, d in kd]
         self.has_skips = config.skips_dim is not None
         self.has_residuals = config.residuals_dim is not None
         self._sd = self._init_state_dict()
@@ -163,7 +167,8 @@ class WaveNet(NativeARM):
     @property
     def _plain(self):
         """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
-        return all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
+        return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
+                and not self._config.reverse_layer_order)
 
     @property
     def generate_params(self):
@@ -171,6 +176,11 @@ class WaveNet(NativeARM):
         its loop can never pass a temperature to WaveNet; the evident intent — and SampleRNN's behaviour
         (sample_rnn_v2.py:309-311) — is {"temperature"}.  Documented deviation."""
         return {"temperature"}
+
+    def _layer_has_res(self, l):
+        """wavenet_v2.py:216 — the layer BUILT last has no conv_res; with reverse_layer_order it is executed first."""
+        L = len(self.dilations)
+        return self.has_residuals and l != (0 if self._config.reverse_layer_order else L - 1)
 
     def _dims(self):
         c = self._config
@@ -190,7 +200,7 @@ class WaveNet(NativeARM):
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
                 e[f"layers.{l}.conv_skip.bias"] = (S,)
-            if self.has_residuals and l != L - 1:   # wavenet_v2.py:216 — never on the last layer
+            if self._layer_has_res(l):
                 e[f"layers.{l}.conv_res.weight"] = (C, C, 1)
                 e[f"layers.{l}.conv_res.bias"] = (C,)
         p = "output_modules.0.estimator.0."
@@ -245,7 +255,7 @@ class WaveNet(NativeARM):
         if self.has_skips:
             d.conv_skip_w = arr("layers.{}.conv_skip.weight")
             d.conv_skip_b = arr("layers.{}.conv_skip.bias")
-        has_res = lambda l: self.has_residuals and l != L - 1
+        has_res = self._layer_has_res
         d.conv_res_w = arr("layers.{}.conv_res.weight", has_res)
         d.conv_res_b = arr("layers.{}.conv_res.bias", has_res)
         p = "output_modules.0.estimator.0."

@@ -353,11 +353,15 @@ class WaveNetOracle:
     `pad_side` does not enter: the generation loop evaluates the LAST position of an rf-long window (eval_slice, :273), whose
     dependency cone never touches the left padding, so pad_side=1 and pad_side=0 give the same value there."""
 
-    def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256, layerwise_inputs=False, n_mlp_hidden=0):
+    def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256, layerwise_inputs=False, n_mlp_hidden=0,
+                 reverse_layer_order=False):
         sd = state_dict
         ks, ds = wavenet_kernels_and_dilations(kernel_sizes, blocks)
         self.kernels = [int(k) for k, _ in zip(ks, ds)]
         self.dilations = [int(d) for _, d in zip(ks, ds)]
+        if reverse_layer_order:                               # wavenet_v2.py:270: nn.ModuleList(reversed(layers))
+            self.kernels.reverse()
+            self.dilations.reverse()
         self.L = len(self.dilations)
         self.Q = q_levels
         self.layerwise_inputs = bool(layerwise_inputs)

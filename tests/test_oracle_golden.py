@@ -244,13 +244,13 @@ def test_samplernn_variant_oracle_vs_reference(name):
         np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
 
 
-WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3"]
+WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed"]
 
 
 def wavenet_variant_kwargs(d):
     m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
     return m, dict(kernel_sizes=(int(m.get("kernel_size", 2)),), layerwise_inputs=bool(int(m.get("layerwise_inputs", 0))),
-                   n_mlp_hidden=int(m.get("n_mlp_layers", 0)))
+                   n_mlp_hidden=int(m.get("n_mlp_layers", 0)), reverse_layer_order=bool(int(m.get("reverse_layer_order", 0))))
 
 
 @pytest.mark.parametrize("name", WN_VARIANTS)

@@ -66,7 +66,8 @@ def _worker512(rank, world, port, B, P, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         prompts, noise, _ = _inputs(B, P, n)
-        q.put((rank, sharding.generate_sharded(FakeARM512(), prompts + 200, n, temperature=0.9, noise=noise)))
+        # numpy, not tensors: a tensor travels through the queue as a shared-memory handle that dies with this process
+        q.put((rank, sharding.generate_sharded(FakeARM512(), prompts + 200, n, temperature=0.9, noise=noise).numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -87,7 +88,7 @@ def test_gather_keeps_wide_alphabets():
         p.join(timeout=60)
         assert p.exitcode == 0
     for r in range(world):
-        assert torch.equal(got[r], want)
+        assert torch.equal(torch.from_numpy(got[r]), want)
     # a block that does not fit its declared alphabet is an error, never a silent truncation
     with pytest.raises(ValueError):
         class One:
@@ -125,7 +126,7 @@ def _worker(rank, world, port, B, P, n, q):
         res["calls"] = net.calls
         feats = sharding.extract_sharded(lambda x: x.float() * 2 + 1, prompts, gather=True)
         res["feats"] = feats
-        q.put((rank, res))
+        q.put((rank, {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()}))   # see _worker512
     finally:
         dist.destroy_process_group()
 
@@ -153,10 +154,10 @@ def test_generate_sharded_equals_single_process(world, B):
     for r in range(world):
         lo, hi = sharding.shard_bounds(B, world, r)
         for k, v in want.items():
-            assert torch.equal(got[r][k], v), (r, k)          # every rank holds the whole batch, in prompt order
-        assert torch.equal(got[r]["local_only"], want["vector_T"][lo:hi])
+            assert torch.equal(torch.from_numpy(got[r][k]), v), (r, k)          # every rank holds the whole batch, in prompt order
+        assert torch.equal(torch.from_numpy(got[r]["local_only"]), want["vector_T"][lo:hi])
         assert got[r]["calls"] == [hi - lo] * 4                # one kernel-path call per run, on its own block only
-        assert torch.equal(got[r]["feats"], prompts.float() * 2 + 1)
+        assert torch.equal(torch.from_numpy(got[r]["feats"]), prompts.float() * 2 + 1)
 
 
 def test_shard_bounds_partition():
