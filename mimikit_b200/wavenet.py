@@ -92,6 +92,8 @@ class WaveNet(NativeARM):
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
         need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
         need(len(c.blocks) > 0, "blocks=() (the reference then keeps conv_res on the last layer)")
+        need(not c.reverse_layer_order or c.skips_dim is not None or c.residuals_dim is None,
+             "reverse_layer_order with residuals and without skips (the head would read the last layer's residual output)")
         ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
         need(all(2 <= k <= 4 for k in ks), "kernel sizes outside [2, 4]")
 
@@ -255,7 +257,9 @@ class WaveNet(NativeARM):
         if self.has_skips:
             d.conv_skip_w = arr("layers.{}.conv_skip.weight")
             d.conv_skip_b = arr("layers.{}.conv_skip.bias")
-        has_res = self._layer_has_res
+        # reverse_layer_order: the layer executed last carries a conv_res whose result nothing reads when the head takes the
+        # skip sum (wavenet_v2.py:286-292): it is not handed to the kernel
+        has_res = lambda l: self._layer_has_res(l) and l != L - 1
         d.conv_res_w = arr("layers.{}.conv_res.weight", has_res)
         d.conv_res_b = arr("layers.{}.conv_res.bias", has_res)
         p = "output_modules.0.estimator.0."
