@@ -94,6 +94,10 @@ struct Params {
     int fast, NKQ, CHP;              // K quarters (H / 128), prompts per block of the walk (2 per warp)
     int s_part, s_hold, s_lin;
     int tc, s_tcbar;                 // tensor-core frame tiers (bf16 operands, fp32 accumulation): compute mode MMK_COMPUTE_BF16_TC
+    // tensor-core mode, fold_head: the bottom tier's up-sampler emits W1 (up(h) + conv_b) + b1 directly (W1 . W_up precomputed), so a
+    // head step starts from `pre` [slot][128 prompts][Hh] and adds (W1 conv_w) lin(q): no x rows, no W1 contraction, no exchange
+    int fold_head, NVh;              // NVh: folded up-sampler columns per CTA (up * Hh / NC)
+    float* pre; const float* hu; const float* hb;     // hu [Hh][fs_last] = W1 . conv_w; hb [NC][NVh] folded biases
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -882,8 +886,10 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
 }
 
 // LinearResampler rows of this CTA (modules/resamplers.py:13-23) on the new hidden image: always behind a grid barrier.
-__device__ __forceinline__ bool tc_up(const Params& P, const Tier& T, const unsigned char* himg, unsigned long long& epoch, Tc& X) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H, NV = T.NV;
+__device__ __forceinline__ bool tc_up(const Params& P, const Tier& T, const unsigned char* himg, unsigned long long& epoch, Tc& X, bool fold) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
+    const int NV = fold ? P.NVh : T.NV;                         // columns of this CTA
+    const int RL = fold ? P.Hh : H;                             // row length of the destination
     if (!grid_barrier(P, epoch)) return false;
     const int nimg = H / 128;
     bool ok = tc_contract(P, X, himg, nimg, himg, 0, T.wuimg + (size_t)c * nimg * TC_B_BYTES, warp, lane);
@@ -895,12 +901,12 @@ __device__ __forceinline__ bool tc_up(const Params& P, const Tier& T, const unsi
         tmem_ld16(X.tmem + ((unsigned)(32 * warp) << 16), v);
         tmem_ld_wait();
         tc_fence_before();
-        const float* ub = T.ub + (size_t)c * NV;
-        const int urow = c * NV, slot = urow / H, k0 = urow - slot * H;     // NV divides H: the CTA's rows share a slot
+        const float* ub = fold ? P.hb + (size_t)c * NV : T.ub + (size_t)c * NV;
+        const int urow = c * NV, slot = urow / RL, k0 = urow - slot * RL;   // NV divides the row length: the CTA's rows share a slot
 #pragma unroll
         for (int col = 0; col < 16; ++col) v[col] += col < NV ? __ldg(ub + col) : 0.0f;
         if (p < P.B) {
-            if (T.oimg != nullptr) {                            // conditioning of the next frame tier: bf16 image of the slot
+            if (!fold && T.oimg != nullptr) {                   // conditioning of the next frame tier: bf16 image of the slot
                 unsigned char* img = T.oimg + (size_t)slot * ((size_t)H * 256);
                 if (NV == 4) {
                     __stcg(reinterpret_cast<uint2*>(img + tile_off(p, k0 >> 3, 128) + (k0 & 7) * 2), make_uint2(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3])));
@@ -912,11 +918,17 @@ __device__ __forceinline__ bool tc_up(const Params& P, const Tier& T, const unsi
                                    make_uint4(bf16x2_bits(v[h8 * 8], v[h8 * 8 + 1]), bf16x2_bits(v[h8 * 8 + 2], v[h8 * 8 + 3]),
                                               bf16x2_bits(v[h8 * 8 + 4], v[h8 * 8 + 5]), bf16x2_bits(v[h8 * 8 + 6], v[h8 * 8 + 7])));
                 }
-            } else {                                            // the head reads fp32 [slot][prompt][H]
-                float* dst = T.obuf + ((size_t)slot * P.Bp + p) * H + k0;
+            } else {                                            // the head reads fp32: [slot][prompt][H] rows of the up-sampler, or (folded)
+                float* dst = (fold ? P.pre : T.obuf) + ((size_t)slot * P.Bp + p) * RL + k0;   // [slot][prompt][Hh] hidden pre-activations
+                if (NV >= 4) {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                    if (q4 * 4 < NV) __stcg(reinterpret_cast<float4*>(dst + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        if (q4 * 4 < NV) __stcg(reinterpret_cast<float4*>(dst + 4 * q4), make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]));
+                } else {
+#pragma unroll
+                    for (int q1 = 0; q1 < 4; ++q1)
+                        if (q1 < NV) __stcg(dst + q1, v[q1]);
+                }
             }
         }
     }
@@ -1032,7 +1044,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         default: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
                     }
                     hsel[i] ^= 1;
-                    if (ok) ok = tc_up(P, T, himg_next, epoch, X);
+                    if (ok) ok = tc_up(P, T, himg_next, epoch, X, P.fold_head != 0 && i == P.n_ft - 1);
                     if (!ok) { dead = true; break; }
                     pending_up = true;
                 }
@@ -1221,6 +1233,24 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
             for (int g = cluster; g < n_groups && !dead; g += n_clusters, ++gl) {
                 const int b0 = g * GP;
                 const unsigned par = head_phase & 1u;
+                if (ENGINE == 2 && P.fold_head) {
+                    // -- 1'-3'. hidden rows of this CTA straight from the folded up-sampler output: mish(pre + (W1 conv_w) lin(q))
+                    const float* preL = P.pre + (size_t)(t % TL.fs) * Bp * Hh;
+                    for (int i = tid; i < RS * GP; i += NTK) {
+                        const int r = i / GP, p = i - r * GP, row = rank * RS + r, b = b0 + p;
+                        float a = (b < P.B) ? __ldcg(preL + (size_t)b * Hh + row) : 0.0f;
+                        for (int f = 0; f < fsl; ++f) {
+                            long long q = 0;
+                            if (b < P.B) {
+                                if (f == fsl - 1 && !P.teacher_forced && t > P.gen_begin) q = (long long)qbuf[gl * GP + p];
+                                else q = __ldcg(P.seq + (size_t)b * P.seq_stride + (tw - fsl + f));
+                            }
+                            a = fmaf(linearize(q, Qf), __ldg(P.hu + (size_t)row * fsl + f), a);
+                        }
+                        hid_s[i] = mish_acc(a);
+                    }
+                    __syncthreads();
+                } else {
                 // -- 1. this CTA's rows of x = Conv1d(lin(q[t-fs:t])) + conditioning (modules/io.py:185-198)
                 for (int idx = tid; idx < KS * GP; idx += NTK) {
                     const int kl = FAST ? idx % KS : idx / GP, p = FAST ? idx / KS : idx - kl * GP, k = rank * KS + kl, b = b0 + p;
@@ -1288,6 +1318,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                     hid_s[i] = mish_acc(s + b1s[i / GP]);
                 }
                 __syncthreads();
+                }
                 // -- 4. partial logits over this CTA's hidden rows, reduce-scattered by prompt
                 {
                     const int tiles = (ZR >> 2) * npq_h;
@@ -1769,6 +1800,12 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
         // ---- tensor-core engine: bf16 weight tiles [16 columns x 128 k] per fill (K = [conditioning | hidden], the top tier: hidden only),
         //      columns gate * 4 + jj with gates r, z, n_i, n_h; the frame Linear and all biases folded into wf / bfold (fp64 -> fp32)
         const int nimg = H / 128, nfill = 2 * nimg;
+        // fold the head's first Linear into the bottom tier's up-sampler when its rows split evenly over the CTAs (see Params::fold_head)
+        bool fold_here = false;
+        if (i == n_ft - 1 && !(getenv("MMK_SR_FOLD") && atoi(getenv("MMK_SR_FOLD")) == 0)) {
+            const int rows = T.up * Hh;
+            if (rows % NC == 0 && rows / NC >= 1 && rows / NC <= 16 && Hh % (rows / NC) == 0) { fold_here = true; p.fold_head = 1; p.NVh = rows / NC; }
+        }
         auto bf = [](float v) { __nv_bfloat16 b = __float2bfloat16_rn(v); unsigned short u; memcpy(&u, &b, 2); return u; };
         std::vector<unsigned char> wgi((size_t)NC * nfill * TC_B_BYTES, 0), wui((size_t)NC * nimg * TC_B_BYTES, 0);
         std::vector<float> wfv((size_t)NC * 16 * T.fs, 0.0f), bfv((size_t)NC * 16, 0.0f);
@@ -1802,12 +1839,50 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
                 if (g4 < 2 || g4 == 3) b += d->b_hh[i][grow];
                 bfv[(size_t)c * 16 + col] = (float)b;
             }
+            if (fold_here) continue;                              // the bottom tier's tiles are packed below from W1 . W_up
             for (int col = 0; col < T.NV; ++col)
                 for (int k = 0; k < H; ++k) {
                     const unsigned short v = bf(d->up_w[i][(size_t)(c * T.NV + col) * H + k]);
                     unsigned char* tile = wui.data() + ((size_t)c * nimg + k / 128) * TC_B_BYTES;
                     memcpy(tile + tile_off(col, (k % 128) / 8, 16) + (k % 8) * 2, &v, 2);
                 }
+        }
+        if (fold_here) {
+            // W'[slot][j][k] = sum_m W1[j][m] W_up[slot H + m][k];  b'[slot][j] = sum_m W1[j][m] (b_up[slot H + m] + conv_b[m]) + b1[j];
+            // hu[j][f] = sum_m W1[j][m] conv_w[m][f]   (fp64 accumulation)
+            const int fsl = p.fs_last, NVh = p.NVh;
+            std::vector<double> wp((size_t)T.up * Hh * H, 0.0);
+            for (int sl = 0; sl < T.up; ++sl)
+                for (int j = 0; j < Hh; ++j) {
+                    double* row = wp.data() + ((size_t)sl * Hh + j) * H;
+                    for (int m = 0; m < H; ++m) {
+                        const double w1 = d->head_w1[(size_t)j * H + m];
+                        const float* wu = d->up_w[i] + ((size_t)sl * H + m) * H;
+                        for (int k = 0; k < H; ++k) row[k] += w1 * (double)wu[k];
+                    }
+                }
+            std::vector<float> hbv((size_t)NC * NVh), huv((size_t)Hh * fsl);
+            for (int c = 0; c < NC; ++c)
+                for (int col = 0; col < NVh; ++col) {
+                    const int urow = c * NVh + col, sl = urow / Hh, j = urow % Hh;
+                    for (int k = 0; k < H; ++k) {
+                        const unsigned short v = bf((float)wp[((size_t)sl * Hh + j) * H + k]);
+                        unsigned char* tile = wui.data() + ((size_t)c * nimg + k / 128) * TC_B_BYTES;
+                        memcpy(tile + tile_off(col, (k % 128) / 8, 16) + (k % 8) * 2, &v, 2);
+                    }
+                    double b = d->head_b1[j];
+                    for (int m = 0; m < H; ++m) b += (double)d->head_w1[(size_t)j * H + m] * ((double)d->up_b[i][(size_t)sl * H + m] + (double)d->conv_b[m]);
+                    hbv[(size_t)c * NVh + col] = (float)b;
+                }
+            for (int j = 0; j < Hh; ++j)
+                for (int f = 0; f < fsl; ++f) {
+                    double a = 0.0;
+                    for (int m = 0; m < H; ++m) a += (double)d->head_w1[(size_t)j * H + m] * (double)d->conv_w[(size_t)m * fsl + f];
+                    huv[(size_t)j * fsl + f] = (float)a;
+                }
+            p.hb = up(hbv.data(), hbv.size());
+            p.hu = up(huv.data(), huv.size());
+            p.pre = up(nullptr, (size_t)T.up * p.Bp * Hh);
         }
         auto upb = [&](const void* src, size_t bytes) { void* q = dev_alloc(bytes, src); ok = ok && q; return (unsigned char*)q; };
         T.wgimg = upb(wgi.data(), wgi.size());

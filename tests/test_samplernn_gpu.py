@@ -166,14 +166,16 @@ def test_lane_major_engine_vs_oracle(monkeypatch, cluster, fs, H, B, P):
     assert _rel_err(lg.cpu().numpy(), ref_logits) <= REL_TOL
 
 
-@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 48), ((8, 2, 1), 512, 128, 24), ((4, 4), 256, 3, 16), ((8, 4, 2, 1), 128, 22, 32),
-                                      ((2, 2, 1), 128, 5, 10), ((8, 4, 2), 256, 70, 40)])
-def test_tensor_core_mode_vs_oracle(fs, H, B, P):
+@pytest.mark.parametrize("fs,H,B,P,mlp", [((8, 2, 1), 512, 37, 48, 32), ((8, 2, 1), 512, 128, 24, 32), ((4, 4), 256, 3, 16, 32),
+                                          ((8, 4, 2, 1), 128, 22, 32, 32), ((2, 2, 1), 128, 5, 10, 32), ((8, 4, 2), 256, 70, 40, 32),
+                                          ((8, 2, 1), 512, 50, 24, 128), ((8, 2, 1), 256, 9, 16, 64)])
+def test_tensor_core_mode_vs_oracle(fs, H, B, P, mlp):
     """compute_dtype bfloat16: the frame tiers' GRU and up-sampler contractions on tcgen05 (bf16 operands, fp32 accumulation in
     TMEM, frame Linear folded into the gate), cell / head / sampler in fp32.  Teacher-forced logits within the north star's 5e-2
     of the fp32 oracle, decisions = argmax of the kernel's own logits, free-running generation deterministic and consistent with
-    its own logits."""
-    net = make_net(fs, H, mlp_dim=32, seed=5).bfloat16()
+    its own logits.  The geometries cover both forms of the head: with the first Linear folded into the bottom tier's up-sampler
+    (when up * mlp_dim rows split evenly over the H / 4 CTAs, e.g. BASELINE's 512 / 128) and without (512 / 32)."""
+    net = make_net(fs, H, mlp_dim=mlp, seed=5).bfloat16()
     info = net.launch_info(B)
     assert info["threads"] == 256 and info["sm_used"] == H // 4, info
     orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
