@@ -415,6 +415,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Packed fp32 pairs (FFMA2 / FADD2, sm_100): one issue slot for two IEEE fp32 operations (the FMA pipe still spends two cycles —
 // scripts/ubench/ffma2_bench.cu — so this buys issue slots for the shuffles, not FMA throughput)
@@ -792,7 +793,7 @@ __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsign
     if (warp >= 5) {
         if (lane == 0) {
             const unsigned s = (unsigned)(warp - 5);
-            fence_proxy_async();     // rows written with st.global by other CTAs before the grid barrier -> async-proxy reads
+            fence_proxy_async_global();   // rows written with st.global by other CTAs before the grid barrier -> async-proxy reads
             for (int j = 0; j < nfill && ok; ++j) {
                 const unsigned g = X.gf + (unsigned)j;
                 if (g % TC_STAGES != s) continue;
@@ -832,20 +833,20 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
                                        const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
     if (pre_barrier && !grid_barrier(P, epoch)) return false;
-    const float Qf = (float)P.Q;
-    for (int idx = tid; idx < 128 * FS; idx += NTF) {          // Linearizer of the frame (modules/io.py:111-112)
-        const int p = idx / FS, f = idx - p * FS;
-        long long q = 0;
-        if (p < P.B) q = __ldcg(P.seq + (size_t)p * P.seq_stride + (tw - FS + f));
-        X.lin[idx] = linearize(q, Qf);
-    }
-    __syncthreads();
     const int nimg = H / 128;                                   // fills per image
     bool ok = tc_contract(P, X, cimg ? cimg : himg, nimg, himg, cimg ? nimg : 0,
                           T.wgimg + (size_t)c * (2 * nimg) * TC_B_BYTES, warp, lane);
     if (warp < 4) {
         const int p = tid;
         const float4 hold = __ldcg(reinterpret_cast<const float4*>(hcur + (size_t)p * H + 4 * c));
+        {   // Linearizer of the prompt's frame (modules/io.py:111-112), under the fills and the MMAs
+            const float Qf = (float)P.Q;
+            long long q[FS];
+#pragma unroll
+            for (int f = 0; f < FS; ++f) q[f] = p < P.B ? __ldcg(P.seq + (size_t)p * P.seq_stride + (tw - FS + f)) : 0;
+#pragma unroll
+            for (int f = 0; f < FS; ++f) X.lin[p * FS + f] = linearize(q[f], Qf);
+        }
         const float* wf = T.wf + (size_t)c * 16 * FS;
         const float* bfo = T.bfold + (size_t)c * 16;
         float pre[16];
