@@ -12,20 +12,15 @@ __device__ __forceinline__ float mish_acc(float x) {
     return x * tanhf(sp);
 }
 
-// One warp decides one prompt.  z: shared-memory row of the Q+1 raw head outputs (overwritten).  logits_out:
-// nullable global row of Q floats.  sample: draw with temperature T and uniform u, else argmax (lowest index wins
-// ties, as torch.argmax).  All 32 lanes must call; every lane returns the decision.
-__device__ __forceinline__ int decide_warp(float* z, int Q, float min_temp, float* logits_out, bool sample, float T,
-                                           float u) {
+// One warp decides one prompt from its SCALED logits z[0..Q) = raw / max(sigmoid(raw[Q]), min_temp) (shared memory, overwritten when
+// sampling).  sample: draw with temperature T and uniform u, else argmax (lowest index wins ties, as torch.argmax).  All 32 lanes
+// must call; every lane returns the decision.
+__device__ __forceinline__ int decide_scaled_warp(float* z, int Q, bool sample, float T, float u) {
     const int lane = threadIdx.x & 31;
-    const float temp = fmaxf(sigmoid_acc(z[Q]), min_temp);        // mlp.py:60-62
     float best = -INFINITY;
     int besti = 0x7fffffff;
-    __syncwarp();
     for (int c = lane; c < Q; c += 32) {
-        const float v = z[c] / temp;
-        z[c] = v;
-        if (logits_out) __stcs(logits_out + c, v);
+        const float v = z[c];
         if (v > best) { best = v; besti = c; }   // strided visit keeps the lowest index per lane
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -68,6 +63,22 @@ __device__ __forceinline__ int decide_warp(float* z, int Q, float min_temp, floa
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     return min(Q - 1, cnt);
+}
+
+// One warp decides one prompt.  z: shared-memory row of the Q+1 raw head outputs (overwritten).  logits_out:
+// nullable global row of Q floats.  All 32 lanes must call; every lane returns the decision.
+__device__ __forceinline__ int decide_warp(float* z, int Q, float min_temp, float* logits_out, bool sample, float T,
+                                           float u) {
+    const int lane = threadIdx.x & 31;
+    const float temp = fmaxf(sigmoid_acc(z[Q]), min_temp);        // mlp.py:60-62
+    __syncwarp();
+    for (int c = lane; c < Q; c += 32) {
+        const float v = z[c] / temp;
+        z[c] = v;
+        if (logits_out) __stcs(logits_out + c, v);
+    }
+    __syncwarp();
+    return decide_scaled_warp(z, Q, sample, T, u);
 }
 
 }  // namespace mmk

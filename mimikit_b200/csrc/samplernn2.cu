@@ -73,7 +73,7 @@ struct Params {
     int KS, RS, ZR;                  // head: x rows per CTA (H/CS), hidden rows per CTA (Hh/CS), padded logit rows
     int off_w1, off_b1, off_w2, cta_block;     // global block offsets
     int so_w1, so_b1, so_w2;
-    int s_region, s_gi, s_bar, smem_floats;
+    int s_region, s_gi, s_bar, s_b2, smem_floats;
     int xstage, wstage, xregion, wregion, region;    // per stage; floats: activation stages, streamed-weight stages, both (= partial sums / head buffers)
     int h_x, h_inh, h_hid, h_un, h_zs;      // head buffers inside the region (float offsets)
     const float* wpack; const float* conv_w; const float* conv_b; const float* b2;
@@ -964,6 +964,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
         float4* dst = reinterpret_cast<float4*>(smem + P.res_soff[r]);
         for (int i = tid; i < P.res_len[r] / 4; i += NTK) dst[i] = __ldg(src + i);
     }
+    for (int i = tid; i <= P.Q; i += NTK) smem[P.s_b2 + i] = __ldg(P.b2 + i);
     const int GP = P.GP, npq_h = GP >> 2;
     const unsigned hid_bytes = (unsigned)(CS * P.RS * GP) * 4u;
     const unsigned z_bytes = (unsigned)((GP / CS) * CS * P.ZR) * 4u;
@@ -1008,6 +1009,8 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
     unsigned long long epoch = 0;
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = globaltimer();
     auto lap = [&](int slot) { if (!FAST && P.dbg && c == 0 && tid == 0) { const unsigned long long n = globaltimer(); tacc[slot] += n - tlast; tlast = n; } };
+    long long hta[6] = {0, 0, 0, 0, 0, 0}, htl = clock64();   // MMK_SR_DEBUG: SM cycles of CTA 0 per head section (+ everything else)
+    auto hlap = [&](int slot) { if (FAST && P.dbg && c == 0 && tid == 0) { const long long n = clock64(); hta[slot] += n - htl; htl = n; } };
     unsigned head_phase = 0;              // completed head exchanges (parity of the three mbarriers)
     bool dead = false;
     bool heads_pending = false;           // head steps ran since the last grid barrier
@@ -1227,6 +1230,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
             float* part_h = region + P.h_un;        // [nq][tiles][16]   (dead before the logits arrive)
             float* inbox_z = region + P.h_un;       // [GP/CS][CS][ZR]
             float* zs = region + P.h_zs;            // [GP/CS][ZR + 4]
+            const float* b2s = smem + P.s_b2;       // [Q + 1] output biases
             unsigned* qbuf = reinterpret_cast<unsigned*>(smem + P.s_bar) + 2 * BAR_COUNT;   // [groups per cluster][GP]
             const int KS = P.KS, RS = P.RS, ZR = P.ZR, Hh = P.Hh, fsl = P.fs_last;
             const long long hstep = t - P.gen_begin, n_gen = P.gen_end - P.gen_begin;
@@ -1234,6 +1238,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
             for (int g = cluster; g < n_groups && !dead; g += n_clusters, ++gl) {
                 const int b0 = g * GP;
                 const unsigned par = head_phase & 1u;
+                hlap(5);
                 if (ENGINE == 2 && P.fold_head) {
                     // -- 1'-3'. hidden rows of this CTA straight from the folded up-sampler output: mish(pre + (W1 conv_w) lin(q))
                     const float* preL = P.pre + (size_t)(t % TL.fs) * Bp * Hh;
@@ -1320,6 +1325,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                 }
                 __syncthreads();
                 }
+                hlap(0);
                 // -- 4. partial logits over this CTA's hidden rows, reduce-scattered by prompt
                 {
                     const int tiles = (ZR >> 2) * npq_h;
@@ -1348,18 +1354,31 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         }
                     }
                 }
+                hlap(1);
                 dead |= !mbar_wait(bar(BAR_Z), par, abort_flag);
                 if (tid == 0) mbar_expect_tx(bar(BAR_Z), z_bytes);
-                // -- 5. one warp per prompt: sum the partial logits in rank order, learned temperature, decision
+                hlap(2);
+                // -- 5a. every thread: one logit of one of this CTA's prompts — partial sums in rank order, bias, learned temperature
+                //        (mlp.py:60-62; the temperature row is re-derived per thread: 4 loads and a sigmoid instead of a barrier)
+                {
+                    const int D = GP / CS;
+                    for (int idx = tid; idx < D * P.Q; idx += NTK) {
+                        const int w = idx / P.Q, o = idx - w * P.Q;
+                        const float* iz = inbox_z + (size_t)(w * CS) * ZR;
+                        float sv = 0.0f, st = 0.0f;
+                        for (int src = 0; src < CS; ++src) { sv += iz[(size_t)src * ZR + o]; st += iz[(size_t)src * ZR + P.Q]; }
+                        const float temp = fmaxf(sigmoid_acc(st + b2s[P.Q]), P.min_temp);
+                        const float v = (sv + b2s[o]) / temp;
+                        zs[w * (ZR + 4) + o] = v;
+                        const int b = b0 + w * CS + rank;
+                        if (P.logits_out && b < P.B) __stcs(P.logits_out + ((size_t)b * n_gen + hstep) * P.Q + o, v);
+                    }
+                    __syncthreads();
+                }
+                // -- 5b. one warp per prompt: the decision
                 if (warp < GP / CS) {
                     const int p = warp * CS + rank, b = b0 + p;
                     float* zr = zs + warp * (ZR + 4);
-                    for (int o = lane; o <= P.Q; o += 32) {
-                        float s = 0.0f;
-                        for (int src = 0; src < CS; ++src) s += inbox_z[(size_t)(warp * CS + src) * ZR + o];
-                        zr[o] = s + __ldg(P.b2 + o);
-                    }
-                    __syncwarp();
                     int choice = 0;
                     if (b < P.B) {
                         const bool sample = P.temperature != nullptr;
@@ -1368,8 +1387,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                             Tt = P.temperature[P.n_temperature == 1 ? 0 : b];
                             u = P.noise[(size_t)b * P.noise_stride + (t - P.noise_t0)];
                         }
-                        float* lout = P.logits_out ? P.logits_out + ((size_t)b * n_gen + hstep) * P.Q : nullptr;
-                        choice = decide_warp(zr, P.Q, P.min_temp, lout, sample, Tt, u);
+                        choice = mmk::decide_scaled_warp(zr, P.Q, sample, Tt, u);
                         if (lane == 0) {
                             if (P.decisions) P.decisions[(size_t)b * n_gen + hstep] = choice;
                             if (!P.teacher_forced) __stcg(P.seq + (size_t)b * P.seq_stride + t, (long long)choice);
@@ -1382,10 +1400,12 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         st_async_u32(win + sbase + off, (unsigned)choice, win + bar(BAR_Q));
                     }
                 }
+                hlap(3);
                 dead |= !mbar_wait(bar(BAR_Q), par, abort_flag);
                 if (tid == 0) mbar_expect_tx(bar(BAR_Q), q_bytes);
                 ++head_phase;
                 if (__syncthreads_or(dead ? 1 : 0)) dead = true;
+                hlap(4);
             }
             heads_pending = true;
             lap(7);
@@ -1397,6 +1417,8 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
         for (int i = 0; i < 8; ++i) P.dbg[i] += tacc[i];
     if (ENGINE == 1 && F.timing)
         for (int i = 0; i < 12; ++i) P.dbg[8 + i] += (unsigned long long)F.ta[i];
+    if (FAST && P.dbg && c == 0 && tid == 0)
+        for (int i = 0; i < 6; ++i) P.dbg[20 + i] += (unsigned long long)hta[i];
     // no CTA may exit while peers can still store into its shared memory
     if (ENGINE == 2) tc_fence_before();
     __syncthreads();
@@ -1518,6 +1540,7 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
     p.s_region = take(p.region);
     p.s_gi = o;
     p.s_bar = take(2 * BAR_COUNT + 16 * GP);
+    p.s_b2 = take(Q + 1);
     p.s_part = take(tc ? 4 : p.NKQ * p.Bp * 16);
     p.s_hold = take(tc ? 4 : p.Bp * 4);
     p.s_lin = take(p.Bp * fs_max);
@@ -1639,6 +1662,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
         p.s_region = take(REGION);
         p.s_gi = take(std::max(p.NG, fs_max) * PBW);
         p.s_bar = take(2 * BAR_COUNT + groups_per_cluster_max * GP);
+        p.s_b2 = take(Q + 1);
         p.n_res = 0;
         const int budget = max_optin / (int)sizeof(float) - 256;     // floats; 1 KB of slack for static shared memory
         auto resident = [&](int goff, int len, int* soff) {
@@ -1892,10 +1916,6 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
         T.bfold = up(bfv.data(), bfv.size());
         T.himg = upb(nullptr, (size_t)2 * H * 256);
         T.oimg = i < n_ft - 1 ? upb(nullptr, (size_t)T.up * H * 256) : nullptr;
-        // ub of the plain order (the tensor-core up-sampler columns are the rows NV c .. in order)
-        std::vector<float> ubp((size_t)NC * T.NV);
-        for (int c = 0; c < NC; ++c) for (int col = 0; col < T.NV; ++col) ubp[(size_t)c * T.NV + col] = d->up_b[i][c * T.NV + col];
-        T.ub = up(ubp.data(), ubp.size());
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
     p.conv_b = up(d->conv_b, H);
@@ -1923,10 +1943,13 @@ int sr2_sync_check(sr2_handle* h, void* stream) {
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MMK_CHECK(aborted == 0, "SampleRNN kernel watchdog fired: a barrier wait timed out (results invalid)");
     if (h->p.dbg) {
-        unsigned long long t[20];
+        unsigned long long t[26];
         MMK_CUDA(cudaMemcpy(t, h->p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
         MMK_CUDA(cudaMemset(h->p.dbg, 0, sizeof(t)));
         if (h->p.fast) {
+            fprintf(stderr, "[sr2] CTA0 head Mcycles: hidden rows %.1f logit partials + send %.1f wait logits %.1f decide %.1f wait index %.1f | outside the head %.1f\n",
+                    t[20] / 1e6, t[21] / 1e6, t[22] / 1e6, t[23] / 1e6, t[24] / 1e6, t[25] / 1e6);
+            if (h->p.tc) return 0;
             static const char* names[12] = {"weights", "pre-barrier", "frame", "gru stream", "gates", "up weights", "barrier", "up stream", "up rows",
                                             "last barrier", "head", "other"};
             fprintf(stderr, "[sr2] CTA0 Mcycles:");
