@@ -285,6 +285,25 @@ def test_s3_full_width_properties():
     assert np.array_equal(seq.cpu().numpy()[sub][:, :P + 32], ref_seq)
 
 
+def test_s3_long_horizon_vs_oracle():
+    """BASELINE cfg 3 geometry over a longer horizon (1 000 generated samples = 625 tier firings after the warm-up) on the default
+    (lane-major) engine: argmax and sampled sequences stay bit-exact with the oracle, logits within tolerance at the far end."""
+    fs = (8, 2, 1)
+    net = make_net(fs, 512, mlp_dim=128, seed=3)
+    assert net.launch_info(128)["threads"] == 256
+    g = torch.Generator().manual_seed(99)
+    B, P, n = 128, 64, 1000
+    prompts = torch.from_numpy(restate.synthetic_prompts(B, P))
+    noise = torch.rand(B, n, generator=g)
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    sub = [5, 126]
+    for temp in (None, 0.9):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), n, temp, noise[sub].numpy())
+        assert np.array_equal(seq.cpu().numpy()[sub], ref_seq), temp
+        assert _rel_err(logits.cpu().numpy()[sub][:, -50:], ref_logits[:, -50:]) <= REL_TOL
+
+
 @pytest.mark.parametrize("name", ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2",
                                   "samplernn_rnn_tanh_mlp1"])
 def test_variant_goldens(name):
