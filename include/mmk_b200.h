@@ -265,7 +265,7 @@ typedef struct {
     const float* head_bh;         /* ...fc.2.bias (Hh) */
     int need_set_hidden;          /* 1 = mmk_samplernn_set_hidden will be used (h0_init "ones" / "randn"): general kernel */
     int compute_mode;             /* MMK_COMPUTE_FP32 (0) | MMK_COMPUTE_BF16_TC (1): frame-tier GRU and up-sampler contractions on
-                                     tcgen05 with bf16 operands and fp32 accumulation (logits within 5e-2 of fp32).  GRU, one layer,
+                                     tcgen05 with bf16 operands and fp32 accumulation (logits within 5e-2 of fp32).  GRU or LSTM, one layer,
                                      zero initial state, plain head, hidden_dim in {128, 256, 512}, max_batch <= 128; else an error */
 } mmk_samplernn_desc_ex;
 int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* desc, int max_batch, mmk_samplernn_t* out);

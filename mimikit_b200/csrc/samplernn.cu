@@ -436,12 +436,15 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
     {   // MMK_SR_KERNEL: "1" = general kernel only, "2" = cluster kernel only, unset = cluster kernel when it fits
         const char* force = getenv("MMK_SR_KERNEL");
         const int tc = dx->compute_mode == MMK_COMPUTE_BF16_TC ? 1 : 0;
-        if (tc && !plain) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU tiers with one layer, a zero initial state and a plain head"); }
-        if (plain && (tc || !force || atoi(force) != 1)) {
+        // the tensor-core engine also hosts nn.LSTM tiers (the reference's default rnn_class); one layer, zero initial state, plain head
+        const bool tc_form = (dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM) && dx->n_rnn == 1 && dx->head_hidden_layers == 0 &&
+                             !dx->need_set_hidden;
+        if (tc && !tc_form) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer, a zero initial state and a plain head"); }
+        if ((plain || (tc && tc_form)) && (tc || !force || atoi(force) != 1)) {
             int unsupported = 0;
             mmk_samplernn_desc d2 = *d;      // the cluster kernel hosts the GRU / one layer / plain head form only
             d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;
-            if (sr2_create(&d2, max_batch, tc, &h->v2, &unsupported) == 0) {
+            if (sr2_create(&d2, max_batch, tc, dx->rnn_type == MMK_RNN_LSTM ? 1 : 0, &h->v2, &unsupported) == 0) {
                 h->max_batch = max_batch; h->rf = d->frame_sizes[0];
                 *out = h;
                 return 0;

@@ -59,6 +59,7 @@ struct Tier {
     int NV;                          // up-sampler rows of a CTA (4 * up)
     // tensor-core engine (Params::tc): bf16 images in the UMMA K-major SWIZZLE_128B layout — [128 prompts x H] activations
     // (16 KB atoms of 64 k), [16 columns x K] weight tiles per CTA
+    float* cbuf;                     // LSTM cell state, fp32 [2][prompt][H] (ping-pong like hbuf); null for GRU tiers
     unsigned char* himg;             // hidden state, two images (ping-pong like hbuf)
     unsigned char* oimg;             // up-sampler output (the next tier's conditioning), one image per slot; null for the bottom frame tier
     const unsigned char* wgimg;      // [NC][fills][4 KB]: r | z | n_i | n_h columns over K = [conditioning | hidden]
@@ -96,6 +97,7 @@ struct Params {
     int tc, s_tcbar;                 // tensor-core frame tiers (bf16 operands, fp32 accumulation): compute mode MMK_COMPUTE_BF16_TC
     // tensor-core mode, fold_head: the bottom tier's up-sampler emits W1 (up(h) + conv_b) + b1 directly (W1 . W_up precomputed), so a
     // head step starts from `pre` [slot][128 prompts][Hh] and adds (W1 conv_w) lin(q): no x rows, no W1 contraction, no exchange
+    int lstm;                        // tensor-core mode only: nn.LSTM tiers (gates i, f, g, o; the reference's default rnn_class)
     int fold_head, NVh;              // NVh: folded up-sampler columns per CTA (up * Hh / NC)
     float* pre; const float* hu; const float* hb;     // hu [Hh][fs_last] = W1 . conv_w; hb [NC][NVh] folded biases
 };
@@ -830,7 +832,7 @@ __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsign
 // GRU cell of frame tier T on this CTA's 4 hidden indices (sample_rnn_v2.py:226-260, modules/io.py:106-133), bf16 tensor-core form.
 template <int FS>
 __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const unsigned char* cimg, const unsigned char* himg, unsigned char* himg_next,
-                                       const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X) {
+                                       const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X, int hs) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
     if (pre_barrier && !grid_barrier(P, epoch)) return false;
     const int nimg = H / 128;                                   // fills per image
@@ -838,7 +840,9 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
                           T.wgimg + (size_t)c * (2 * nimg) * TC_B_BYTES, warp, lane);
     if (warp < 4) {
         const int p = tid;
-        const float4 hold = __ldcg(reinterpret_cast<const float4*>(hcur + (size_t)p * H + 4 * c));
+        // the state this thread carries: h_old (GRU) or c_old (LSTM: cbuf ping-pongs with the hidden state, side hs)
+        const float* sold = P.lstm ? T.cbuf + (size_t)hs * H * P.Bp : hcur;
+        const float4 hold = __ldcg(reinterpret_cast<const float4*>(sold + (size_t)p * H + 4 * c));
         {   // Linearizer of the prompt's frame (modules/io.py:111-112), under the fills and the MMAs
             const float Qf = (float)P.Q;
             long long q[FS];
@@ -853,7 +857,7 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
 #pragma unroll
         for (int col = 0; col < 16; ++col) {
             float a = __ldg(bfo + col);
-            if (col < 12) {
+            if (col < 12 || P.lstm) {                           // GRU: the n_h column takes no input term
 #pragma unroll
                 for (int f = 0; f < FS; ++f) a = fmaf(__ldg(wf + col * FS + f), X.lin[p * FS + f], a);
             }
@@ -866,13 +870,27 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
         tmem_ld_wait();
         tc_fence_before();
         const float ho[4] = {hold.x, hold.y, hold.z, hold.w};
-        float hn[4];
+        float hn[4], cn[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (P.lstm) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {                        // PyTorch GRU cell, gates r, z, n
-            const float r = sigmoid_acc(v[jj] + pre[jj]);
-            const float zg = sigmoid_acc(v[4 + jj] + pre[4 + jj]);
-            const float n = tanhf((v[8 + jj] + pre[8 + jj]) + r * (v[12 + jj] + pre[12 + jj]));
-            hn[jj] = (1.0f - zg) * n + zg * ho[jj];
+            for (int jj = 0; jj < 4; ++jj) {                    // PyTorch LSTM cell, gates i, f, g, o
+                const float ig = sigmoid_acc(v[jj] + pre[jj]);
+                const float fg = sigmoid_acc(v[4 + jj] + pre[4 + jj]);
+                const float gg = tanhf(v[8 + jj] + pre[8 + jj]);
+                const float og = sigmoid_acc(v[12 + jj] + pre[12 + jj]);
+                cn[jj] = fg * ho[jj] + ig * gg;
+                hn[jj] = og * tanhf(cn[jj]);
+            }
+            if (p < P.B)
+                __stcg(reinterpret_cast<float4*>(T.cbuf + (size_t)(hs ^ 1) * H * P.Bp + (size_t)p * H + 4 * c), make_float4(cn[0], cn[1], cn[2], cn[3]));
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {                    // PyTorch GRU cell, gates r, z, n
+                const float r = sigmoid_acc(v[jj] + pre[jj]);
+                const float zg = sigmoid_acc(v[4 + jj] + pre[4 + jj]);
+                const float n = tanhf((v[8 + jj] + pre[8 + jj]) + r * (v[12 + jj] + pre[12 + jj]));
+                hn[jj] = (1.0f - zg) * n + zg * ho[jj];
+            }
         }
         if (p < P.B) {
             __stcg(reinterpret_cast<float4*>(hnext + (size_t)p * H + 4 * c), make_float4(hn[0], hn[1], hn[2], hn[3]));
@@ -1042,10 +1060,10 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                     float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
                     bool ok = false;
                     switch (T.fs) {
-                        case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
-                        case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
-                        case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
-                        default: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X); break;
+                        case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        default: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
                     }
                     hsel[i] ^= 1;
                     if (ok) ok = tc_up(P, T, himg_next, epoch, X, P.fold_head != 0 && i == P.n_ft - 1);
@@ -1584,7 +1602,7 @@ static void pack_up(float* dst, const float* up_w, int c, int H) {
         }
 }
 
-int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** out, int* unsupported) {
+int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2_handle** out, int* unsupported) {
     *unsupported = 1;
     const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels;
     if (H % KC != 0 || Hh % 4 != 0 || n_ft > MAX_TIERS) return 1;
@@ -1607,6 +1625,8 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
             if (plan_fast(d, max_batch, CS, sms, max_optin, tc != 0, &best, &best_smem)) { found = true; break; }
         }
     if (tc && !found) { sr2_destroy(h); return 1; }            // the tensor-core engine hosts H in {128, 256, 512}, <= 128 prompts
+    if (lstm && !tc) { sr2_destroy(h); return 1; }             // LSTM tiers: tensor-core engine only (fp32: the general kernel)
+    best.lstm = lstm ? 1 : 0;
     for (int CS : {8, 4, 2, 1}) {
         if (found) break;
         if (force_cs && atoi(force_cs) != CS) continue;
@@ -1838,10 +1858,11 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
         for (int c = 0; c < NC; ++c) {
             for (int col = 0; col < 16; ++col) {
                 const int g4 = col / 4, jj = col % 4, j = 4 * c + jj;
-                const int grow = (g4 == 0 ? 0 : g4 == 1 ? 1 : 2) * H + j;          // row of W_ih / W_hh (r, z, n)
+                // row of W_ih / W_hh: GRU (r, z, n; columns n_i and n_h both read row n), LSTM (i, f, g, o)
+                const int grow = (p.lstm ? g4 : (g4 == 0 ? 0 : g4 == 1 ? 1 : 2)) * H + j;
                 for (int part = 0; part < 2; ++part) {            // 0: conditioning (W_ih), 1: hidden (W_hh)
                     if (part == 0 && i == 0) continue;            // the top tier has no conditioning
-                    const bool zero = (part == 0 && g4 == 3) || (part == 1 && g4 == 2);
+                    const bool zero = !p.lstm && ((part == 0 && g4 == 3) || (part == 1 && g4 == 2));
                     const float* W = part == 0 ? Wih : Whh;
                     const int fill0 = (i == 0) ? 0 : part * nimg;
                     for (int k = 0; k < H; ++k) {
@@ -1852,7 +1873,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
                 }
                 // folded terms (the input x = in_w lin + in_b + conditioning enters W_ih only: columns r, z, n_i)
                 double b = 0.0;
-                if (g4 < 3) {
+                if (g4 < 3 || p.lstm) {
                     b = d->b_ih[i][grow];
                     for (int k = 0; k < H; ++k) b += (double)Wih[(size_t)grow * H + k] * (double)d->in_b[i][k];
                     for (int f = 0; f < T.fs; ++f) {
@@ -1861,7 +1882,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
                         wfv[((size_t)c * 16 + col) * T.fs + f] = (float)a;
                     }
                 }
-                if (g4 < 2 || g4 == 3) b += d->b_hh[i][grow];
+                if (g4 < 2 || g4 == 3 || p.lstm) b += d->b_hh[i][grow];
                 bfv[(size_t)c * 16 + col] = (float)b;
             }
             if (fold_here) continue;                              // the bottom tier's tiles are packed below from W1 . W_up
@@ -1915,6 +1936,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, sr2_handle** 
         T.wf = up(wfv.data(), wfv.size());
         T.bfold = up(bfv.data(), bfv.size());
         T.himg = upb(nullptr, (size_t)2 * H * 256);
+        T.cbuf = p.lstm ? up(nullptr, h->hbuf_floats[i]) : nullptr;
         T.oimg = i < n_ft - 1 ? upb(nullptr, (size_t)T.up * H * 256) : nullptr;
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);
@@ -1973,6 +1995,7 @@ int sr2_run(sr2_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
         for (int i = 0; i < h->p.n_ft; ++i) {
             MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].hbuf, 0, h->hbuf_floats[i] * sizeof(float), st));
             if (h->p.tc) MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].himg, 0, (size_t)2 * h->p.H * 256, st));
+            if (h->p.tiers[i].cbuf) MMK_CUDA(cudaMemsetAsync(h->p.tiers[i].cbuf, 0, h->hbuf_floats[i] * sizeof(float), st));
             h->p.hsel[i] = 0;
         }
     }

@@ -19,11 +19,11 @@ def _rel_err(got, ref):
     return float(np.abs(got - ref).max() / max(1e-6, np.abs(ref).max()))
 
 
-def make_net(frame_sizes, hidden, mlp_dim=128, sd=None, seed=0):
+def make_net(frame_sizes, hidden, mlp_dim=128, sd=None, seed=0, rnn_class="gru"):
     from mimikit_b200 import IOSpec, SampleRNN
     torch.manual_seed(seed)
     cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=mlp_dim)),
-                           frame_sizes=tuple(frame_sizes), hidden_dim=hidden, rnn_class="gru")
+                           frame_sizes=tuple(frame_sizes), hidden_dim=hidden, rnn_class=rnn_class)
     net = SampleRNN.from_config(cfg).to("cuda")
     if sd is not None:
         net.load_state_dict(sd)
@@ -199,6 +199,43 @@ def test_tensor_core_mode_vs_oracle(fs, H, B, P, mlp):
     net.float()
     seq32 = net.generate(prompts[sub], n)
     assert np.array_equal(seq32.cpu().numpy(), ref_seq)
+
+
+@pytest.mark.parametrize("fs,H,B,P,mlp", [((8, 2, 1), 512, 33, 24, 128), ((8, 4, 2, 1), 128, 22, 32, 32), ((4, 4), 256, 7, 16, 64)])
+def test_tensor_core_mode_lstm(fs, H, B, P, mlp):
+    """nn.LSTM tiers — the reference's DEFAULT rnn_class (sample_rnn_v2.py:40-66) — on the tcgen05 engine: gates i, f, g, o as the
+    16 accumulator columns of a CTA, the cell state carried in fp32.  Same criteria as the GRU form; fp32 mode of the same net
+    (general kernel) still reproduces the oracle bit for bit."""
+    net = make_net(fs, H, mlp_dim=mlp, seed=7, rnn_class="lstm").bfloat16()
+    info = net.launch_info(B)
+    assert info["threads"] == 256 and info["sm_used"] == H // 4, info
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs, rnn_class="lstm")
+    g = torch.Generator().manual_seed(23)
+    n = 24
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    sub = list(range(B)) if B <= 24 else [0, 1, B // 2, B - 2, B - 1]
+    ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), n, None, None)
+    full = torch.cat([prompts, torch.zeros(B, n, dtype=torch.long)], 1)
+    full[sub] = torch.from_numpy(ref_seq)
+    lg, dec = net.teacher_forced(full, P)
+    rel = _rel_err(lg.cpu().numpy()[sub], ref_logits)
+    print(f"bf16 SampleRNN LSTM {fs} H={H} B={B}: teacher-forced logits rel err {rel:.2e}")
+    assert rel <= 5e-2
+    assert np.array_equal(dec.cpu().numpy(), restate.argmax_first(lg.cpu().numpy()))
+    seq, logits = net.generate(prompts, n, return_logits=True)
+    assert torch.equal(seq, net.generate(prompts, n))
+    assert np.array_equal(seq.cpu().numpy()[:, P:], restate.argmax_first(logits.cpu().numpy()))
+    # chunked continuation carries h and c: two halves == one launch
+    a = net.generate(prompts, n // 2)
+    b = net.generate_more(n - n // 2)
+    assert torch.equal(torch.cat([a, b], 1), seq)
+    net.float()
+    try:
+        seq32 = net.generate(prompts[sub], n)
+    except _capi.MmkError as e:       # the general fp32 kernel keeps every weight resident: LSTM-512 does not fit it
+        assert "shared memory" in str(e) and H == 512
+    else:
+        assert np.array_equal(seq32.cpu().numpy(), ref_seq)
 
 
 def test_stepwise_protocol_and_loop():
