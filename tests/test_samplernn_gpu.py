@@ -195,6 +195,14 @@ def test_tensor_core_mode_vs_oracle(fs, H, B, P, mlp):
     seq2 = net.generate(prompts, n)
     assert torch.equal(seq, seq2)
     assert np.array_equal(seq.cpu().numpy()[:, P:], restate.argmax_first(logits.cpu().numpy()))
+    # sampled: every decision is the oracle's inverse-CDF draw applied to the kernel's own logits (scalar and per-prompt T)
+    noise = torch.rand(B, n, generator=g)
+    for T in (torch.tensor([0.9]), torch.linspace(0.8, 1.1, B)):
+        sseq, slog = net.generate(prompts, n, temperature=T, noise=noise, return_logits=True)
+        sl = slog.cpu().numpy()
+        for j in range(n):
+            want = restate.sample_inverse_cdf(sl[:, j], T.numpy(), noise[:, j].numpy())
+            assert np.array_equal(sseq.cpu().numpy()[:, P + j], want), (j, T.shape)
     # and back: the fp32 engine of the same object still reproduces the oracle bit for bit
     net.float()
     seq32 = net.generate(prompts[sub], n)
