@@ -246,8 +246,8 @@ int mmk_samplernn_create(const mmk_samplernn_desc* desc, int max_batch, mmk_samp
 
 /* The rest of SampleRNNTier's configuration surface (sample_rnn_v2.py:40-66, 101-119; networks/mlp.py:44-50):
  * rnn_class "lstm" (the reference default) / "gru" / "rnn", n_rnn stacked layers, a non-zero initial state, and
- * n_hidden_layers > 0 in the MLP head.  The GRU / one layer / zero state / plain head form runs in the cluster kernel
- * (csrc/samplernn2.cu); everything else in the general kernel (csrc/samplernn.cu). */
+ * n_hidden_layers > 0 in the MLP head.  The GRU or LSTM / one layer / zero state / plain head form runs in the cluster kernel
+ * (csrc/samplernn2.cu: LSTM at hidden_dim 128, 256, 512); everything else in the general kernel (csrc/samplernn.cu). */
 #define MMK_RNN_GRU 0
 #define MMK_RNN_LSTM 1
 #define MMK_RNN_TANH 2

@@ -440,7 +440,9 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
         const bool tc_form = (dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM) && dx->n_rnn == 1 && dx->head_hidden_layers == 0 &&
                              !dx->need_set_hidden;
         if (tc && !tc_form) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer, a zero initial state and a plain head"); }
-        if ((plain || (tc && tc_form)) && (tc || !force || atoi(force) != 1)) {
+        // ... and so does the lane-major fp32 engine (sequences bit-exact): GRU or LSTM, tried first; what it cannot host falls to the
+        // general kernel below
+        if ((plain || tc_form) && (tc || !force || atoi(force) != 1)) {
             int unsupported = 0;
             mmk_samplernn_desc d2 = *d;      // the cluster kernel hosts the GRU / one layer / plain head form only
             d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;

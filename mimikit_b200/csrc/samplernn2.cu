@@ -621,6 +621,145 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
     return true;
 }
 
+// nn.LSTM cell of frame tier T (the reference's default rnn_class, sample_rnn_v2.py:40-66) on this CTA's 4 hidden indices, lane-major
+// fp32 form: the 16 gate rows (i, f, g, o of 4 indices) are 16 homogeneous columns fed by both operands — the contraction of fast_up<16>
+// with [x | h] as its input.  64 weight pairs per lane (pack_fast: entry m * 32 + i2 * 4 + k = (W_m[slot 2 i2][k], W_m[slot 2 i2 + 1][k]),
+// slot i = column i ^ fast_col<16>(lane), column = gate * 4 + hidden index).  The frame Linear rows are re-read from L1 per prompt
+// when the frame is longer than 2 (the register file holds 128 weight registers here).
+template <int FS>
+__device__ __forceinline__ bool fast_lstm(const Params& P, const Tier& T, const float* cond, const float* hcur, float* hnext,
+                                          const float* ccur, float* cnext, long long tw, bool pre_barrier, unsigned long long& epoch, Fast& F) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
+    const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
+    const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
+    constexpr bool HOIST = FS <= 2;
+    ulonglong2 wq[32], iw[HOIST ? FS : 1], ib;
+    const ulonglong2* iwp = reinterpret_cast<const ulonglong2*>(T.iw4) + kq * 32 + lane;
+    {
+        const ulonglong2* w = reinterpret_cast<const ulonglong2*>(T.wg4) + (size_t)c * 32 * TW + kq * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wq[i] = __ldg(w + i * TW);
+        if (HOIST) {
+#pragma unroll
+            for (int f = 0; f < FS; ++f) iw[f] = __ldg(iwp + f * TW);
+        }
+        ib = __ldg(reinterpret_cast<const ulonglong2*>(T.ib4) + kq * 32 + lane);
+    }
+#define WL(e) (((e) & 1) ? wq[(e) >> 1].y : wq[(e) >> 1].x)
+    fast_lap(F, 0);
+    if (pre_barrier && !grid_barrier(P, epoch)) return false;
+    fast_lap(F, 1);
+    const int Bl = (P.B + CHP - 1) / CHP * CHP, nchunk = Bl / CHP;
+    const int rot = (int)(((long long)c * nchunk) / P.NC);
+    auto rotated = [&](int ch) { const int x = ch + rot; return x >= nchunk ? x - nchunk : x; };
+    const int koff = kq * 128 + 4 * lane;
+    float4 hn[2], cn[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const size_t row = (size_t)(rotated(0) * CHP + pg + q * NPG) * H + koff;
+        hn[q] = __ldcg(reinterpret_cast<const float4*>(hcur + row));
+        cn[q] = cond != nullptr ? __ldcg(reinterpret_cast<const float4*>(cond + row)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    const float Qf = (float)P.Q;
+    for (int idx = tid; idx < Bl * FS; idx += NTF) {           // Linearizer of the frame (modules/io.py:111-112)
+        const int p = idx / FS, f = idx - p * FS;
+        long long q = 0;
+        if (p < P.B) q = __ldcg(P.seq + (size_t)p * P.seq_stride + (tw - FS + f));
+        F.lin[idx] = linearize(q, Qf);
+    }
+    __syncthreads();
+    fast_lap(F, 2);
+    {
+        const int col = fast_col<16>(lane);
+        const bool writer = fast_writer<16>(lane);
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int pr[2] = {rotated(ch) * CHP + pg, rotated(ch) * CHP + pg + NPG};
+            float4 h4[2], c4[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { h4[q] = hn[q]; c4[q] = cn[q]; }
+            if (ch + 1 < nchunk) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const size_t row = (size_t)(rotated(ch + 1) * CHP + pg + q * NPG) * H + koff;
+                    hn[q] = __ldcg(reinterpret_cast<const float4*>(hcur + row));
+                    if (cond != nullptr) cn[q] = __ldcg(reinterpret_cast<const float4*>(cond + row));
+                }
+            }
+            u64 a2[2][8];                                       // (slot 2 i2, slot 2 i2 + 1)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float* lp = F.lin + pr[q] * FS;
+                u64 x01 = 0ull, x23 = 0ull;
+#pragma unroll
+                for (int f = 0; f < FS; ++f) {                 // FramedLinearIO: Linear(frame) + bias (+ conditioning)
+                    const float l = lp[f];
+                    const u64 ll = pack2(l, l);
+                    const ulonglong2 w = HOIST ? iw[HOIST ? f : 0] : __ldg(iwp + f * TW);
+                    x01 = fma2(ll, w.x, x01); x23 = fma2(ll, w.y, x23);
+                }
+                x01 = add2(x01, ib.x); x23 = add2(x23, ib.y);
+                if (cond != nullptr) { x01 = add2(x01, pack2(c4[q].x, c4[q].y)); x23 = add2(x23, pack2(c4[q].z, c4[q].w)); }
+                float x0, x1, x2, x3;
+                unpack2(x01, x0, x1); unpack2(x23, x2, x3);
+                const u64 xd[4] = {pack2(x0, x0), pack2(x1, x1), pack2(x2, x2), pack2(x3, x3)};
+                const u64 hd[4] = {pack2(h4[q].x, h4[q].x), pack2(h4[q].y, h4[q].y), pack2(h4[q].z, h4[q].z), pack2(h4[q].w, h4[q].w)};
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    u64 a = 0ull;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a = fma2(WL(i2 * 4 + k), xd[k], a);          // input side, k ascending ...
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a = fma2(WL(32 + i2 * 4 + k), hd[k], a);     // ... then the hidden side
+                    a2[q][i2] = a;
+                }
+            }
+            float acc[2];
+            int bit = 16;
+#pragma unroll
+            for (int half = 4; half >= 1; half >>= 1, bit >>= 1)      // folds of whole pairs
+#pragma unroll
+                for (int i = 0; i < half; ++i)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) a2[q][i] = add2(a2[q][i], shfl2(a2[q][half + i], bit));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                       // the last fold: slot 1 into slot 0
+                float lo, hi;
+                unpack2(a2[q][0], lo, hi);
+                acc[q] = lo + __shfl_xor_sync(0xffffffffu, hi, 2);
+                acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
+            }
+            if (writer)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) F.part[((size_t)kq * Bp + pr[q]) * 16 + col] = acc[q];
+        }
+    }
+#undef WL
+    __syncthreads();
+    fast_lap(F, 3);
+    const float* gb = T.gb + (size_t)c * 32;                    // b_ih (16 columns), then b_hh
+    for (int o = tid; o < Bl * 4; o += NTF) {                  // PyTorch LSTM cell, gates i, f, g, o
+        const int p = o >> 2, jj = o & 3;
+        float sg[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sg[g] = F.part[(size_t)p * 16 + g * 4 + jj];
+        for (int q = 1; q < NKQ; ++q)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) sg[g] += F.part[((size_t)q * Bp + p) * 16 + g * 4 + jj];
+        const float ig = sigmoid_acc((sg[0] + __ldg(gb + jj)) + __ldg(gb + 16 + jj));
+        const float fg = sigmoid_acc((sg[1] + __ldg(gb + 4 + jj)) + __ldg(gb + 20 + jj));
+        const float gg = tanhf((sg[2] + __ldg(gb + 8 + jj)) + __ldg(gb + 24 + jj));
+        const float og = sigmoid_acc((sg[3] + __ldg(gb + 12 + jj)) + __ldg(gb + 28 + jj));
+        const float cold = __ldcg(ccur + (size_t)p * H + c * 4 + jj);
+        const float cnew = fg * cold + ig * gg;
+        if (p < P.B) {
+            __stcg(cnext + (size_t)p * H + c * 4 + jj, cnew);
+            __stcg(hnext + (size_t)p * H + c * 4 + jj, og * tanhf(cnew));
+        }
+    }
+    fast_lap(F, 4);
+    return true;
+}
+
 // LinearResampler rows of this CTA (modules/resamplers.py:13-23) on the freshly written hidden state: always behind a
 // grid barrier.  Row u = NV c + col of the (up * H) rows goes to obuf[u / H][prompt][u % H].
 template <int NV>
@@ -1088,6 +1227,16 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                     const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
                     float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
                     bool ok = false;
+                    if (P.lstm) {
+                        const float* ccur = T.cbuf + (size_t)hsel[i] * H * Bp;
+                        float* cnext = T.cbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
+                        switch (T.fs) {
+                            case 1: ok = fast_lstm<1>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                            case 2: ok = fast_lstm<2>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                            case 4: ok = fast_lstm<4>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                            default: ok = fast_lstm<8>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                        }
+                    } else
                     switch (T.fs) {
                         case 1: ok = fast_gru<1>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
                         case 2: ok = fast_gru<2>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
@@ -1625,7 +1774,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
             if (plan_fast(d, max_batch, CS, sms, max_optin, tc != 0, &best, &best_smem)) { found = true; break; }
         }
     if (tc && !found) { sr2_destroy(h); return 1; }            // the tensor-core engine hosts H in {128, 256, 512}, <= 128 prompts
-    if (lstm && !tc) { sr2_destroy(h); return 1; }             // LSTM tiers: tensor-core engine only (fp32: the general kernel)
+    if (lstm && !found) { sr2_destroy(h); return 1; }          // LSTM tiers: the lane-major or the tensor-core engine, never the tile engine
     best.lstm = lstm ? 1 : 0;
     for (int CS : {8, 4, 2, 1}) {
         if (found) break;
@@ -1804,9 +1953,29 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
         T.obuf = up(nullptr, (size_t)T.up_rows * p.Bp);
         if (!p.fast) continue;
         const int TW = H / 4;
-        std::vector<float> wg((size_t)NC * 24 * TW * 4), wu((size_t)NC * T.NV * TW * 4), iw((size_t)T.fs * TW * 4), gb((size_t)NC * 24),
+        const int NWG = p.lstm ? 32 : 24;                       // float4 of recurrent weights per lane
+        std::vector<float> wg((size_t)NC * NWG * TW * 4), wu((size_t)NC * T.NV * TW * 4), iw((size_t)T.fs * TW * 4), gb((size_t)NC * NWG),
             ub((size_t)NC * T.NV);
-        for (int c = 0; c < NC; ++c) {
+        for (int c = 0; c < NC && p.lstm; ++c) {
+            // LSTM: 64 pairs per lane, e = m * 32 + i2 * 4 + k: (W_m[slot 2 i2][k], W_m[slot 2 i2 + 1][k]); slot i = column i ^ fast_col<16>(l),
+            // column = gate * 4 + hidden index (gates i, f, g, o)
+            auto row_of = [&](int col) { return (col / 4) * H + 4 * c + (col % 4); };
+            for (int t = 0; t < TW; ++t) {
+                const int mask = fast_col<16>(t & 31);
+                for (int e = 0; e < 64; ++e) {
+                    const int m = e / 32, r = e % 32, i2 = r / 4, k = r % 4;
+                    const float* W = m == 0 ? d->w_ih[i] : d->w_hh[i];
+                    float* dst = wg.data() + (((size_t)c * 32 + e / 2) * TW + t) * 4 + (e & 1) * 2;
+                    dst[0] = W[(size_t)row_of((2 * i2) ^ mask) * H + 4 * t + k];
+                    dst[1] = W[(size_t)row_of((2 * i2 + 1) ^ mask) * H + 4 * t + k];
+                }
+            }
+            for (int col = 0; col < 16; ++col) {
+                gb[(size_t)c * 32 + col] = d->b_ih[i][row_of(col)];
+                gb[(size_t)c * 32 + 16 + col] = d->b_hh[i][row_of(col)];
+            }
+        }
+        for (int c = 0; c < NC && !p.lstm; ++c) {
             // 48 pairs per lane, e = 0..47: [0,16) (W_ir, W_iz)[slot e / 4][k = e % 4], [16,24) (W_in[slot 2a'], W_in[slot 2a'+1])[k],
             // [24,48) the same of W_hh; slot a of lane l is hidden index 4c + (a ^ jm(l)).  Pair e lives in float4 e / 2 of the lane.
             for (int t = 0; t < TW; ++t) {
@@ -1827,6 +1996,8 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
                 for (int g = 0; g < 3; ++g)
                     for (int a = 0; a < 4; ++a) gb[(size_t)c * 24 + m * 12 + g * 4 + a] = b[g * H + 4 * c + a];
             }
+        }
+        for (int c = 0; c < NC; ++c) {
             float* wuc = wu.data() + (size_t)c * T.NV * TW * 4;
             if (T.NV == 4) pack_up<4>(wuc, d->up_w[i], c, H);
             else if (T.NV == 8) pack_up<8>(wuc, d->up_w[i], c, H);
@@ -1841,6 +2012,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
         T.ib4 = reinterpret_cast<const float4*>(T.in_b);
         T.gb = up(gb.data(), gb.size());
         T.ub = up(ub.data(), ub.size());
+        T.cbuf = p.lstm ? up(nullptr, h->hbuf_floats[i]) : nullptr;
         if (!p.tc) continue;
         // ---- tensor-core engine: bf16 weight tiles [16 columns x 128 k] per fill (K = [conditioning | hidden], the top tier: hidden only),
         //      columns gate * 4 + jj with gates r, z, n_i, n_h; the frame Linear and all biases folded into wf / bfold (fp64 -> fp32)
@@ -1936,7 +2108,6 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
         T.wf = up(wfv.data(), wfv.size());
         T.bfold = up(bfv.data(), bfv.size());
         T.himg = upb(nullptr, (size_t)2 * H * 256);
-        T.cbuf = p.lstm ? up(nullptr, h->hbuf_floats[i]) : nullptr;
         T.oimg = i < n_ft - 1 ? upb(nullptr, (size_t)T.up * H * 256) : nullptr;
     }
     p.conv_w = up(d->conv_w, (size_t)H * p.fs_last);

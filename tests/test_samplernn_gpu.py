@@ -246,6 +246,32 @@ def test_tensor_core_mode_lstm(fs, H, B, P, mlp):
         assert np.array_equal(seq32.cpu().numpy(), ref_seq)
 
 
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 40), ((8, 4, 2, 1), 128, 22, 27), ((4, 4), 256, 3, 16), ((2, 2, 1), 128, 5, 9)])
+def test_lane_major_lstm_vs_oracle(fs, H, B, P):
+    """nn.LSTM tiers (the reference's default rnn_class) on the lane-major fp32 engine: 16 homogeneous gate columns fed by [x | h],
+    cell state in fp32.  Sequences bit-exact with the oracle (argmax and sampled), logits within tolerance, teacher-forced
+    decisions, chunked continuation == one launch."""
+    net = make_net(fs, H, mlp_dim=32, seed=9, rnn_class="lstm")
+    info = net.launch_info(B)
+    assert info["threads"] == 256 and info["sm_used"] == H // 4, info
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs, rnn_class="lstm")
+    g = torch.Generator().manual_seed(31)
+    n = 24
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    sub = list(range(B)) if B <= 24 else [0, 1, B // 2, B - 2, B - 1]
+    for temp in (None, 0.95):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts[sub].numpy(), n, temp, noise[sub].numpy())
+        assert np.array_equal(seq.cpu().numpy()[sub], ref_seq), temp
+        assert _rel_err(logits.cpu().numpy()[sub], ref_logits) <= REL_TOL
+    lg, dec = net.teacher_forced(torch.from_numpy(ref_seq), P, 0.95, noise[sub])
+    assert np.array_equal(dec.cpu().numpy(), ref_seq[:, P:])
+    a = net.generate(prompts, n // 2)
+    b = net.generate_more(n - n // 2)
+    assert torch.equal(torch.cat([a, b], 1), net.generate(prompts, n))
+
+
 def test_stepwise_protocol_and_loop():
     """before_generate / generate_step / after_generate == whole-sequence path == oracle; GenerateLoopV2 integration as
     the reference's tests/test_sample_rnn.py:90-112 (batch 2, 512-sample prompt + 512 steps, temperature=(1.,))."""
