@@ -391,7 +391,7 @@ __device__ __forceinline__ void reduce_partials(float (&acc)[16], const Map& m, 
 
 // ------------------------------------------------------------------------------------------------------------
 // Lane-major frame-tier engine (Params::fast; H = 4 * NC, H in {128, 256, 512}, frame sizes and up-sampling factors
-// in {1, 2, 4, 8} / {1, 2, 4}).  The column split over the CTAs stays (CTA c owns hidden indices 4c .. 4c + 3 and the
+// in {1, 2, 4, 8, 16} / {1, 2, 4, 8}; GRU and LSTM tiers).  The column split over the CTAs stays (CTA c owns hidden indices 4c .. 4c + 3 and the
 // up-sampler rows NV c .. NV c + NV - 1), but a contraction is laid out the other way round:
 //   * activations live in HBM as [prompt][H]; lane l of K-quarter warp q owns k = 128 q + 4 l .. + 3, so a warp reads
 //     its 512 bytes of a prompt's x and h rows with one coalesced 16-byte load per lane straight from L2 into
@@ -461,13 +461,17 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
     const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
     const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
     // 48 weight pairs per lane (pack_fast): [0,16) (W_ir, W_iz)[slot a][k], [16,24) (W_in[2a'], W_in[2a'+1])[k], [24,48) the same of W_hh
-    ulonglong2 wq[24], iw[FS], ib;
+    constexpr bool HOIST = FS <= 8;                            // longer frames: the frame Linear rows are re-read from L1 per prompt
+    ulonglong2 wq[24], iw[HOIST ? FS : 1], ib;
+    const ulonglong2* iwp = reinterpret_cast<const ulonglong2*>(T.iw4) + kq * 32 + lane;
     {                                                          // issued before the barrier wait: the latency hides behind it
         const ulonglong2* w = reinterpret_cast<const ulonglong2*>(T.wg4) + (size_t)c * 24 * TW + kq * 32 + lane;
 #pragma unroll
         for (int i = 0; i < 24; ++i) wq[i] = __ldg(w + i * TW);
+        if (HOIST) {
 #pragma unroll
-        for (int f = 0; f < FS; ++f) iw[f] = __ldg(reinterpret_cast<const ulonglong2*>(T.iw4) + f * TW + kq * 32 + lane);
+            for (int f = 0; f < FS; ++f) iw[f] = __ldg(iwp + f * TW);
+        }
         ib = __ldg(reinterpret_cast<const ulonglong2*>(T.ib4) + kq * 32 + lane);
     }
 #define WQ(e) (((e) & 1) ? wq[(e) >> 1].y : wq[(e) >> 1].x)
@@ -525,7 +529,8 @@ __device__ __forceinline__ bool fast_gru(const Params& P, const Tier& T, const f
                 for (int f = 0; f < FS; ++f) {                 // FramedLinearIO: Linear(frame) + bias (+ conditioning)
                     const float l = lp[f];
                     const u64 ll = pack2(l, l);
-                    x01 = fma2(ll, iw[f].x, x01); x23 = fma2(ll, iw[f].y, x23);
+                    const ulonglong2 wf = HOIST ? iw[HOIST ? f : 0] : __ldg(iwp + f * TW);
+                    x01 = fma2(ll, wf.x, x01); x23 = fma2(ll, wf.y, x23);
                 }
                 x01 = add2(x01, ib.x); x23 = add2(x23, ib.y);
                 if (cond != nullptr) { x01 = add2(x01, pack2(c4[q].x, c4[q].y)); x23 = add2(x23, pack2(c4[q].z, c4[q].w)); }
@@ -767,6 +772,7 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
     const int H = P.H, NKQ = P.NKQ, CHP = P.CHP, Bp = P.Bp, TW = NKQ * 32;
     const int kq = warp % NKQ, pg = warp / NKQ, NPG = 8 / NKQ;
+    constexpr int PS = NV > 16 ? 32 : 16;   // floats per (K quarter, prompt) in the partial-sum buffer
     ulonglong2 wu[NV];           // 2 NV weight pairs per lane (pack_up): entry i2 * 4 + k = (W[slot 2 i2][k], W[slot 2 i2 + 1][k])
     {
         const ulonglong2* w = reinterpret_cast<const ulonglong2*>(T.wu4) + (size_t)c * NV * TW + kq * 32 + lane;
@@ -830,7 +836,7 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
                 for (int q = 0; q < 2; ++q) acc[q][0] += __shfl_xor_sync(0xffffffffu, acc[q][0], bit);
             if (writer)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) F.part[((size_t)kq * Bp + rotated(ch) * CHP + pg + q * NPG) * 16 + col] = acc[q][0];
+                for (int q = 0; q < 2; ++q) F.part[((size_t)kq * Bp + rotated(ch) * CHP + pg + q * NPG) * PS + col] = acc[q][0];
         }
     }
 #undef WU
@@ -839,8 +845,8 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
     const float* ub = T.ub + (size_t)c * NV;
     for (int o = tid; o < Bl * NV; o += NTF) {
         const int p = o / NV, col = o - p * NV;
-        float sv = F.part[(size_t)p * 16 + col];
-        for (int q = 1; q < NKQ; ++q) sv += F.part[((size_t)q * Bp + p) * 16 + col];
+        float sv = F.part[(size_t)p * PS + col];
+        for (int q = 1; q < NKQ; ++q) sv += F.part[((size_t)q * Bp + p) * PS + col];
         sv += __ldg(ub + col);
         const int urow = c * NV + col, slot = urow / H, kk = urow - slot * H;
         if (p < P.B) __stcg(T.obuf + ((size_t)slot * Bp + p) * H + kk, sv);
@@ -1234,20 +1240,23 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                             case 1: ok = fast_lstm<1>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
                             case 2: ok = fast_lstm<2>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
                             case 4: ok = fast_lstm<4>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
-                            default: ok = fast_lstm<8>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                            case 8: ok = fast_lstm<8>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
+                            default: ok = fast_lstm<16>(P, T, cond, hcur, hnext, ccur, cnext, tw, pre, epoch, F); break;
                         }
                     } else
                     switch (T.fs) {
                         case 1: ok = fast_gru<1>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
                         case 2: ok = fast_gru<2>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
                         case 4: ok = fast_gru<4>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
-                        default: ok = fast_gru<8>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                        case 8: ok = fast_gru<8>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
+                        default: ok = fast_gru<16>(P, T, cond, hcur, hnext, tw, pre, epoch, F); break;
                     }
                     hsel[i] ^= 1;
                     if (ok) switch (T.NV) {
                         case 4: ok = fast_up<4>(P, T, hnext, epoch, F); break;
                         case 8: ok = fast_up<8>(P, T, hnext, epoch, F); break;
-                        default: ok = fast_up<16>(P, T, hnext, epoch, F); break;
+                        case 16: ok = fast_up<16>(P, T, hnext, epoch, F); break;
+                        default: ok = fast_up<32>(P, T, hnext, epoch, F); break;
                     }
                     if (!ok) { dead = true; break; }
                     pending_up = true;
@@ -1641,16 +1650,17 @@ static int sr2_max_clusters(int CS, size_t smem, int sms, int engine) {
 
 
 // ---- lane-major engine: plan (shared-memory map, cluster size) and per-lane weight packing
-static bool fast_supported(const mmk_samplernn_desc* d, int sms) {
+static bool fast_supported(const mmk_samplernn_desc* d, int sms, bool tc) {
     const int n_ft = d->n_tiers - 1, H = d->hidden_dim;
     if (getenv("MMK_SR_ENGINE") && atoi(getenv("MMK_SR_ENGINE")) == 2) return false;     // 2: the tile engine
     if (H % 128 != 0 || (H != 128 && H != 256 && H != 512) || H / 4 > sms || d->head_hidden % 4 != 0 || n_ft > MAX_TIERS) return false;
     for (int i = 0; i < n_ft; ++i) {
         const int fs = d->frame_sizes[i], nxt = i < n_ft - 1 ? d->frame_sizes[i + 1] : 1;
-        if (fs != 1 && fs != 2 && fs != 4 && fs != 8) return false;
+        // the lane-major engine also hosts the reference's default geometry (16, 8, 8): frames of 16, up-sampling by 8
+        if (fs != 1 && fs != 2 && fs != 4 && fs != 8 && (tc || fs != 16)) return false;
         if (fs % nxt != 0) return false;
         const int up = fs / nxt;
-        if (up != 1 && up != 2 && up != 4) return false;
+        if (up != 1 && up != 2 && up != 4 && (tc || up != 8)) return false;
     }
     return true;
 }
@@ -1708,7 +1718,9 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
     p.s_gi = o;
     p.s_bar = take(2 * BAR_COUNT + 16 * GP);
     p.s_b2 = take(Q + 1);
-    p.s_part = take(tc ? 4 : p.NKQ * p.Bp * 16);
+    int nv_max = 16;
+    for (int i = 0; i < n_ft; ++i) nv_max = std::max(nv_max, p.tiers[i].NV);
+    p.s_part = take(tc ? 4 : p.NKQ * p.Bp * (nv_max > 16 ? 32 : 16));
     p.s_hold = take(tc ? 4 : p.Bp * 4);
     p.s_lin = take(p.Bp * fs_max);
     p.s_tcbar = take(2 * TCB_COUNT + 4);
@@ -1768,7 +1780,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
     size_t best_smem = 0;
     bool found = false;
     const int groups_per_cluster_max = 16;
-    if (fast_supported(d, sms))
+    if (fast_supported(d, sms, tc != 0))
         for (int CS : {4, 8, 2, 1}) {
             if (force_cs && atoi(force_cs) != CS) continue;
             if (plan_fast(d, max_batch, CS, sms, max_optin, tc != 0, &best, &best_smem)) { found = true; break; }
@@ -2001,7 +2013,8 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
             float* wuc = wu.data() + (size_t)c * T.NV * TW * 4;
             if (T.NV == 4) pack_up<4>(wuc, d->up_w[i], c, H);
             else if (T.NV == 8) pack_up<8>(wuc, d->up_w[i], c, H);
-            else pack_up<16>(wuc, d->up_w[i], c, H);
+            else if (T.NV == 16) pack_up<16>(wuc, d->up_w[i], c, H);
+            else pack_up<32>(wuc, d->up_w[i], c, H);
             for (int col = 0; col < T.NV; ++col) ub[(size_t)c * T.NV + col] = d->up_b[i][c * T.NV + col];
         }
         for (int f = 0; f < T.fs; ++f)

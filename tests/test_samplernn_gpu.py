@@ -136,7 +136,8 @@ def test_cluster_kernel_vs_oracle(monkeypatch, cluster, ctas, fs, H, B, P):
 
 @pytest.mark.parametrize("cluster", [None, "1", "2", "8"])
 @pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 43), ((8, 2, 1), 512, 128, 24), ((4, 4), 256, 3, 16), ((8, 4, 2, 1), 128, 22, 27),
-                                      ((4, 2), 128, 9, 10), ((8, 4, 2), 256, 70, 40), ((2, 2, 1), 128, 5, 9), ((2, 1, 1), 128, 4, 8)])
+                                      ((4, 2), 128, 9, 10), ((8, 4, 2), 256, 70, 40), ((2, 2, 1), 128, 5, 9), ((2, 1, 1), 128, 4, 8),
+                                      ((16, 8, 8), 256, 9, 48), ((16, 8, 8), 512, 40, 35), ((16, 2, 1), 128, 6, 33)])
 def test_lane_major_engine_vs_oracle(monkeypatch, cluster, fs, H, B, P):
     """The lane-major frame-tier engine of samplernn2.cu (H in {128, 256, 512}: weights in registers, [prompt][H] rows
     prefetched into registers, transposing shuffle trees): every supported K-quarter count, up-sampling factor and frame
@@ -246,11 +247,13 @@ def test_tensor_core_mode_lstm(fs, H, B, P, mlp):
         assert np.array_equal(seq32.cpu().numpy(), ref_seq)
 
 
-@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 40), ((8, 4, 2, 1), 128, 22, 27), ((4, 4), 256, 3, 16), ((2, 2, 1), 128, 5, 9)])
+@pytest.mark.parametrize("fs,H,B,P", [((8, 2, 1), 512, 37, 40), ((8, 4, 2, 1), 128, 22, 27), ((4, 4), 256, 3, 16), ((2, 2, 1), 128, 5, 9),
+                                      ((16, 8, 8), 256, 9, 48), ((16, 8, 8), 128, 33, 37)])
 def test_lane_major_lstm_vs_oracle(fs, H, B, P):
     """nn.LSTM tiers (the reference's default rnn_class) on the lane-major fp32 engine: 16 homogeneous gate columns fed by [x | h],
     cell state in fp32.  Sequences bit-exact with the oracle (argmax and sampled), logits within tolerance, teacher-forced
-    decisions, chunked continuation == one launch."""
+    decisions, chunked continuation == one launch.  (16, 8, 8) / 256 / LSTM is SampleRNN.Config()'s own default
+    (sample_rnn_v2.py:124-131): frames of 16, up-sampling by 8, an 8-tap sample tier."""
     net = make_net(fs, H, mlp_dim=32, seed=9, rnn_class="lstm")
     info = net.launch_info(B)
     assert info["threads"] == 256 and info["sm_used"] == H // 4, info
