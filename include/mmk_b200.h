@@ -266,7 +266,7 @@ typedef struct {
     int need_set_hidden;          /* 1 = mmk_samplernn_set_hidden will be used (h0_init "ones" / "randn"): general kernel */
     int compute_mode;             /* MMK_COMPUTE_FP32 (0) | MMK_COMPUTE_BF16_TC (1): frame-tier GRU and up-sampler contractions on
                                      tcgen05 with bf16 operands and fp32 accumulation (logits within 5e-2 of fp32).  GRU or LSTM, one layer,
-                                     zero initial state, plain head, hidden_dim in {128, 256, 512}, max_batch <= 128; else an error */
+                                     zero initial state, plain head, hidden_dim in {128, 256, 512}, frame sizes in {1, 2, 4, 8, 16}, max_batch <= 128; else an error */
 } mmk_samplernn_desc_ex;
 int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* desc, int max_batch, mmk_samplernn_t* out);
 /* Installs an initial state — SampleRNNTier._reset_hidden / _init_h0 (sample_rnn_v2.py:101-119) with h0_init "ones" or

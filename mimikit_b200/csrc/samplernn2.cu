@@ -1208,7 +1208,8 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
                         case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
                         case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
-                        default: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        case 8: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        default: ok = tc_gru<16>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
                     }
                     hsel[i] ^= 1;
                     if (ok) ok = tc_up(P, T, himg_next, epoch, X, P.fold_head != 0 && i == P.n_ft - 1);
@@ -1656,11 +1657,18 @@ static bool fast_supported(const mmk_samplernn_desc* d, int sms, bool tc) {
     if (H % 128 != 0 || (H != 128 && H != 256 && H != 512) || H / 4 > sms || d->head_hidden % 4 != 0 || n_ft > MAX_TIERS) return false;
     for (int i = 0; i < n_ft; ++i) {
         const int fs = d->frame_sizes[i], nxt = i < n_ft - 1 ? d->frame_sizes[i + 1] : 1;
-        // the lane-major engine also hosts the reference's default geometry (16, 8, 8): frames of 16, up-sampling by 8
-        if (fs != 1 && fs != 2 && fs != 4 && fs != 8 && (tc || fs != 16)) return false;
+        // both engines also host the reference's default geometry (16, 8, 8): frames of 16, up-sampling by 8 — the tensor-core one only
+        // when the bottom tier's up-sampler is folded with the head's first Linear (16 columns per CTA instead of 32)
+        if (fs != 1 && fs != 2 && fs != 4 && fs != 8 && fs != 16) return false;
         if (fs % nxt != 0) return false;
         const int up = fs / nxt;
-        if (up != 1 && up != 2 && up != 4 && (tc || up != 8)) return false;
+        if (up != 1 && up != 2 && up != 4 && up != 8) return false;
+        if (up == 8 && tc) {
+            const int rows = up * d->head_hidden, NC = H / 4;
+            const bool fold = i == n_ft - 1 && !(getenv("MMK_SR_FOLD") && atoi(getenv("MMK_SR_FOLD")) == 0) && rows % NC == 0 && rows / NC <= 16 &&
+                              d->head_hidden % (rows / NC) == 0;
+            if (!fold) return false;
+        }
     }
     return true;
 }

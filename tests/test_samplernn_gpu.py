@@ -169,7 +169,7 @@ def test_lane_major_engine_vs_oracle(monkeypatch, cluster, fs, H, B, P):
 
 @pytest.mark.parametrize("fs,H,B,P,mlp", [((8, 2, 1), 512, 37, 48, 32), ((8, 2, 1), 512, 128, 24, 32), ((4, 4), 256, 3, 16, 32),
                                           ((8, 4, 2, 1), 128, 22, 32, 32), ((2, 2, 1), 128, 5, 10, 32), ((8, 4, 2), 256, 70, 40, 32),
-                                          ((8, 2, 1), 512, 50, 24, 128), ((8, 2, 1), 256, 9, 16, 64)])
+                                          ((8, 2, 1), 512, 50, 24, 128), ((8, 2, 1), 256, 9, 16, 64), ((16, 8, 8), 256, 12, 48, 128)])
 def test_tensor_core_mode_vs_oracle(fs, H, B, P, mlp):
     """compute_dtype bfloat16: the frame tiers' GRU and up-sampler contractions on tcgen05 (bf16 operands, fp32 accumulation in
     TMEM, frame Linear folded into the gate), cell / head / sampler in fp32.  Teacher-forced logits within the north star's 5e-2
@@ -210,7 +210,8 @@ def test_tensor_core_mode_vs_oracle(fs, H, B, P, mlp):
     assert np.array_equal(seq32.cpu().numpy(), ref_seq)
 
 
-@pytest.mark.parametrize("fs,H,B,P,mlp", [((8, 2, 1), 512, 33, 24, 128), ((8, 4, 2, 1), 128, 22, 32, 32), ((4, 4), 256, 7, 16, 64)])
+@pytest.mark.parametrize("fs,H,B,P,mlp", [((8, 2, 1), 512, 33, 24, 128), ((8, 4, 2, 1), 128, 22, 32, 32), ((4, 4), 256, 7, 16, 64),
+                                          ((16, 8, 8), 256, 20, 48, 128)])
 def test_tensor_core_mode_lstm(fs, H, B, P, mlp):
     """nn.LSTM tiers — the reference's DEFAULT rnn_class (sample_rnn_v2.py:40-66) — on the tcgen05 engine: gates i, f, g, o as the
     16 accumulator columns of a CTA, the cell state carried in fp32.  Same criteria as the GRU form; fp32 mode of the same net
