@@ -313,7 +313,7 @@ __device__ __forceinline__ float head_row1(const float* __restrict__ w, const fl
 // thread = (k-slice s of 16, channel quad q): 4 channels (8 gate rows / 4 residual rows / 4 skip rows) x C/16 steps.
 // ------------------------------------------------------------------------------------------------------------
 template <int C, bool TRACE>
-__global__ void __maxnreg__(216) wavenet6_kernel(const __grid_constant__ Params P) {
+__global__ void __maxnreg__(255) wavenet6_kernel(const __grid_constant__ Params P) {
     constexpr int NT = 2 * C, NW = NT / 32, KJ = C / KS, CH = C / 2, NQ = C / 8;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31;
