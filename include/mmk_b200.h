@@ -263,10 +263,10 @@ typedef struct {
                                      hidden layers share the weights given here */
     const float* head_wh;         /* output_modules.0.estimator.0.fc.2.weight (Hh, Hh) when head_hidden_layers > 0 */
     const float* head_bh;         /* ...fc.2.bias (Hh) */
-    int need_set_hidden;          /* 1 = mmk_samplernn_set_hidden will be used (h0_init "ones" / "randn"): general kernel */
+    int need_set_hidden;          /* 1 = mmk_samplernn_set_hidden will be used (h0_init "ones" / "randn"): never the tile engine */
     int compute_mode;             /* MMK_COMPUTE_FP32 (0) | MMK_COMPUTE_BF16_TC (1): frame-tier GRU and up-sampler contractions on
                                      tcgen05 with bf16 operands and fp32 accumulation (logits within 5e-2 of fp32).  GRU or LSTM, one layer,
-                                     zero initial state, plain head, hidden_dim in {128, 256, 512}, frame sizes in {1, 2, 4, 8, 16}, max_batch <= 128; else an error */
+                                     plain head, hidden_dim in {128, 256, 512}, frame sizes in {1, 2, 4, 8, 16}, max_batch <= 128; else an error */
 } mmk_samplernn_desc_ex;
 int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* desc, int max_batch, mmk_samplernn_t* out);
 /* Installs an initial state — SampleRNNTier._reset_hidden / _init_h0 (sample_rnn_v2.py:101-119) with h0_init "ones" or

@@ -437,16 +437,15 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
         const char* force = getenv("MMK_SR_KERNEL");
         const int tc = dx->compute_mode == MMK_COMPUTE_BF16_TC ? 1 : 0;
         // the tensor-core engine also hosts nn.LSTM tiers (the reference's default rnn_class); one layer, zero initial state, plain head
-        const bool tc_form = (dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM) && dx->n_rnn == 1 && dx->head_hidden_layers == 0 &&
-                             !dx->need_set_hidden;
-        if (tc && !tc_form) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer, a zero initial state and a plain head"); }
+        const bool tc_form = (dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM) && dx->n_rnn == 1 && dx->head_hidden_layers == 0;
+        if (tc && !tc_form) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer and a plain head"); }
         // ... and so does the lane-major fp32 engine (sequences bit-exact): GRU or LSTM, tried first; what it cannot host falls to the
         // general kernel below
         if ((plain || tc_form) && (tc || !force || atoi(force) != 1)) {
             int unsupported = 0;
             mmk_samplernn_desc d2 = *d;      // the cluster kernel hosts the GRU / one layer / plain head form only
             d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;
-            if (sr2_create(&d2, max_batch, tc, dx->rnn_type == MMK_RNN_LSTM ? 1 : 0, &h->v2, &unsupported) == 0) {
+            if (sr2_create(&d2, max_batch, tc, dx->rnn_type == MMK_RNN_LSTM ? 1 : 0, dx->need_set_hidden ? 1 : 0, &h->v2, &unsupported) == 0) {
                 h->max_batch = max_batch; h->rf = d->frame_sizes[0];
                 *out = h;
                 return 0;
@@ -670,7 +669,10 @@ __global__ void sr_set_hidden_kernel(float* dst, const float* src, int B, int H,
 extern "C" int mmk_samplernn_set_hidden(mmk_samplernn_t h, int tier, int layer, int which, const float* d_values, int B,
                                         void* stream) {
     MMK_CHECK(h && d_values, "mmk_samplernn_set_hidden: null argument");
-    MMK_CHECK(!h->v2, "this handle runs the cluster kernel (zero initial state only): create it with need_set_hidden = 1");
+    if (h->v2) {
+        MMK_CHECK(layer == 0, "layer out of range");
+        return sr2_set_hidden(h->v2, tier, which, d_values, B, stream);
+    }
     const SrParams& p = h->p;
     MMK_CHECK(tier >= 0 && tier < p.n_ft && layer >= 0 && layer < p.n_rnn, "tier / layer out of range");
     MMK_CHECK(which == 0 || (which == 1 && p.rnn_type == MMK_RNN_LSTM), "which: 0 = hidden state, 1 = LSTM cell state");

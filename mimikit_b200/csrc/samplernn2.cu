@@ -1771,7 +1771,7 @@ static void pack_up(float* dst, const float* up_w, int c, int H) {
         }
 }
 
-int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2_handle** out, int* unsupported) {
+int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, int need_set_hidden, sr2_handle** out, int* unsupported) {
     *unsupported = 1;
     const int n_ft = d->n_tiers - 1, H = d->hidden_dim, Hh = d->head_hidden, Q = d->q_levels;
     if (H % KC != 0 || Hh % 4 != 0 || n_ft > MAX_TIERS) return 1;
@@ -1794,7 +1794,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
             if (plan_fast(d, max_batch, CS, sms, max_optin, tc != 0, &best, &best_smem)) { found = true; break; }
         }
     if (tc && !found) { sr2_destroy(h); return 1; }            // the tensor-core engine hosts H in {128, 256, 512}, <= 128 prompts
-    if (lstm && !found) { sr2_destroy(h); return 1; }          // LSTM tiers: the lane-major or the tensor-core engine, never the tile engine
+    if ((lstm || need_set_hidden) && !found) { sr2_destroy(h); return 1; }   // LSTM tiers / a non-zero initial state: never the tile engine
     best.lstm = lstm ? 1 : 0;
     for (int CS : {8, 4, 2, 1}) {
         if (found) break;
@@ -2142,6 +2142,36 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2
     if (const char* e = getenv("MMK_SR_EXP")) p.exp = atoi(e);
     MMK_CUDA(cudaDeviceSynchronize());
     *out = h;
+    return 0;
+}
+
+// A non-zero initial state (SampleRNNTier._init_h0, sample_rnn_v2.py:101-119) for the lane-major / tensor-core engines: rows (B, H)
+// fp32 go to the [prompt][H] state buffer as they are; the tensor-core engine also needs them as its bf16 operand image.
+__global__ void sr2_image_rows_kernel(unsigned char* img, const float* __restrict__ v, int B, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 k) of one prompt row
+    if (i >= B * (H / 8)) return;
+    const int p = i / (H / 8), kc = i - p * (H / 8);
+    const float* s = v + (size_t)p * H + kc * 8;
+    *reinterpret_cast<uint4*>(img + mmk_sr2::tile_off(p, kc, 128)) =
+        make_uint4(mmk_sr2::bf16x2_bits(s[0], s[1]), mmk_sr2::bf16x2_bits(s[2], s[3]), mmk_sr2::bf16x2_bits(s[4], s[5]), mmk_sr2::bf16x2_bits(s[6], s[7]));
+}
+
+int sr2_set_hidden(sr2_handle* h, int tier, int which, const float* d_values, int B, void* stream) {
+    const Params& p = h->p;
+    MMK_CHECK(p.fast, "this geometry runs the tile engine of the cluster kernel (zero initial state only)");
+    MMK_CHECK(tier >= 0 && tier < p.n_ft, "tier out of range");
+    MMK_CHECK(which == 0 || (which == 1 && p.lstm), "which: 0 = hidden state, 1 = LSTM cell state");
+    MMK_CHECK(B >= 1 && B <= h->max_batch, "batch exceeds the max_batch the handle was created for");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Tier& T = p.tiers[tier];
+    float* dst = (which == 0 ? T.hbuf : T.cbuf) + (size_t)p.hsel[tier] * p.H * p.Bp;
+    MMK_CUDA(cudaMemcpyAsync(dst, d_values, (size_t)B * p.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (which == 0 && p.tc) {
+        unsigned char* img = T.himg + (size_t)p.hsel[tier] * p.H * 256;
+        const int n = B * (p.H / 8);
+        sr2_image_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(img, d_values, B, p.H);
+        MMK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

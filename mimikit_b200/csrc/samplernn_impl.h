@@ -6,7 +6,8 @@ struct sr2_handle;
 
 // Returns 0 and a handle when the configuration fits the cluster kernel; returns 1 with *unsupported = 1 when the
 // caller should use the general kernel, or 1 with *unsupported = 0 on a real error (message set).
-int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, sr2_handle** out, int* unsupported);
+int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, int need_set_hidden, sr2_handle** out, int* unsupported);
+int sr2_set_hidden(sr2_handle* h, int tier, int which, const float* d_values, int B, void* stream);
 int sr2_destroy(sr2_handle* h);
 int sr2_launch_info(sr2_handle* h, mmk_launch_info* out);
 int sr2_sync_check(sr2_handle* h, void* stream);

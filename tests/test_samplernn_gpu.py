@@ -276,6 +276,42 @@ def test_lane_major_lstm_vs_oracle(fs, H, B, P):
     assert torch.equal(torch.cat([a, b], 1), net.generate(prompts, n))
 
 
+@pytest.mark.parametrize("rnn,h0_init,H,mode", [("gru", "ones", 128, "f32"), ("lstm", "randn", 256, "f32"), ("lstm", "ones", 128, "bf16"),
+                                                ("gru", "randn", 256, "bf16")])
+def test_initial_state_on_the_fast_engines(rnn, h0_init, H, mode):
+    """h0_init 'ones' / 'randn' (SampleRNNTier._init_h0, sample_rnn_v2.py:101-119) with explicit states: the lane-major (fp32) and
+    tensor-core (bf16) engines take them through mmk_samplernn_set_hidden — fp32 bit-exact with the oracle fed the same states,
+    bf16 within 5e-2 on teacher-forced logits."""
+    from mimikit_b200 import IOSpec, SampleRNN
+    fs = (8, 2, 1)
+    torch.manual_seed(13)
+    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=32)), frame_sizes=fs, hidden_dim=H, rnn_class=rnn, h0_init=h0_init)
+    net = SampleRNN.from_config(cfg).to("cuda")
+    if mode == "bf16":
+        net.bfloat16()
+    B, P, n = 7, 27, 20
+    assert net.launch_info(B)["threads"] == 256          # one of the two fast engines, not the general kernel
+    g = torch.Generator().manual_seed(4)
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    h0 = {}
+    for i in range(len(fs) - 1):
+        for which in ((0, 1) if rnn == "lstm" else (0,)):
+            h0[(i, 0, which)] = torch.ones(B, H) if h0_init == "ones" else torch.randn(B, H, generator=g)
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs, rnn_class=rnn)
+    ref_seq, ref_logits = orc.generate(prompts.numpy(), n, 0.9, noise.numpy(), h0={k: v.numpy() for k, v in h0.items()})
+    if mode == "f32":
+        seq, logits = net.generate(prompts, n, temperature=0.9, noise=noise, return_logits=True, h0=h0)
+        assert np.array_equal(seq.cpu().numpy(), ref_seq)
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+    else:
+        lg, dec = net.teacher_forced(torch.from_numpy(ref_seq), P, 0.9, noise, h0=h0)
+        assert _rel_err(lg.cpu().numpy(), ref_logits) <= 5e-2
+    # the states matter: the zero-state run differs
+    z_seq, z_logits = orc.generate(prompts.numpy(), n, 0.9, noise.numpy())
+    assert _rel_err(z_logits, ref_logits) > 1e-3
+
+
 def test_stepwise_protocol_and_loop():
     """before_generate / generate_step / after_generate == whole-sequence path == oracle; GenerateLoopV2 integration as
     the reference's tests/test_sample_rnn.py:90-112 (batch 2, 512-sample prompt + 512 steps, temperature=(1.,))."""
