@@ -1172,7 +1172,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
     unsigned long long epoch = 0;
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = globaltimer();
     auto lap = [&](int slot) { if (!FAST && P.dbg && c == 0 && tid == 0) { const unsigned long long n = globaltimer(); tacc[slot] += n - tlast; tlast = n; } };
-    long long hta[6] = {0, 0, 0, 0, 0, 0}, htl = clock64();   // MMK_SR_DEBUG: SM cycles of CTA 0 per head section (+ everything else)
+    long long hta[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, htl = clock64();   // MMK_SR_DEBUG: SM cycles of CTA 0 per head section (+ everything else)
     auto hlap = [&](int slot) { if (FAST && P.dbg && c == 0 && tid == 0) { const long long n = clock64(); hta[slot] += n - htl; htl = n; } };
     unsigned head_phase = 0;              // completed head exchanges (parity of the three mbarriers)
     bool dead = false;
@@ -1451,6 +1451,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                     xh[kl * GP + p] = a;
                 }
                 __syncthreads();
+                hlap(6);
                 // -- 2. partial hidden over this CTA's K slice, reduce-scattered by hidden row
                 {
                     const int tiles = (Hh >> 2) * npq_h;
@@ -1464,6 +1465,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                             float acc[16];
 #pragma unroll
                             for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+#pragma unroll 4
                             for (int kl = s; kl < KS; kl += nq) {
                                 const float4 w = *reinterpret_cast<const float4*>(W1s + (size_t)kl * Hh + 4 * rq);
                                 const float4 x = *reinterpret_cast<const float4*>(xh + kl * GP + 4 * pq);
@@ -1492,8 +1494,10 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         st_async_v4(win + sbase + off, v, win + bar(BAR_HID));
                     }
                 }
+                hlap(7);
                 dead |= !mbar_wait(bar(BAR_HID), par, abort_flag);
                 if (tid == 0) mbar_expect_tx(bar(BAR_HID), hid_bytes);
+                hlap(8);
                 // -- 3. hidden rows of this CTA: sum the partials in rank order, bias, Mish (mlp.py:44-53)
                 for (int i = tid; i < RS * GP; i += NTK) {
                     float s = 0.0f;
@@ -1511,6 +1515,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                         float acc[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+#pragma unroll 4
                         for (int k = 0; k < RS; ++k) {
                             const float4 w = *reinterpret_cast<const float4*>(W2s + (size_t)k * ZR + 4 * rq);
                             const float4 x = *reinterpret_cast<const float4*>(hid_s + k * GP + 4 * pq);
@@ -1595,7 +1600,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
     if (ENGINE == 1 && F.timing)
         for (int i = 0; i < 12; ++i) P.dbg[8 + i] += (unsigned long long)F.ta[i];
     if (FAST && P.dbg && c == 0 && tid == 0)
-        for (int i = 0; i < 6; ++i) P.dbg[20 + i] += (unsigned long long)hta[i];
+        for (int i = 0; i < 9; ++i) P.dbg[20 + i] += (unsigned long long)hta[i];
     // no CTA may exit while peers can still store into its shared memory
     if (ENGINE == 2) tc_fence_before();
     __syncthreads();
@@ -2187,12 +2192,13 @@ int sr2_sync_check(sr2_handle* h, void* stream) {
     MMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     MMK_CHECK(aborted == 0, "SampleRNN kernel watchdog fired: a barrier wait timed out (results invalid)");
     if (h->p.dbg) {
-        unsigned long long t[26];
+        unsigned long long t[29];
         MMK_CUDA(cudaMemcpy(t, h->p.dbg, sizeof(t), cudaMemcpyDeviceToHost));
         MMK_CUDA(cudaMemset(h->p.dbg, 0, sizeof(t)));
         if (h->p.fast) {
-            fprintf(stderr, "[sr2] CTA0 head Mcycles: hidden rows %.1f logit partials + send %.1f wait logits %.1f decide %.1f wait index %.1f | outside the head %.1f\n",
-                    t[20] / 1e6, t[21] / 1e6, t[22] / 1e6, t[23] / 1e6, t[24] / 1e6, t[25] / 1e6);
+            fprintf(stderr, "[sr2] CTA0 head Mcycles: hidden rows %.1f (unfolded head: x rows %.1f, W1 partials + send %.1f, wait %.1f, then Mish) logit partials + send %.1f "
+                            "wait logits %.1f decide %.1f wait index %.1f | outside the head %.1f\n",
+                    (t[20] + t[26] + t[27] + t[28]) / 1e6, t[26] / 1e6, t[27] / 1e6, t[28] / 1e6, t[21] / 1e6, t[22] / 1e6, t[23] / 1e6, t[24] / 1e6, t[25] / 1e6);
             if (h->p.tc) return 0;
             static const char* names[12] = {"weights", "pre-barrier", "frame", "gru stream", "gates", "up weights", "barrier", "up stream", "up rows",
                                             "last barrier", "head", "other"};
