@@ -85,7 +85,8 @@ class WaveNet(NativeARM):
              "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
         need(not c.apply_residuals and not c.with_affine_residuals, "apply_residuals / with_affine_residuals")
         need(c.groups == 1, "groups > 1")
-        need(str(c.act_f) == "Tanh" and str(c.act_g) == "Sigmoid", "activations other than Tanh/Sigmoid gating")
+        need(str(c.act_f) == "Tanh" and (c.act_g is None or str(c.act_g) == "Sigmoid"),
+             "activations other than Tanh filters with a Sigmoid gate or no gate")
         need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
         # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
         # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
@@ -170,7 +171,7 @@ class WaveNet(NativeARM):
     def _plain(self):
         """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
         return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
-                and not self._config.reverse_layer_order)
+                and not self._config.reverse_layer_order and self._gated)
 
     @property
     def generate_params(self):
@@ -178,6 +179,10 @@ class WaveNet(NativeARM):
         its loop can never pass a temperature to WaveNet; the evident intent — and SampleRNN's behaviour
         (sample_rnn_v2.py:309-311) — is {"temperature"}.  Documented deviation."""
         return {"temperature"}
+
+    @property
+    def _gated(self):
+        return self._config.act_g is not None
 
     def _layer_has_res(self, l):
         """wavenet_v2.py:216 — the layer BUILT last has no conv_res; with reverse_layer_order it is executed first."""
@@ -197,8 +202,12 @@ class WaveNet(NativeARM):
         e = OrderedDict()
         e["input_modules.0.0.weight"] = (self._config.io_spec.inputs[0].class_size, C)
         for l in range(L):
-            e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, self.kernels[l])
-            e[f"layers.{l}.conv_dil.0.0.bias"] = (2 * C,)
+            if self._gated:
+                e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, self.kernels[l])
+                e[f"layers.{l}.conv_dil.0.0.bias"] = (2 * C,)
+            else:                                       # wavenet_v2.py:109-112: a bare Conv1d (no Sequential / Chunk) without gated units
+                e[f"layers.{l}.conv_dil.0.weight"] = (C, C, self.kernels[l])
+                e[f"layers.{l}.conv_dil.0.bias"] = (C,)
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
                 e[f"layers.{l}.conv_skip.bias"] = (S,)
@@ -252,8 +261,21 @@ class WaveNet(NativeARM):
             a = self._warray([fmt.format(l) if present(l) else None for l in range(L)])
             keep.append(a)
             return a
-        d.conv_dil_w = arr("layers.{}.conv_dil.0.0.weight")
-        d.conv_dil_b = arr("layers.{}.conv_dil.0.0.bias")
+        if self._gated:
+            d.conv_dil_w = arr("layers.{}.conv_dil.0.0.weight")
+            d.conv_dil_b = arr("layers.{}.conv_dil.0.0.bias")
+        else:
+            # act_g=None (wavenet_v2.py:160-163): y = tanh(conv(x)).  Hosted by the gated kernel with a gate that is exactly one:
+            # zero gate weights and a gate bias of 40 — sigmoid(40) = 1 / (1 + exp(-40)) rounds to 1.0f, and tanh(a) * 1.0f = tanh(a)
+            self._ungated_pack = {}
+            for l in range(L):
+                w, b = self._sd[f"layers.{l}.conv_dil.0.weight"], self._sd[f"layers.{l}.conv_dil.0.bias"]
+                self._ungated_pack[f"w{l}"] = torch.cat([w, torch.zeros_like(w)], 0).contiguous()
+                self._ungated_pack[f"b{l}"] = torch.cat([b, torch.full_like(b, 40.0)], 0).contiguous()
+            wa = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._ungated_pack[f"w{l}"]) for l in range(L)])
+            ba = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._ungated_pack[f"b{l}"]) for l in range(L)])
+            keep += [wa, ba]
+            d.conv_dil_w, d.conv_dil_b = wa, ba
         if self.has_skips:
             d.conv_skip_w = arr("layers.{}.conv_skip.weight")
             d.conv_skip_b = arr("layers.{}.conv_skip.bias")

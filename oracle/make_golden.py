@@ -133,6 +133,12 @@ def main():
         net = ref_loader.make_wavenet(seed=15, reverse_layer_order=True, **kw)
         gen_network("wavenet_reversed", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, reverse_layer_order=1))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_nongated":      # act_g=None (wavenet_v2.py:109-112, 160-163)
+        g = torch.Generator().manual_seed(90)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=16, gated=False, **kw)
+        gen_network("wavenet_nongated", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, nongated=1))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

@@ -371,10 +371,12 @@ class WaveNetOracle:
         self.Wd, self.bd, self.Ws, self.bs, self.Wr, self.br = [], [], [], [], [], []
         self.has_skips = "layers.0.conv_skip.weight" in sd
         for l in range(self.L):
-            w = _np(sd, f"layers.{l}.conv_dil.0.0.weight")  # (2C, C, k): tap 0 = oldest sample (cross-correlation)
+            self.gated = f"layers.{l}.conv_dil.0.0.weight" in sd     # act_g=None: a bare Conv1d, y = tanh(conv) (wavenet_v2.py:109-112, 160-163)
+            pre = f"layers.{l}.conv_dil.0.0." if self.gated else f"layers.{l}.conv_dil.0."
+            w = _np(sd, pre + "weight")  # (2C | C, C, k): tap 0 = oldest sample (cross-correlation)
             assert w.shape[2] == self.kernels[l]
             self.Wd.append([np.ascontiguousarray(w[:, :, j]) for j in range(w.shape[2])])
-            self.bd.append(_np(sd, f"layers.{l}.conv_dil.0.0.bias"))
+            self.bd.append(_np(sd, pre + "bias"))
             if self.has_skips:
                 self.Ws.append(_np(sd, f"layers.{l}.conv_skip.weight")[:, :, 0])
                 self.bs.append(_np(sd, f"layers.{l}.conv_skip.bias"))
@@ -406,7 +408,10 @@ class WaveNetOracle:
         for w, x in zip(self.Wd[l], taps):                               # wavenet_v2.py:101,150
             a = x @ w.T + a if a.ndim == 1 else a + x @ w.T
         a = a.astype(f32)
-        y = (np.tanh(a[..., :C]) * _sigmoid(a[..., C:])).astype(f32)     # :102,151
+        if self.gated:
+            y = (np.tanh(a[..., :C]) * _sigmoid(a[..., C:])).astype(f32)     # :102,151
+        else:
+            y = np.tanh(a).astype(f32)                                       # :160-163 (act_g=None)
         if self.has_skips:
             s = y @ self.Ws[l].T + self.bs[l]                            # :165-171
             skips = s if skips is None else (s + skips).astype(f32)
