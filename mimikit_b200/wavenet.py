@@ -84,7 +84,7 @@ class WaveNet(NativeARM):
         need(c.residuals_dim is None or c.residuals_dim == c.dims_dilated[0],
              "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
         need(not c.apply_residuals and not c.with_affine_residuals, "apply_residuals / with_affine_residuals")
-        need(c.groups == 1, "groups > 1")
+        need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
         need(str(c.act_f) == "Tanh" and (c.act_g is None or str(c.act_g) == "Sigmoid"),
              "activations other than Tanh filters with a Sigmoid gate or no gate")
         need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
@@ -171,7 +171,7 @@ class WaveNet(NativeARM):
     def _plain(self):
         """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
         return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
-                and not self._config.reverse_layer_order and self._gated)
+                and not self._config.reverse_layer_order and self._gated and self._config.groups == 1)
 
     @property
     def generate_params(self):
@@ -202,11 +202,12 @@ class WaveNet(NativeARM):
         e = OrderedDict()
         e["input_modules.0.0.weight"] = (self._config.io_spec.inputs[0].class_size, C)
         for l in range(L):
+            Cg = C // self._config.groups               # grouped dilated convs (wavenet_v2.py:92): weight (out, in / groups, k)
             if self._gated:
-                e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, C, self.kernels[l])
+                e[f"layers.{l}.conv_dil.0.0.weight"] = (2 * C, Cg, self.kernels[l])
                 e[f"layers.{l}.conv_dil.0.0.bias"] = (2 * C,)
             else:                                       # wavenet_v2.py:109-112: a bare Conv1d (no Sequential / Chunk) without gated units
-                e[f"layers.{l}.conv_dil.0.weight"] = (C, C, self.kernels[l])
+                e[f"layers.{l}.conv_dil.0.weight"] = (C, Cg, self.kernels[l])
                 e[f"layers.{l}.conv_dil.0.bias"] = (C,)
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
@@ -261,19 +262,31 @@ class WaveNet(NativeARM):
             a = self._warray([fmt.format(l) if present(l) else None for l in range(L)])
             keep.append(a)
             return a
-        if self._gated:
+        if self._gated and self._config.groups == 1:
             d.conv_dil_w = arr("layers.{}.conv_dil.0.0.weight")
             d.conv_dil_b = arr("layers.{}.conv_dil.0.0.bias")
         else:
-            # act_g=None (wavenet_v2.py:160-163): y = tanh(conv(x)).  Hosted by the gated kernel with a gate that is exactly one:
-            # zero gate weights and a gate bias of 40 — sigmoid(40) = 1 / (1 + exp(-40)) rounds to 1.0f, and tanh(a) * 1.0f = tanh(a)
-            self._ungated_pack = {}
+            # Two forms are hosted by the dense gated kernel through their weights alone:
+            #  * groups > 1 (wavenet_v2.py:92): the block-diagonal conv written out densely — the zero blocks add exact zeros;
+            #  * act_g=None (wavenet_v2.py:160-163): y = tanh(conv(x)) as a gated unit whose gate is exactly one: zero gate weights
+            #    and a gate bias of 40 — sigmoid(40) = 1 / (1 + exp(-40)) rounds to 1.0f, and tanh(a) * 1.0f = tanh(a).
+            self._dense_pack = {}
+            G = int(self._config.groups)
             for l in range(L):
-                w, b = self._sd[f"layers.{l}.conv_dil.0.weight"], self._sd[f"layers.{l}.conv_dil.0.bias"]
-                self._ungated_pack[f"w{l}"] = torch.cat([w, torch.zeros_like(w)], 0).contiguous()
-                self._ungated_pack[f"b{l}"] = torch.cat([b, torch.full_like(b, 40.0)], 0).contiguous()
-            wa = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._ungated_pack[f"w{l}"]) for l in range(L)])
-            ba = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._ungated_pack[f"b{l}"]) for l in range(L)])
+                pre = f"layers.{l}.conv_dil.0.0." if self._gated else f"layers.{l}.conv_dil.0."
+                w, b = self._sd[pre + "weight"], self._sd[pre + "bias"]
+                if G > 1:
+                    O, Cg, K = w.shape
+                    dense = torch.zeros((O, C, K), dtype=w.dtype)
+                    for gi in range(G):
+                        dense[gi * (O // G):(gi + 1) * (O // G), gi * Cg:(gi + 1) * Cg] = w[gi * (O // G):(gi + 1) * (O // G)]
+                    w = dense
+                if not self._gated:
+                    w = torch.cat([w, torch.zeros_like(w)], 0)
+                    b = torch.cat([b, torch.full_like(b, 40.0)], 0)
+                self._dense_pack[f"w{l}"], self._dense_pack[f"b{l}"] = w.contiguous(), b.contiguous()
+            wa = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._dense_pack[f"w{l}"]) for l in range(L)])
+            ba = (ctypes.POINTER(ctypes.c_float) * L)(*[_capi.fptr(self._dense_pack[f"b{l}"]) for l in range(L)])
             keep += [wa, ba]
             d.conv_dil_w, d.conv_dil_b = wa, ba
         if self.has_skips:

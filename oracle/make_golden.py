@@ -139,6 +139,12 @@ def main():
         net = ref_loader.make_wavenet(seed=16, gated=False, **kw)
         gen_network("wavenet_nongated", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, nongated=1))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_groups":        # grouped dilated convs (wavenet_v2.py:92; FreqNet uses groups=8)
+        g = torch.Generator().manual_seed(91)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=17, groups=4, **kw)
+        gen_network("wavenet_groups4", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, groups=4))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

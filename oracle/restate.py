@@ -373,8 +373,15 @@ class WaveNetOracle:
         for l in range(self.L):
             self.gated = f"layers.{l}.conv_dil.0.0.weight" in sd     # act_g=None: a bare Conv1d, y = tanh(conv) (wavenet_v2.py:109-112, 160-163)
             pre = f"layers.{l}.conv_dil.0.0." if self.gated else f"layers.{l}.conv_dil.0."
-            w = _np(sd, pre + "weight")  # (2C | C, C, k): tap 0 = oldest sample (cross-correlation)
+            w = _np(sd, pre + "weight")  # (2C | C, C / groups, k): tap 0 = oldest sample (cross-correlation)
             assert w.shape[2] == self.kernels[l]
+            if w.shape[1] != self.C:     # grouped conv (wavenet_v2.py:92): the block-diagonal weight written out densely
+                G = self.C // w.shape[1]
+                dense = np.zeros((w.shape[0], self.C, w.shape[2]), dtype=f32)
+                og, cg = w.shape[0] // G, w.shape[1]
+                for gi in range(G):
+                    dense[gi * og:(gi + 1) * og, gi * cg:(gi + 1) * cg] = w[gi * og:(gi + 1) * og]
+                w = dense
             self.Wd.append([np.ascontiguousarray(w[:, :, j]) for j in range(w.shape[2])])
             self.bd.append(_np(sd, pre + "bias"))
             if self.has_skips:

@@ -239,7 +239,7 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3",
-                                  "wavenet_reversed", "wavenet_nongated"])
+                                  "wavenet_reversed", "wavenet_nongated", "wavenet_groups4"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
@@ -254,7 +254,7 @@ def test_variant_goldens(name):
                          residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
                          skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
                          layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)),
-                         reverse_layer_order=kw["reverse_layer_order"], **({"act_g": None} if int(m.get("nongated", 0)) else {}))
+                         reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), **({"act_g": None} if int(m.get("nongated", 0)) else {}))
     net = WaveNet.from_config(cfg).to("cuda")
     net.load_state_dict(golden_state_dict(d))
     prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
