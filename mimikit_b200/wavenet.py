@@ -83,7 +83,8 @@ class WaveNet(NativeARM):
         need(len(c.dims_dilated) == 1 and not c.dims_1x1, "dims_1x1 conditioning inputs")
         need(c.residuals_dim is None or c.residuals_dim == c.dims_dilated[0],
              "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
-        need(not c.apply_residuals and not c.with_affine_residuals, "apply_residuals / with_affine_residuals")
+        # apply_residuals is stored by WNLayer (wavenet_v2.py:63) and read nowhere in its forward: accepted, changes nothing
+        need(not c.with_affine_residuals, "with_affine_residuals")
         need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
         need(str(c.act_f) == "Tanh" and (c.act_g is None or str(c.act_g) == "Sigmoid"),
              "activations other than Tanh filters with a Sigmoid gate or no gate")
