@@ -33,6 +33,10 @@ W30 = dict(blocks=(8, 8, 7, 7), dims=128, residuals_dim=128, skips_dim=128, mlp_
 S3 = dict(frame_sizes=(8, 2, 1), hidden_dim=512, mlp_dim=128)
 # algorithmic work per generated sample per prompt
 FLOP_PER_SAMPLE = {"wavenet": 2 * 2_982_016, "samplernn": 2 * 1_476_224}
+# work of the prefill inside the same launch, per prompt sample it pushes through the net (no head, no sampler):
+# WaveNet: the 30 layers (2 932 736 MAC) for the last rf = 765 prompt samples; SampleRNN: the frame tiers (tier 0 every 8 samples, tier 1
+# every 2: GRUs + up-samplers 1 376 256 + frame Linears 1 024 = 1 377 280 MAC) for every prompt sample (before_generate's warm-up)
+PREFILL_FLOP_PER_SAMPLE = {"wavenet": 2 * 2_932_736, "samplernn": 2 * 1_377_280}
 
 
 def parse():
@@ -348,7 +352,8 @@ def run_b200(args):
         except OSError:
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        flop_launch = FLOP_PER_SAMPLE[wl] * B * n
+        n_prefill = min(P, net.rf) if wl == "wavenet" else P
+        flop_launch = FLOP_PER_SAMPLE[wl] * B * n + PREFILL_FLOP_PER_SAMPLE[wl] * B * n_prefill
         kernel_ms = ms / args.steps            # the persistent kernel IS the step (prefill included)
         ach = flop_launch / (kernel_ms / 1e3) / 1e12
         sm_mhz = ck["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
@@ -374,6 +379,8 @@ def run_b200(args):
         # dram bytes of one launch from the committed ncu capture (profiles/ncu_traffic.json), scaled from the captured launch to
         # this one by the samples a launch pushes through the net (prompt prefill + generated, per prompt: sequence reads, ring
         # spill, mailboxes, sequence writes all go with them); null when no capture is committed
+        roof["flops_counted"] = (f"{B} prompts x ({n} generated samples x {FLOP_PER_SAMPLE[wl]} + {n_prefill} prefill samples x "
+                                 f"{PREFILL_FLOP_PER_SAMPLE[wl]}) flop per launch (the launch covers the prefill)")
         roof["traffic"] = None if not tr else tr["dram_bytes"] * (B * (P + n)) / max(1, tr["prompts"] * (tr["prompt_len"] + tr["n_steps"]))
         if tr:
             roof["traffic_source"] = tr.get("source")
