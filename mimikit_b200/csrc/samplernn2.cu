@@ -64,6 +64,9 @@ struct Tier {
     unsigned char* oimg;             // up-sampler output (the next tier's conditioning), one image per slot; null for the bottom frame tier
     const unsigned char* wgimg;      // [NC][fills][4 KB]: r | z | n_i | n_h columns over K = [conditioning | hidden]
     const unsigned char* wuimg;      // [NC][H / 128][4 KB]
+    const unsigned char* wximg;      // fold_gx: [NC][H / 128][up * 4 KB] tiles of W_ih(next tier) . W_up(slot), up * 16 columns
+    const float* xb;                 // fold_gx: [NC][up][16] = W_ih(next tier) . b_up(slot)
+    float* gx;                       // fold_gx: [up][128 prompts][NC][16] fp32, written and read by the same CTA
     const float* wf;                 // [NC][16][fs]: W_ih . in_w rows of the columns (frame Linear folded into the gate)
     const float* bfold;              // [NC][16]: b_ih + b_hh + W_ih . in_b (n_i: without b_hh; n_h: b_hh alone)
 };
@@ -99,6 +102,10 @@ struct Params {
     // head step starts from `pre` [slot][128 prompts][Hh] and adds (W1 conv_w) lin(q): no x rows, no W1 contraction, no exchange
     int lstm;                        // tensor-core mode only: nn.LSTM tiers (gates i, f, g, o; the reference's default rnn_class)
     int fold_head, NVh;              // NVh: folded up-sampler columns per CTA (up * Hh / NC)
+    // tensor-core mode, fold_gx: a frame tier's up-sampler emits, per slot, the INPUT-side gate pre-activations of the tier below for
+    // this CTA's own 16 columns (W_ih . (W_up h + b_up), products precomputed): the tier below then contracts over its hidden
+    // state only (K halves), and no conditioning image is written or pulled.  tc_bbytes: B area of a stage (4 KB, or 16 KB with fold_gx)
+    int fold_gx, tc_bbytes;
     float* pre; const float* hu; const float* hb;     // hu [Hh][fs_last] = W1 . conv_w; hb [NC][NVh] folded biases
 };
 
@@ -870,7 +877,8 @@ __device__ __forceinline__ bool fast_up(const Params& P, const Tier& T, const fl
 //     (the next operand).  The head stays the fp32 cluster head.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int TC_STAGES = 3;
-constexpr unsigned TC_A_BYTES = 32768u, TC_B_BYTES = 4096u, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;   // 128 k per fill
+constexpr unsigned TC_A_BYTES = 32768u, TC_B_BYTES = 4096u;   // per fill of 128 k: 128 prompts x 128 k of A, 16 columns x 128 k of B
+constexpr unsigned TC_BX_BYTES = 16384u;                      // widest B fill (fold_gx: up to 4 slots x 16 columns)
 enum { TCB_FULL = 0, TCB_EMPTY = TC_STAGES, TCB_ACC = 2 * TC_STAGES, TCB_COUNT };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -934,8 +942,10 @@ __device__ __forceinline__ unsigned tc_bar(const Tc& X, int i) { return X.bar0 +
 // Warps 5..7 (one issuing lane each, stage = warp - 5) stream the fills, warp 4 issues the MMAs: D (TMEM columns 0..15)
 // = sum over the fills of A_fill[128 x 128] . B_fill[16 x 128]^T.  Fill j < n0 comes from img0, the rest from img1.
 __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsigned char* img0, int n0, const unsigned char* img1, int n1,
-                                            const unsigned char* wimg, int warp, int lane) {
+                                            const unsigned char* wimg, int warp, int lane, int ncols = 16) {
     const int nfill = n0 + n1;
+    const unsigned bbytes = (unsigned)ncols * 256u;             // ncols rows x 128 k of bf16
+    const unsigned sbytes = TC_A_BYTES + (unsigned)P.tc_bbytes; // stage stride
     bool ok = true;
     if (warp >= 5) {
         if (lane == 0) {
@@ -946,14 +956,14 @@ __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsign
                 if (g % TC_STAGES != s) continue;
                 const unsigned u = g / TC_STAGES;
                 if (u > 0) ok = mbar_wait(tc_bar(X, TCB_EMPTY + s), (u - 1u) & 1u, P.abort_flag);
-                mbar_expect_tx(tc_bar(X, TCB_FULL + s), TC_STAGE_BYTES);
+                mbar_expect_tx(tc_bar(X, TCB_FULL + s), TC_A_BYTES + bbytes);
                 const unsigned char* src = j < n0 ? img0 + (size_t)j * TC_A_BYTES : img1 + (size_t)(j - n0) * TC_A_BYTES;
-                bulk_g2s(X.stage0 + s * TC_STAGE_BYTES, src, TC_A_BYTES, tc_bar(X, TCB_FULL + s));
-                bulk_g2s(X.stage0 + s * TC_STAGE_BYTES + TC_A_BYTES, wimg + (size_t)j * TC_B_BYTES, TC_B_BYTES, tc_bar(X, TCB_FULL + s));
+                bulk_g2s(X.stage0 + s * sbytes, src, TC_A_BYTES, tc_bar(X, TCB_FULL + s));
+                bulk_g2s(X.stage0 + s * sbytes + TC_A_BYTES, wimg + (size_t)j * bbytes, bbytes, tc_bar(X, TCB_FULL + s));
             }
         }
     } else if (warp == 4) {
-        const unsigned idesc = umma_idesc(16);
+        const unsigned idesc = umma_idesc(ncols);
         for (int j = 0; j < nfill; ++j) {
             const unsigned g = X.gf + (unsigned)j, s = g % TC_STAGES, u = g / TC_STAGES;
             ok = __all_sync(0xffffffffu, (mbar_wait(tc_bar(X, TCB_FULL + s), u & 1u, P.abort_flag) && ok) ? 1 : 0) != 0;
@@ -962,9 +972,9 @@ __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsign
             unsigned pred;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
             if (pred) {
-                const unsigned long long dA = umma_desc(X.stage0 + s * TC_STAGE_BYTES), dB = umma_desc(X.stage0 + s * TC_STAGE_BYTES + TC_A_BYTES);
+                const unsigned long long dA = umma_desc(X.stage0 + s * sbytes), dB = umma_desc(X.stage0 + s * sbytes + TC_A_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) umma_bf16(X.tmem, dA + kstep16(kk, 128), dB + kstep16(kk, 16), idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 8; ++kk) umma_bf16(X.tmem, dA + kstep16(kk, 128), dB + kstep16(kk, ncols), idesc, (j > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(tc_bar(X, TCB_EMPTY + s));
                 if (j == nfill - 1) umma_commit(tc_bar(X, TCB_ACC));
             }
@@ -977,12 +987,14 @@ __device__ __forceinline__ bool tc_contract(const Params& P, Tc& X, const unsign
 // GRU cell of frame tier T on this CTA's 4 hidden indices (sample_rnn_v2.py:226-260, modules/io.py:106-133), bf16 tensor-core form.
 template <int FS>
 __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const unsigned char* cimg, const unsigned char* himg, unsigned char* himg_next,
-                                       const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X, int hs) {
+                                       const float* hcur, float* hnext, long long tw, bool pre_barrier, unsigned long long& epoch, Tc& X, int hs,
+                                       const float* gxrow) {   // fold_gx: this CTA's [128 prompts][NC][16] input-side pre-activations of the slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
     if (pre_barrier && !grid_barrier(P, epoch)) return false;
     const int nimg = H / 128;                                   // fills per image
-    bool ok = tc_contract(P, X, cimg ? cimg : himg, nimg, himg, cimg ? nimg : 0,
-                          T.wgimg + (size_t)c * (2 * nimg) * TC_B_BYTES, warp, lane);
+    // weight fills of the CTA: [conditioning part | hidden part] (the top tier: hidden part first); with fold_gx only the hidden part runs
+    const unsigned char* wimg = T.wgimg + (size_t)c * (2 * nimg) * TC_B_BYTES + (gxrow ? (size_t)nimg * TC_B_BYTES : 0);
+    bool ok = tc_contract(P, X, cimg ? cimg : himg, nimg, himg, cimg ? nimg : 0, wimg, warp, lane);
     if (warp < 4) {
         const int p = tid;
         // the state this thread carries: h_old (GRU) or c_old (LSTM: cbuf ping-pongs with the hidden state, side hs)
@@ -998,6 +1010,11 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
         }
         const float* wf = T.wf + (size_t)c * 16 * FS;
         const float* bfo = T.bfold + (size_t)c * 16;
+        float4 gxv[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (gxrow) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gxv[i] = __ldcg(reinterpret_cast<const float4*>(gxrow + ((size_t)p * P.NC + c) * 16) + i);
+        }
         float pre[16];
 #pragma unroll
         for (int col = 0; col < 16; ++col) {
@@ -1006,7 +1023,7 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
 #pragma unroll
                 for (int f = 0; f < FS; ++f) a = fmaf(__ldg(wf + col * FS + f), X.lin[p * FS + f], a);
             }
-            pre[col] = a;
+            pre[col] = a + reinterpret_cast<const float*>(gxv)[col];
         }
         ok = mbar_wait(tc_bar(X, TCB_ACC), X.na & 1u, P.abort_flag) && ok;
         tc_fence_after();
@@ -1045,6 +1062,36 @@ __device__ __forceinline__ bool tc_gru(const Params& P, const Tier& T, const uns
         }
     }
     X.gf += (unsigned)(cimg ? 2 * nimg : nimg);
+    X.na += 1u;
+    return __syncthreads_or(ok ? 0 : 1) == 0;
+}
+
+// fold_gx: the up-sampler of tier T as the input-side gate pre-activations of the tier below, for this CTA's own columns: one
+// accumulation D[128 x up * 16] = h_new . (W_ih(next) W_up(slot))^T, written to T.gx [slot][prompt][CTA][16] (fp32; same CTA reads it).
+__device__ __forceinline__ bool tc_up_gx(const Params& P, const Tier& T, const unsigned char* himg, unsigned long long& epoch, Tc& X) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x, H = P.H;
+    const int ncols = T.up * 16;
+    if (!grid_barrier(P, epoch)) return false;
+    const int nimg = H / 128;
+    bool ok = tc_contract(P, X, himg, nimg, himg, 0, T.wximg + (size_t)c * nimg * ((size_t)ncols * 256), warp, lane, ncols);
+    if (warp < 4) {
+        const int p = tid;
+        ok = mbar_wait(tc_bar(X, TCB_ACC), X.na & 1u, P.abort_flag) && ok;
+        tc_fence_after();
+        for (int sl = 0; sl < T.up; ++sl) {
+            float v[16];
+            tmem_ld16(X.tmem + ((unsigned)(32 * warp) << 16) + 16u * (unsigned)sl, v);
+            tmem_ld_wait();
+            const float* xb = T.xb + ((size_t)c * T.up + sl) * 16;
+            float4* dst = reinterpret_cast<float4*>(T.gx + (((size_t)sl * 128 + p) * P.NC + c) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                __stcg(dst + i, make_float4(v[4 * i] + __ldg(xb + 4 * i), v[4 * i + 1] + __ldg(xb + 4 * i + 1), v[4 * i + 2] + __ldg(xb + 4 * i + 2),
+                                            v[4 * i + 3] + __ldg(xb + 4 * i + 3)));
+        }
+        tc_fence_before();
+    }
+    X.gf += (unsigned)nimg;
     X.na += 1u;
     return __syncthreads_or(ok ? 0 : 1) == 0;
 }
@@ -1152,7 +1199,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
             for (int i = 0; i < TCB_COUNT; ++i) mbar_init(tc_bar(X, i), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (warp == 4) { tmem_alloc(smem_u32(s_tmem), 32); tmem_relinquish(); }
+        if (warp == 4) { tmem_alloc(smem_u32(s_tmem), 64); tmem_relinquish(); }
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -1198,21 +1245,24 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
                     heads_pending = false;
                     fired = true;
                     const size_t img = (size_t)H * 256;           // bytes of a [128 x H] bf16 image
-                    const unsigned char* cimg = i > 0 ? P.tiers[i - 1].oimg + (size_t)((t / T.fs) % T.kdiv) * img : nullptr;
+                    const bool gx_in = P.fold_gx && i > 0;                  // the tier above emitted this tier's input-side pre-activations
+                    const unsigned char* cimg = (i > 0 && !gx_in) ? P.tiers[i - 1].oimg + (size_t)((t / T.fs) % T.kdiv) * img : nullptr;
+                    const float* gxrow = gx_in ? P.tiers[i - 1].gx + (size_t)((t / T.fs) % T.kdiv) * 128 * P.NC * 16 : nullptr;
                     const unsigned char* himg = T.himg + (size_t)hsel[i] * img;
                     unsigned char* himg_next = T.himg + (size_t)(hsel[i] ^ 1) * img;
                     const float* hcur = T.hbuf + (size_t)hsel[i] * H * Bp;
                     float* hnext = T.hbuf + (size_t)(hsel[i] ^ 1) * H * Bp;
                     bool ok = false;
                     switch (T.fs) {
-                        case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
-                        case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
-                        case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
-                        case 8: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
-                        default: ok = tc_gru<16>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i]); break;
+                        case 1: ok = tc_gru<1>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i], gxrow); break;
+                        case 2: ok = tc_gru<2>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i], gxrow); break;
+                        case 4: ok = tc_gru<4>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i], gxrow); break;
+                        case 8: ok = tc_gru<8>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i], gxrow); break;
+                        default: ok = tc_gru<16>(P, T, cimg, himg, himg_next, hcur, hnext, tw, pre, epoch, X, hsel[i], gxrow); break;
                     }
                     hsel[i] ^= 1;
-                    if (ok) ok = tc_up(P, T, himg_next, epoch, X, P.fold_head != 0 && i == P.n_ft - 1);
+                    if (ok) ok = (P.fold_gx && i < P.n_ft - 1) ? tc_up_gx(P, T, himg_next, epoch, X)
+                                                               : tc_up(P, T, himg_next, epoch, X, P.fold_head != 0 && i == P.n_ft - 1);
                     if (!ok) { dead = true; break; }
                     pending_up = true;
                 }
@@ -1604,7 +1654,7 @@ __global__ void __launch_bounds__(ENGINE ? NTF : NT, 1) samplernn_cluster_kernel
     // no CTA may exit while peers can still store into its shared memory
     if (ENGINE == 2) tc_fence_before();
     __syncthreads();
-    if (ENGINE == 2 && warp == 4) { tc_fence_after(); tmem_dealloc(X.tmem, 32); }
+    if (ENGINE == 2 && warp == 4) { tc_fence_after(); tmem_dealloc(X.tmem, 64); }
     cluster_sync_all();
 }
 
@@ -1723,41 +1773,55 @@ static bool plan_fast(const mmk_samplernn_desc* d, int max_batch, int CS, int sm
     p.h_zs = p.h_un + pad4(inz_floats);
     const int head_floats = ho + std::max(part_floats, pad4(inz_floats) + (GP / CS) * (p.ZR + 4));
     const int budget = max_optin / (int)sizeof(float) - 256;
-    o = 0;
-    // tensor-core engine: the stages (1024-byte aligned inside the region: 1 KB of slack) share the region with the head buffers
-    p.region = tc ? std::max(head_floats, (int)(TC_STAGES * TC_STAGE_BYTES + 1024) / 4) : head_floats;
-    p.xregion = p.wregion = p.xstage = p.wstage = 0;
-    p.s_region = take(p.region);
-    p.s_gi = o;
-    p.s_bar = take(2 * BAR_COUNT + 16 * GP);
-    p.s_b2 = take(Q + 1);
-    int nv_max = 16;
-    for (int i = 0; i < n_ft; ++i) nv_max = std::max(nv_max, p.tiers[i].NV);
-    p.s_part = take(tc ? 4 : p.NKQ * p.Bp * (nv_max > 16 ? 32 : 16));
-    p.s_hold = take(tc ? 4 : p.Bp * 4);
-    p.s_lin = take(p.Bp * fs_max);
-    p.s_tcbar = take(2 * TCB_COUNT + 4);
-    p.n_res = 0;
-    bool ok = true;
-    auto resident = [&](int goff, int len, int* soff) {
-        len = pad4(len);
-        if (o + len > budget) { ok = false; return; }
-        *soff = o;
-        p.res_goff[p.n_res] = goff; p.res_soff[p.n_res] = o; p.res_len[p.n_res] = len; ++p.n_res;
-        o += len;
-    };
-    resident(p.off_w1, p.KS * Hh, &p.so_w1);
-    resident(p.off_b1, p.RS, &p.so_b1);
-    resident(p.off_w2, p.RS * p.ZR, &p.so_w2);
-    if (!ok) return false;
-    p.smem_floats = o;
-    const size_t smem = (size_t)o * sizeof(float);
-    const int max_clusters = sr2_max_clusters(CS, smem, sms, tc ? 2 : 1);
-    if (getenv("MMK_SR_DEBUG"))
-        fprintf(stderr, "[sr2] lane-major engine: CS=%d NC=%d GP=%d smem=%zu max_clusters=%d\n", CS, NC, GP, smem, max_clusters);
-    if (max_clusters * CS < NC) return false;
-    *out = p; *out_smem = smem;
-    return true;
+    // tensor-core engine: which folds apply (MMK_SR_FOLD=0: none)
+    const bool folds = tc && !(getenv("MMK_SR_FOLD") && atoi(getenv("MMK_SR_FOLD")) == 0);
+    {
+        const int rows = p.tiers[n_ft - 1].up * Hh;           // the head's first Linear into the bottom tier's up-sampler
+        if (folds && rows % NC == 0 && rows / NC >= 1 && rows / NC <= 16 && Hh % (rows / NC) == 0) { p.fold_head = 1; p.NVh = rows / NC; }
+    }
+    bool gx_ok = folds && n_ft >= 2;                           // a tier's up-sampler into the input side of the tier below
+    for (int i = 0; i + 1 < n_ft; ++i) gx_ok = gx_ok && p.tiers[i].up <= (int)(TC_BX_BYTES / TC_B_BYTES);
+    for (int attempt = gx_ok ? 0 : 1; attempt < 2; ++attempt) {
+        p.fold_gx = attempt == 0 ? 1 : 0;
+        p.tc_bbytes = p.fold_gx ? (int)TC_BX_BYTES : (int)TC_B_BYTES;
+        o = 0;
+        // the stages (1024-byte aligned inside the region: 1 KB of slack) share the region with the head buffers
+        p.region = tc ? std::max(head_floats, (int)(TC_STAGES * (TC_A_BYTES + (unsigned)p.tc_bbytes) + 1024) / 4) : head_floats;
+        p.xregion = p.wregion = p.xstage = p.wstage = 0;
+        p.s_region = take(p.region);
+        p.s_gi = o;
+        p.s_bar = take(2 * BAR_COUNT + 16 * GP);
+        p.s_b2 = take(Q + 1);
+        int nv_max = 16;
+        for (int i = 0; i < n_ft; ++i) nv_max = std::max(nv_max, p.tiers[i].NV);
+        p.s_part = take(tc ? 4 : p.NKQ * p.Bp * (nv_max > 16 ? 32 : 16));
+        p.s_hold = take(tc ? 4 : p.Bp * 4);
+        p.s_lin = take(p.Bp * fs_max);
+        p.s_tcbar = take(2 * TCB_COUNT + 4);
+        p.n_res = 0;
+        bool ok = true;
+        auto resident = [&](int goff, int len, int* soff) {
+            len = pad4(len);
+            if (o + len > budget) { ok = false; return; }
+            *soff = o;
+            p.res_goff[p.n_res] = goff; p.res_soff[p.n_res] = o; p.res_len[p.n_res] = len; ++p.n_res;
+            o += len;
+        };
+        if (p.fold_head) p.so_w1 = p.so_b1 = 0;              // the folded head never touches W1 / b1
+        else { resident(p.off_w1, p.KS * Hh, &p.so_w1); resident(p.off_b1, p.RS, &p.so_b1); }
+        resident(p.off_w2, p.RS * p.ZR, &p.so_w2);
+        if (!ok) continue;
+        p.smem_floats = o;
+        const size_t smem = (size_t)o * sizeof(float);
+        const int max_clusters = sr2_max_clusters(CS, smem, sms, tc ? 2 : 1);
+        if (getenv("MMK_SR_DEBUG"))
+            fprintf(stderr, "[sr2] %s engine: CS=%d NC=%d GP=%d smem=%zu max_clusters=%d fold_head=%d fold_gx=%d\n", tc ? "tcgen05" : "lane-major", CS, NC, GP, smem,
+                    max_clusters, p.fold_head, p.fold_gx);
+        if (max_clusters * CS < NC) continue;
+        *out = p; *out_smem = smem;
+        return true;
+    }
+    return false;
 }
 
 // Per-lane packing.  Thread t = 32 q + l of a weight row owns k = 4 t .. 4 t + 3 (q = K quarter, l = lane).
@@ -2044,11 +2108,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, int
         //      columns gate * 4 + jj with gates r, z, n_i, n_h; the frame Linear and all biases folded into wf / bfold (fp64 -> fp32)
         const int nimg = H / 128, nfill = 2 * nimg;
         // fold the head's first Linear into the bottom tier's up-sampler when its rows split evenly over the CTAs (see Params::fold_head)
-        bool fold_here = false;
-        if (i == n_ft - 1 && !(getenv("MMK_SR_FOLD") && atoi(getenv("MMK_SR_FOLD")) == 0)) {
-            const int rows = T.up * Hh;
-            if (rows % NC == 0 && rows / NC >= 1 && rows / NC <= 16 && Hh % (rows / NC) == 0) { fold_here = true; p.fold_head = 1; p.NVh = rows / NC; }
-        }
+        const bool fold_here = p.fold_head && i == n_ft - 1;   // decided by the plan (shared-memory map)
         auto bf = [](float v) { __nv_bfloat16 b = __float2bfloat16_rn(v); unsigned short u; memcpy(&u, &b, 2); return u; };
         std::vector<unsigned char> wgi((size_t)NC * nfill * TC_B_BYTES, 0), wui((size_t)NC * nimg * TC_B_BYTES, 0);
         std::vector<float> wfv((size_t)NC * 16 * T.fs, 0.0f), bfv((size_t)NC * 16, 0.0f);
@@ -2128,7 +2188,45 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, int
             p.hu = up(huv.data(), huv.size());
             p.pre = up(nullptr, (size_t)T.up * p.Bp * Hh);
         }
+        std::vector<unsigned char> wxi;
+        std::vector<float> xbv;
+        if (p.fold_gx && i < n_ft - 1) {
+            // gx of the tier below (i + 1): column (slot s, col) of CTA c = row grow(col) of W_ih(i + 1) applied to slot s of this tier's
+            // up-sampler: W''[k] = sum_m W_ih1[grow][m] W_up[s H + m][k];  xb = sum_m W_ih1[grow][m] b_up[s H + m]   (fp64)
+            const int ncols = T.up * 16;
+            const size_t bfill = (size_t)ncols * 256;
+            wxi.assign((size_t)NC * nimg * bfill, 0);
+            xbv.assign((size_t)NC * T.up * 16, 0.0f);
+            const float* Wih1 = d->w_ih[i + 1];
+            std::vector<double> row(H);
+            for (int sl = 0; sl < T.up; ++sl)
+                for (int c = 0; c < NC; ++c)
+                    for (int col = 0; col < 16; ++col) {
+                        const int g4 = col / 4, jj = col % 4;
+                        if (!p.lstm && g4 == 3) continue;                    // GRU: the n_h column takes no input term
+                        const int grow = (p.lstm ? g4 : g4) * H + 4 * c + jj;   // rows r, z, n (GRU) / i, f, g, o (LSTM) of the tier below
+                        std::fill(row.begin(), row.end(), 0.0);
+                        double bsum = 0.0;
+                        for (int m = 0; m < H; ++m) {
+                            const double w1 = Wih1[(size_t)grow * H + m];
+                            const float* wu = d->up_w[i] + ((size_t)sl * H + m) * H;
+                            for (int k = 0; k < H; ++k) row[k] += w1 * (double)wu[k];
+                            bsum += w1 * (double)d->up_b[i][(size_t)sl * H + m];
+                        }
+                        for (int k = 0; k < H; ++k) {
+                            const unsigned short v = bf((float)row[k]);
+                            unsigned char* tile = wxi.data() + ((size_t)c * nimg + k / 128) * bfill;
+                            memcpy(tile + tile_off(sl * 16 + col, (k % 128) / 8, ncols) + (k % 8) * 2, &v, 2);
+                        }
+                        xbv[((size_t)c * T.up + sl) * 16 + col] = (float)bsum;
+                    }
+        }
         auto upb = [&](const void* src, size_t bytes) { void* q = dev_alloc(bytes, src); ok = ok && q; return (unsigned char*)q; };
+        if (!wxi.empty()) {
+            T.wximg = upb(wxi.data(), wxi.size());
+            T.xb = up(xbv.data(), xbv.size());
+            T.gx = up(nullptr, (size_t)T.up * 128 * NC * 16);
+        }
         T.wgimg = upb(wgi.data(), wgi.size());
         T.wuimg = upb(wui.data(), wui.size());
         T.wf = up(wfv.data(), wfv.size());
