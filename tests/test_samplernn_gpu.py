@@ -312,6 +312,25 @@ def test_initial_state_on_the_fast_engines(rnn, h0_init, H, mode):
     assert _rel_err(z_logits, ref_logits) > 1e-3
 
 
+def test_tensor_core_mode_without_folds(monkeypatch):
+    """MMK_SR_FOLD=0: the tensor-core engine without its algebraic folds (conditioning as a bf16 image and a K = 2H contraction,
+    the head's first Linear in the cluster head) — the same criteria, and logits close to the folded form's."""
+    fs, H, B, P, n = (8, 2, 1), 512, 19, 24, 16
+    net = make_net(fs, H, mlp_dim=128, seed=5).bfloat16()
+    g = torch.Generator().manual_seed(17)
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    orc = restate.SampleRNNOracle({k: v.numpy() for k, v in net.state_dict().items()}, fs)
+    ref_seq, ref_logits = orc.generate(prompts.numpy(), n, None, None)
+    folded, _ = net.teacher_forced(torch.from_numpy(ref_seq), P)
+    monkeypatch.setenv("MMK_SR_FOLD", "0")
+    net2 = make_net(fs, H, mlp_dim=128, seed=5).bfloat16()
+    plain, dec = net2.teacher_forced(torch.from_numpy(ref_seq), P)
+    assert _rel_err(plain.cpu().numpy(), ref_logits) <= 5e-2
+    assert np.array_equal(dec.cpu().numpy(), restate.argmax_first(plain.cpu().numpy()))
+    assert _rel_err(plain.cpu().numpy(), folded.cpu().numpy()) <= 5e-3
+    assert not torch.equal(plain, folded)          # two different arithmetic forms did run
+
+
 def test_stepwise_protocol_and_loop():
     """before_generate / generate_step / after_generate == whole-sequence path == oracle; GenerateLoopV2 integration as
     the reference's tests/test_sample_rnn.py:90-112 (batch 2, 512-sample prompt + 512 steps, temperature=(1.,))."""
