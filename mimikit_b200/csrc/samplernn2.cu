@@ -2,18 +2,20 @@
 // samplernn.cu (the general kernel; see that file for the reference lines: sample_rnn_v2.py:83-119, 226-260;
 // modules/io.py:106-133, 185-198; modules/resamplers.py:13-23; networks/mlp.py:44-63; modules/targets.py:40-52).
 //
-// What changed against the general kernel, and why (B = 128 prompts, (8,2,1)/512: 126 us per sample there):
+// One persistent launch covers before_generate's warm-up over the prompt and every generated sample.
 //   * the sample-level tier + MLP head + sampler never touch a grid barrier.  A thread-block cluster of CS CTAs owns a
-//     group of 8 prompts end to end: W1 and W2 are split along K over the cluster (a CTA needs only its H/CS rows of
+//     group of prompts end to end: W1 and W2 are split along K over the cluster (a CTA needs only its H/CS rows of
 //     the conditioning vector), partial sums meet through distributed shared memory (st.async + mbarrier
-//     complete_tx): partial hidden -> reduce-scatter by row, Mish, partial logits -> reduce-scatter by prompt, one
-//     warp per prompt applies the learned temperature and samples, the index is broadcast to the cluster.  Three
-//     DSMEM exchanges per sample instead of three grid barriers and three full-batch activation reloads per CTA.
-//   * frame tiers stay weight-stationary over all CTAs (GRU rows split by hidden index, up-sampler rows evenly; the
-//     19 MB of fp32 weights only fit spread over >= 100 SMs), but the activations now stream through a 3-stage
-//     cp.async pipeline (16 rows x <=128 prompts per chunk, one __syncthreads per chunk) into 4x4 register tiles; the
-//     frame-linear input term is added by the thread that issued the copy, so it costs no extra barrier.
-//   * grid barriers only around tier firings: 3 per firing step instead of 3 per sample + 2 per firing.
+//     complete_tx): partial hidden -> reduce-scatter by row, Mish, partial logits -> reduce-scatter by prompt, every
+//     thread scales one logit, one warp per prompt samples, the index is broadcast to the cluster.
+//   * frame tiers stay weight-stationary over all CTAs (recurrent rows split by hidden index, up-sampler rows evenly), with
+//     grid barriers only around tier firings.  Three engines (template parameter ENGINE of the kernel):
+//       0  tile engine (round 1): activations [H][B] streamed through cp.async stages into 4x4 register tiles, weights in
+//          shared memory.  Any hidden size that splits over the CTAs; GRU, zero initial state.
+//       1  lane-major fp32 engine: activations [prompt][H] prefetched into registers, the lane's weights in registers for a
+//          whole firing, transposing shuffle trees.  H in {128, 256, 512}; GRU and LSTM; bit-exact with the oracle.
+//       2  tcgen05 engine (compute mode bf16): one tensor-core accumulation per contraction, activations kept as UMMA tiles,
+//          frame Linear / head / conditioning folded into precomputed products.  H in {128, 256, 512}, <= 128 prompts.
 #include "common.cuh"
 #include "sampler.cuh"
 #include "samplernn_impl.h"
