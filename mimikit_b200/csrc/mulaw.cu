@@ -427,7 +427,6 @@ extern "C" int mmk_mulaw_compress(const float* d_x, int64_t* d_q, size_t n, int 
     if (t) {
         int wide = (((uintptr_t)d_q % 32) == 0) ? MULAW_WIDE_DEFAULT : 0;
         if (wide == 2 && ((uintptr_t)d_x % 32) != 0) wide = 1;
-        if (const char* e = getenv("MMK_MULAW_WIDE")) wide = std::min(wide, std::max(0, atoi(e)));
         const int grid = feature_grid(n / 4 + 1);
         const size_t sm = q_levels * sizeof(float2);
         long long* q = reinterpret_cast<long long*>(d_q);

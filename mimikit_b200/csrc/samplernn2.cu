@@ -37,12 +37,12 @@ using mmk::sigmoid_acc;
 constexpr int NT = 512;          // threads per CTA
 constexpr int HT = 256;          // threads that take tiles in the head contractions
 constexpr int KC = 16;           // activation rows per streamed chunk at full width (x 2, 4, 8 for narrower batches)
-constexpr int NSTAGE_DEFAULT = 2; // full-width cp.async stages (MMK_SR_NSTAGE; more stages when the chunks are small)
-constexpr int KCFULL_DEFAULT = 64; // rows per full-width chunk (MMK_SR_KC)
+constexpr int NSTAGE_DEFAULT = 2; // full-width cp.async stages (more stages when the chunks are small)
+constexpr int KCFULL_DEFAULT = 64; // rows per full-width chunk (measured optimum of the tile engine)
 constexpr int PBW = 128;         // prompts per streamed block
 constexpr int WMAX = 32;         // widest streamed weight slice (columns per CTA)
 constexpr int MAX_TIERS = 6;
-// floats per stage (activations, streamed weights) = kcfull * PBW, kcfull * WMAX with kcfull = MMK_SR_KC (default KC)
+// floats per stage (activations, streamed weights) = kcfull * PBW, kcfull * WMAX
 constexpr int MAXST = 8;
 constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;
 
@@ -1911,9 +1911,7 @@ int sr2_create(const mmk_samplernn_desc* d, int max_batch, int tc, int lstm, int
         // ---- shared memory: buffers first, then the resident weights by priority until the budget is spent
         o = 0;
         int nstage = NSTAGE_DEFAULT;
-        if (const char* e = getenv("MMK_SR_NSTAGE")) nstage = std::max(2, std::min(MAXST, atoi(e)));
         int kcfull = KCFULL_DEFAULT;
-        if (const char* e = getenv("MMK_SR_KC")) kcfull = std::max(KC, std::min(128, atoi(e) / KC * KC));
         int wmax = p.NG;
         for (int i = 0; i < n_ft; ++i) wmax = std::max(wmax, p.tiers[i].NU);
         p.xstage = kcfull * PBW; p.wstage = kcfull * std::min(WMAX, wmax);

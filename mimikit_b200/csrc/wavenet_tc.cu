@@ -107,7 +107,7 @@ struct Params {
     const float* temperature; const float* noise;
     long long noise_stride, noise_t0;
     float* logits_out; long long* decisions; unsigned long long* step_ts;
-    int exp;                               // MMK_TC_EXP: timing experiments (bit 0: no weight copies, bit 1: no tap copies; results invalid)
+    int exp;                               // timing experiments (bit 0: no weight copies, bit 1: no tap copies; results invalid): always 0 in a build
     long long* trace; long long trace_t;   // MMK_TC_TRACE_T: clock64 stamps of group 0 at that step, [role][layer][16]
 };
 constexpr int TRACE_EV = 16;
@@ -987,7 +987,6 @@ int wn4_run(wn4_handle* h, int64_t* d_seq, int B, int64_t seq_stride, int64_t se
     p.noise = d_noise; p.noise_stride = noise_stride; p.noise_t0 = noise_t0;
     p.logits_out = d_logits_out; p.decisions = reinterpret_cast<long long*>(d_decisions); p.step_ts = d_step_ts;
     p.trace = h->d_trace; p.trace_t = h->trace_t;
-    if (const char* e = getenv("MMK_TC_EXP")) p.exp = atoi(e);
     const int groups = (B + MROWS - 1) / MROWS;
     MMK_CHECK(groups <= h->max_groups, "batch exceeds the max_batch the handle was created for");
     MMK_CUDA(cudaMemsetAsync(p.abort_flag, 0, sizeof(unsigned), (cudaStream_t)stream));
