@@ -431,6 +431,10 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
         MMK_CHECK(d->frame_sizes[i - 1] % d->frame_sizes[i] == 0, "frame sizes must divide each other");
 
     auto* h = new mmk_samplernn_s();
+    struct Guard {                 // every early return below (MMK_CHECK / MMK_CUDA / MMK_FAIL) releases the handle and what it owns
+        mmk_samplernn_s* h;
+        ~Guard() { }
+    } guard{h};
     SrParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
     {   // MMK_SR_KERNEL: "1" = general kernel only, "2" = cluster kernel only, unset = cluster kernel when it fits
@@ -438,7 +442,7 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
         const int tc = dx->compute_mode == MMK_COMPUTE_BF16_TC ? 1 : 0;
         // the tensor-core engine also hosts nn.LSTM tiers (the reference's default rnn_class); one layer, zero initial state, plain head
         const bool tc_form = (dx->rnn_type == MMK_RNN_GRU || dx->rnn_type == MMK_RNN_LSTM) && dx->n_rnn == 1 && dx->head_hidden_layers == 0;
-        if (tc && !tc_form) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer and a plain head"); }
+        if (tc && !tc_form) { MMK_FAIL("the bf16 tensor-core mode hosts GRU / LSTM tiers with one layer and a plain head"); }
         // ... and so does the lane-major fp32 engine (sequences bit-exact): GRU or LSTM, tried first; what it cannot host falls to the
         // general kernel below
         if ((plain || tc_form) && (tc || !force || atoi(force) != 1)) {
@@ -447,20 +451,21 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
             d2.w_ih = dx->w_ih; d2.w_hh = dx->w_hh; d2.b_ih = dx->b_ih; d2.b_hh = dx->b_hh;
             if (sr2_create(&d2, max_batch, tc, dx->rnn_type == MMK_RNN_LSTM ? 1 : 0, dx->need_set_hidden ? 1 : 0, &h->v2, &unsupported) == 0) {
                 h->max_batch = max_batch; h->rf = d->frame_sizes[0];
+                guard.h = nullptr;
                 *out = h;
                 return 0;
             }
             h->v2 = nullptr;
-            if (!unsupported) { sr_free(h); return 1; }
-            if (tc) { sr_free(h); MMK_FAIL("the bf16 tensor-core mode needs hidden_dim in {128, 256, 512}, frame sizes / up-sampling factors in {1,2,4,8} / {1,2,4} and max_batch <= 128"); }
-            if (force && atoi(force) == 2) { sr_free(h); MMK_FAIL("configuration not supported by the cluster kernel (MMK_SR_KERNEL=2)"); }
+            if (!unsupported) { return 1; }
+            if (tc) { MMK_FAIL("the bf16 tensor-core mode needs hidden_dim in {128, 256, 512}, frame sizes / up-sampling factors in {1,2,4,8} / {1,2,4} and max_batch <= 128"); }
+            if (force && atoi(force) == 2) { MMK_FAIL("configuration not supported by the cluster kernel (MMK_SR_KERNEL=2)"); }
         }
     }
     int sms = 0, max_optin = 0, coop = 0;
     MMK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     MMK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     MMK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    if (!coop) { sr_free(h); MMK_FAIL("device does not support cooperative launches"); }
+    if (!coop) { MMK_FAIL("device does not support cooperative launches"); }
     // as many CTAs as SMs, trimmed so that the hidden indices split evenly (no padded GRU columns)
     int NC = std::min(sms, H);
     NC = std::min(NC, H / ceil_div(H, NC));
@@ -503,12 +508,12 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
     p.off_lin = take(SR_PB * fs_max);
     p.smem_floats = o;
     h->smem_bytes = (size_t)o * sizeof(float);
-    if ((SR_PB / 2) * (widest / 4) > SR_NT) { sr_free(h); MMK_FAIL("SampleRNN rows per CTA too wide for one contraction pass"); }
-    if (h->smem_bytes > (size_t)max_optin) { sr_free(h); MMK_FAIL("SampleRNN configuration does not fit in shared memory (weights are kept resident)"); }
+    if ((SR_PB / 2) * (widest / 4) > SR_NT) { MMK_FAIL("SampleRNN rows per CTA too wide for one contraction pass"); }
+    if (h->smem_bytes > (size_t)max_optin) { MMK_FAIL("SampleRNN configuration does not fit in shared memory (weights are kept resident)"); }
     MMK_CUDA(cudaFuncSetAttribute(samplernn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     int per_sm = 0;
     MMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, samplernn_kernel, SR_NT, h->smem_bytes));
-    if (per_sm * sms < NC) { sr_free(h); MMK_FAIL("SampleRNN grid cannot be co-resident"); }
+    if (per_sm * sms < NC) { MMK_FAIL("SampleRNN grid cannot be co-resident"); }
 
     // ---- pack per-CTA weight blocks
     std::vector<float> wpack((size_t)NC * p.cta_block, 0.0f);
@@ -585,9 +590,10 @@ extern "C" int mmk_samplernn_create_ex(const mmk_samplernn_desc_ex* dx, int max_
     p.z = up(nullptr, (size_t)(Q + 1) * p.Bp);
     p.bar = (unsigned long long*)dev_alloc(64, nullptr);
     ok = ok && p.bar;
-    if (!ok) { sr_free(h); MMK_FAIL("cudaMalloc failed while creating the SampleRNN handle"); }
+    if (!ok) { MMK_FAIL("cudaMalloc failed while creating the SampleRNN handle"); }
     p.abort_flag = (unsigned*)(p.bar + 1);
     MMK_CUDA(cudaDeviceSynchronize());
+    guard.h = nullptr;
     *out = h;
     return 0;
 }

@@ -697,6 +697,8 @@ extern "C" int mmk_wavenet_create_ex(const mmk_wavenet_desc* d, int max_batch, i
     return mmk_wavenet_create_cfg(&dx, max_batch, compute_mode, out);
 }
 
+extern "C" int mmk_wavenet_destroy(mmk_wavenet_t h);
+
 extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_batch, int compute_mode, mmk_wavenet_t* out) {
     MMK_CHECK(dx && out, "mmk_wavenet_create: null argument");
     const mmk_wavenet_desc* d = &dx->base;
@@ -726,29 +728,35 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     MMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: mmk_b200 has no CPU fallback");
 
     auto* h = new mmk_wavenet_s();
+    struct Guard {                 // every early return below (MMK_CHECK / MMK_CUDA / MMK_FAIL) releases the handle and what it owns
+        mmk_wavenet_s* h;
+        ~Guard() { if (h) mmk_wavenet_destroy(h); }
+    } guard{h};
     WnParams& p = h->p;
     MMK_CUDA(cudaGetDevice(&h->device));
     if (compute_mode == MMK_COMPUTE_BF16_TC) {
         // explicit request: no silent fall-back to another precision
         int unsupported = 0;
         for (int l = 0; l < d->n_layers; ++l)
-            if (!d->conv_dil_w[l] || !d->conv_dil_b[l]) { delete h; MMK_FAIL("missing conv_dil weights"); }
+            if (!d->conv_dil_w[l] || !d->conv_dil_b[l]) { MMK_FAIL("missing conv_dil weights"); }
         {
             int unsup7 = 0;
             if (wn7_create(d, max_batch, &h->v7, &unsup7) == 0) {
                 int rf7 = 1;
                 for (int l = 0; l < d->n_layers; ++l) rf7 += d->dilations[l];
                 h->rf = rf7; h->max_batch = max_batch;
+                guard.h = nullptr;
                 *out = h;
                 return 0;
             }
             h->v7 = nullptr;
-            if (!unsup7) { delete h; return 1; }
+            if (!unsup7) { return 1; }
         }
-        if (wn4_create(d, max_batch, &h->v4, &unsupported) != 0) { delete h; return 1; }
+        if (wn4_create(d, max_batch, &h->v4, &unsupported) != 0) { return 1; }
         int rf4 = 1;
         for (int l = 0; l < d->n_layers; ++l) rf4 += d->dilations[l];
         h->rf = rf4; h->max_batch = max_batch;
+        guard.h = nullptr;
         *out = h;
         return 0;
     }
@@ -760,12 +768,13 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
                 int rf6 = 1;
                 for (int l = 0; l < d->n_layers; ++l) rf6 += d->dilations[l];
                 h->rf = rf6; h->max_batch = max_batch;
+                guard.h = nullptr;
                 *out = h;
                 return 0;
             }
             h->v6 = nullptr;
-            if (!unsupported) { delete h; return 1; }
-            if (force) { delete h; MMK_FAIL("configuration not supported by the layer-pipelined fp32 kernel (MMK_WN_KERNEL=6)"); }
+            if (!unsupported) { return 1; }
+            if (force) { MMK_FAIL("configuration not supported by the layer-pipelined fp32 kernel (MMK_WN_KERNEL=6)"); }
         }
     }
     p.L = d->n_layers; p.C = d->dilated_dim; p.S = d->skips_dim; p.Hh = d->head_hidden; p.Q = d->q_levels;
@@ -813,7 +822,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         WnParams q = p;
         size_t smem_min = wn_plan(q, CS, (p.L + nst_min - 1) / nst_min, true);
         int max_clusters = 0;
-        if (wn_query_clusters(CS, smem_min, &max_clusters)) { delete h; return 1; }
+        if (wn_query_clusters(CS, smem_min, &max_clusters)) { return 1; }
         if (max_clusters < nst_min) continue;
         int nst = std::min(std::min(max_clusters, p.L), WN_MAX_STAGES);
         if (force_nst) nst = std::max(nst_min, std::min(nst, atoi(force_nst)));
@@ -823,7 +832,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         best_cs = CS; best_nst = nst; best_smem = smem;
         break;
     }
-    if (!best_cs) { delete h; MMK_FAIL("WaveNet configuration does not fit the persistent kernel (shared memory / cluster limits)"); }
+    if (!best_cs) { MMK_FAIL("WaveNet configuration does not fit the persistent kernel (shared memory / cluster limits)"); }
     const int CS = best_cs, NST = best_nst;
     p.NST = NST;
     const int per = (p.L + NST - 1) / NST;
@@ -925,6 +934,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     p.ready = (unsigned*)(p.avail + p.G);
     p.ack = p.ready + (size_t)NST * p.G;
     p.abort_flag = p.ack + (size_t)NST * p.G;
+    guard.h = nullptr;
     *out = h;
     return 0;
 }
