@@ -155,8 +155,8 @@ int mmk_wavenet_create(const mmk_wavenet_desc* desc, int max_batch, mmk_wavenet_
 #define MMK_COMPUTE_BF16_TC 1
 int mmk_wavenet_create_ex(const mmk_wavenet_desc* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
 /* The rest of the WaveNet configuration surface that changes only ring depth, tap count and one add:
- * per-layer kernel sizes (wavenet_v2.py:295-327; conv_dil_w[l] is then (2C, C, k_l)), layerwise_inputs (:283-284) and
- * n_hidden_layers > 0 in the MLP head (networks/mlp.py:47-50: one shared Linear).  These run in the general fp32 kernel;
+ * per-layer kernel sizes (wavenet_v2.py:295-327; conv_dil_w[l] is then (2C, C, k_l)), layerwise_inputs (:283-284),
+ * n_hidden_layers > 0 in the MLP head (networks/mlp.py:47-50: one shared Linear) and with_affine_residuals.  These run in the general fp32 kernel;
  * a desc with kernel sizes all 2, no layerwise inputs and a plain head takes the same route as mmk_wavenet_create_ex.
  * (pad_side = 1 needs nothing here: the generation loop evaluates the last position of an rf-long window, where the
  * padded and the unpadded network agree.) */
@@ -167,6 +167,11 @@ typedef struct {
     int head_hidden_layers;       /* MLP n_hidden_layers; base.head_w2 is then the LAST Linear (fc.{2 + 2 n}) */
     const float* head_wh;         /* output_modules.0.estimator.0.fc.2.weight (Hh, Hh) when head_hidden_layers > 0 */
     const float* head_bh;         /* ...fc.2.bias (Hh) */
+    /* with_affine_residuals (wavenet_v2.py:121-122, 148-149, 164-165; networks/parametrized.py:34-47): every layer's input
+     * first goes through aff_res, z = x_hat * a + b with (x_hat | a | b) the three C-row chunks of one 1x1 conv; the dilated
+     * conv and the residual add read z.  NULL arrays = the network has none; otherwise one entry per layer. */
+    const float* const* aff_res_w;   /* layers.l.aff_res.params.weight (3C, C, 1) */
+    const float* const* aff_res_b;   /* layers.l.aff_res.params.bias   (3C)       */
 } mmk_wavenet_desc_ex;
 int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
 /* Diagnostic for the tensor-core path: d_D (128, N) fp32 = d_A (128, K) . d_B (N, K)^T with operands rounded to bf16,

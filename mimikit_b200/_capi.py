@@ -42,7 +42,8 @@ class WaveNetDesc(Structure):
 
 class WaveNetDescEx(Structure):
     _fields_ = [("base", WaveNetDesc), ("kernel_sizes", POINTER(c_int)), ("layerwise_inputs", c_int),
-                ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float))]
+                ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float)),
+                ("aff_res_w", _fpp), ("aff_res_b", _fpp)]
 
 
 class SampleRNNDesc(Structure):

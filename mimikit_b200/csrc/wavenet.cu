@@ -59,6 +59,8 @@ struct WnParams {
     int kmax;                  // largest conv kernel size of the network
     int layerwise;             // layerwise_inputs (wavenet_v2.py:283-284): the embedded input is added to every layer's output
     int n_hh;                  // hidden layers of the MLP head (one shared Linear, mlp.py:47-50)
+    int affine;                // with_affine_residuals: every layer input goes through aff_res first (wavenet_v2.py:148-149)
+    int NC;                    // 3 * nf padded to a multiple of 4 (x_hat | a | b columns of aff_res), 0 without it
     int G;                     // groups the rings are laid out for
     float min_temp;
     WnLayer layers[WN_MAX_LAYERS];
@@ -339,6 +341,28 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                 float* yc = ybuf + par * blk;
                 const bool last_owned = (l == l_hi - 1);
                 const bool last_layer = (l == P.L - 1);
+
+                // (0) with_affine_residuals: the layer input becomes z = x_hat * a + b, (x_hat | a | b) = aff_res.params(h_l)
+                //     (parametrized.py:44-47: mul, then add — two roundings).  Everything below (taps, ring, residual) reads z.
+                if (P.affine) {
+                    const float* W3 = b2 + P.NB;                                  // [C][NC]
+                    const float* b3 = W3 + (size_t)C * P.NC;                      // [NC]
+                    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    const Tile tl = make_tile(P.NC);
+                    gemm_accum(acc, tl, W3, P.NC, x1, C);
+                    gemm_store_partials(acc, tl, part);
+                    __syncthreads();
+                    for (int o = tid; o < nf * GB; o += WN_NT) {
+                        const int i = o / GB, p = o - i * GB;
+                        const float xh = gemm_reduce(part, P.NC, i, p) + b3[i];
+                        const float aa = gemm_reduce(part, P.NC, nf + i, p) + b3[nf + i];
+                        const float bb = gemm_reduce(part, P.NC, 2 * nf + i, p) + b3[2 * nf + i];
+                        slice[o] = __fadd_rn(__fmul_rn(xh, aa), bb);
+                    }
+                    cluster_sync_all<CS>();   // every CTA of the cluster is done reading h_l from its x1
+                    scatter_slice<CS>(cluster, x1 + (size_t)rank * nf * GB, slice, nf * GB / 4);
+                    cluster_sync_all<CS>();   // z complete everywhere
+                }
 
                 // (a) ring read landed everywhere in this CTA
                 cp_async_wait_all();
@@ -663,7 +687,8 @@ static size_t wn_plan(WnParams& p, int CS, int max_layers_per_stage, bool has_he
     p.nf = p.C / CS; p.ns = p.S / CS; p.nh = p.Hh / CS; p.nz = (p.Q + 1 + CS - 1) / CS;
     p.NA = pad4(2 * p.nf); p.NB = std::max(4, pad4(p.nf + p.ns)); p.NH = pad4(p.nh); p.NZ = pad4(p.nz);
     if (p.kmax < 2) p.kmax = 2;
-    p.layer_block = pad4(p.kmax * p.C * p.NA + p.NA + p.C * p.NB + p.NB);
+    p.NC = p.affine ? pad4(3 * p.nf) : 0;
+    p.layer_block = pad4(p.kmax * p.C * p.NA + p.NA + p.C * p.NB + p.NB + p.C * p.NC + p.NC);
     p.head_block = pad4(p.Kh * p.NH + p.NH + p.Hh * p.NZ + p.NZ + (p.n_hh > 0 ? p.Hh * p.NH + p.NH : 0));
     const int n = (p.Q + 31) / 32;
     p.zrow = pad4(p.Q + 1 + 4);
@@ -705,7 +730,8 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     MMK_CHECK(dx->head_hidden_layers >= 0 && dx->head_hidden_layers <= 8, "head_hidden_layers must be in [0, 8]");
     MMK_CHECK(dx->head_hidden_layers == 0 || (dx->head_wh && dx->head_bh), "missing head hidden-layer weights");
     int kmax = 2;
-    bool plain = dx->layerwise_inputs == 0 && dx->head_hidden_layers == 0;
+    MMK_CHECK((dx->aff_res_w != nullptr) == (dx->aff_res_b != nullptr), "aff_res_w and aff_res_b come together");
+    bool plain = dx->layerwise_inputs == 0 && dx->head_hidden_layers == 0 && !dx->aff_res_w;
     if (dx->kernel_sizes)
         for (int l = 0; l < d->n_layers; ++l) {
             MMK_CHECK(dx->kernel_sizes[l] >= 2 && dx->kernel_sizes[l] <= WN_MAX_K, "kernel sizes must be in [2, 4]");
@@ -713,7 +739,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
             plain = plain && dx->kernel_sizes[l] == 2;
         }
     MMK_CHECK(plain || compute_mode == MMK_COMPUTE_FP32,
-              "kernel sizes > 2, layerwise_inputs and hidden MLP layers run in the fp32 general kernel only");
+              "kernel sizes > 2, layerwise_inputs, hidden MLP layers and affine residuals run in the fp32 general kernel only");
     MMK_CHECK(compute_mode == MMK_COMPUTE_FP32 || compute_mode == MMK_COMPUTE_BF16_TC, "unknown compute_mode");
     MMK_CHECK(d->n_layers >= 1 && d->n_layers <= WN_MAX_LAYERS, "n_layers out of range [1, 96]");
     MMK_CHECK(d->dilated_dim >= 4 && d->dilated_dim % 4 == 0, "dilated_dim must be a positive multiple of 4");
@@ -780,6 +806,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     p.L = d->n_layers; p.C = d->dilated_dim; p.S = d->skips_dim; p.Hh = d->head_hidden; p.Q = d->q_levels;
     p.Kh = p.S > 0 ? p.S : p.C;
     p.kmax = kmax; p.layerwise = dx->layerwise_inputs ? 1 : 0; p.n_hh = dx->head_hidden_layers;
+    p.affine = dx->aff_res_w ? 1 : 0;
     p.min_temp = d->min_temperature;
     h->max_batch = max_batch;
     p.G = (max_batch + WN_GB - 1) / WN_GB;
@@ -788,6 +815,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         MMK_CHECK(d->dilations[l] >= 1, "dilation must be >= 1");
         rf += d->dilations[l] * ((dx->kernel_sizes ? dx->kernel_sizes[l] : 2) - 1);
         MMK_CHECK(d->conv_dil_w[l] && d->conv_dil_b[l], "missing conv_dil weights");
+        MMK_CHECK(!p.affine || (dx->aff_res_w[l] && dx->aff_res_b[l]), "missing aff_res weights");
         MMK_CHECK(!(l == p.L - 1 && d->conv_res_w[l]), "the last layer never has a residual conv (wavenet_v2.py:216)");
     }
     h->rf = rf;
@@ -808,7 +836,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         {   // every contraction must fit one pass of (GB/2) x (columns/4) register tiles over the CTA's threads
             WnParams q = p;
             wn_plan(q, CS, 1, true);
-            const int widest = std::max(std::max(q.NA, q.NB), std::max(q.NH, q.NZ));
+            const int widest = std::max(std::max(std::max(q.NA, q.NB), std::max(q.NH, q.NZ)), q.NC);
             if ((WN_GB / 2) * (widest / 4) > WN_NT) continue;
         }
         // smallest number of stages for which the weights fit
@@ -884,6 +912,14 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
                 const int o = r * ns + j;
                 for (int c = 0; c < C; ++c) W2[(size_t)c * p.NB + col] = d->conv_skip_w[l][(size_t)o * C + c];
                 b2[col] = d->conv_skip_b[l][o];
+            }
+            if (p.affine) {   // aff_res.params (3C, C, 1): this CTA's channels of x_hat, then of a, then of b
+                float* W3 = b2 + p.NB; float* b3 = W3 + (size_t)C * p.NC;
+                for (int j = 0; j < 3 * nf; ++j) {
+                    const int o = (j / nf) * C + r * nf + (j % nf);
+                    for (int c = 0; c < C; ++c) W3[(size_t)c * p.NC + j] = dx->aff_res_w[l][(size_t)o * C + c];
+                    b3[j] = dx->aff_res_b[l][o];
+                }
             }
         }
     }

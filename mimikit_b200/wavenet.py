@@ -84,7 +84,7 @@ class WaveNet(NativeARM):
         need(c.residuals_dim is None or c.residuals_dim == c.dims_dilated[0],
              "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
         # apply_residuals is stored by WNLayer (wavenet_v2.py:63) and read nowhere in its forward: accepted, changes nothing
-        need(not c.with_affine_residuals, "with_affine_residuals")
+        # with_affine_residuals (wavenet_v2.py:121-122, 148-149): hosted by the general fp32 kernel (aff_res stage per layer)
         need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
         need(str(c.act_f) == "Tanh" and (c.act_g is None or str(c.act_g) == "Sigmoid"),
              "activations other than Tanh filters with a Sigmoid gate or no gate")
@@ -172,7 +172,8 @@ class WaveNet(NativeARM):
     def _plain(self):
         """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
         return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
-                and not self._config.reverse_layer_order and self._gated and self._config.groups == 1)
+                and not self._config.reverse_layer_order and self._gated and self._config.groups == 1
+                and not self._config.with_affine_residuals)
 
     @property
     def generate_params(self):
@@ -210,6 +211,9 @@ class WaveNet(NativeARM):
             else:                                       # wavenet_v2.py:109-112: a bare Conv1d (no Sequential / Chunk) without gated units
                 e[f"layers.{l}.conv_dil.0.weight"] = (C, Cg, self.kernels[l])
                 e[f"layers.{l}.conv_dil.0.bias"] = (C,)
+            if self._config.with_affine_residuals:      # wavenet_v2.py:121-122: ParametrizedLinear(C, C, as_1x1_conv=True)
+                e[f"layers.{l}.aff_res.params.weight"] = (3 * C, C, 1)
+                e[f"layers.{l}.aff_res.params.bias"] = (3 * C,)
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
                 e[f"layers.{l}.conv_skip.bias"] = (S,)
@@ -302,6 +306,9 @@ class WaveNet(NativeARM):
         nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
         d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        if self._config.with_affine_residuals:
+            dx.aff_res_w = arr("layers.{}.aff_res.params.weight")
+            dx.aff_res_b = arr("layers.{}.aff_res.params.bias")
         ks = (ctypes.c_int * L)(*self.kernels)
         keep.append(ks)
         dx.kernel_sizes = ks

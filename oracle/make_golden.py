@@ -145,6 +145,16 @@ def main():
         net = ref_loader.make_wavenet(seed=17, groups=4, **kw)
         gen_network("wavenet_groups4", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, groups=4))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_affine":        # with_affine_residuals (wavenet_v2.py:121-122, 148-149; parametrized.py:34-47)
+        g = torch.Generator().manual_seed(92)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=18, with_affine_residuals=True, **kw)
+        gen_network("wavenet_affine_res", net, torch.randint(0, 256, (3, 24), generator=g), 32, dict(kw, affine=1))
+        kw2 = dict(blocks=(4,), dims=32, mlp_dim=32)                 # no residual / skip convs, not gated, pad_side=1
+        net = ref_loader.make_wavenet(seed=19, with_affine_residuals=True, gated=False, pad_side=1, **kw2)
+        gen_network("wavenet_affine_plain", net, torch.randint(0, 256, (2, 20), generator=g), 28,
+                    dict(kw2, affine=1, nongated=1, pad_side=1))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

@@ -351,7 +351,10 @@ class WaveNetOracle:
     any kernel sizes (tap j of a size-k layer reads the sample (k - 1 - j) dilations back), `layerwise_inputs` (:283-284:
     the embedded network input is added to every layer's output) and hidden MLP layers (mlp.py:47-50: one shared Linear).
     `pad_side` does not enter: the generation loop evaluates the LAST position of an rf-long window (eval_slice, :273), whose
-    dependency cone never touches the left padding, so pad_side=1 and pad_side=0 give the same value there."""
+    dependency cone never touches the left padding, so pad_side=1 and pad_side=0 give the same value there.
+    `with_affine_residuals` (:121-122, 148-149, 164-165; parametrized.py:34-47): a layer's input first goes through
+    aff_res, z = x_hat * a + b with (x_hat, a, b) the three chunks of one 1x1 conv; the dilated conv AND the residual add
+    (:174 trims the re-bound `inputs_dilated`) then read z, so the per-layer history holds z."""
 
     def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256, layerwise_inputs=False, n_mlp_hidden=0,
                  reverse_layer_order=False):
@@ -369,6 +372,7 @@ class WaveNetOracle:
         self.E = _np(sd, "input_modules.0.0.weight")
         self.C = self.E.shape[1]
         self.Wd, self.bd, self.Ws, self.bs, self.Wr, self.br = [], [], [], [], [], []
+        self.Wa, self.ba = [], []
         self.has_skips = "layers.0.conv_skip.weight" in sd
         for l in range(self.L):
             self.gated = f"layers.{l}.conv_dil.0.0.weight" in sd     # act_g=None: a bare Conv1d, y = tanh(conv) (wavenet_v2.py:109-112, 160-163)
@@ -384,6 +388,12 @@ class WaveNetOracle:
                 w = dense
             self.Wd.append([np.ascontiguousarray(w[:, :, j]) for j in range(w.shape[2])])
             self.bd.append(_np(sd, pre + "bias"))
+            if f"layers.{l}.aff_res.params.weight" in sd:
+                self.Wa.append(_np(sd, f"layers.{l}.aff_res.params.weight")[:, :, 0])
+                self.ba.append(_np(sd, f"layers.{l}.aff_res.params.bias"))
+            else:
+                self.Wa.append(None)
+                self.ba.append(None)
             if self.has_skips:
                 self.Ws.append(_np(sd, f"layers.{l}.conv_skip.weight")[:, :, 0])
                 self.bs.append(_np(sd, f"layers.{l}.conv_skip.bias"))
@@ -427,6 +437,14 @@ class WaveNetOracle:
             h = (h + e).astype(f32)                                      # :283-284
         return h, skips
 
+    def _aff(self, l, x):
+        """aff_res of layer l on its input (parametrized.py:44-47: x_hat.mul(a).add(b), two roundings)."""
+        if self.Wa[l] is None:
+            return x
+        C = self.C
+        p = (x @ self.Wa[l].T + self.ba[l]).astype(f32)
+        return ((p[..., :C] * p[..., C:2 * C]).astype(f32) + p[..., 2 * C:]).astype(f32)
+
     def _dense_taps(self, l, h):
         k, d = self.kernels[l], self.dilations[l]
         n = h.shape[1] - (k - 1) * d
@@ -438,7 +456,7 @@ class WaveNetOracle:
         h0 = h = self.E[np.asarray(x)]
         skips = None
         for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
-            taps = self._dense_taps(l, h)
+            taps = self._dense_taps(l, self._aff(l, h))
             sk = None if skips is None else skips[:, (k - 1) * d:]
             e = h0[:, -taps[-1].shape[1]:] if self.layerwise_inputs else None
             h, skips = self._layer(l, taps, sk, e)
@@ -461,6 +479,7 @@ class WaveNetOracle:
         h0 = h = self.E[prompts[:, P - W:]]
         off = 0
         for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
+            h = self._aff(l, h)
             hist[l][:, off:W] = h
             taps = self._dense_taps(l, h)
             h, _ = self._layer(l, taps, None, h0[:, -taps[-1].shape[1]:] if self.layerwise_inputs else None)
@@ -473,7 +492,7 @@ class WaveNetOracle:
             e = x1 = self.E[src[:, t - 1]]
             skips = None
             for l, (k, d) in enumerate(zip(self.kernels, self.dilations)):
-                hist[l][:, j] = x1
+                hist[l][:, j] = self._aff(l, x1)
                 taps = [hist[l][:, j - (k - 1 - a) * d] for a in range(k)]
                 x1, skips = self._layer(l, taps, skips, e if self.layerwise_inputs else None)
             out = skips if self.has_skips else x1

@@ -244,7 +244,8 @@ def test_samplernn_variant_oracle_vs_reference(name):
         np.testing.assert_allclose(lg, d["logits_" + tag], rtol=1e-3, atol=1e-5)
 
 
-WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed", "wavenet_nongated", "wavenet_groups4"]
+WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed", "wavenet_nongated", "wavenet_groups4",
+               "wavenet_affine_res", "wavenet_affine_plain"]
 
 
 def wavenet_variant_kwargs(d):

@@ -239,7 +239,8 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3",
-                                  "wavenet_reversed", "wavenet_nongated", "wavenet_groups4"])
+                                  "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
+                                  "wavenet_affine_plain"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
@@ -254,7 +255,8 @@ def test_variant_goldens(name):
                          residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
                          skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
                          layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)),
-                         reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), **({"act_g": None} if int(m.get("nongated", 0)) else {}))
+                         reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), with_affine_residuals=bool(int(m.get("affine", 0))),
+                         **({"act_g": None} if int(m.get("nongated", 0)) else {}))
     net = WaveNet.from_config(cfg).to("cuda")
     net.load_state_dict(golden_state_dict(d))
     prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
@@ -271,6 +273,35 @@ def test_variant_goldens(name):
     for t in range(P, P + n):
         x[:, t:t + 1] = net.generate_step((x[:, t - net.rf:t],), t=t)[0]
     assert np.array_equal(x.cpu().numpy(), d["seq_argmax"])
+
+
+@pytest.mark.parametrize("cluster", ["2", "4", "8"])
+def test_affine_residuals_vs_oracle_bigger(monkeypatch, cluster):
+    """with_affine_residuals (wavenet_v2.py:121-122, 148-149, 164-165) together with kernel size 3, layerwise inputs,
+    several prompt groups and pipeline stages of the general kernel, every cluster split of the aff_res columns, vs the oracle."""
+    from mimikit_b200 import IOSpec, WaveNet
+    monkeypatch.setenv("MMK_WN_CLUSTER", cluster)
+    monkeypatch.setenv("MMK_WN_STAGES", "2")
+    torch.manual_seed(23)
+    blocks, ks = (3, 2), (2, 3, 2, 2, 3)
+    cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=64)),
+                         blocks=blocks, kernel_sizes=ks, dims_dilated=(64,), residuals_dim=64, skips_dim=32,
+                         layerwise_inputs=True, with_affine_residuals=True)
+    net = WaveNet.from_config(cfg).to("cuda")
+    orc = restate.WaveNetOracle({k: v.numpy() for k, v in net.state_dict().items()}, blocks, kernel_sizes=ks,
+                                layerwise_inputs=True)
+    assert net.rf == orc.rf and orc.Wa[0] is not None
+    g = torch.Generator().manual_seed(5)
+    B, P, n = 19, orc.rf + 3, 30
+    prompts = torch.randint(0, 256, (B, P), generator=g)
+    noise = torch.rand(B, n, generator=g)
+    for temp in (None, 0.9):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert np.array_equal(seq.cpu().numpy(), ref_seq), temp
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+    with pytest.raises(Exception):          # the tensor-core mode does not host it: explicit error, no silent fp32
+        WaveNet.from_config(cfg).to("cuda").bfloat16().generate(prompts, 2)
 
 
 @pytest.mark.parametrize("cluster", ["2", "4"])
