@@ -160,6 +160,16 @@ int mmk_wavenet_create_ex(const mmk_wavenet_desc* desc, int max_batch, int compu
  * a desc with kernel sizes all 2, no layerwise inputs and a plain head takes the same route as mmk_wavenet_create_ex.
  * (pad_side = 1 needs nothing here: the generation loop evaluates the last position of an rf-long window, where the
  * padded and the unpadded network agree.) */
+#define MMK_ACT_DEFAULT 0
+#define MMK_ACT_TANH 1
+#define MMK_ACT_SIGMOID 2
+#define MMK_ACT_MISH 3
+#define MMK_ACT_RELU 4
+#define MMK_ACT_SOFTPLUS 5     /* beta = 1, threshold = 20 (torch.nn.Softplus defaults) */
+#define MMK_ACT_IDENTITY 6
+#define MMK_ACT_ABS 7
+#define MMK_ACT_SIN 8
+#define MMK_ACT_COS 9
 typedef struct {
     mmk_wavenet_desc base;
     const int* kernel_sizes;      /* [n_layers], each 2..4; NULL = all 2 */
@@ -172,6 +182,10 @@ typedef struct {
      * conv and the residual add read z.  NULL arrays = the network has none; otherwise one entry per layer. */
     const float* const* aff_res_w;   /* layers.l.aff_res.params.weight (3C, C, 1) */
     const float* const* aff_res_b;   /* layers.l.aff_res.params.bias   (3C)       */
+    /* act_f / act_g of the gated unit y = act_f(a_f) * act_g(a_g) (wavenet_v2.py:198-199, 224-225, 151): the point-wise members
+     * of ActivationEnum (modules/activations.py:26-40).  0 = the default (Tanh filter, Sigmoid gate). */
+    int act_f;                       /* MMK_ACT_* */
+    int act_g;                       /* MMK_ACT_* */
 } mmk_wavenet_desc_ex;
 int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* desc, int max_batch, int compute_mode, mmk_wavenet_t* out);
 /* Diagnostic for the tensor-core path: d_D (128, N) fp32 = d_A (128, K) . d_B (N, K)^T with operands rounded to bf16,

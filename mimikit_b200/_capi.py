@@ -43,7 +43,7 @@ class WaveNetDesc(Structure):
 class WaveNetDescEx(Structure):
     _fields_ = [("base", WaveNetDesc), ("kernel_sizes", POINTER(c_int)), ("layerwise_inputs", c_int),
                 ("head_hidden_layers", c_int), ("head_wh", POINTER(c_float)), ("head_bh", POINTER(c_float)),
-                ("aff_res_w", _fpp), ("aff_res_b", _fpp)]
+                ("aff_res_w", _fpp), ("aff_res_b", _fpp), ("act_f", c_int), ("act_g", c_int)]
 
 
 class SampleRNNDesc(Structure):

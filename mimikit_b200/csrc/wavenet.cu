@@ -59,6 +59,7 @@ struct WnParams {
     int kmax;                  // largest conv kernel size of the network
     int layerwise;             // layerwise_inputs (wavenet_v2.py:283-284): the embedded input is added to every layer's output
     int n_hh;                  // hidden layers of the MLP head (one shared Linear, mlp.py:47-50)
+    int act_f, act_g;          // MMK_ACT_* of the gated unit (resolved: never MMK_ACT_DEFAULT)
     int affine;                // with_affine_residuals: every layer input goes through aff_res first (wavenet_v2.py:148-149)
     int NC;                    // 3 * nf padded to a multiple of 4 (x_hat | a | b columns of aff_res), 0 without it
     int G;                     // groups the rings are laid out for
@@ -157,6 +158,22 @@ __device__ __forceinline__ void wait_s64(const long long* flag, long long target
     __syncthreads();
 }
 
+
+// act_f / act_g of the gated unit: the point-wise members of ActivationEnum (modules/activations.py:26-40, 70-83)
+__device__ __forceinline__ float apply_act(int code, float x) {
+    switch (code) {
+        case MMK_ACT_TANH: return tanhf(x);
+        case MMK_ACT_SIGMOID: return sigmoid_acc(x);
+        case MMK_ACT_MISH: return mish_acc(x);
+        case MMK_ACT_RELU: return fmaxf(x, 0.0f);
+        case MMK_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(expf(x));
+        case MMK_ACT_IDENTITY: return x;
+        case MMK_ACT_ABS: return fabsf(x);
+        case MMK_ACT_SIN: return sinf(x);
+        case MMK_ACT_COS: return cosf(x);
+    }
+    return x;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Slice contraction.  out[col][p] = sum_k W[k][col] * x[k][p] for the CTA's ncolp (multiple of 4) columns and GB
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                         const int i = o / GB, p = o - i * GB;
                         const float f = gemm_reduce(part, P.NA, i, p) + b1[i];
                         const float gg = gemm_reduce(part, P.NA, nf + i, p) + b1[nf + i];
-                        slice[o] = tanhf(f) * sigmoid_acc(gg);
+                        slice[o] = apply_act(P.act_f, f) * apply_act(P.act_g, gg);
                     }
                     __syncthreads();
                     scatter_slice<CS>(cluster, yc + (size_t)rank * nf * GB, slice, nf * GB / 4);
@@ -731,7 +748,12 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     MMK_CHECK(dx->head_hidden_layers == 0 || (dx->head_wh && dx->head_bh), "missing head hidden-layer weights");
     int kmax = 2;
     MMK_CHECK((dx->aff_res_w != nullptr) == (dx->aff_res_b != nullptr), "aff_res_w and aff_res_b come together");
-    bool plain = dx->layerwise_inputs == 0 && dx->head_hidden_layers == 0 && !dx->aff_res_w;
+    MMK_CHECK(dx->act_f >= MMK_ACT_DEFAULT && dx->act_f <= MMK_ACT_COS && dx->act_g >= MMK_ACT_DEFAULT && dx->act_g <= MMK_ACT_COS,
+              "act_f / act_g must be MMK_ACT_* codes");
+    const int act_f = dx->act_f == MMK_ACT_DEFAULT ? MMK_ACT_TANH : dx->act_f;
+    const int act_g = dx->act_g == MMK_ACT_DEFAULT ? MMK_ACT_SIGMOID : dx->act_g;
+    bool plain = dx->layerwise_inputs == 0 && dx->head_hidden_layers == 0 && !dx->aff_res_w && act_f == MMK_ACT_TANH &&
+                 act_g == MMK_ACT_SIGMOID;
     if (dx->kernel_sizes)
         for (int l = 0; l < d->n_layers; ++l) {
             MMK_CHECK(dx->kernel_sizes[l] >= 2 && dx->kernel_sizes[l] <= WN_MAX_K, "kernel sizes must be in [2, 4]");
@@ -739,7 +761,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
             plain = plain && dx->kernel_sizes[l] == 2;
         }
     MMK_CHECK(plain || compute_mode == MMK_COMPUTE_FP32,
-              "kernel sizes > 2, layerwise_inputs, hidden MLP layers and affine residuals run in the fp32 general kernel only");
+              "kernel sizes > 2, layerwise_inputs, hidden MLP layers, affine residuals and other activations run in the fp32 general kernel only");
     MMK_CHECK(compute_mode == MMK_COMPUTE_FP32 || compute_mode == MMK_COMPUTE_BF16_TC, "unknown compute_mode");
     MMK_CHECK(d->n_layers >= 1 && d->n_layers <= WN_MAX_LAYERS, "n_layers out of range [1, 96]");
     MMK_CHECK(d->dilated_dim >= 4 && d->dilated_dim % 4 == 0, "dilated_dim must be a positive multiple of 4");
@@ -807,6 +829,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     p.Kh = p.S > 0 ? p.S : p.C;
     p.kmax = kmax; p.layerwise = dx->layerwise_inputs ? 1 : 0; p.n_hh = dx->head_hidden_layers;
     p.affine = dx->aff_res_w ? 1 : 0;
+    p.act_f = act_f; p.act_g = act_g;
     p.min_temp = d->min_temperature;
     h->max_batch = max_batch;
     p.G = (max_batch + WN_GB - 1) / WN_GB;

@@ -22,6 +22,9 @@ from .io_spec import IOSpec
 
 __all__ = ["WaveNet"]
 
+# MMK_ACT_* (include/mmk_b200.h): the point-wise members of ActivationEnum (modules/activations.py:26-40)
+ACT_CODES = {"Tanh": 1, "Sigmoid": 2, "Mish": 3, "ReLU": 4, "Softplus": 5, "Identity": 6, "Abs": 7, "Sin": 8, "Cos": 9}
+
 
 class WaveNet(NativeARM):
     @dtc.dataclass
@@ -86,8 +89,8 @@ class WaveNet(NativeARM):
         # apply_residuals is stored by WNLayer (wavenet_v2.py:63) and read nowhere in its forward: accepted, changes nothing
         # with_affine_residuals (wavenet_v2.py:121-122, 148-149): hosted by the general fp32 kernel (aff_res stage per layer)
         need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
-        need(str(c.act_f) == "Tanh" and (c.act_g is None or str(c.act_g) == "Sigmoid"),
-             "activations other than Tanh filters with a Sigmoid gate or no gate")
+        need(str(c.act_f) in ACT_CODES and (c.act_g is None or str(c.act_g) in ACT_CODES),
+             "activations outside the point-wise members of ActivationEnum (PhaseA/B/C, GLU, Softmax)")
         need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
         # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
         # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
@@ -173,7 +176,8 @@ class WaveNet(NativeARM):
         """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
         return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
                 and not self._config.reverse_layer_order and self._gated and self._config.groups == 1
-                and not self._config.with_affine_residuals)
+                and not self._config.with_affine_residuals and str(self._config.act_f) == "Tanh"
+                and str(self._config.act_g) == "Sigmoid")
 
     @property
     def generate_params(self):
@@ -306,6 +310,8 @@ class WaveNet(NativeARM):
         nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
         d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        dx.act_f = ACT_CODES[str(self._config.act_f)]
+        dx.act_g = ACT_CODES[str(self._config.act_g)] if self._gated else ACT_CODES["Sigmoid"]   # not gated: the exact-one gate below
         if self._config.with_affine_residuals:
             dx.aff_res_w = arr("layers.{}.aff_res.params.weight")
             dx.aff_res_b = arr("layers.{}.aff_res.params.bias")

@@ -155,6 +155,14 @@ def main():
         gen_network("wavenet_affine_plain", net, torch.randint(0, 256, (2, 20), generator=g), 28,
                     dict(kw2, affine=1, nongated=1, pad_side=1))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_acts":          # act_f / act_g other than Tanh / Sigmoid (wavenet_v2.py:198-199, 224-225;
+        g = torch.Generator().manual_seed(93)                        # modules/activations.py:26-67): every point-wise member of ActivationEnum
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        for i, (f, gt) in enumerate([("Mish", "Softplus"), ("Sin", "Cos"), ("ReLU", "Identity"), ("Abs", "Tanh"), ("Sigmoid", None)]):
+            net = ref_loader.make_wavenet(seed=20 + i, act_f=f, act_g=gt or "Sigmoid", gated=gt is not None, **kw)
+            meta = dict(kw, act_f=f, **(dict(act_g=gt) if gt else dict(nongated=1)))
+            gen_network(f"wavenet_act_{f.lower()}_{(gt or 'none').lower()}", net, torch.randint(0, 256, (2, 24), generator=g), 16, meta)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

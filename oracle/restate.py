@@ -268,6 +268,25 @@ def _mish(x):
     return (x * np.tanh(sp)).astype(f32)
 
 
+def _softplus(x):
+    x = x.astype(f32)
+    return np.where(x > 20.0, x, np.log1p(np.exp(np.minimum(x, 20.0)))).astype(f32)  # nn.Softplus(beta=1, threshold=20)
+
+
+# the point-wise members of ActivationEnum (modules/activations.py:26-40, 70-88; torch.nn for the rest)
+ACTIVATIONS = {
+    "Tanh": lambda x: np.tanh(x.astype(f32)).astype(f32),
+    "Sigmoid": _sigmoid,
+    "Mish": _mish,
+    "ReLU": lambda x: np.maximum(x.astype(f32), f32(0)),
+    "Softplus": _softplus,
+    "Identity": lambda x: x.astype(f32),
+    "Abs": lambda x: np.abs(x.astype(f32)),
+    "Sin": lambda x: np.sin(x.astype(f32)).astype(f32),
+    "Cos": lambda x: np.cos(x.astype(f32)).astype(f32),
+}
+
+
 def mlp_head(x, W1, b1, W2, b2, min_temp, Q, Wh=None, bh=None, n_hidden=0):
     """networks/mlp.py:44-63: Linear, Mish, n_hidden x (the SAME Linear(Hh, Hh), Mish — the tuple repetition of :47-50 shares
     one module), Linear(+1), learned-temperature divide."""
@@ -357,8 +376,9 @@ class WaveNetOracle:
     (:174 trims the re-bound `inputs_dilated`) then read z, so the per-layer history holds z."""
 
     def __init__(self, state_dict, blocks, kernel_sizes=(2,), q_levels=256, layerwise_inputs=False, n_mlp_hidden=0,
-                 reverse_layer_order=False):
+                 reverse_layer_order=False, act_f="Tanh", act_g="Sigmoid"):
         sd = state_dict
+        self.act_f, self.act_g = ACTIVATIONS[str(act_f)], ACTIVATIONS[str(act_g or "Sigmoid")]   # wavenet_v2.py:198-199, 224-225
         ks, ds = wavenet_kernels_and_dilations(kernel_sizes, blocks)
         self.kernels = [int(k) for k, _ in zip(ks, ds)]
         self.dilations = [int(d) for _, d in zip(ks, ds)]
@@ -426,9 +446,9 @@ class WaveNetOracle:
             a = x @ w.T + a if a.ndim == 1 else a + x @ w.T
         a = a.astype(f32)
         if self.gated:
-            y = (np.tanh(a[..., :C]) * _sigmoid(a[..., C:])).astype(f32)     # :102,151
+            y = (self.act_f(a[..., :C]) * self.act_g(a[..., C:])).astype(f32)   # :102,151
         else:
-            y = np.tanh(a).astype(f32)                                       # :160-163 (act_g=None)
+            y = self.act_f(a).astype(f32)                                    # :160-163 (act_g=None)
         if self.has_skips:
             s = y @ self.Ws[l].T + self.bs[l]                            # :165-171
             skips = s if skips is None else (s + skips).astype(f32)

@@ -195,6 +195,8 @@ def test_errors():
         WaveNet.from_config(WaveNet.Config(io_spec=io, dims_1x1=(16,)))
     with pytest.raises(NotImplementedError):
         WaveNet.from_config(WaveNet.Config(io_spec=io, blocks=()))
+    with pytest.raises(NotImplementedError):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, act_g="GLU"))
     assert WaveNet.from_config(WaveNet.Config(io_spec=io, pad_side=1, blocks=(3,))).shift == 1
     with pytest.raises(RuntimeError):
         net.load_state_dict({"bogus": torch.zeros(1)})
@@ -240,7 +242,8 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
 
 @pytest.mark.parametrize("name", ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3",
                                   "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
-                                  "wavenet_affine_plain"])
+                                  "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
+                                  "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
@@ -256,7 +259,7 @@ def test_variant_goldens(name):
                          skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
                          layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)),
                          reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), with_affine_residuals=bool(int(m.get("affine", 0))),
-                         **({"act_g": None} if int(m.get("nongated", 0)) else {}))
+                         act_f=kw["act_f"], act_g=None if int(m.get("nongated", 0)) else kw["act_g"])
     net = WaveNet.from_config(cfg).to("cuda")
     net.load_state_dict(golden_state_dict(d))
     prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
