@@ -124,7 +124,9 @@ typedef struct {
     int skips_dim;                /* S, 0 = no skip convs */
     int head_hidden;              /* MLPIO.hidden_dim */
     int q_levels;                 /* Q; head emits Q+1 values (learned temperature channel) */
-    float min_temperature;        /* MLP.min_temp buffer */
+    float min_temperature;        /* MLP.min_temp buffer.  A head built with min_temperature=None (mlp.py:29, 54-62: Q outputs, no
+                                   * division) is passed as Q + 1 rows whose last row is zero with bias 40 and min_temperature 0:
+                                   * sigmoid(40) rounds to 1.0f, so the division is exact (mimikit_b200/arm.py:_head_last) */
     const int* dilations;         /* [n_layers] */
     /* HOST pointers, fp32, in the reference state_dict layouts (key names in comments) */
     const float* embedding;                /* input_modules.0.0.weight        (Q, C)     */

@@ -130,6 +130,23 @@ class NativeARM:
     def _w(self, key):
         return _capi.fptr(self._sd[key])
 
+    @property
+    def _learns_temperature(self):
+        """networks/mlp.py:29, 54-62: MLP(min_temperature=None) has Q outputs, no `min_temp` buffer and no division."""
+        return self._config.io_spec.targets[0].module.min_temperature is not None
+
+    def _head_last(self, wkey, bkey):
+        """(weight pointer, bias pointer, min_temperature) of the head's last Linear as the kernels expect it: Q + 1 rows, the
+        last one the temperature logit.  A head WITHOUT the learned temperature is hosted through its weights alone: a zero
+        row with bias 40 is appended and min_temperature is 0, so the kernels divide by max(sigmoid(40), 0) = 1 / (1 + exp(-40)),
+        which rounds to exactly 1.0f — logits / 1.0f are the logits, bit for bit."""
+        if self._learns_temperature:
+            return self._w(wkey), self._w(bkey), float(self._sd["output_modules.0.estimator.0.min_temp"])
+        w, b = self._sd[wkey], self._sd[bkey]
+        self._head_pad = (torch.cat([w, torch.zeros_like(w[:1])], 0).contiguous(),
+                          torch.cat([b, torch.full_like(b[:1], 40.0)], 0).contiguous())
+        return _capi.fptr(self._head_pad[0]), _capi.fptr(self._head_pad[1]), 0.0
+
     def _warray(self, keys):
         """const float* const* over per-layer tensors; a None key gives a NULL entry."""
         arr = (ctypes.POINTER(ctypes.c_float) * len(keys))()

@@ -49,7 +49,6 @@ class SampleRNN(NativeARM):
         need(str(c.inputs_mode) == "sum", "inputs_mode other than 'sum'")
         need(len(c.frame_sizes) >= 2, "fewer than two tiers")
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
-        need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
         fs = c.frame_sizes
         for i in range(len(fs) - 2):
             need(fs[i] % fs[i + 1] == 0, "frame sizes that do not divide each other")
@@ -144,7 +143,8 @@ class SampleRNN(NativeARM):
         e[p + "weight"] = (H, 1, fs[-1])
         e[p + "bias"] = (H,)
         p = "output_modules.0.estimator.0."
-        e[p + "min_temp"] = ()
+        if self._learns_temperature:                      # mlp.py:29, 54-57: without it, Q outputs and no buffer
+            e[p + "min_temp"] = ()
         e[p + "fc.0.weight"] = (Hh, H)
         e[p + "fc.0.bias"] = (Hh,)
         # networks/mlp.py:47-50 builds the hidden layers by repeating a TUPLE that holds one nn.Linear: fc.2, fc.4, ... are
@@ -153,8 +153,8 @@ class SampleRNN(NativeARM):
         for r in range(nh):
             e[p + f"fc.{2 + 2 * r}.weight"] = (Hh, Hh)
             e[p + f"fc.{2 + 2 * r}.bias"] = (Hh,)
-        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + 1, Hh)
-        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + 1,)
+        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + int(self._learns_temperature), Hh)
+        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + int(self._learns_temperature),)
         return e
 
     def _init_state_dict(self):
@@ -190,7 +190,6 @@ class SampleRNN(NativeARM):
         d.n_tiers, d.hidden_dim, d.head_hidden, d.q_levels = n, H, Hh, Q
         fsa = (ctypes.c_int * n)(*fs)
         d.frame_sizes = fsa
-        d.min_temperature = float(self._sd["output_modules.0.estimator.0.min_temp"])
         keep = [fsa]
         def arr(fmt):
             a = self._warray([fmt.format(i) for i in range(n - 1)])
@@ -211,7 +210,7 @@ class SampleRNN(NativeARM):
         p = "output_modules.0.estimator.0."
         nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
-        d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        d.head_w2, d.head_b2, d.min_temperature = self._head_last(p + f"fc.{2 + 2 * nh}.weight", p + f"fc.{2 + 2 * nh}.bias")
         dx.head_hidden_layers = nh
         if nh > 0:
             for r in range(1, nh):

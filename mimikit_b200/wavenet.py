@@ -95,7 +95,6 @@ class WaveNet(NativeARM):
         # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
         # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
-        need(c.io_spec.targets[0].module.min_temperature is not None, "an MLP head without the learned temperature")
         need(len(c.blocks) > 0, "blocks=() (the reference then keeps conv_res on the last layer)")
         need(not c.reverse_layer_order or c.skips_dim is not None or c.residuals_dim is None,
              "reverse_layer_order with residuals and without skips (the head would read the last layer's residual output)")
@@ -215,25 +214,26 @@ class WaveNet(NativeARM):
             else:                                       # wavenet_v2.py:109-112: a bare Conv1d (no Sequential / Chunk) without gated units
                 e[f"layers.{l}.conv_dil.0.weight"] = (C, Cg, self.kernels[l])
                 e[f"layers.{l}.conv_dil.0.bias"] = (C,)
-            if self._config.with_affine_residuals:      # wavenet_v2.py:121-122: ParametrizedLinear(C, C, as_1x1_conv=True)
-                e[f"layers.{l}.aff_res.params.weight"] = (3 * C, C, 1)
-                e[f"layers.{l}.aff_res.params.bias"] = (3 * C,)
             if self.has_skips:
                 e[f"layers.{l}.conv_skip.weight"] = (S, C, 1)
                 e[f"layers.{l}.conv_skip.bias"] = (S,)
             if self._layer_has_res(l):
                 e[f"layers.{l}.conv_res.weight"] = (C, C, 1)
                 e[f"layers.{l}.conv_res.bias"] = (C,)
+            if self._config.with_affine_residuals:      # wavenet_v2.py:121-122: ParametrizedLinear(C, C, as_1x1_conv=True)
+                e[f"layers.{l}.aff_res.params.weight"] = (3 * C, C, 1)
+                e[f"layers.{l}.aff_res.params.bias"] = (3 * C,)
         p = "output_modules.0.estimator.0."
-        e[p + "min_temp"] = ()
+        if self._learns_temperature:                      # mlp.py:29, 54-57: without it, Q outputs and no buffer
+            e[p + "min_temp"] = ()
         e[p + "fc.0.weight"] = (Hh, S if self.has_skips else C)
         e[p + "fc.0.bias"] = (Hh,)
         nh = self._n_mlp_hidden                           # mlp.py:47-50: fc.2, fc.4, ... are ONE shared Linear(Hh, Hh)
         for r in range(nh):
             e[p + f"fc.{2 + 2 * r}.weight"] = (Hh, Hh)
             e[p + f"fc.{2 + 2 * r}.bias"] = (Hh,)
-        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + 1, Hh)
-        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + 1,)
+        e[p + f"fc.{2 + 2 * nh}.weight"] = (Q + int(self._learns_temperature), Hh)
+        e[p + f"fc.{2 + 2 * nh}.bias"] = (Q + int(self._learns_temperature),)
         return e
 
     def _init_state_dict(self):
@@ -262,7 +262,6 @@ class WaveNet(NativeARM):
         dx = _capi.WaveNetDescEx()
         d = dx.base
         d.n_layers, d.dilated_dim, d.skips_dim, d.head_hidden, d.q_levels = L, C, S, Hh, Q
-        d.min_temperature = float(self._sd["output_modules.0.estimator.0.min_temp"])
         dil = (ctypes.c_int * L)(*self.dilations)
         d.dilations = dil
         d.embedding = self._w("input_modules.0.0.weight")
@@ -309,7 +308,7 @@ class WaveNet(NativeARM):
         p = "output_modules.0.estimator.0."
         nh = self._n_mlp_hidden
         d.head_w1, d.head_b1 = self._w(p + "fc.0.weight"), self._w(p + "fc.0.bias")
-        d.head_w2, d.head_b2 = self._w(p + f"fc.{2 + 2 * nh}.weight"), self._w(p + f"fc.{2 + 2 * nh}.bias")
+        d.head_w2, d.head_b2, d.min_temperature = self._head_last(p + f"fc.{2 + 2 * nh}.weight", p + f"fc.{2 + 2 * nh}.bias")
         dx.act_f = ACT_CODES[str(self._config.act_f)]
         dx.act_g = ACT_CODES[str(self._config.act_g)] if self._gated else ACT_CODES["Sigmoid"]   # not gated: the exact-one gate below
         if self._config.with_affine_residuals:

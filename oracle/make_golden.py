@@ -27,10 +27,14 @@ def gen_samplernn_variant(name, prompts, n_steps, h0_seed=None, **kw):
     default), stacked layers, h0_init ones / randn, hidden MLP layers.  For randn the reference draws its initial states
     from torch's global generator at the first forward of every tier (sample_rnn_v2.py:101-119): the generator is seeded
     right before each run and the same draws, in the same order, are stored as `h0/<tier>_<layer>_<which>`."""
+    kw = dict(kw)
+    no_temp = kw.pop("no_temperature", False)
+    if no_temp:
+        kw["min_temperature"] = None
     net = ref_loader.make_samplernn(**kw)
     B = prompts.shape[0]
     noise = torch.rand(B, n_steps, generator=torch.Generator().manual_seed(4321))
-    meta = dict(frame_sizes=kw["frame_sizes"], hidden_dim=kw["hidden_dim"], mlp_dim=kw["mlp_dim"],
+    meta = dict(frame_sizes=kw["frame_sizes"], hidden_dim=kw["hidden_dim"], mlp_dim=kw["mlp_dim"], no_temperature=int(no_temp),
                 rnn_class=kw.get("rnn_class", "gru"), n_rnn=kw.get("n_rnn", 1), h0_init=kw.get("h0_init", "zeros"),
                 n_mlp_layers=kw.get("n_mlp_layers", 0))
     out = dict(sd_arrays(net.state_dict()), prompts=prompts.numpy(), noise=noise.numpy(),
@@ -162,6 +166,14 @@ def main():
             net = ref_loader.make_wavenet(seed=20 + i, act_f=f, act_g=gt or "Sigmoid", gated=gt is not None, **kw)
             meta = dict(kw, act_f=f, **(dict(act_g=gt) if gt else dict(nongated=1)))
             gen_network(f"wavenet_act_{f.lower()}_{(gt or 'none').lower()}", net, torch.randint(0, 256, (2, 24), generator=g), 16, meta)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "no_temperature":        # MLP(min_temperature=None): Q outputs, no learned temperature (mlp.py:29, 54-62)
+        g = torch.Generator().manual_seed(94)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=30, min_temperature=None, **kw)
+        gen_network("wavenet_no_temperature", net, torch.randint(0, 256, (2, 24), generator=g), 16, dict(kw, no_temperature=1))
+        gen_samplernn_variant("samplernn_no_temperature", torch.randint(0, 256, (2, 24), generator=g), 16, no_temperature=True,
+                              frame_sizes=(4, 2, 1), hidden_dim=32, mlp_dim=32, seed=31)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)

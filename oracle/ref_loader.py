@@ -139,13 +139,15 @@ def load():
 
 def make_wavenet(blocks=(4,), dims=128, residuals_dim=None, skips_dim=None, seed=0, pad_side=0,
                  mlp_dim=128, sr=16000, layerwise_inputs=False, n_mlp_layers=0, kernel_sizes=(2,), reverse_layer_order=False,
-                 gated=True, groups=1, with_affine_residuals=False, act_f="Tanh", act_g="Sigmoid"):
+                 gated=True, groups=1, with_affine_residuals=False, act_f="Tanh", act_g="Sigmoid",
+                 min_temperature=1e-4):
     import torch
     ref = load()
     torch.manual_seed(seed)
     cfg = ref.WaveNet.Config(
         io_spec=ref.IOSpec.mulaw_io(ref.IOSpec.MuLawIOConfig(sr=sr, input_module_type="embedding",
-                                                             mlp_dim=mlp_dim, n_mlp_layers=n_mlp_layers)),
+                                                             mlp_dim=mlp_dim, n_mlp_layers=n_mlp_layers,
+                                                             min_temperature=min_temperature)),
         blocks=tuple(blocks), dims_dilated=(dims,), residuals_dim=residuals_dim, skips_dim=skips_dim,
         pad_side=pad_side, layerwise_inputs=layerwise_inputs, kernel_sizes=tuple(kernel_sizes),
         reverse_layer_order=reverse_layer_order, groups=groups, with_affine_residuals=with_affine_residuals,
@@ -154,12 +156,13 @@ def make_wavenet(blocks=(4,), dims=128, residuals_dim=None, skips_dim=None, seed
 
 
 def make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=512, seed=0, mlp_dim=128, sr=16000,
-                   rnn_class="gru", h0_init="zeros", n_rnn=1, n_mlp_layers=0):
+                   rnn_class="gru", h0_init="zeros", n_rnn=1, n_mlp_layers=0, min_temperature=1e-4):
     import torch
     ref = load()
     torch.manual_seed(seed)
     cfg = ref.SampleRNN.Config(
-        io_spec=ref.IOSpec.mulaw_io(ref.IOSpec.MuLawIOConfig(sr=sr, mlp_dim=mlp_dim, n_mlp_layers=n_mlp_layers)),
+        io_spec=ref.IOSpec.mulaw_io(ref.IOSpec.MuLawIOConfig(sr=sr, mlp_dim=mlp_dim, n_mlp_layers=n_mlp_layers,
+                                                             min_temperature=min_temperature)),
         frame_sizes=tuple(frame_sizes), hidden_dim=hidden_dim, rnn_class=rnn_class, h0_init=h0_init, n_rnn=n_rnn)
     return ref.SampleRNN.from_config(cfg)
 

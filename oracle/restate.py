@@ -294,6 +294,8 @@ def mlp_head(x, W1, b1, W2, b2, min_temp, Q, Wh=None, bh=None, n_hidden=0):
     for _ in range(n_hidden):
         hid = _mish((hid @ Wh.T + bh).astype(f32))
     z = hid @ W2.T + b2
+    if min_temp is None:                       # MLP(min_temperature=None): Q outputs, no temperature column (mlp.py:29, 54-62)
+        return z.astype(f32)
     temp = np.maximum(_sigmoid(z[..., Q:Q + 1]), f32(min_temp))
     return (z[..., :Q] / temp).astype(f32)
 
@@ -431,7 +433,7 @@ class WaveNetOracle:
         self.Wh = _np(sd, p + "fc.2.weight") if self.n_mlp_hidden else None
         self.bh = _np(sd, p + "fc.2.bias") if self.n_mlp_hidden else None
         self.W2, self.b2 = _np(sd, p + f"fc.{last}.weight"), _np(sd, p + f"fc.{last}.bias")
-        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
+        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0]) if p + "min_temp" in sd else None
         self.rf = sum((k - 1) * d for k, d in zip(self.kernels, self.dilations)) + 1
 
     def _head(self, out):
@@ -581,6 +583,9 @@ class WaveNetBf16Oracle(WaveNetOracle):
                 A = q((SK + self.cbs).astype(f32))
                 hid = q(_mish((A @ self.qW1.T + self.b1).astype(f32)))
                 z = (hid @ self.qW2.T + self.b2).astype(f32)
+                if self.min_temp is None:                  # MLP(min_temperature=None), mlp.py:29, 54-62
+                    out[:, t + 1 - P] = z
+                    continue
                 temp = np.maximum(_sigmoid(z[:, self.Q]), f32(self.min_temp)).astype(f32)
                 out[:, t + 1 - P] = (z[:, :self.Q] / temp[:, None]).astype(f32)
         return out
@@ -624,7 +629,7 @@ class SampleRNNOracle:
         self.Wh = _np(sd, p + "fc.2.weight") if self.n_mlp_hidden else None      # ONE shared Linear (mlp.py:47-50)
         self.bh = _np(sd, p + "fc.2.bias") if self.n_mlp_hidden else None
         self.W2, self.b2 = _np(sd, p + f"fc.{last}.weight"), _np(sd, p + f"fc.{last}.bias")
-        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0])
+        self.min_temp = float(_np(sd, p + "min_temp").reshape(-1)[0]) if p + "min_temp" in sd else None
         self.rf = self.fs[0]
         # sample_rnn_v2.py:155-158
         self.up = [self.fs[i] // (self.fs[i + 1] if i < self.n_tiers - 2 else 1) for i in range(self.n_tiers - 1)]

@@ -35,6 +35,22 @@ def test_wavenet_export_roundtrip(tmp_path):
     assert all(torch.equal(again.state_dict()[k], sd[k]) for k in sd)
 
 
+def test_wavenet_config_surface_export_roundtrip(tmp_path):
+    """A reference WaveNet off the W-30 form — affine residuals, Mish / Softplus gate units, kernel size 3, an MLP head WITHOUT
+    the learned temperature (no min_temp buffer, Q-row last Linear) — exported and reloaded key for key."""
+    ref_net = ref_loader.make_wavenet(blocks=(2, 2), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32, seed=4,
+                                      with_affine_residuals=True, act_f="Mish", act_g="Softplus", kernel_sizes=(3,),
+                                      min_temperature=None)
+    ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)
+    assert ours.rf == ref_net.rf and list(sd) == [k for k in sd_ref]
+    assert "layers.0.aff_res.params.weight" in sd and "output_modules.0.estimator.0.min_temp" not in sd
+    assert tuple(sd["output_modules.0.estimator.0.fc.2.weight"].shape) == (256, 32)
+    for k in sd_ref:
+        assert torch.equal(sd[k], sd_ref[k].float().cpu()), k
+    c = ours.config
+    assert c.with_affine_residuals and str(c.act_f) == "Mish" and str(c.act_g) == "Softplus" and d["io"]["min_temperature"] is None
+
+
 def test_samplernn_export_roundtrip_and_errors(tmp_path):
     ref_net = ref_loader.make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=64, mlp_dim=32, seed=5)
     ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)

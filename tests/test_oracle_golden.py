@@ -212,7 +212,8 @@ def test_product_wavenet_structure_matches_the_reference_kats():
         assert sum((int(a) - 1) * int(b) for a, b in zip(ks, ds)) + 1 == k["rf"]
 
 
-VARIANTS = ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2", "samplernn_rnn_tanh_mlp1"]
+VARIANTS = ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2", "samplernn_rnn_tanh_mlp1",
+            "samplernn_no_temperature"]
 
 
 def variant_setup(d):
@@ -246,7 +247,7 @@ def test_samplernn_variant_oracle_vs_reference(name):
 
 WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed", "wavenet_nongated", "wavenet_groups4",
                "wavenet_affine_res", "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
-               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none"]
+               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none", "wavenet_no_temperature"]
 
 
 def wavenet_variant_kwargs(d):

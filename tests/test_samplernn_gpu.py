@@ -435,7 +435,7 @@ def test_s3_long_horizon_vs_oracle():
 
 
 @pytest.mark.parametrize("name", ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2",
-                                  "samplernn_rnn_tanh_mlp1"])
+                                  "samplernn_rnn_tanh_mlp1", "samplernn_no_temperature"])
 def test_variant_goldens(name):
     """The rest of SampleRNNTier's configuration surface against the live reference (tests/golden, generated by
     oracle/make_golden.py samplernn_variants): rnn_class "lstm" (the reference DEFAULT) / "rnn", n_rnn 2 and 3, h0_init
@@ -445,7 +445,9 @@ def test_variant_goldens(name):
     d = load_golden(name)
     m, kw, h0 = variant_setup(d)
     fs = tuple(int(f) for f in m["frame_sizes"])
-    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]), n_mlp_layers=kw["n_mlp_hidden"])),
+    head = dict(min_temperature=None) if int(m.get("no_temperature", 0)) else {}      # MLP(min_temperature=None), mlp.py:29, 54-62
+    cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]), n_mlp_layers=kw["n_mlp_hidden"],
+                                                                        **head)),
                            frame_sizes=fs, hidden_dim=int(m["hidden_dim"]), rnn_class=kw["rnn_class"], n_rnn=kw["n_rnn"],
                            h0_init=str(m["h0_init"]))
     net = SampleRNN.from_config(cfg).to("cuda")

@@ -243,7 +243,8 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
 @pytest.mark.parametrize("name", ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3",
                                   "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
                                   "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
-                                  "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none"])
+                                  "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none",
+                                  "wavenet_no_temperature"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
@@ -252,8 +253,9 @@ def test_variant_goldens(name):
     from test_oracle_golden import wavenet_variant_kwargs
     d = load_golden(name)
     m, kw = wavenet_variant_kwargs(d)
+    head = dict(min_temperature=None) if int(m.get("no_temperature", 0)) else {}      # MLP(min_temperature=None), mlp.py:29, 54-62
     cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=int(m["mlp_dim"]),
-                                                                      n_mlp_layers=kw["n_mlp_hidden"])),
+                                                                      n_mlp_layers=kw["n_mlp_hidden"], **head)),
                          blocks=tuple(int(b) for b in m["blocks"]), dims_dilated=(int(m["dims"]),),
                          residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
                          skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
@@ -276,6 +278,37 @@ def test_variant_goldens(name):
     for t in range(P, P + n):
         x[:, t:t + 1] = net.generate_step((x[:, t - net.rf:t],), t=t)[0]
     assert np.array_equal(x.cpu().numpy(), d["seq_argmax"])
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_head_without_learned_temperature_on_the_fast_kernels(bf16):
+    """MLP(min_temperature=None) (mlp.py:29, 54-62) is hosted through the weights (a zero row with bias 40: the kernels divide by
+    exactly 1.0f), so it runs on the layer-pipelined fp32 kernel and on the tcgen05 kernel as well: vs the oracle."""
+    from mimikit_b200 import IOSpec, WaveNet
+    torch.manual_seed(31)
+    blocks = (4, 3)
+    cfg = WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=128,
+                                                                      min_temperature=None)),
+                         blocks=blocks, dims_dilated=(128,), residuals_dim=128, skips_dim=128)
+    net = WaveNet.from_config(cfg).to("cuda")
+    sd = {k: v.numpy() for k, v in net.state_dict().items()}
+    assert "output_modules.0.estimator.0.min_temp" not in sd and sd["output_modules.0.estimator.0.fc.2.weight"].shape == (256, 128)
+    g = torch.Generator().manual_seed(6)
+    B, n = 9, 24
+    if bf16:
+        orc = restate.WaveNetBf16Oracle(sd, blocks)
+        seq = torch.randint(0, 256, (B, orc.rf + 3 + n), generator=g)
+        logits, _ = net.bfloat16().teacher_forced(seq, orc.rf + 3)
+        assert _rel_err(logits.cpu().numpy(), orc.logits_for(seq.numpy(), orc.rf + 3)) <= 5e-2
+        return
+    orc = restate.WaveNetOracle(sd, blocks)
+    prompts, noise = torch.randint(0, 256, (B, orc.rf + 2), generator=g), torch.rand(B, n, generator=g)
+    for temp in (None, 0.9):
+        seq, logits = net.generate(prompts, n, temperature=temp, noise=noise, return_logits=True)
+        ref_seq, ref_logits = orc.generate(prompts.numpy(), n, temp, noise.numpy())
+        assert np.array_equal(seq.cpu().numpy(), ref_seq), temp
+        assert _rel_err(logits.cpu().numpy(), ref_logits) <= REL_TOL
+    assert net.launch_info(B)["cluster_size"] == 16      # the layer-pipelined kernel, not the general one
 
 
 @pytest.mark.parametrize("cluster", ["2", "4", "8"])
