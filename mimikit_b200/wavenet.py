@@ -95,7 +95,10 @@ class WaveNet(NativeARM):
         # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
         # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
-        need(len(c.blocks) > 0, "blocks=() (the reference then keeps conv_res on the last layer)")
+        # blocks=() (wavenet_v2.py:304-307, 216): `n != sum(blocks) - 1` never holds, so EVERY layer keeps its conv_res; the last
+        # one's output is read by nothing when the head takes the skip sum (it is then not handed to the kernel)
+        need(len(c.blocks) > 0 or c.skips_dim is not None or c.residuals_dim is None,
+             "blocks=() with residuals and without skips (the head would read the last layer's residual output)")
         need(not c.reverse_layer_order or c.skips_dim is not None or c.residuals_dim is None,
              "reverse_layer_order with residuals and without skips (the head would read the last layer's residual output)")
         ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
@@ -192,6 +195,8 @@ class WaveNet(NativeARM):
     def _layer_has_res(self, l):
         """wavenet_v2.py:216 — the layer BUILT last has no conv_res; with reverse_layer_order it is executed first."""
         L = len(self.dilations)
+        if not self._config.blocks:          # sum(()) - 1 == -1: no layer is the "last" one, all of them keep conv_res
+            return self.has_residuals
         return self.has_residuals and l != (0 if self._config.reverse_layer_order else L - 1)
 
     def _dims(self):

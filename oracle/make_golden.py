@@ -175,6 +175,13 @@ def main():
         gen_samplernn_variant("samplernn_no_temperature", torch.randint(0, 256, (2, 24), generator=g), 16, no_temperature=True,
                               frame_sizes=(4, 2, 1), hidden_dim=32, mlp_dim=32, seed=31)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_noblocks":      # blocks=() (wavenet_v2.py:304-307: one layer per kernel size, dilations their
+        g = torch.Generator().manual_seed(95)                        # running product; :216 `n != sum(blocks) - 1` then never drops a conv_res)
+        kw = dict(blocks=(), dims=32, residuals_dim=32, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=32, kernel_sizes=(2, 3, 2, 2), **kw)
+        assert "layers.3.conv_res.weight" in net.state_dict()
+        gen_network("wavenet_noblocks", net, torch.randint(0, 256, (2, 30), generator=g), 16, dict(kw, kernel_sizes=(2, 3, 2, 2)))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_variants":
         g = torch.Generator().manual_seed(77)
         gen_samplernn_variant("samplernn_lstm_default", torch.randint(0, 256, (3, 40), generator=g), 36,

@@ -247,12 +247,13 @@ def test_samplernn_variant_oracle_vs_reference(name):
 
 WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed", "wavenet_nongated", "wavenet_groups4",
                "wavenet_affine_res", "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
-               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none", "wavenet_no_temperature"]
+               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none", "wavenet_no_temperature", "wavenet_noblocks"]
 
 
 def wavenet_variant_kwargs(d):
     m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
-    return m, dict(kernel_sizes=(int(m.get("kernel_size", 2)),), layerwise_inputs=bool(int(m.get("layerwise_inputs", 0))),
+    ks = tuple(int(k) for k in m["kernel_sizes"]) if "kernel_sizes" in m else (int(m.get("kernel_size", 2)),)
+    return m, dict(kernel_sizes=ks, layerwise_inputs=bool(int(m.get("layerwise_inputs", 0))),
                    n_mlp_hidden=int(m.get("n_mlp_layers", 0)), reverse_layer_order=bool(int(m.get("reverse_layer_order", 0))),
                    act_f=str(m.get("act_f", "Tanh")), act_g=str(m.get("act_g", "Sigmoid")))
 
