@@ -44,7 +44,7 @@ class SampleRNN(NativeARM):
              "more than one input/target")
         need(c.io_spec.inputs[0].module_type == "framed_linear", "input_module_type other than 'framed_linear'")
         need(str(c.rnn_class) in ("gru", "lstm", "rnn"), "rnn_class other than 'lstm', 'gru' or 'rnn'")
-        need(1 <= c.n_rnn <= 4 and c.rnn_bias, "n_rnn outside [1, 4] or rnn_bias=False")
+        need(1 <= c.n_rnn <= 4, "n_rnn outside [1, 4]")     # rnn_bias=False: no rnn.bias_* parameters; the kernels get zero biases
         need(str(c.h0_init) in ("zeros", "ones", "randn"), "h0_init other than 'zeros', 'ones' or 'randn'")
         need(str(c.inputs_mode) == "sum", "inputs_mode other than 'sum'")
         need(len(c.frame_sizes) >= 2, "fewer than two tiers")
@@ -135,8 +135,9 @@ class SampleRNN(NativeARM):
             for k in range(self._config.n_rnn):       # nn.GRU / nn.LSTM / nn.RNN parameter names, layer by layer
                 e[p + f"rnn.weight_ih_l{k}"] = (self._gates * H, H)
                 e[p + f"rnn.weight_hh_l{k}"] = (self._gates * H, H)
-                e[p + f"rnn.bias_ih_l{k}"] = (self._gates * H,)
-                e[p + f"rnn.bias_hh_l{k}"] = (self._gates * H,)
+                if self._config.rnn_bias:             # sample_rnn_v2.py:66: nn.GRU / nn.LSTM / nn.RNN(bias=rnn_bias)
+                    e[p + f"rnn.bias_ih_l{k}"] = (self._gates * H,)
+                    e[p + f"rnn.bias_hh_l{k}"] = (self._gates * H,)
             e[p + "up_sampler.fc.weight"] = (H * self._up(i), H)
             e[p + "up_sampler.fc.bias"] = (H * self._up(i),)
         p = f"tiers.{len(fs) - 1}.input_module.heads.0.2.2.cv."
@@ -203,7 +204,13 @@ class SampleRNN(NativeARM):
         dx.rnn_type = {"gru": 0, "lstm": 1, "rnn": 2}[str(c.rnn_class)]
         dx.n_rnn = int(c.n_rnn)
         dx.w_ih, dx.w_hh = rnn_arr("weight_ih"), rnn_arr("weight_hh")
-        dx.b_ih, dx.b_hh = rnn_arr("bias_ih"), rnn_arr("bias_hh")
+        if c.rnn_bias:
+            dx.b_ih, dx.b_hh = rnn_arr("bias_ih"), rnn_arr("bias_hh")
+        else:                                         # adding 0.0f changes no value: the bias-free cell, bit for bit
+            self._zero_bias = torch.zeros(self._gates * H, dtype=torch.float32)
+            za = (ctypes.POINTER(ctypes.c_float) * ((n - 1) * c.n_rnn))(*([_capi.fptr(self._zero_bias)] * ((n - 1) * c.n_rnn)))
+            keep.append(za)
+            dx.b_ih = dx.b_hh = za
         d.up_w, d.up_b = arr("tiers.{}.up_sampler.fc.weight"), arr("tiers.{}.up_sampler.fc.bias")
         p = f"tiers.{n - 1}.input_module.heads.0.2.2.cv."
         d.conv_w, d.conv_b = self._w(p + "weight"), self._w(p + "bias")

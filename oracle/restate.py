@@ -615,8 +615,9 @@ class SampleRNNOracle:
                 Win=_np(sd, p + "input_module.heads.0.2.weight"), bin=_np(sd, p + "input_module.heads.0.2.bias"),
                 Wih=[_np(sd, p + f"rnn.weight_ih_l{k}") for k in range(n_rnn)],
                 Whh=[_np(sd, p + f"rnn.weight_hh_l{k}") for k in range(n_rnn)],
-                bih=[_np(sd, p + f"rnn.bias_ih_l{k}") for k in range(n_rnn)],
-                bhh=[_np(sd, p + f"rnn.bias_hh_l{k}") for k in range(n_rnn)],
+                # rnn_bias=False (sample_rnn_v2.py:66): torch registers no bias parameters; adding 0.0f changes no value
+                bih=[_np(sd, p + f"rnn.bias_ih_l{k}") if p + f"rnn.bias_ih_l{k}" in sd else f32(0) for k in range(n_rnn)],
+                bhh=[_np(sd, p + f"rnn.bias_hh_l{k}") if p + f"rnn.bias_hh_l{k}" in sd else f32(0) for k in range(n_rnn)],
                 Wup=_np(sd, p + "up_sampler.fc.weight"), bup=_np(sd, p + "up_sampler.fc.bias")))
         p = f"tiers.{self.n_tiers - 1}.input_module.heads.0.2.2.cv."
         self.Wc = _np(sd, p + "weight")[:, 0, :]  # (H, fs_last)
