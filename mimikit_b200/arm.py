@@ -36,6 +36,7 @@ class NativeARM:
 
     def __init__(self):
         self._sd = OrderedDict()
+        self._absent = {}        # zero stand-ins for the biases of modules the reference built with bias=False
         self._handle = None
         self._handle_batch = 0
         self._handle_device = None
@@ -128,7 +129,10 @@ class NativeARM:
         return self._handle
 
     def _w(self, key):
-        return _capi.fptr(self._sd[key])
+        t = self._sd.get(key)
+        if t is None:                                  # a bias the reference did not build (bias=False): zeros stand in for it
+            t = self._absent[key]
+        return _capi.fptr(t)
 
     @property
     def _learns_temperature(self):

@@ -91,7 +91,8 @@ class WaveNet(NativeARM):
         need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
         need(str(c.act_f) in ACT_CODES and (c.act_g is None or str(c.act_g) in ACT_CODES),
              "activations outside the point-wise members of ActivationEnum (PhaseA/B/C, GLU, Softmax)")
-        need(c.pad_side in (0, 1) and c.stride == 1 and c.bias, "pad_side < 0, stride != 1 or bias=False")
+        # bias=False (wavenet_v2.py:92-93): conv_dil / conv_skip / conv_res carry no bias; the kernels get zeros, which change no value
+        need(c.pad_side in (0, 1) and c.stride == 1, "pad_side < 0 or stride != 1")
         # tie_io_weights (wavenet_v2.py:247-255) re-ties nn.Linear weights of the input module to the output module; the
         # embedding input module holds no nn.Linear, so with the only supported input type it changes nothing: accepted as a no-op
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
@@ -207,6 +208,18 @@ class WaveNet(NativeARM):
         return C, S, head.hidden_dim, c.io_spec.targets[0].out_dim
 
     def _expected_shapes(self):
+        e = self._all_shapes()
+        if not self._config.bias:
+            for k in self._absent_biases(e):
+                del e[k]
+        return e
+
+    @staticmethod
+    def _absent_biases(e):
+        """bias=False reaches the three convs of a layer (wavenet_v2.py:92-93); aff_res keeps its own bias (:122)."""
+        return [k for k in e if k.startswith("layers.") and k.endswith(".bias") and ".aff_res." not in k]
+
+    def _all_shapes(self):
         C, S, Hh, Q = self._dims()
         L = len(self.dilations)
         e = OrderedDict()
@@ -264,6 +277,8 @@ class WaveNet(NativeARM):
     def _create_handle(self, max_batch):
         C, S, Hh, Q = self._dims()
         L = len(self.dilations)
+        e = self._all_shapes()
+        self._absent = {} if self._config.bias else {k: torch.zeros(e[k], dtype=torch.float32) for k in self._absent_biases(e)}
         dx = _capi.WaveNetDescEx()
         d = dx.base
         d.n_layers, d.dilated_dim, d.skips_dim, d.head_hidden, d.q_levels = L, C, S, Hh, Q
@@ -287,7 +302,7 @@ class WaveNet(NativeARM):
             G = int(self._config.groups)
             for l in range(L):
                 pre = f"layers.{l}.conv_dil.0.0." if self._gated else f"layers.{l}.conv_dil.0."
-                w, b = self._sd[pre + "weight"], self._sd[pre + "bias"]
+                w, b = self._sd[pre + "weight"], self._sd[pre + "bias"] if self._config.bias else self._absent[pre + "bias"]
                 if G > 1:
                     O, Cg, K = w.shape
                     dense = torch.zeros((O, C, K), dtype=w.dtype)

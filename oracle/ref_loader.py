@@ -140,7 +140,7 @@ def load():
 def make_wavenet(blocks=(4,), dims=128, residuals_dim=None, skips_dim=None, seed=0, pad_side=0,
                  mlp_dim=128, sr=16000, layerwise_inputs=False, n_mlp_layers=0, kernel_sizes=(2,), reverse_layer_order=False,
                  gated=True, groups=1, with_affine_residuals=False, act_f="Tanh", act_g="Sigmoid",
-                 min_temperature=1e-4):
+                 min_temperature=1e-4, bias=True):
     import torch
     ref = load()
     torch.manual_seed(seed)
@@ -151,7 +151,7 @@ def make_wavenet(blocks=(4,), dims=128, residuals_dim=None, skips_dim=None, seed
         blocks=tuple(blocks), dims_dilated=(dims,), residuals_dim=residuals_dim, skips_dim=skips_dim,
         pad_side=pad_side, layerwise_inputs=layerwise_inputs, kernel_sizes=tuple(kernel_sizes),
         reverse_layer_order=reverse_layer_order, groups=groups, with_affine_residuals=with_affine_residuals,
-        act_f=act_f, act_g=act_g if gated else None)
+        act_f=act_f, act_g=act_g if gated else None, bias=bias)
     return ref.WaveNet.from_config(cfg)
 
 

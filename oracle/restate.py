@@ -305,6 +305,11 @@ def _np(sd, key):
     return np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=f32)
 
 
+def _np_or0(sd, key):
+    """A bias of a module built with bias=False is absent from the state dict; adding 0.0f changes no value."""
+    return _np(sd, key) if key in sd else f32(0)
+
+
 def fold_weight_norm(sd):
     """nn.utils.weight_norm (sample_rnn_v2.py:67-81): w = g * v / ||v|| with the norm over all dims but 0."""
     out = {}
@@ -409,19 +414,19 @@ class WaveNetOracle:
                     dense[gi * og:(gi + 1) * og, gi * cg:(gi + 1) * cg] = w[gi * og:(gi + 1) * og]
                 w = dense
             self.Wd.append([np.ascontiguousarray(w[:, :, j]) for j in range(w.shape[2])])
-            self.bd.append(_np(sd, pre + "bias"))
+            self.bd.append(_np_or0(sd, pre + "bias"))                # WaveNet.Config.bias=False (wavenet_v2.py:92-93): no layer biases
             if f"layers.{l}.aff_res.params.weight" in sd:
                 self.Wa.append(_np(sd, f"layers.{l}.aff_res.params.weight")[:, :, 0])
-                self.ba.append(_np(sd, f"layers.{l}.aff_res.params.bias"))
+                self.ba.append(_np_or0(sd, f"layers.{l}.aff_res.params.bias"))
             else:
                 self.Wa.append(None)
                 self.ba.append(None)
             if self.has_skips:
                 self.Ws.append(_np(sd, f"layers.{l}.conv_skip.weight")[:, :, 0])
-                self.bs.append(_np(sd, f"layers.{l}.conv_skip.bias"))
+                self.bs.append(_np_or0(sd, f"layers.{l}.conv_skip.bias"))
             if f"layers.{l}.conv_res.weight" in sd:
                 self.Wr.append(_np(sd, f"layers.{l}.conv_res.weight")[:, :, 0])
-                self.br.append(_np(sd, f"layers.{l}.conv_res.bias"))
+                self.br.append(_np_or0(sd, f"layers.{l}.conv_res.bias"))
             else:
                 self.Wr.append(None)
                 self.br.append(None)

@@ -245,7 +245,7 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
                                   "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
                                   "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
                                   "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none",
-                                  "wavenet_no_temperature", "wavenet_noblocks"])
+                                  "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
@@ -261,7 +261,7 @@ def test_variant_goldens(name):
                          residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
                          skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
                          layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)),
-                         reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), with_affine_residuals=bool(int(m.get("affine", 0))),
+                         reverse_layer_order=kw["reverse_layer_order"], groups=int(m.get("groups", 1)), with_affine_residuals=bool(int(m.get("affine", 0))), bias=not int(m.get("nobias", 0)),
                          act_f=kw["act_f"], act_g=None if int(m.get("nongated", 0)) else kw["act_g"])
     net = WaveNet.from_config(cfg).to("cuda")
     net.load_state_dict(golden_state_dict(d))
