@@ -84,8 +84,7 @@ class WaveNet(NativeARM):
              "more than one input/target")
         need(c.io_spec.inputs[0].module_type == "embedding", "input_module_type other than 'embedding'")
         need(len(c.dims_dilated) == 1 and not c.dims_1x1, "dims_1x1 conditioning inputs")
-        need(c.residuals_dim is None or c.residuals_dim == c.dims_dilated[0],
-             "residuals_dim != dims_dilated[0] (the reference silently drops such residuals, wavenet_v2.py:78)")
+        # residuals_dim != dims_dilated[0]: WNLayer silently builds no residual path (wavenet_v2.py:78, has_residuals); so do we
         # apply_residuals is stored by WNLayer (wavenet_v2.py:63) and read nowhere in its forward: accepted, changes nothing
         # with_affine_residuals (wavenet_v2.py:121-122, 148-149): hosted by the general fp32 kernel (aff_res stage per layer)
         need(c.groups >= 1 and c.dims_dilated[0] % c.groups == 0, "groups that do not divide the channels")
@@ -98,9 +97,10 @@ class WaveNet(NativeARM):
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
         # blocks=() (wavenet_v2.py:304-307, 216): `n != sum(blocks) - 1` never holds, so EVERY layer keeps its conv_res; the last
         # one's output is read by nothing when the head takes the skip sum (it is then not handed to the kernel)
-        need(len(c.blocks) > 0 or c.skips_dim is not None or c.residuals_dim is None,
+        no_res = c.residuals_dim is None or c.residuals_dim != c.dims_dilated[0]
+        need(len(c.blocks) > 0 or c.skips_dim is not None or no_res,
              "blocks=() with residuals and without skips (the head would read the last layer's residual output)")
-        need(not c.reverse_layer_order or c.skips_dim is not None or c.residuals_dim is None,
+        need(not c.reverse_layer_order or c.skips_dim is not None or no_res,
              "reverse_layer_order with residuals and without skips (the head would read the last layer's residual output)")
         ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
         need(all(2 <= k <= 4 for k in ks), "kernel sizes outside [2, 4]")
@@ -121,7 +121,7 @@ class WaveNet(NativeARM):
         self.kernels = [k for k, _ in kd]
         self.dilations = [d for _, d in kd]
         self.has_skips = config.skips_dim is not None
-        self.has_residuals = config.residuals_dim is not None
+        self.has_residuals = config.residuals_dim is not None and config.residuals_dim == config.dims_dilated[0]   # wavenet_v2.py:78
         self._sd = self._init_state_dict()
         self._gen = None  # state of the step-wise protocol
         self._cont = None  # where the last generate() stopped (generate_more continues from the rings as they are)

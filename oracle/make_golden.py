@@ -189,6 +189,13 @@ def main():
         assert not any(k.startswith("layers.") and k.endswith(".bias") and "aff_res" not in k for k in net.state_dict())   # :122 keeps its own
         gen_network("wavenet_nobias_affine", net, torch.randint(0, 256, (2, 24), generator=g), 16, dict(kw, affine=1, nobias=1))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_dropped_res":   # residuals_dim != dims_dilated[0]: WNLayer drops the residual path (wavenet_v2.py:78)
+        g = torch.Generator().manual_seed(98)
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=16, skips_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=36, **kw)
+        assert not any("conv_res" in k for k in net.state_dict())
+        gen_network("wavenet_dropped_res", net, torch.randint(0, 256, (2, 24), generator=g), 16, kw)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_nobias":      # rnn_bias=False (sample_rnn_v2.py:66, 130): no rnn.bias_* parameters
         g = torch.Generator().manual_seed(96)
         gen_samplernn_variant("samplernn_lstm_nobias", torch.randint(0, 256, (2, 24), generator=g), 16, frame_sizes=(4, 2, 1),

@@ -245,7 +245,7 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
                                   "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
                                   "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
                                   "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none",
-                                  "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine"])
+                                  "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine", "wavenet_dropped_res"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
