@@ -134,7 +134,8 @@ typedef struct {
     const float* const* conv_dil_b;        /* layers.l.conv_dil.0.0.bias      (2C)       */
     const float* const* conv_skip_w;       /* layers.l.conv_skip.weight       (S, C, 1)  or NULL array when S == 0 */
     const float* const* conv_skip_b;       /* layers.l.conv_skip.bias         (S)        */
-    const float* const* conv_res_w;        /* layers.l.conv_res.weight        (C, C, 1)  entry NULL = layer has none */
+    const float* const* conv_res_w;        /* layers.l.conv_res.weight        (C, C, 1)  entry NULL = layer has none; on the last
+                                            * layer (reverse_layer_order, blocks=()) only the fp32 general kernel takes one */
     const float* const* conv_res_b;        /* layers.l.conv_res.bias          (C)        */
     const float* head_w1;                  /* output_modules.0.estimator.0.fc.0.weight (Hh, S|C) */
     const float* head_b1;                  /* ....fc.0.bias   (Hh)      */

@@ -445,8 +445,9 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                     __syncthreads();
                 }
                 const float* hnext_slice = own_slice ? slice : (yc + (size_t)rank * nf * GB);
-                if (last_layer && ns == 0 && P.layerwise && head_on) {
-                    // no skips: the head reads h_L = y + inputs[0]: gather it where the skip sum would have gone
+                if (last_layer && ns == 0 && own_slice && head_on) {
+                    // no skips: the head reads h_L = y + inputs[0] (layerwise) or x + conv_res(y) (a conv_res on the layer executed
+                    // last: reverse_layer_order, blocks=()): gather it where the skip sum would have gone
                     scatter_slice<CS>(cluster, hin + (size_t)rank * nf * GB, slice, nf * GB / 4);
                     cluster_sync_all<CS>();
                 }
@@ -495,7 +496,8 @@ __global__ void __launch_bounds__(WN_NT, 1) wavenet_pipe_kernel(const __grid_con
                     cluster_sync_all<CS>();
                     head_in = hin;
                 } else {
-                    head_in = P.layerwise ? hin : ylast;         // no skips: the head reads h_L = y (+ inputs[0]) of the last layer
+                    // no skips: the head reads h_L of the last layer — y itself, or the gathered y + inputs[0] / x + conv_res(y)
+                    head_in = (P.layerwise || P.layers[P.L - 1].nres > 0) ? hin : ylast;
                 }
                 {   // hidden = mish(W1 x + b1)
                     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -772,6 +774,10 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
     MMK_CHECK(d->dilations && d->embedding && d->conv_dil_w && d->conv_dil_b && d->conv_res_w && d->conv_res_b &&
               d->head_w1 && d->head_b1 && d->head_w2 && d->head_b2, "missing weight pointers");
     MMK_CHECK(d->skips_dim == 0 || (d->conv_skip_w && d->conv_skip_b), "skips_dim > 0 needs conv_skip weights");
+    // a conv_res on the layer executed last (reverse_layer_order, blocks=(): wavenet_v2.py:216, 270): without skips the head reads
+    // h_L = x + conv_res(y) (:286-292); only the general kernel hosts it
+    const bool last_res = d->conv_res_w[d->n_layers - 1] != nullptr;
+    MMK_CHECK(!last_res || compute_mode == MMK_COMPUTE_FP32, "a residual conv on the last layer runs in the fp32 general kernel only");
     int ndev = 0;
     MMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: mmk_b200 has no CPU fallback");
 
@@ -809,7 +815,7 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         return 0;
     }
     {
-        const char* force = plain ? getenv("MMK_WN_KERNEL") : "1";   // "1" = general kernel only, "6" = layer-pipelined kernel only
+        const char* force = (plain && !last_res) ? getenv("MMK_WN_KERNEL") : "1";   // "1" = general kernel only, "6" = layer-pipelined kernel only
         if (!force || atoi(force) == 6) {
             int unsupported = 0;
             if (wn6_create(d, max_batch, &h->v6, &unsupported) == 0) {
@@ -839,7 +845,6 @@ extern "C" int mmk_wavenet_create_cfg(const mmk_wavenet_desc_ex* dx, int max_bat
         rf += d->dilations[l] * ((dx->kernel_sizes ? dx->kernel_sizes[l] : 2) - 1);
         MMK_CHECK(d->conv_dil_w[l] && d->conv_dil_b[l], "missing conv_dil weights");
         MMK_CHECK(!p.affine || (dx->aff_res_w[l] && dx->aff_res_b[l]), "missing aff_res weights");
-        MMK_CHECK(!(l == p.L - 1 && d->conv_res_w[l]), "the last layer never has a residual conv (wavenet_v2.py:216)");
     }
     h->rf = rf;
 

@@ -97,11 +97,7 @@ class WaveNet(NativeARM):
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
         # blocks=() (wavenet_v2.py:304-307, 216): `n != sum(blocks) - 1` never holds, so EVERY layer keeps its conv_res; the last
         # one's output is read by nothing when the head takes the skip sum (it is then not handed to the kernel)
-        no_res = c.residuals_dim is None or c.residuals_dim != c.dims_dilated[0]
-        need(len(c.blocks) > 0 or c.skips_dim is not None or no_res,
-             "blocks=() with residuals and without skips (the head would read the last layer's residual output)")
-        need(not c.reverse_layer_order or c.skips_dim is not None or no_res,
-             "reverse_layer_order with residuals and without skips (the head would read the last layer's residual output)")
+        # (without skips the head then reads the last layer's x + conv_res(y): the general kernel gathers it, wavenet.cu)
         ks, _ = cls.get_kernels_and_dilation(c.kernel_sizes, c.blocks)
         need(all(2 <= k <= 4 for k in ks), "kernel sizes outside [2, 4]")
 
@@ -173,14 +169,6 @@ class WaveNet(NativeARM):
     @property
     def _n_mlp_hidden(self):
         return int(self._config.io_spec.targets[0].module.n_hidden_layers)
-
-    @property
-    def _plain(self):
-        """The configuration the pipelined kernels host; anything else runs in the general fp32 kernel."""
-        return (all(k == 2 for k in self.kernels) and not self._config.layerwise_inputs and self._n_mlp_hidden == 0
-                and not self._config.reverse_layer_order and self._gated and self._config.groups == 1
-                and not self._config.with_affine_residuals and str(self._config.act_f) == "Tanh"
-                and str(self._config.act_g) == "Sigmoid")
 
     @property
     def generate_params(self):
@@ -322,7 +310,7 @@ class WaveNet(NativeARM):
             d.conv_skip_b = arr("layers.{}.conv_skip.bias")
         # reverse_layer_order: the layer executed last carries a conv_res whose result nothing reads when the head takes the
         # skip sum (wavenet_v2.py:286-292): it is not handed to the kernel
-        has_res = lambda l: self._layer_has_res(l) and l != L - 1
+        has_res = lambda l: self._layer_has_res(l) and (l != L - 1 or not self.has_skips)
         d.conv_res_w = arr("layers.{}.conv_res.weight", has_res)
         d.conv_res_b = arr("layers.{}.conv_res.bias", has_res)
         p = "output_modules.0.estimator.0."

@@ -196,6 +196,17 @@ def main():
         assert not any("conv_res" in k for k in net.state_dict())
         gen_network("wavenet_dropped_res", net, torch.randint(0, 256, (2, 24), generator=g), 16, kw)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wavenet_last_res":      # a conv_res on the layer executed LAST and no skips: the head reads x + conv_res(y)
+        g = torch.Generator().manual_seed(99)                        # (wavenet_v2.py:216, 270, 286-292): reverse_layer_order, and blocks=()
+        kw = dict(blocks=(3, 2), dims=32, residuals_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=37, reverse_layer_order=True, **kw)
+        assert "layers.4.conv_res.weight" in net.state_dict() and "layers.0.conv_res.weight" not in net.state_dict()
+        gen_network("wavenet_reversed_noskip", net, torch.randint(0, 256, (2, 24), generator=g), 16, dict(kw, reverse_layer_order=1))
+        kw = dict(blocks=(), dims=32, residuals_dim=32, mlp_dim=32)
+        net = ref_loader.make_wavenet(seed=38, kernel_sizes=(2, 2, 3), **kw)
+        assert "layers.2.conv_res.weight" in net.state_dict()
+        gen_network("wavenet_noblocks_noskip", net, torch.randint(0, 256, (2, 24), generator=g), 16, dict(kw, kernel_sizes=(2, 2, 3)))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_nobias":      # rnn_bias=False (sample_rnn_v2.py:66, 130): no rnn.bias_* parameters
         g = torch.Generator().manual_seed(96)
         gen_samplernn_variant("samplernn_lstm_nobias", torch.randint(0, 256, (2, 24), generator=g), 16, frame_sizes=(4, 2, 1),

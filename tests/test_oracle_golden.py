@@ -247,7 +247,8 @@ def test_samplernn_variant_oracle_vs_reference(name):
 
 WN_VARIANTS = ["wavenet_pad_side1", "wavenet_layerwise_inputs", "wavenet_layerwise_noskip_mlp2", "wavenet_kernel3", "wavenet_reversed", "wavenet_nongated", "wavenet_groups4",
                "wavenet_affine_res", "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
-               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none", "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine", "wavenet_dropped_res"]
+               "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none", "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine", "wavenet_dropped_res",
+               "wavenet_reversed_noskip", "wavenet_noblocks_noskip"]
 
 
 def wavenet_variant_kwargs(d):

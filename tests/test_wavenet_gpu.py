@@ -193,8 +193,6 @@ def test_errors():
         WaveNet.from_config(WaveNet.Config(io_spec=io, kernel_sizes=(5,)))
     with pytest.raises(NotImplementedError):
         WaveNet.from_config(WaveNet.Config(io_spec=io, dims_1x1=(16,)))
-    with pytest.raises(NotImplementedError):     # blocks=() keeps conv_res on the last layer: without skips the head would read it
-        WaveNet.from_config(WaveNet.Config(io_spec=io, blocks=(), kernel_sizes=(2, 2), residuals_dim=128))
     assert WaveNet.from_config(WaveNet.Config(io_spec=io, blocks=(), kernel_sizes=(2, 3, 2))).rf == 1 + 1 + 4 + 6
     with pytest.raises(NotImplementedError):
         WaveNet.from_config(WaveNet.Config(io_spec=io, act_g="GLU"))
@@ -245,7 +243,8 @@ def test_exported_checkpoint_generates_the_golden_sequence(tmp_path):
                                   "wavenet_reversed", "wavenet_nongated", "wavenet_groups4", "wavenet_affine_res",
                                   "wavenet_affine_plain", "wavenet_act_mish_softplus", "wavenet_act_sin_cos",
                                   "wavenet_act_relu_identity", "wavenet_act_abs_tanh", "wavenet_act_sigmoid_none",
-                                  "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine", "wavenet_dropped_res"])
+                                  "wavenet_no_temperature", "wavenet_noblocks", "wavenet_nobias_affine", "wavenet_dropped_res",
+                                  "wavenet_reversed_noskip", "wavenet_noblocks_noskip"])
 def test_variant_goldens(name):
     """SURVEY §8 f3, first slice, against the live reference (tests/golden, oracle/make_golden.py wavenet_variants):
     pad_side=1, layerwise_inputs (with skips, and without skips + 2 hidden MLP layers), kernel_size 3.  Sequences bit-exact,
