@@ -46,7 +46,9 @@ class SampleRNN(NativeARM):
         need(str(c.rnn_class) in ("gru", "lstm", "rnn"), "rnn_class other than 'lstm', 'gru' or 'rnn'")
         need(1 <= c.n_rnn <= 4, "n_rnn outside [1, 4]")     # rnn_bias=False: no rnn.bias_* parameters; the kernels get zero biases
         need(str(c.h0_init) in ("zeros", "ones", "randn"), "h0_init other than 'zeros', 'ones' or 'randn'")
-        need(str(c.inputs_mode) == "sum", "inputs_mode other than 'sum'")
+        # ZipReduceVariables (modules/io.py:289-313) over the ONE input of the mu-law path: "sum" and "mean" weigh it by 1 and 1 / 1,
+        # "static_mix" by the softmax of a one-element parameter — exactly 1.0f in all three; static_mix adds `input_module.weights`
+        need(str(c.inputs_mode) in ("sum", "mean", "static_mix"), "inputs_mode other than 'sum', 'mean' or 'static_mix'")
         need(len(c.frame_sizes) >= 2, "fewer than two tiers")
         need(0 <= c.io_spec.targets[0].module.n_hidden_layers <= 8, "more than 8 hidden MLP layers")
         fs = c.frame_sizes
@@ -130,6 +132,8 @@ class SampleRNN(NativeARM):
         e = OrderedDict()
         for i in range(len(fs) - 1):
             p = f"tiers.{i}."
+            if str(self._config.inputs_mode) == "static_mix":
+                e[p + "input_module.weights"] = (1,)
             e[p + "input_module.heads.0.2.weight"] = (H, fs[i])
             e[p + "input_module.heads.0.2.bias"] = (H,)
             for k in range(self._config.n_rnn):       # nn.GRU / nn.LSTM / nn.RNN parameter names, layer by layer
@@ -140,6 +144,8 @@ class SampleRNN(NativeARM):
                     e[p + f"rnn.bias_hh_l{k}"] = (self._gates * H,)
             e[p + "up_sampler.fc.weight"] = (H * self._up(i), H)
             e[p + "up_sampler.fc.bias"] = (H * self._up(i),)
+        if str(self._config.inputs_mode) == "static_mix":
+            e[f"tiers.{len(fs) - 1}.input_module.weights"] = (1,)
         p = f"tiers.{len(fs) - 1}.input_module.heads.0.2.2.cv."
         e[p + "weight"] = (H, 1, fs[-1])
         e[p + "bias"] = (H,)
@@ -167,6 +173,9 @@ class SampleRNN(NativeARM):
             if k.endswith("min_temp"):
                 mt = self._config.io_spec.targets[0].module.min_temperature
                 sd[k] = torch.tensor(1e-4 if mt is None else float(mt), dtype=torch.float32)
+                continue
+            if k.endswith("input_module.weights"):        # modules/io.py:304
+                sd[k] = -torch.rand(shape)
                 continue
             if ".rnn." in k:
                 bound = 1.0 / math.sqrt(H)

@@ -36,7 +36,7 @@ def gen_samplernn_variant(name, prompts, n_steps, h0_seed=None, **kw):
     noise = torch.rand(B, n_steps, generator=torch.Generator().manual_seed(4321))
     meta = dict(frame_sizes=kw["frame_sizes"], hidden_dim=kw["hidden_dim"], mlp_dim=kw["mlp_dim"], no_temperature=int(no_temp),
                 rnn_class=kw.get("rnn_class", "gru"), n_rnn=kw.get("n_rnn", 1), h0_init=kw.get("h0_init", "zeros"),
-                n_mlp_layers=kw.get("n_mlp_layers", 0), rnn_bias=int(kw.get("rnn_bias", True)))
+                n_mlp_layers=kw.get("n_mlp_layers", 0), rnn_bias=int(kw.get("rnn_bias", True)), inputs_mode=kw.get("inputs_mode", "sum"))
     out = dict(sd_arrays(net.state_dict()), prompts=prompts.numpy(), noise=noise.numpy(),
                **{"meta/" + k: np.asarray(v) for k, v in meta.items()})
     H, n_rnn, lstm = kw["hidden_dim"], meta["n_rnn"], meta["rnn_class"] == "lstm"
@@ -206,6 +206,13 @@ def main():
         net = ref_loader.make_wavenet(seed=38, kernel_sizes=(2, 2, 3), **kw)
         assert "layers.2.conv_res.weight" in net.state_dict()
         gen_network("wavenet_noblocks_noskip", net, torch.randint(0, 256, (2, 24), generator=g), 16, dict(kw, kernel_sizes=(2, 2, 3)))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "samplernn_zipmodes":    # inputs_mode "mean" / "static_mix" (modules/io.py:283-313) with the ONE input of
+        g = torch.Generator().manual_seed(100)                       # the mu-law path: weights 1 / 1 and softmax of one element, both exactly 1.0
+        gen_samplernn_variant("samplernn_static_mix", torch.randint(0, 256, (2, 24), generator=g), 16, frame_sizes=(4, 2, 1),
+                              hidden_dim=32, mlp_dim=32, seed=39, rnn_class="lstm", inputs_mode="static_mix")
+        gen_samplernn_variant("samplernn_mean", torch.randint(0, 256, (2, 24), generator=g), 16, frame_sizes=(4, 2, 1),
+                              hidden_dim=32, mlp_dim=32, seed=40, rnn_class="gru", inputs_mode="mean")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "samplernn_nobias":      # rnn_bias=False (sample_rnn_v2.py:66, 130): no rnn.bias_* parameters
         g = torch.Generator().manual_seed(96)

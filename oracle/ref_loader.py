@@ -156,14 +156,14 @@ def make_wavenet(blocks=(4,), dims=128, residuals_dim=None, skips_dim=None, seed
 
 
 def make_samplernn(frame_sizes=(8, 2, 1), hidden_dim=512, seed=0, mlp_dim=128, sr=16000,
-                   rnn_class="gru", h0_init="zeros", n_rnn=1, n_mlp_layers=0, min_temperature=1e-4, rnn_bias=True):
+                   rnn_class="gru", h0_init="zeros", n_rnn=1, n_mlp_layers=0, min_temperature=1e-4, rnn_bias=True, inputs_mode="sum"):
     import torch
     ref = load()
     torch.manual_seed(seed)
     cfg = ref.SampleRNN.Config(
         io_spec=ref.IOSpec.mulaw_io(ref.IOSpec.MuLawIOConfig(sr=sr, mlp_dim=mlp_dim, n_mlp_layers=n_mlp_layers,
                                                              min_temperature=min_temperature)),
-        frame_sizes=tuple(frame_sizes), hidden_dim=hidden_dim, rnn_class=rnn_class, h0_init=h0_init, n_rnn=n_rnn, rnn_bias=rnn_bias)
+        frame_sizes=tuple(frame_sizes), hidden_dim=hidden_dim, rnn_class=rnn_class, h0_init=h0_init, n_rnn=n_rnn, rnn_bias=rnn_bias, inputs_mode=inputs_mode)
     return ref.SampleRNN.from_config(cfg)
 
 

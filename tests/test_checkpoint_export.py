@@ -86,3 +86,17 @@ def test_samplernn_reference_defaults_export_roundtrip(tmp_path):
     p = "output_modules.0.estimator.0."
     assert torch.equal(sd[p + "fc.2.weight"], sd[p + "fc.4.weight"]) and tuple(sd[p + "fc.6.weight"].shape) == (257, 32)
     assert tuple(sd["tiers.0.rnn.weight_ih_l1"].shape) == (128, 32)
+
+
+def test_samplernn_config_surface_export_roundtrip(tmp_path):
+    """rnn_bias=False (no rnn.bias_* parameters), inputs_mode 'static_mix' (an `input_module.weights` parameter per tier) and
+    a head without the learned temperature: the exported network reloads with the reference's keys, in the reference's order."""
+    ref_net = ref_loader.make_samplernn(frame_sizes=(4, 2, 1), hidden_dim=32, mlp_dim=32, seed=6, rnn_class="gru", rnn_bias=False,
+                                        inputs_mode="static_mix", min_temperature=None)
+    ours, sd_ref, sd, d = _roundtrip(ref_net, tmp_path)
+    assert list(sd) == [k for k in sd_ref]
+    assert "tiers.0.rnn.bias_ih_l0" not in sd and tuple(sd["tiers.2.input_module.weights"].shape) == (1,)
+    assert "output_modules.0.estimator.0.min_temp" not in sd
+    for k in sd_ref:
+        assert torch.equal(sd[k], sd_ref[k].float().cpu()), k
+    assert d["config"]["inputs_mode"] == "static_mix" and d["config"]["rnn_bias"] is False

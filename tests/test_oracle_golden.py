@@ -213,7 +213,8 @@ def test_product_wavenet_structure_matches_the_reference_kats():
 
 
 VARIANTS = ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2", "samplernn_rnn_tanh_mlp1",
-            "samplernn_no_temperature", "samplernn_lstm_nobias", "samplernn_gru_nobias_2layers"]
+            "samplernn_no_temperature", "samplernn_lstm_nobias", "samplernn_gru_nobias_2layers",
+            "samplernn_static_mix", "samplernn_mean"]
 
 
 def variant_setup(d):

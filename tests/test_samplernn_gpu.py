@@ -436,7 +436,7 @@ def test_s3_long_horizon_vs_oracle():
 
 @pytest.mark.parametrize("name", ["samplernn_lstm_default", "samplernn_lstm_2layers_ones", "samplernn_gru_3layers_randn_mlp2",
                                   "samplernn_rnn_tanh_mlp1", "samplernn_no_temperature", "samplernn_lstm_nobias",
-                                  "samplernn_gru_nobias_2layers"])
+                                  "samplernn_gru_nobias_2layers", "samplernn_static_mix", "samplernn_mean"])
 def test_variant_goldens(name):
     """The rest of SampleRNNTier's configuration surface against the live reference (tests/golden, generated by
     oracle/make_golden.py samplernn_variants): rnn_class "lstm" (the reference DEFAULT) / "rnn", n_rnn 2 and 3, h0_init
@@ -450,7 +450,8 @@ def test_variant_goldens(name):
     cfg = SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]), n_mlp_layers=kw["n_mlp_hidden"],
                                                                         **head)),
                            frame_sizes=fs, hidden_dim=int(m["hidden_dim"]), rnn_class=kw["rnn_class"], n_rnn=kw["n_rnn"],
-                           h0_init=str(m["h0_init"]), rnn_bias=bool(int(m.get("rnn_bias", 1))))
+                           h0_init=str(m["h0_init"]), rnn_bias=bool(int(m.get("rnn_bias", 1))),
+                           inputs_mode=str(m.get("inputs_mode", "sum")))
     net = SampleRNN.from_config(cfg).to("cuda")
     net.load_state_dict(golden_state_dict(d))
     prompts, noise = torch.from_numpy(d["prompts"]), torch.from_numpy(d["noise"])
