@@ -388,7 +388,7 @@ def test_weight_norm_checkpoint_and_errors():
     with pytest.raises(NotImplementedError):
         SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), rnn_class="gru", n_rnn=5))
     with pytest.raises(NotImplementedError):
-        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), inputs_mode="mean"))
+        SampleRNN.from_config(SampleRNN.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig()), inputs_mode="prod"))  # not a ZipMode
 
 
 def test_s3_full_width_properties():
