@@ -276,3 +276,75 @@ def test_wavenet_variant_oracle_vs_reference(name):
     tf = orc.logits_teacher_forced(d["seq_argmax"])
     P = d["prompts"].shape[1]
     np.testing.assert_allclose(tf[:, P - orc.rf:P - orc.rf + n], d["logits_argmax"], rtol=1e-3, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host logic of the drop-in networks (no GPU): every golden state dict of the live reference loads into the product
+# network built from the same configuration — same keys, same order, same shapes — and unsupported ones raise
+# ---------------------------------------------------------------------------------------------------------------
+def product_wavenet_config(d):
+    from mimikit_b200 import IOSpec, WaveNet
+    m, kw = wavenet_variant_kwargs(d)
+    head = dict(min_temperature=None) if int(m.get("no_temperature", 0)) else {}
+    return WaveNet.Config(
+        io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding", mlp_dim=int(m["mlp_dim"]),
+                                                     n_mlp_layers=kw["n_mlp_hidden"], **head)),
+        blocks=tuple(int(b) for b in m["blocks"]), dims_dilated=(int(m["dims"]),),
+        residuals_dim=int(m["residuals_dim"]) if "residuals_dim" in m else None,
+        skips_dim=int(m["skips_dim"]) if "skips_dim" in m else None, kernel_sizes=kw["kernel_sizes"],
+        layerwise_inputs=kw["layerwise_inputs"], pad_side=int(m.get("pad_side", 0)), reverse_layer_order=kw["reverse_layer_order"],
+        groups=int(m.get("groups", 1)), with_affine_residuals=bool(int(m.get("affine", 0))), bias=not int(m.get("nobias", 0)),
+        act_f=kw["act_f"], act_g=None if int(m.get("nongated", 0)) else kw["act_g"])
+
+
+@pytest.mark.parametrize("name", WN_VARIANTS + ["wavenet_default_small", "wavenet_res_skip_small", "wavenet_res_skip_mid"])
+def test_product_wavenet_takes_the_reference_state_dict(name):
+    from mimikit_b200 import WaveNet
+    d = load_golden(name)
+    sd = golden_state_dict(d)
+    net = WaveNet.from_config(product_wavenet_config(d))
+    assert list(net.state_dict()) == list(sd), name                       # the reference's keys in the reference's order
+    net.load_state_dict(sd)
+    for k, v in net.state_dict().items():
+        assert np.array_equal(v.numpy(), np.asarray(sd[k], dtype=np.float32)), (name, k)
+    orc = restate.WaveNetOracle(sd, tuple(int(b) for b in d["meta/blocks"]), **wavenet_variant_kwargs(d)[1])
+    assert net.rf == orc.rf and net.dilations == orc.dilations and net.kernels == orc.kernels
+
+
+@pytest.mark.parametrize("name", VARIANTS + ["samplernn_821_small", "samplernn_1642_small", "samplernn_41_small"])
+def test_product_samplernn_takes_the_reference_state_dict(name):
+    from mimikit_b200 import IOSpec, SampleRNN
+    d = load_golden(name)
+    sd = golden_state_dict(d)
+    m = {k[5:]: v for k, v in d.items() if k.startswith("meta/")}
+    head = dict(min_temperature=None) if int(m.get("no_temperature", 0)) else {}
+    cfg = SampleRNN.Config(
+        io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig(mlp_dim=int(m["mlp_dim"]), n_mlp_layers=int(m.get("n_mlp_layers", 0)), **head)),
+        frame_sizes=tuple(int(f) for f in m["frame_sizes"]), hidden_dim=int(m["hidden_dim"]), rnn_class=str(m.get("rnn_class", "gru")),
+        n_rnn=int(m.get("n_rnn", 1)), h0_init=str(m.get("h0_init", "zeros")), rnn_bias=bool(int(m.get("rnn_bias", 1))),
+        inputs_mode=str(m.get("inputs_mode", "sum")))
+    net = SampleRNN.from_config(cfg)
+    assert list(net.state_dict()) == list(sd), name
+    net.load_state_dict(sd)
+    for k, v in net.state_dict().items():
+        assert np.array_equal(v.numpy(), np.asarray(sd[k], dtype=np.float32)), (name, k)
+
+
+def test_product_config_surface_rejections():
+    """What the kernels do not host raises NotImplementedError at from_config — never a silent change of the computation."""
+    from mimikit_b200 import IOSpec, SampleRNN, WaveNet
+    io = IOSpec.mulaw_io(IOSpec.MuLawIOConfig(input_module_type="embedding"))
+    for bad in (dict(pad_side=-1), dict(stride=2), dict(kernel_sizes=(5,)), dict(dims_1x1=(16,)), dict(act_f="GLU"),
+                dict(act_g="PhaseA"), dict(act_f="Softmax")):
+        with pytest.raises(NotImplementedError):
+            WaveNet.from_config(WaveNet.Config(io_spec=io, **bad))
+    with pytest.raises(NotImplementedError):      # the reference's own default input type raises in the reference too (DESIGN §2)
+        WaveNet.from_config(WaveNet.Config(io_spec=IOSpec.mulaw_io(IOSpec.MuLawIOConfig())))
+    fio = IOSpec.mulaw_io(IOSpec.MuLawIOConfig())
+    for bad in (dict(rnn_class="none"), dict(n_rnn=5), dict(inputs_mode="prod"), dict(h0_init="uniform"), dict(frame_sizes=(4,)),
+                dict(frame_sizes=(8, 3, 1))):
+        with pytest.raises(NotImplementedError):
+            SampleRNN.from_config(SampleRNN.Config(io_spec=fio, **bad))
+    for ok in (dict(blocks=(), kernel_sizes=(2, 3), residuals_dim=128), dict(reverse_layer_order=True, residuals_dim=128),
+               dict(residuals_dim=64), dict(bias=False), dict(with_affine_residuals=True), dict(act_f="Sin", act_g="Cos")):
+        WaveNet.from_config(WaveNet.Config(io_spec=io, **ok))
